@@ -1,0 +1,166 @@
+/*
+ * liger_b200 -- C ABI of the B200-native iNMF / UINMF alternating-NNLS path.
+ *
+ * This header is the drop-in boundary.  Every entry point
+ * replaces one native call the reference makes on this path (citations are
+ * into the reference tree, welch-lab/liger):
+ *
+ *   lgr_inmf            <- RcppPlanc::inmf(objectList, k, lambda, niter, Hinit, Vinit, Winit, nCores, verbose)
+ *                          call sites R/integration.R:438-441, R/cINMF.R:294-297, R/suggestK.R:78-88
+ *   lgr_uinmf           <- RcppPlanc::uinmf(object, unsharedList, k, lambda, niter, nCores, verbose)
+ *                          call site  R/integration.R:1285-1287
+ *   lgr_bppnnls_prod    <- RcppPlanc::bppnnls_prod(CtC, CtB, nCores)
+ *                          call sites R/cINMF.R:481,489,501; R/optimizeNewParam.R:104,118,134,291,329
+ *   lgr_objerr_i        <- objErr_i(H, W, V, E, lambda)      src/objErr.cpp:13-31 (glue src/RcppExports.cpp:270-284)
+ *   lgr_r_set_seed / lgr_r_runif
+ *                       <- set.seed(seed); runif(n, 0, 2)    R/integration.R:412-437 (seeded initialisation)
+ *
+ * Conventions
+ *   - plain C, POD structs, no exceptions cross this boundary; every function that can fail
+ *     returns 0 on success and a non-zero lgr_status otherwise, with a message in lgr_last_error().
+ *   - all matrices are R layout: dense = column-major double; sparse = dgCMatrix slots
+ *     (@p int32 column pointers, @i int32 0-based row indices, @x values, @Dim).
+ *   - the library never retains or frees caller pointers; outputs are written only into
+ *     caller-allocated buffers.  All device memory is owned by the library.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     LGR_ERR_NO_DEVICE.
+ */
+#ifndef LIGER_B200_H
+#define LIGER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LGR_API __attribute__((visibility("default")))
+#else
+#define LGR_API
+#endif
+
+#define LGR_VERSION_MAJOR 0
+#define LGR_VERSION_MINOR 1
+#define LGR_MAX_K 64 /* factors; passive sets are 64-bit masks */
+
+typedef enum lgr_status {
+    LGR_OK = 0,
+    LGR_ERR_INVALID = 1,   /* bad argument (message says which) */
+    LGR_ERR_NO_DEVICE = 2, /* no usable CUDA device: there is no CPU path */
+    LGR_ERR_CUDA = 3,      /* CUDA runtime / kernel failure */
+    LGR_ERR_NCCL = 4,      /* NCCL failure or libnccl not loadable */
+    LGR_ERR_ALLOC = 5,
+    LGR_ERR_INTERRUPT = 6  /* the caller's interrupt callback asked to stop */
+} lgr_status;
+
+typedef enum lgr_dtype { LGR_F64 = 0, LGR_F32 = 1 } lgr_dtype;
+
+/* One dgCMatrix (genes x cells, CSC).  `values` is double (R) or float (pre-converted). */
+typedef struct lgr_csc {
+    int64_t nrow;
+    int64_t ncol;
+    const int32_t* colptr; /* ncol + 1 */
+    const int32_t* rowidx; /* nnz, 0-based; need not be sorted within a column */
+    const void* values;    /* nnz */
+    int32_t value_dtype;   /* lgr_dtype */
+    int32_t reserved;
+} lgr_csc;
+
+/* flags for lgr_inmf_args.flags */
+#define LGR_FLAG_TRAJECTORY 0x1u  /* evaluate the objective after every iteration into out->obj_traj */
+#define LGR_FLAG_COLD_START 0x2u  /* disable NNLS warm starts (every solve starts from the empty passive set) */
+#define LGR_FLAG_PINNED_IO 0x4u   /* caller promises host buffers are page-locked (faster copies) */
+
+/* Arguments of one iNMF / UINMF factorisation.  iNMF: P == NULL, Uinit == NULL. */
+typedef struct lgr_inmf_args {
+    int32_t d;     /* number of datasets */
+    int32_t k;     /* factors, 1..LGR_MAX_K */
+    int32_t niter; /* ANLS iterations (H, V, W per iteration) */
+    uint32_t flags;
+    int64_t m;             /* shared features (rows of every E[i]) */
+    const lgr_csc* E;      /* d shared blocks, m x n_i */
+    const lgr_csc* P;      /* NULL, or d unshared blocks u_i x n_i (nrow == 0 => none for that dataset) */
+    const double* lambda;  /* d penalties (iNMF: the scalar repeated) */
+    const double* Winit;   /* m x k */
+    const double* const* Vinit; /* d pointers, each m x k */
+    const double* const* Uinit; /* NULL, or d pointers, each u_i x k (NULL where u_i == 0) */
+    const double* const* Hinit; /* NULL, or d pointers, each n_i x k.  H is solved first, so Hinit only
+                                   matters when niter == 0 (as in RcppPlanc). */
+    /* execution */
+    int32_t device; /* CUDA ordinal; -1 = current device */
+    int32_t rank;   /* cell-shard rank of this process, 0 when world == 1 */
+    int32_t world;  /* number of processes sharing the factorisation (one GPU each) */
+    int32_t reserved;
+    const void* nccl_unique_id; /* 128 bytes from lgr_nccl_unique_id() (same on all ranks); NULL if world == 1 */
+    /* optional: polled between iterations; non-zero return aborts with LGR_ERR_INTERRUPT */
+    int (*interrupt)(void* user);
+    void* interrupt_user;
+} lgr_inmf_args;
+
+typedef struct lgr_timings {
+    double upload_ms;   /* H2D + on-device layout conversion */
+    double loop_ms;     /* the ANLS loop (device time, CUDA events) */
+    double download_ms; /* D2H of factors */
+    double h_phase_ms, vw_phase_ms, comm_ms;
+    int64_t kernel_launches; /* kernels launched inside the loop */
+    int64_t nnls_unconverged; /* columns that hit the pivot cap (expected 0) */
+    int64_t nnls_pivots;      /* total BPP pivots over all H solves */
+} lgr_timings;
+
+/* Caller-allocated outputs.  Any pointer may be NULL to skip that output. */
+typedef struct lgr_inmf_out {
+    double* W;          /* m x k */
+    double* const* V;   /* d pointers, m x k */
+    double* const* U;   /* d pointers, u_i x k (UINMF) */
+    double* const* H;   /* d pointers, n_i x k  (cell x factor, as RcppPlanc returns it; the R wrapper
+                           transposes, R/integration.R:453) */
+    uint64_t* const* H_passive; /* optional: d pointers, n_i passive-set bitmasks (bit f set <=> H[j,f] free) */
+    double* obj_traj;   /* niter values when LGR_FLAG_TRAJECTORY */
+    double objErr;      /* final objective (sum over datasets of objErr_i) */
+    lgr_timings timings;
+} lgr_inmf_out;
+
+/* ---- one-shot calls with HOST buffers (what the Rcpp shim binds) ------------------------- */
+LGR_API int lgr_inmf(const lgr_inmf_args* args, lgr_inmf_out* out);
+LGR_API int lgr_uinmf(const lgr_inmf_args* args, lgr_inmf_out* out);
+
+/* X = argmin_{X>=0} ||C X - B|| from CtC (k x k) and CtB (k x c); X is k x c.  FP64 on the device. */
+LGR_API int lgr_bppnnls_prod(int32_t k, int64_t c, const double* CtC, const double* CtB, double* X, int32_t device);
+
+/* objErr_i: H is k x n (as in src/objErr.cpp), W, V are m x k, E is m x n. */
+LGR_API int lgr_objerr_i(int32_t k, const double* H, const double* W, const double* V, const lgr_csc* E, double lambda,
+                 int32_t device, double* err);
+
+/* ---- resident-handle API (data stays in HBM between calls; used by bench + multi-GPU hosts) ---- */
+typedef struct lgr_ctx lgr_ctx;
+LGR_API int lgr_ctx_create(const lgr_inmf_args* args, lgr_ctx** ctx); /* uploads E/P, builds device layouts, sets inits */
+LGR_API int lgr_ctx_reset(lgr_ctx* ctx, const double* Winit, const double* const* Vinit, const double* const* Uinit);
+LGR_API int lgr_ctx_iterate(lgr_ctx* ctx, int32_t niter, double* obj_traj /* NULL or niter */);
+LGR_API int lgr_ctx_objective(lgr_ctx* ctx, double* obj);
+LGR_API int lgr_ctx_download(lgr_ctx* ctx, lgr_inmf_out* out);
+LGR_API int lgr_ctx_timings(lgr_ctx* ctx, lgr_timings* t);
+LGR_API void* lgr_ctx_stream(lgr_ctx* ctx); /* the cudaStream_t all kernels are launched on */
+/* per-kernel device time of the last lgr_ctx_iterate (CUDA events on the launch stream):
+   names[i] / ms[i] / launches[i] for i < *n (n in: capacity, out: count). */
+LGR_API int lgr_ctx_kernel_times(lgr_ctx* ctx, int32_t* n, const char** names, double* ms, int64_t* launches);
+LGR_API int lgr_ctx_set_kernel_timing(lgr_ctx* ctx, int32_t on); /* record CUDA events around every kernel of the loop */
+LGR_API void lgr_ctx_destroy(lgr_ctx* ctx);
+
+/* ---- seeded initialisation: R's Mersenne-Twister stream (R/integration.R:412-437) ---------- */
+typedef struct lgr_rng lgr_rng;
+LGR_API lgr_rng* lgr_r_set_seed(uint32_t seed);
+LGR_API void lgr_r_runif(lgr_rng* rng, int64_t n, double lo, double hi, double* out); /* abs() applied by caller */
+LGR_API void lgr_r_free(lgr_rng* rng);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+LGR_API const char* lgr_last_error(void);
+LGR_API int lgr_device_count(void);
+LGR_API int lgr_version(void);                      /* major * 1000 + minor */
+LGR_API int lgr_nccl_unique_id(void* out128);       /* rank 0 calls this and ships the 128 bytes to the others */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGER_B200_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of include/liger_b200.h (the C ABI of the CUDA library).
+
+There is no Python or CPU implementation behind these calls: if the shared library is
+missing, or no CUDA device is present, the calls fail loudly."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libliger_b200.so")
+
+LGR_F64, LGR_F32 = 0, 1
+FLAG_TRAJECTORY, FLAG_COLD_START, FLAG_PINNED_IO = 0x1, 0x2, 0x4
+STATUS = {0: "OK", 1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "NCCL", 5: "ALLOC", 6: "INTERRUPT"}
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_uint64_p = C.POINTER(C.c_uint64)
+
+
+class lgr_csc(C.Structure):
+    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("colptr", c_int32_p), ("rowidx", c_int32_p),
+                ("values", C.c_void_p), ("value_dtype", C.c_int32), ("reserved", C.c_int32)]
+
+
+INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class lgr_inmf_args(C.Structure):
+    _fields_ = [("d", C.c_int32), ("k", C.c_int32), ("niter", C.c_int32), ("flags", C.c_uint32),
+                ("m", C.c_int64), ("E", C.POINTER(lgr_csc)), ("P", C.POINTER(lgr_csc)),
+                ("lambda_", c_double_p), ("Winit", c_double_p), ("Vinit", C.POINTER(c_double_p)),
+                ("Uinit", C.POINTER(c_double_p)), ("Hinit", C.POINTER(c_double_p)),
+                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32),
+                ("nccl_unique_id", C.c_void_p), ("interrupt", INTERRUPT_FN), ("interrupt_user", C.c_void_p)]
+
+
+class lgr_timings(C.Structure):
+    _fields_ = [("upload_ms", C.c_double), ("loop_ms", C.c_double), ("download_ms", C.c_double),
+                ("h_phase_ms", C.c_double), ("vw_phase_ms", C.c_double), ("comm_ms", C.c_double),
+                ("kernel_launches", C.c_int64), ("nnls_unconverged", C.c_int64), ("nnls_pivots", C.c_int64)]
+
+
+class lgr_inmf_out(C.Structure):
+    _fields_ = [("W", c_double_p), ("V", C.POINTER(c_double_p)), ("U", C.POINTER(c_double_p)),
+                ("H", C.POINTER(c_double_p)), ("H_passive", C.POINTER(c_uint64_p)), ("obj_traj", c_double_p),
+                ("objErr", C.c_double), ("timings", lgr_timings)]
+
+
+class LigerB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liger_b200 [{STATUS.get(code, code)}]: {msg}")
+        self.code = code
+
+
+_lib = None
+
+# every symbol include/liger_b200.h declares (tests check that the .so exports all of them)
+EXPORTS = [
+    "lgr_inmf", "lgr_uinmf", "lgr_bppnnls_prod", "lgr_objerr_i", "lgr_ctx_create", "lgr_ctx_reset",
+    "lgr_ctx_iterate", "lgr_ctx_objective", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
+    "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
+    "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id",
+]
+
+
+def lib():
+    """Load libliger_b200.so (built in-tree by `python -m liger_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LigerB200Error(2, f"{LIB_PATH} is missing: build it with `python -m liger_b200.build` "
+                                "(there is no Python/CPU fallback for the iNMF hot path)")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L.lgr_last_error.restype = C.c_char_p
+    L.lgr_inmf.argtypes = [C.POINTER(lgr_inmf_args), C.POINTER(lgr_inmf_out)]
+    L.lgr_uinmf.argtypes = [C.POINTER(lgr_inmf_args), C.POINTER(lgr_inmf_out)]
+    L.lgr_bppnnls_prod.argtypes = [C.c_int32, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_int32]
+    L.lgr_objerr_i.argtypes = [C.c_int32, c_double_p, c_double_p, c_double_p, C.POINTER(lgr_csc), C.c_double,
+                               C.c_int32, c_double_p]
+    L.lgr_ctx_create.argtypes = [C.POINTER(lgr_inmf_args), C.POINTER(C.c_void_p)]
+    L.lgr_ctx_reset.argtypes = [C.c_void_p, c_double_p, C.POINTER(c_double_p), C.POINTER(c_double_p)]
+    L.lgr_ctx_iterate.argtypes = [C.c_void_p, C.c_int32, c_double_p]
+    L.lgr_ctx_objective.argtypes = [C.c_void_p, c_double_p]
+    L.lgr_ctx_download.argtypes = [C.c_void_p, C.POINTER(lgr_inmf_out)]
+    L.lgr_ctx_timings.argtypes = [C.c_void_p, C.POINTER(lgr_timings)]
+    L.lgr_ctx_stream.argtypes = [C.c_void_p]
+    L.lgr_ctx_stream.restype = C.c_void_p
+    L.lgr_ctx_kernel_times.argtypes = [C.c_void_p, c_int32_p, C.POINTER(C.c_char_p), c_double_p,
+                                       C.POINTER(C.c_int64)]
+    L.lgr_ctx_set_kernel_timing.argtypes = [C.c_void_p, C.c_int32]
+    L.lgr_ctx_destroy.argtypes = [C.c_void_p]
+    L.lgr_ctx_destroy.restype = None
+    L.lgr_r_set_seed.argtypes = [C.c_uint32]
+    L.lgr_r_set_seed.restype = C.c_void_p
+    L.lgr_r_runif.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, c_double_p]
+    L.lgr_r_runif.restype = None
+    L.lgr_r_free.argtypes = [C.c_void_p]
+    L.lgr_r_free.restype = None
+    L.lgr_nccl_unique_id.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != 0:
+        raise LigerB200Error(code, lib().lgr_last_error().decode("utf-8", "replace"))

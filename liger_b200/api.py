@@ -1,0 +1,324 @@
+"""Host-side mirror of the native calls rliger makes on the iNMF / UINMF path.
+
+Function names, argument names/meaning and return shapes follow the reference's call sites
+(welch-lab/liger):
+
+    inmf(objectList, k, lambda_, niter, Hinit, Vinit, Winit, nCores, verbose)
+        <- RcppPlanc::inmf            R/integration.R:438-441
+    uinmf(objectList, unsharedList, k, lambda_, niter, nCores, verbose)
+        <- RcppPlanc::uinmf           R/integration.R:1285-1287
+    bppnnls_prod(CtC, CtB, nCores)    <- RcppPlanc::bppnnls_prod   R/cINMF.R:481,489,501
+    objErr_i(H, W, V, E, lambda_)     <- objErr_i                  src/objErr.cpp:13-31
+
+Everything is computed by the CUDA library behind include/liger_b200.h; this module only
+marshals numpy / scipy buffers (the ctypes analogue of the Rcpp shim in INTEGRATION.md).
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _ffi
+from ._ffi import lgr_csc, lgr_inmf_args, lgr_inmf_out, c_double_p, c_int32_p, c_uint64_p
+
+
+def _f64(a, order="F"):
+    return np.require(np.asarray(a, dtype=np.float64), dtype=np.float64, requirements=[order.upper() + "_CONTIGUOUS", "ALIGNED"])
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+class _Csc:
+    """Keeps the numpy buffers of one dgCMatrix-like input alive and exposes an lgr_csc view."""
+
+    def __init__(self, mat, keep_f32=False):
+        if sp.issparse(mat):
+            m = mat.tocsc()
+            indptr, indices, data, shape = m.indptr, m.indices, m.data, m.shape
+        else:  # (indptr, indices, data, shape) tuple, e.g. pinned buffers prepared by bench.py
+            indptr, indices, data, shape = mat
+        if int(indptr[-1]) >= 2 ** 31:
+            raise ValueError("more than 2^31-1 non-zeros in one matrix (dgCMatrix limit)")
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        if data.dtype == np.float32 and keep_f32:
+            self.data = np.ascontiguousarray(data)
+            dt = _ffi.LGR_F32
+        else:
+            self.data = np.ascontiguousarray(data, dtype=np.float64)
+            dt = _ffi.LGR_F64
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.struct = lgr_csc(self.shape[0], self.shape[1], self.indptr.ctypes.data_as(c_int32_p),
+                              self.indices.ctypes.data_as(c_int32_p), self.data.ctypes.data_as(C.c_void_p), dt, 0)
+
+
+class _Args:
+    """Builds lgr_inmf_args and owns every buffer it points to."""
+
+    def __init__(self, objectList, k, lambda_, niter, Winit, Vinit, Hinit=None, unsharedList=None, Uinit=None,
+                 flags=0, device=-1, rank=0, world=1, nccl_id=None, keep_f32=False):
+        d = len(objectList)
+        if d < 1:
+            raise ValueError("objectList is empty")
+        self.E = [_Csc(x, keep_f32) for x in objectList]
+        self.m = self.E[0].shape[0]
+        self.k = int(k)
+        self.d = d
+        self.n = [e.shape[1] for e in self.E]
+        self.u = [0] * d
+        self.Earr = (lgr_csc * d)(*[e.struct for e in self.E])
+        self.Parr = None
+        self.P = [None] * d
+        if unsharedList is not None:
+            ps = []
+            for i, p in enumerate(unsharedList):
+                if p is None or p.shape[0] == 0:
+                    ps.append(lgr_csc(0, self.n[i], None, None, None, 0, 0))
+                else:
+                    self.P[i] = _Csc(p, keep_f32)
+                    self.u[i] = self.P[i].shape[0]
+                    ps.append(self.P[i].struct)
+            self.Parr = (lgr_csc * d)(*ps)
+        lam = np.broadcast_to(np.asarray(lambda_, dtype=np.float64), (d,)).copy()
+        self.lam = lam
+        self.W0 = _f64(Winit)
+        if self.W0.shape != (self.m, self.k):
+            raise ValueError(f"Winit must be {self.m} x {self.k}")
+        self.V0 = [_f64(v) for v in Vinit]
+        for v in self.V0:
+            if v.shape != (self.m, self.k):
+                raise ValueError(f"every Vinit must be {self.m} x {self.k}")
+        self.Varr = (c_double_p * d)(*[_dp(v) for v in self.V0])
+        self.Uarr = None
+        if unsharedList is not None:
+            self.U0 = [None if self.u[i] == 0 else _f64(Uinit[i]) for i in range(d)]
+            self.Uarr = (c_double_p * d)(*[(_dp(x) if x is not None else None) for x in self.U0])
+        self.Harr = None
+        if Hinit is not None:
+            self.H0 = [_f64(h) for h in Hinit]
+            for h, n in zip(self.H0, self.n):
+                if h.shape != (n, self.k):
+                    raise ValueError("every Hinit must be n_i x k")
+            self.Harr = (c_double_p * d)(*[_dp(h) for h in self.H0])
+        self.nccl_id = nccl_id
+        a = lgr_inmf_args()
+        a.d, a.k, a.niter, a.flags, a.m = d, self.k, int(niter), int(flags), self.m
+        a.E = self.Earr
+        a.P = self.Parr
+        a.lambda_ = _dp(lam)
+        a.Winit = _dp(self.W0)
+        a.Vinit = self.Varr
+        a.Uinit = self.Uarr
+        a.Hinit = self.Harr
+        a.device, a.rank, a.world = int(device), int(rank), int(world)
+        if nccl_id is not None:
+            self._idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+            a.nccl_unique_id = C.cast(self._idbuf, C.c_void_p)
+        self.struct = a
+
+
+class _Out:
+    def __init__(self, args, want_passive=False, traj=False):
+        d, k, m = args.d, args.k, args.m
+        self.W = np.zeros((m, k), order="F")
+        self.V = [np.zeros((m, k), order="F") for _ in range(d)]
+        self.H = [np.zeros((n, k), order="F") for n in args.n]
+        self.U = [np.zeros((u, k), order="F") if u > 0 else None for u in args.u]
+        self.Varr = (c_double_p * d)(*[_dp(v) for v in self.V])
+        self.Harr = (c_double_p * d)(*[_dp(h) for h in self.H])
+        self.Uarr = (c_double_p * d)(*[(_dp(u) if u is not None else None) for u in self.U])
+        o = lgr_inmf_out()
+        o.W = _dp(self.W)
+        o.V = self.Varr
+        o.H = self.Harr
+        o.U = self.Uarr
+        self.passive = None
+        if want_passive:
+            self.passive = [np.zeros(n, dtype=np.uint64) for n in args.n]
+            self.Parr = (c_uint64_p * d)(*[p.ctypes.data_as(c_uint64_p) for p in self.passive])
+            o.H_passive = self.Parr
+        self.traj = None
+        if traj:
+            self.traj = np.zeros(max(int(args.struct.niter), 1))
+            o.obj_traj = _dp(self.traj)
+        self.struct = o
+
+    def timings(self):
+        t = self.struct.timings
+        return {f: getattr(t, f) for f, _ in _ffi.lgr_timings._fields_}
+
+
+def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
+         trajectory=False, device=-1, return_passive=False, cold_start=False):
+    """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
+
+    objectList: list of scipy CSC matrices (genes x cells; the `scaleData` of each dataset).
+    Hinit: list of n_i x k, Vinit: list of m x k, Winit: m x k.  `nCores`/`verbose` are accepted for
+    signature parity and ignored (the work runs on the GPU).
+    Returns dict(H=[n_i x k], V=[m x k], W=m x k, objErr=float) exactly like RcppPlanc
+    (H is cell x factor; the caller transposes, R/integration.R:453).
+    """
+    if Winit is None or Vinit is None:
+        raise ValueError("liger_b200.inmf needs explicit Winit/Vinit (rliger's .runINMF.list always passes them; "
+                         "use liger_b200.integration.run_inmf_list for the seeded initialisation)")
+    flags = (_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0)
+    a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device)
+    o = _Out(a, want_passive=return_passive, traj=trajectory)
+    _ffi.check(_ffi.lib().lgr_inmf(C.byref(a.struct), C.byref(o.struct)))
+    res = {"H": o.H, "V": o.V, "W": o.W, "objErr": float(o.struct.objErr), "timings": o.timings()}
+    if trajectory:
+        res["traj"] = o.traj[:niter].copy()
+    if return_passive:
+        res["H_passive"] = o.passive
+    return res
+
+
+def uinmf(objectList, unsharedList, k=20, lambda_=5.0, niter=30, nCores=2, verbose=False, Winit=None, Vinit=None,
+          Uinit=None, trajectory=False, device=-1):
+    """Drop-in for RcppPlanc::uinmf (reference call site R/integration.R:1285-1287).
+
+    unsharedList[i]: u_i x n_i CSC or None.  lambda_: scalar or per-dataset vector
+    (vignettes/articles/STARmap_dropviz_vig.Rmd:72).  The reference passes no inits (RcppPlanc draws
+    them internally -- parity unpinned); here explicit W/V/U inits are required at this level and
+    liger_b200.integration.run_uinmf_list draws them from R's RNG stream.
+    Returns dict(H, V, W, U, objErr)."""
+    if Winit is None or Vinit is None or Uinit is None:
+        raise ValueError("liger_b200.uinmf needs explicit Winit/Vinit/Uinit; use integration.run_uinmf_list")
+    flags = _ffi.FLAG_TRAJECTORY if trajectory else 0
+    a = _Args(objectList, k, lambda_, niter, Winit, Vinit, None, unsharedList=unsharedList, Uinit=Uinit, flags=flags,
+              device=device)
+    o = _Out(a, traj=trajectory)
+    _ffi.check(_ffi.lib().lgr_uinmf(C.byref(a.struct), C.byref(o.struct)))
+    res = {"H": o.H, "V": o.V, "W": o.W, "U": o.U, "objErr": float(o.struct.objErr), "timings": o.timings()}
+    if trajectory:
+        res["traj"] = o.traj[:niter].copy()
+    return res
+
+
+def bppnnls_prod(CtC, CtB, nCores=2, device=-1):
+    """Drop-in for RcppPlanc::bppnnls_prod(CtC, CtB, nCores) (R/cINMF.R:481): returns X (k x c) >= 0."""
+    G = _f64(CtC)
+    B = _f64(CtB)
+    if B.ndim == 1:
+        B = _f64(B[:, None])
+    k, c = B.shape
+    if G.shape != (k, k):
+        raise ValueError("CtC must be k x k and CtB k x c")
+    X = np.zeros((k, c), order="F")
+    _ffi.check(_ffi.lib().lgr_bppnnls_prod(k, c, _dp(G), _dp(B), _dp(X), device))
+    return X
+
+
+def objErr_i(H, W, V, E, lambda_, device=-1):
+    """Drop-in for objErr_i (src/objErr.cpp:13-31): H is k x n, W/V are m x k, E is m x n sparse."""
+    H = _f64(H)   # k x n column-major == [cell][k]
+    W = _f64(W)
+    V = _f64(V)
+    e = _Csc(E)
+    k = H.shape[0]
+    if H.shape[1] != e.shape[1] or W.shape != (e.shape[0], k) or V.shape != W.shape:
+        raise ValueError("objErr_i: inconsistent shapes")
+    out = C.c_double(0.0)
+    _ffi.check(_ffi.lib().lgr_objerr_i(k, _dp(H), _dp(W), _dp(V), C.byref(e.struct), float(lambda_), device,
+                                       C.byref(out)))
+    return float(out.value)
+
+
+class Context:
+    """Resident-handle API: inputs stay in HBM between calls (bench.py, multi-GPU hosts)."""
+
+    def __init__(self, objectList, k, lambda_, Winit, Vinit, unsharedList=None, Uinit=None, Hinit=None, device=-1,
+                 rank=0, world=1, nccl_id=None, flags=0, keep_f32=False):
+        self.args = _Args(objectList, k, lambda_, 0, Winit, Vinit, Hinit, unsharedList=unsharedList, Uinit=Uinit,
+                          flags=flags, device=device, rank=rank, world=world, nccl_id=nccl_id, keep_f32=keep_f32)
+        self.h = C.c_void_p()
+        _ffi.check(_ffi.lib().lgr_ctx_create(C.byref(self.args.struct), C.byref(self.h)))
+
+    def reset(self, Winit, Vinit, Uinit=None):
+        W0 = _f64(Winit)
+        V0 = [_f64(v) for v in Vinit]
+        d = self.args.d
+        Varr = (c_double_p * d)(*[_dp(v) for v in V0])
+        Uarr = None
+        if Uinit is not None:
+            U0 = [None if u is None else _f64(u) for u in Uinit]
+            Uarr = (c_double_p * d)(*[(_dp(x) if x is not None else None) for x in U0])
+        _ffi.check(_ffi.lib().lgr_ctx_reset(self.h, _dp(W0), Varr, Uarr))
+
+    def iterate(self, niter, trajectory=False):
+        traj = np.zeros(max(niter, 1)) if trajectory else None
+        _ffi.check(_ffi.lib().lgr_ctx_iterate(self.h, int(niter), _dp(traj) if trajectory else None))
+        return traj[:niter] if trajectory else None
+
+    def objective(self):
+        out = C.c_double(0.0)
+        _ffi.check(_ffi.lib().lgr_ctx_objective(self.h, C.byref(out)))
+        return float(out.value)
+
+    def download(self, want_passive=False):
+        o = _Out(self.args, want_passive=want_passive)
+        _ffi.check(_ffi.lib().lgr_ctx_download(self.h, C.byref(o.struct)))
+        res = {"H": o.H, "V": o.V, "W": o.W, "U": o.U, "timings": o.timings()}
+        if want_passive:
+            res["H_passive"] = o.passive
+        return res
+
+    def timings(self):
+        t = _ffi.lgr_timings()
+        _ffi.check(_ffi.lib().lgr_ctx_timings(self.h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in _ffi.lgr_timings._fields_}
+
+    def set_kernel_timing(self, on=True):
+        _ffi.check(_ffi.lib().lgr_ctx_set_kernel_timing(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        n = C.c_int32(32)
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        cnt = (C.c_int64 * 32)()
+        _ffi.check(_ffi.lib().lgr_ctx_kernel_times(self.h, C.byref(n), names, ms, cnt))
+        return {names[i].decode(): {"ms": ms[i], "launches": cnt[i]} for i in range(min(n.value, 32))}
+
+    def stream(self):
+        return _ffi.lib().lgr_ctx_stream(self.h)
+
+    def close(self):
+        if self.h:
+            _ffi.lib().lgr_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _ffi.check(_ffi.lib().lgr_nccl_unique_id(buf))
+    return buf.raw
+
+
+def device_count():
+    return int(_ffi.lib().lgr_device_count())
+
+
+class RRandom:
+    """R's `set.seed(seed); runif(n, lo, hi)` stream (host C++ in csrc/lgr_rng.cpp)."""
+
+    def __init__(self, seed):
+        self._h = _ffi.lib().lgr_r_set_seed(int(seed) & 0xFFFFFFFF)
+
+    def runif(self, n, lo=0.0, hi=1.0):
+        out = np.empty(int(n), dtype=np.float64)
+        _ffi.lib().lgr_r_runif(self._h, int(n), float(lo), float(hi), _dp(out))
+        return out
+
+    def __del__(self):
+        try:
+            _ffi.lib().lgr_r_free(self._h)
+        except Exception:
+            pass

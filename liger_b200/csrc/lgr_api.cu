@@ -1,0 +1,799 @@
+// liger_b200 -- host side of the iNMF / UINMF path and the C ABI (include/liger_b200.h).
+//
+// The ANLS loop restates what RcppPlanc::inmf does behind rliger's .runINMF.list
+// (reference R/integration.R:438-441): per iteration  H_i for all i  ->  V_i (U_i) for all i with the old W
+// -> W with the new V_i   (update equations: reference R/cINMF.R:477-503), objective as src/objErr.cpp:13-31.
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+
+#include "lgr_common.cuh"
+#include "lgr_nccl.h"
+
+namespace lgr {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+struct KernelTimer {
+    // CUDA events around every launch of the loop (on the launch stream), resolved after the loop.
+    struct Rec {
+        int id;
+        cudaEvent_t a, b;
+    };
+    std::vector<cudaEvent_t> pool;
+    std::vector<Rec> recs;
+    size_t next = 0;
+    bool on = false;
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<int64_t> launches;
+    int id_of(const char* name) {
+        for (size_t i = 0; i < names.size(); ++i)
+            if (names[i] == name) return (int)i;
+        names.push_back(name);
+        ms.push_back(0.0);
+        launches.push_back(0);
+        return (int)names.size() - 1;
+    }
+    cudaEvent_t get() {
+        if (next == pool.size()) {
+            cudaEvent_t e;
+            LGR_CUDA(cudaEventCreate(&e));
+            pool.push_back(e);
+        }
+        return pool[next++];
+    }
+    void begin_loop() {
+        recs.clear();
+        next = 0;
+        std::fill(ms.begin(), ms.end(), 0.0);
+        std::fill(launches.begin(), launches.end(), 0);
+    }
+    void resolve() {
+        for (auto& r : recs) {
+            float t = 0.f;
+            LGR_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+            ms[r.id] += t;
+            launches[r.id] += 1;
+        }
+        recs.clear();
+        next = 0;
+    }
+    ~KernelTimer() {
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
+struct Dataset {
+    int n_full = 0, n = 0, c0 = 0, rows = 0, u = 0;
+    size_t nnz = 0;
+    double lambda = 0.0;
+    DBuf<int> colptr, rowidx, tptr;
+    DBuf<float> val, tval, L, H;
+    DBuf<unsigned short> tcell;
+    DBuf<unsigned long long> hmask, vmask;
+    DBuf<double> V, CtBv;
+    size_t b_off = 0, r_off = 0;
+};
+
+}  // namespace
+}  // namespace lgr
+
+using namespace lgr;
+
+struct lgr_ctx {
+    int d = 0, k = 0, kp = 32, m = 0, device = 0, rank = 0, world = 1, tc = 1024, num_sms = 148;
+    uint32_t flags = 0;
+    cudaStream_t st = nullptr;
+    std::vector<Dataset> ds;
+    std::vector<DsDev> ds_host;
+    DBuf<DsDev> ds_dev;
+    DBuf<double> W, CtBw, Gsum, Garena, gram_arena, objbuf, sq;
+    DBuf<unsigned long long> wmask;
+    DBuf<float> Bbuf, Rarena, scratchF;
+    DBuf<double> scratchD;
+    DBuf<NnlsGroup> grpH, grpV, grpW;
+    DBuf<Counters> counters;
+    NnlsConfig cfgF{}, cfgD{};
+    int blocksH = 0, blocksV = 0, blocksW = 0, ltx_blocks = 0, xh_tiles = 0, prep_blocks = 0, max_rows = 0;
+    size_t N_local = 0;
+    NcclComm* comm = nullptr;
+    bool stats_valid = false;  // R / G arenas hold the statistics of the current H
+    bool h_valid = false;
+    lgr_timings tm{};
+    KernelTimer kt;
+    int (*interrupt)(void*) = nullptr;
+    void* interrupt_user = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    ~lgr_ctx() {
+        if (comm) nccl_destroy(comm);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evA) cudaEventDestroy(evA);
+        if (evB) cudaEventDestroy(evB);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+namespace {
+
+struct Timed {
+    lgr_ctx* c;
+    int id = -1;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Timed(lgr_ctx* c_, const char* name) : c(c_) {
+        c->tm.kernel_launches += 1;
+        if (c->kt.on) {
+            id = c->kt.id_of(name);
+            a = c->kt.get();
+            b = c->kt.get();
+            cudaEventRecord(a, c->st);
+        }
+    }
+    ~Timed() {
+        if (c->kt.on) {
+            cudaEventRecord(b, c->st);
+            c->kt.recs.push_back({id, a, b});
+        }
+    }
+};
+
+void check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        throw Error(LGR_ERR_NO_DEVICE,
+                    "liger_b200: no CUDA device is available; this library has no CPU path (the iNMF/UINMF hot path "
+                    "runs only on the GPU)");
+    }
+}
+
+// upload one CSC block's local column range [c0, c1) as fp32 device CSC
+void upload_csc(const lgr_csc& M, int c0, int c1, DBuf<int>& colptr, DBuf<int>& rowidx, DBuf<float>& val, size_t& nnz,
+                cudaStream_t st) {
+    const int n = c1 - c0;
+    std::vector<int> p((size_t)n + 1);
+    const int base = M.colptr[c0];
+    for (int j = 0; j <= n; ++j) {
+        const int v = M.colptr[c0 + j] - base;
+        LGR_REQUIRE(v >= 0 && (j == 0 || v >= p[j - 1]), "CSC column pointers must be non-decreasing");
+        p[j] = v;
+    }
+    nnz = (size_t)p[n];
+    colptr.alloc((size_t)n + 1);
+    LGR_CUDA(cudaMemcpyAsync(colptr.p, p.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    LGR_CUDA(cudaStreamSynchronize(st));  // p is a stack-owned staging vector
+    rowidx.alloc(nnz);
+    val.alloc(nnz);
+    if (nnz) {
+        LGR_CUDA(cudaMemcpyAsync(rowidx.p, M.rowidx + base, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (M.value_dtype == LGR_F32) {
+            LGR_CUDA(cudaMemcpyAsync(val.p, static_cast<const float*>(M.values) + base, nnz * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        } else {
+            DBuf<double> tmp(nnz);
+            LGR_CUDA(cudaMemcpyAsync(tmp.p, static_cast<const double*>(M.values) + base, nnz * sizeof(double),
+                                     cudaMemcpyHostToDevice, st));
+            dev_f64_to_f32(tmp.p, val.p, nnz, st);
+            LGR_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+}
+
+void upload_factor(const double* host, double* dev_padded, int rows, int k, int kp, cudaStream_t st) {
+    if (rows == 0) return;
+    DBuf<double> tmp((size_t)rows * k);
+    LGR_CUDA(cudaMemcpyAsync(tmp.p, host, (size_t)rows * k * sizeof(double), cudaMemcpyHostToDevice, st));
+    dev_colmajor_to_padded(tmp.p, dev_padded, rows, k, kp, st);
+    LGR_CUDA(cudaStreamSynchronize(st));
+}
+
+void set_inits(lgr_ctx* c, const double* Winit, const double* const* Vinit, const double* const* Uinit) {
+    LGR_REQUIRE(Winit && Vinit, "Winit and Vinit are required");
+    upload_factor(Winit, c->W.p, c->m, c->k, c->kp, c->st);
+    for (int i = 0; i < c->d; ++i) {
+        Dataset& D = c->ds[i];
+        LGR_REQUIRE(Vinit[i], "Vinit[i] is NULL");
+        upload_factor(Vinit[i], D.V.p, c->m, c->k, c->kp, c->st);
+        if (D.u > 0) {
+            LGR_REQUIRE(Uinit && Uinit[i], "Uinit[i] is required for datasets with unshared features");
+            upload_factor(Uinit[i], D.V.p + (size_t)c->m * c->kp, D.u, c->k, c->kp, c->st);
+        }
+        D.hmask.zero(c->st);
+        D.vmask.zero(c->st);
+    }
+    c->wmask.zero(c->st);
+    c->counters.zero(c->st);
+    c->stats_valid = false;
+    c->h_valid = false;
+    c->tm.nnls_pivots = c->tm.nnls_unconverged = 0;
+}
+
+void allreduce_stats(lgr_ctx* c) {
+    if (c->world <= 1) return;
+    cudaEventRecord(c->evA, c->st);
+    nccl_group_start();
+    nccl_allreduce_sum_f32(c->comm, c->Rarena.p, c->Rarena.n, c->st);
+    nccl_allreduce_sum_f64(c->comm, c->Garena.p, c->Garena.n, c->st);
+    nccl_group_end();
+    cudaEventRecord(c->evB, c->st);
+}
+
+void run_prep(lgr_ctx* c) {
+    c->gram_arena.zero(c->st);
+    Timed t(c, "k_prep");
+    launch_prep(c->ds_dev.p, c->d, c->prep_blocks, c->W.p, c->k, c->kp, c->st);
+}
+void run_stats(lgr_ctx* c) {  // R = X H, G = H^T H (+ all-reduce)
+    c->Rarena.zero(c->st);
+    c->Garena.zero(c->st);
+    {
+        Timed t(c, "k_spmm_xh");
+        launch_spmm_xh(c->ds_dev.p, c->d, c->xh_tiles, c->k, c->kp, c->tc, c->st);
+    }
+    allreduce_stats(c);
+    c->stats_valid = true;
+}
+void run_objective(lgr_ctx* c, double* slot) {
+    LGR_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), c->st));
+    Timed t(c, "k_objective");
+    launch_objective(c->ds_dev.p, c->d, c->k, c->kp, slot, c->st);
+}
+
+void iterate(lgr_ctx* c, int niter, double* traj_host) {
+    const bool traj = traj_host != nullptr;
+    const int cold = (c->flags & LGR_FLAG_COLD_START) ? 1 : 0;
+    if (traj) c->objbuf.alloc((size_t)niter + 1);
+    c->kt.begin_loop();
+    c->tm.kernel_launches = 0;
+    LGR_CUDA(cudaEventRecord(c->ev0, c->st));
+    for (int it = 0; it < niter; ++it) {
+        if (c->interrupt && c->interrupt(c->interrupt_user)) throw Error(LGR_ERR_INTERRUPT, "interrupted by caller");
+        run_prep(c);
+        if (traj && it > 0) run_objective(c, c->objbuf.p + (it - 1));
+        // ---- H phase ----
+        {
+            Timed t(c, "k_spmm_ltx");
+            launch_spmm_ltx(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->st);
+        }
+        {
+            Timed t(c, "k_nnls_H");
+            launch_nnls(false, c->grpH.p, c->d, c->blocksH, c->k, c->kp, c->cfgF, c->scratchF.p, c->counters.p, cold, c->st);
+        }
+        c->h_valid = true;
+        // ---- sufficient statistics of the V / W solves ----
+        run_stats(c);
+        // ---- V_i (and U_i): old W ----
+        {
+            Timed t(c, "k_vrhs");
+            launch_vrhs(c->ds_dev.p, c->d, c->W.p, c->k, c->kp, c->max_rows, c->st);
+        }
+        {
+            Timed t(c, "k_nnls_V");
+            launch_nnls(true, c->grpV.p, c->d, c->blocksV, c->k, c->kp, c->cfgD, c->scratchD.p, c->counters.p, cold, c->st);
+        }
+        // ---- W: new V_i ----
+        {
+            Timed t(c, "k_wrhs");
+            launch_wrhs(c->ds_dev.p, c->d, c->m, c->CtBw.p, c->Gsum.p, c->k, c->kp, c->st);
+        }
+        {
+            Timed t(c, "k_nnls_W");
+            launch_nnls(true, c->grpW.p, 1, c->blocksW, c->k, c->kp, c->cfgD, c->scratchD.p, c->counters.p, cold, c->st);
+        }
+    }
+    if (traj && niter > 0) {
+        run_prep(c);
+        run_objective(c, c->objbuf.p + (niter - 1));
+    }
+    LGR_CUDA(cudaEventRecord(c->ev1, c->st));
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+    float ms = 0.f;
+    LGR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->tm.loop_ms = ms;
+    if (c->kt.on) c->kt.resolve();
+    if (traj && niter > 0)
+        LGR_CUDA(cudaMemcpy(traj_host, c->objbuf.p, (size_t)niter * sizeof(double), cudaMemcpyDeviceToHost));
+    Counters cn;
+    LGR_CUDA(cudaMemcpy(&cn, c->counters.p, sizeof(cn), cudaMemcpyDeviceToHost));
+    c->tm.nnls_pivots = (int64_t)cn.nnls_pivots;
+    c->tm.nnls_unconverged = (int64_t)cn.nnls_unconverged;
+}
+
+double objective(lgr_ctx* c) {
+    if (!c->stats_valid) {
+        LGR_REQUIRE(c->h_valid, "objective requested before any H is available (niter == 0 needs Hinit)");
+        run_stats(c);
+    }
+    run_prep(c);
+    if (c->objbuf.n < 1) c->objbuf.alloc(1);
+    DBuf<double> slot(1);
+    run_objective(c, slot.p);
+    double v = 0.0;
+    LGR_CUDA(cudaMemcpyAsync(&v, slot.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+    return v;
+}
+
+void create(const lgr_inmf_args* a, lgr_ctx** out) {
+    LGR_REQUIRE(a && out, "null argument");
+    check_device();
+    LGR_REQUIRE(a->d >= 1, "d must be >= 1");
+    LGR_REQUIRE(a->k >= 1 && a->k <= LGR_MAX_K, "k must be in 1..64");
+    LGR_REQUIRE(a->m >= 1 && a->m < (1 << 30), "m out of range");
+    LGR_REQUIRE(a->E && a->lambda, "E and lambda are required");
+    LGR_REQUIRE(a->niter >= 0, "niter must be >= 0");
+    LGR_REQUIRE(a->world >= 1 && a->rank >= 0 && a->rank < a->world, "bad rank/world");
+    std::unique_ptr<lgr_ctx> c(new lgr_ctx);
+    c->d = a->d;
+    c->k = a->k;
+    c->kp = a->k <= 32 ? 32 : 64;
+    c->m = (int)a->m;
+    c->flags = a->flags;
+    c->rank = a->rank;
+    c->world = a->world;
+    c->interrupt = a->interrupt;
+    c->interrupt_user = a->interrupt_user;
+    if (a->device >= 0) LGR_CUDA(cudaSetDevice(a->device));
+    LGR_CUDA(cudaGetDevice(&c->device));
+    cudaDeviceProp prop;
+    LGR_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    LGR_REQUIRE(prop.major >= 10, "liger_b200 kernels are built for sm_100a (Blackwell B200) only");
+    c->num_sms = prop.multiProcessorCount;
+    static std::once_flag once;
+    std::call_once(once, [] { kernels_init(); });
+    LGR_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    LGR_CUDA(cudaEventCreate(&c->ev0));
+    LGR_CUDA(cudaEventCreate(&c->ev1));
+    LGR_CUDA(cudaEventCreate(&c->evA));
+    LGR_CUDA(cudaEventCreate(&c->evB));
+    c->tc = c->kp == 32 ? 1024 : 512;
+    if (const char* e = getenv("LGR_TC")) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= 65536 && (size_t)v * c->kp * 4 <= 200 * 1024) c->tc = v;
+    }
+    if (const char* e = getenv("LGR_KERNEL_TIMING")) c->kt.on = atoi(e) != 0;
+    if (c->world > 1) {
+        LGR_REQUIRE(a->nccl_unique_id, "world > 1 needs nccl_unique_id");
+        c->comm = nccl_init(a->nccl_unique_id, c->rank, c->world);
+    }
+    cudaEvent_t u0, u1;
+    LGR_CUDA(cudaEventCreate(&u0));
+    LGR_CUDA(cudaEventCreate(&u1));
+    LGR_CUDA(cudaEventRecord(u0, c->st));
+
+    const int k = c->k, kp = c->kp, m = c->m;
+    c->ds.resize(c->d);
+    size_t b_total = 0, r_total = 0;
+    int max_rows = 0;
+    for (int i = 0; i < c->d; ++i) {
+        Dataset& D = c->ds[i];
+        const lgr_csc& E = a->E[i];
+        LGR_REQUIRE(E.nrow == a->m, "every E[i] must have m rows");
+        LGR_REQUIRE(E.ncol >= 1 && E.ncol < (int64_t)0x7fffffff, "E[i].ncol out of range");
+        LGR_REQUIRE(E.colptr && (E.colptr[E.ncol] == 0 || (E.rowidx && E.values)), "E[i] has null arrays");
+        D.n_full = (int)E.ncol;
+        D.c0 = (int)((int64_t)D.n_full * c->rank / c->world);
+        const int c1 = (int)((int64_t)D.n_full * (c->rank + 1) / c->world);
+        D.n = c1 - D.c0;
+        D.lambda = a->lambda[i];
+        D.u = 0;
+        const lgr_csc* P = (a->P && a->P[i].nrow > 0) ? &a->P[i] : nullptr;
+        if (P) {
+            LGR_REQUIRE(P->ncol == E.ncol, "P[i] must have the same cells as E[i]");
+            LGR_REQUIRE(P->nrow < (1 << 30), "P[i].nrow out of range");
+            D.u = (int)P->nrow;
+        }
+        D.rows = m + D.u;
+        max_rows = std::max(max_rows, D.rows);
+        if (!P) {
+            upload_csc(E, D.c0, c1, D.colptr, D.rowidx, D.val, D.nnz, c->st);
+        } else {
+            DBuf<int> pE, iE, pP, iP;
+            DBuf<float> vE, vP;
+            size_t nE = 0, nP = 0;
+            upload_csc(E, D.c0, c1, pE, iE, vE, nE, c->st);
+            upload_csc(*P, D.c0, c1, pP, iP, vP, nP, c->st);
+            D.nnz = nE + nP;
+            D.colptr.alloc((size_t)D.n + 1);
+            D.rowidx.alloc(D.nnz);
+            D.val.alloc(D.nnz);
+            dev_stack_csc(D.n, pE.p, iE.p, vE.p, pP.p, iP.p, vP.p, m, D.colptr.p, D.rowidx.p, D.val.p, c->st);
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+        const int ntiles = (D.n + c->tc - 1) / c->tc;
+        D.tptr.alloc((size_t)ntiles * D.rows + 1);
+        D.tcell.alloc(D.nnz);
+        D.tval.alloc(D.nnz);
+        dev_build_tiled_csr(D.n, D.rows, c->tc, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr.p, D.tcell.p, D.tval.p, c->st);
+        D.L.alloc((size_t)D.rows * kp);
+        D.H.alloc((size_t)std::max(D.n, 1) * kp);
+        D.H.zero(c->st);
+        D.hmask.alloc((size_t)std::max(D.n, 1));
+        D.vmask.alloc((size_t)D.rows);
+        D.V.alloc((size_t)D.rows * kp);
+        D.V.zero(c->st);
+        D.CtBv.alloc((size_t)D.rows * kp);
+        D.b_off = b_total;
+        b_total += (size_t)D.n * kp;
+        D.r_off = r_total;
+        r_total += (size_t)D.rows * kp;
+    }
+    c->max_rows = max_rows;
+    c->N_local = b_total / kp;
+    c->Bbuf.alloc(std::max<size_t>(b_total, 1));
+    c->Rarena.alloc(r_total);
+    c->Garena.alloc((size_t)c->d * kp * kp);
+    c->gram_arena.alloc((size_t)2 * c->d * kp * kp);
+    c->W.alloc((size_t)m * kp);
+    c->CtBw.alloc((size_t)m * kp);
+    c->Gsum.alloc((size_t)kp * kp);
+    c->wmask.alloc((size_t)m);
+    c->counters.alloc(1);
+    c->sq.alloc((size_t)c->d);
+    c->sq.zero(c->st);
+    for (int i = 0; i < c->d; ++i) dev_sumsq(c->ds[i].val.p, c->ds[i].nnz, c->sq.p + i, c->st);
+    if (c->world > 1) nccl_allreduce_sum_f64(c->comm, c->sq.p, (size_t)c->d, c->st);
+    std::vector<double> sq((size_t)c->d);
+    LGR_CUDA(cudaMemcpyAsync(sq.data(), c->sq.p, sq.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+
+    // device-side dataset table + NNLS groups
+    c->cfgF = nnls_config(k, kp, false, c->num_sms);
+    c->cfgD = nnls_config(k, kp, true, c->num_sms);
+    if (c->cfgF.scratch_elems_per_thread)
+        c->scratchF.alloc((size_t)c->cfgF.grid_cap * c->cfgF.threads * c->cfgF.scratch_elems_per_thread);
+    if (c->cfgD.scratch_elems_per_thread)
+        c->scratchD.alloc((size_t)c->cfgD.grid_cap * c->cfgD.threads * c->cfgD.scratch_elems_per_thread);
+    c->ds_host.resize(c->d);
+    std::vector<NnlsGroup> gH(c->d), gV(c->d), gW(1);
+    int ltx = 0, xh = 0, prep = 0, bH = 0, bV = 0;
+    const int rb = prep_rows_per_block(kp);
+    for (int i = 0; i < c->d; ++i) {
+        Dataset& D = c->ds[i];
+        DsDev& h = c->ds_host[i];
+        memset(&h, 0, sizeof(h));
+        h.n = D.n;
+        h.rows = D.rows;
+        h.m = m;
+        h.u = D.u;
+        h.ntiles = (D.n + c->tc - 1) / c->tc;
+        h.ltx_blk_off = ltx;
+        h.xh_blk_off = xh;
+        h.prep_blk_off = prep;
+        ltx += (D.n + LTX_CELLS_PER_BLOCK - 1) / LTX_CELLS_PER_BLOCK;
+        xh += h.ntiles;
+        prep += (D.rows + rb - 1) / rb;
+        h.colptr = D.colptr.p;
+        h.rowidx = D.rowidx.p;
+        h.val = D.val.p;
+        h.tptr = D.tptr.p;
+        h.tcell = D.tcell.p;
+        h.tval = D.tval.p;
+        h.L = D.L.p;
+        h.H = D.H.p;
+        h.B = c->Bbuf.p + D.b_off;
+        h.hmask = D.hmask.p;
+        h.V = D.V.p;
+        h.CtBv = D.CtBv.p;
+        h.vmask = D.vmask.p;
+        h.R = c->Rarena.p + D.r_off;
+        h.G = c->Garena.p + (size_t)i * kp * kp;
+        h.LtL = c->gram_arena.p + (size_t)(2 * i) * kp * kp;
+        h.VtV = c->gram_arena.p + (size_t)(2 * i + 1) * kp * kp;
+        h.lambda = D.lambda;
+        h.sqnorm = sq[i];
+        // H solve: CtC = LtL + lambda VtV, rhs = B (fp32), x = H
+        gH[i] = NnlsGroup{h.LtL, h.VtV, 1.0, D.lambda, h.B, h.H, h.hmask, D.n, kp, bH, 0};
+        bH += (D.n + c->cfgF.threads - 1) / c->cfgF.threads;
+        // V/U solve: CtC = (1 + lambda) G_i, rhs = CtBv (fp64), x = V
+        gV[i] = NnlsGroup{h.G, nullptr, 1.0 + D.lambda, 0.0, h.CtBv, h.V, h.vmask, D.rows, kp, bV, 0};
+        bV += (D.rows + c->cfgD.threads - 1) / c->cfgD.threads;
+    }
+    gW[0] = NnlsGroup{c->Gsum.p, nullptr, 1.0, 0.0, c->CtBw.p, c->W.p, c->wmask.p, m, kp, 0, 0};
+    c->ltx_blocks = ltx;
+    c->xh_tiles = xh;
+    c->prep_blocks = prep;
+    c->blocksH = bH;
+    c->blocksV = bV;
+    c->blocksW = (m + c->cfgD.threads - 1) / c->cfgD.threads;
+    c->ds_dev.alloc((size_t)c->d);
+    c->grpH.alloc((size_t)c->d);
+    c->grpV.alloc((size_t)c->d);
+    c->grpW.alloc(1);
+    LGR_CUDA(cudaMemcpyAsync(c->ds_dev.p, c->ds_host.data(), sizeof(DsDev) * c->d, cudaMemcpyHostToDevice, c->st));
+    LGR_CUDA(cudaMemcpyAsync(c->grpH.p, gH.data(), sizeof(NnlsGroup) * c->d, cudaMemcpyHostToDevice, c->st));
+    LGR_CUDA(cudaMemcpyAsync(c->grpV.p, gV.data(), sizeof(NnlsGroup) * c->d, cudaMemcpyHostToDevice, c->st));
+    LGR_CUDA(cudaMemcpyAsync(c->grpW.p, gW.data(), sizeof(NnlsGroup), cudaMemcpyHostToDevice, c->st));
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+
+    set_inits(c.get(), a->Winit, a->Vinit, a->Uinit);
+    if (a->Hinit) {
+        for (int i = 0; i < c->d; ++i) {
+            Dataset& D = c->ds[i];
+            if (!a->Hinit[i] || D.n == 0) continue;
+            // local rows [c0, c0+n) of the n_full x k column-major matrix
+            DBuf<double> tmp((size_t)D.n * k);
+            LGR_CUDA(cudaMemcpy2DAsync(tmp.p, (size_t)D.n * sizeof(double), a->Hinit[i] + D.c0,
+                                       (size_t)D.n_full * sizeof(double), (size_t)D.n * sizeof(double), (size_t)k,
+                                       cudaMemcpyHostToDevice, c->st));
+            dev_colmajor_to_hpad(tmp.p, D.H.p, D.n, k, kp, c->st);
+            dev_mask_from_positive(D.H.p, D.hmask.p, D.n, k, kp, c->st);
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+        c->h_valid = true;
+    }
+    LGR_CUDA(cudaEventRecord(u1, c->st));
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, u0, u1);
+    c->tm.upload_ms = ms;
+    cudaEventDestroy(u0);
+    cudaEventDestroy(u1);
+    *out = c.release();
+}
+
+void download(lgr_ctx* c, lgr_inmf_out* o) {
+    cudaEvent_t u0, u1;
+    LGR_CUDA(cudaEventCreate(&u0));
+    LGR_CUDA(cudaEventCreate(&u1));
+    LGR_CUDA(cudaEventRecord(u0, c->st));
+    const int k = c->k, kp = c->kp, m = c->m;
+    if (o->W) {
+        DBuf<double> tmp((size_t)m * k);
+        dev_padded_to_colmajor(c->W.p, tmp.p, m, k, kp, c->st);
+        LGR_CUDA(cudaMemcpyAsync(o->W, tmp.p, (size_t)m * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        LGR_CUDA(cudaStreamSynchronize(c->st));
+    }
+    for (int i = 0; i < c->d; ++i) {
+        Dataset& D = c->ds[i];
+        if (o->V && o->V[i]) {
+            DBuf<double> tmp((size_t)m * k);
+            dev_padded_to_colmajor(D.V.p, tmp.p, m, k, kp, c->st);
+            LGR_CUDA(cudaMemcpyAsync(o->V[i], tmp.p, (size_t)m * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+        if (o->U && o->U[i] && D.u > 0) {
+            DBuf<double> tmp((size_t)D.u * k);
+            dev_padded_to_colmajor(D.V.p + (size_t)m * kp, tmp.p, D.u, k, kp, c->st);
+            LGR_CUDA(cudaMemcpyAsync(o->U[i], tmp.p, (size_t)D.u * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+        if (o->H && o->H[i] && D.n > 0) {
+            DBuf<double> tmp((size_t)D.n * k);
+            dev_hpad_to_colmajor(D.H.p, tmp.p, D.n, k, kp, c->st);
+            LGR_CUDA(cudaMemcpy2DAsync(o->H[i] + D.c0, (size_t)D.n_full * sizeof(double), tmp.p,
+                                       (size_t)D.n * sizeof(double), (size_t)D.n * sizeof(double), (size_t)k,
+                                       cudaMemcpyDeviceToHost, c->st));
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+        if (o->H_passive && o->H_passive[i] && D.n > 0) {
+            LGR_CUDA(cudaMemcpyAsync(o->H_passive[i] + D.c0, D.hmask.p, (size_t)D.n * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, c->st));
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+    }
+    LGR_CUDA(cudaEventRecord(u1, c->st));
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, u0, u1);
+    c->tm.download_ms = ms;
+    cudaEventDestroy(u0);
+    cudaEventDestroy(u1);
+    o->timings = c->tm;
+}
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return LGR_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return LGR_ERR_ALLOC;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return LGR_ERR_INVALID;
+    } catch (...) {
+        set_last_error("unknown error");
+        return LGR_ERR_INVALID;
+    }
+}
+
+int run_oneshot(const lgr_inmf_args* args, lgr_inmf_out* out, bool need_unshared) {
+    return guarded([&] {
+        LGR_REQUIRE(args && out, "null argument");
+        if (need_unshared) {
+            LGR_REQUIRE(args->P, "uinmf: unshared blocks (P) are required");
+            bool any = false;
+            for (int i = 0; i < args->d; ++i) any = any || args->P[i].nrow > 0;
+            LGR_REQUIRE(any, "uinmf: at least one dataset must carry unshared features");
+        }
+        lgr_ctx* raw = nullptr;
+        create(args, &raw);
+        std::unique_ptr<lgr_ctx> c(raw);
+        iterate(c.get(), args->niter, (args->flags & LGR_FLAG_TRAJECTORY) ? out->obj_traj : nullptr);
+        out->objErr = objective(c.get());
+        download(c.get(), out);
+    });
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* lgr_last_error(void) { return g_last_error.c_str(); }
+
+int lgr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lgr_version(void) { return LGR_VERSION_MAJOR * 1000 + LGR_VERSION_MINOR; }
+
+int lgr_nccl_unique_id(void* out128) {
+    return guarded([&] {
+        LGR_REQUIRE(out128, "null argument");
+        nccl_unique_id(out128);
+    });
+}
+
+int lgr_inmf(const lgr_inmf_args* args, lgr_inmf_out* out) { return run_oneshot(args, out, false); }
+int lgr_uinmf(const lgr_inmf_args* args, lgr_inmf_out* out) { return run_oneshot(args, out, true); }
+
+int lgr_ctx_create(const lgr_inmf_args* args, lgr_ctx** ctx) {
+    return guarded([&] { create(args, ctx); });
+}
+int lgr_ctx_reset(lgr_ctx* c, const double* Winit, const double* const* Vinit, const double* const* Uinit) {
+    return guarded([&] {
+        LGR_REQUIRE(c, "null ctx");
+        LGR_CUDA(cudaSetDevice(c->device));
+        set_inits(c, Winit, Vinit, Uinit);
+    });
+}
+int lgr_ctx_iterate(lgr_ctx* c, int32_t niter, double* obj_traj) {
+    return guarded([&] {
+        LGR_REQUIRE(c && niter >= 0, "bad argument");
+        LGR_CUDA(cudaSetDevice(c->device));
+        iterate(c, niter, obj_traj);
+    });
+}
+int lgr_ctx_objective(lgr_ctx* c, double* obj) {
+    return guarded([&] {
+        LGR_REQUIRE(c && obj, "bad argument");
+        LGR_CUDA(cudaSetDevice(c->device));
+        *obj = objective(c);
+    });
+}
+int lgr_ctx_download(lgr_ctx* c, lgr_inmf_out* out) {
+    return guarded([&] {
+        LGR_REQUIRE(c && out, "bad argument");
+        LGR_CUDA(cudaSetDevice(c->device));
+        download(c, out);
+    });
+}
+int lgr_ctx_timings(lgr_ctx* c, lgr_timings* t) {
+    return guarded([&] {
+        LGR_REQUIRE(c && t, "bad argument");
+        *t = c->tm;
+    });
+}
+void* lgr_ctx_stream(lgr_ctx* c) { return c ? (void*)c->st : nullptr; }
+int lgr_ctx_set_kernel_timing(lgr_ctx* c, int32_t on) {
+    return guarded([&] {
+        LGR_REQUIRE(c, "null ctx");
+        c->kt.on = on != 0;
+    });
+}
+int lgr_ctx_kernel_times(lgr_ctx* c, int32_t* n, const char** names, double* ms, int64_t* launches) {
+    return guarded([&] {
+        LGR_REQUIRE(c && n, "bad argument");
+        const int cap = *n;
+        const int cnt = (int)c->kt.names.size();
+        for (int i = 0; i < cnt && i < cap; ++i) {
+            if (names) names[i] = c->kt.names[i].c_str();
+            if (ms) ms[i] = c->kt.ms[i];
+            if (launches) launches[i] = c->kt.launches[i];
+        }
+        *n = cnt;
+    });
+}
+void lgr_ctx_destroy(lgr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    delete c;
+}
+
+int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* CtB, double* X, int32_t device) {
+    return guarded([&] {
+        check_device();
+        LGR_REQUIRE(k >= 1 && k <= LGR_MAX_K, "k must be in 1..64");
+        LGR_REQUIRE(ncols >= 0 && ncols < (int64_t)0x7fffffff, "column count out of range");
+        LGR_REQUIRE(CtC && (ncols == 0 || (CtB && X)), "null argument");
+        if (ncols == 0) return;
+        if (device >= 0) LGR_CUDA(cudaSetDevice(device));
+        static std::once_flag once;
+        std::call_once(once, [] { kernels_init(); });
+        cudaDeviceProp prop;
+        int dev = 0;
+        LGR_CUDA(cudaGetDevice(&dev));
+        LGR_CUDA(cudaGetDeviceProperties(&prop, dev));
+        const int kp = k <= 32 ? 32 : 64;
+        cudaStream_t st;
+        LGR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        try {
+            DBuf<double> dG((size_t)k * k), dGp((size_t)kp * kp), dB((size_t)k * ncols), dX((size_t)k * ncols);
+            DBuf<unsigned long long> mask((size_t)ncols);
+            DBuf<Counters> cnt(1);
+            DBuf<NnlsGroup> grp(1);
+            mask.zero(st);
+            cnt.zero(st);
+            LGR_CUDA(cudaMemcpyAsync(dG.p, CtC, (size_t)k * k * sizeof(double), cudaMemcpyHostToDevice, st));
+            LGR_CUDA(cudaMemcpyAsync(dB.p, CtB, (size_t)k * ncols * sizeof(double), cudaMemcpyHostToDevice, st));
+            dev_colmajor_to_padded(dG.p, dGp.p, k, k, kp, st);  // symmetric: layout orientation is irrelevant
+            NnlsConfig cfg = nnls_config(k, kp, true, prop.multiProcessorCount);
+            DBuf<double> scratch;
+            if (cfg.scratch_elems_per_thread)
+                scratch.alloc((size_t)cfg.grid_cap * cfg.threads * cfg.scratch_elems_per_thread);
+            NnlsGroup g{dGp.p, nullptr, 1.0, 0.0, dB.p, dX.p, mask.p, (int)ncols, k, 0, 0};
+            LGR_CUDA(cudaMemcpyAsync(grp.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
+            const int blocks = (int)((ncols + cfg.threads - 1) / cfg.threads);
+            launch_nnls(true, grp.p, 1, blocks, k, kp, cfg, scratch.p, cnt.p, 1, st);
+            LGR_CUDA(cudaMemcpyAsync(X, dX.p, (size_t)k * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+            LGR_CUDA(cudaStreamSynchronize(st));
+        } catch (...) {
+            cudaStreamDestroy(st);
+            throw;
+        }
+        cudaStreamDestroy(st);
+    });
+}
+
+int lgr_objerr_i(int32_t k, const double* H, const double* W, const double* V, const lgr_csc* E, double lambda,
+                 int32_t device, double* err) {
+    return guarded([&] {
+        LGR_REQUIRE(H && W && V && E && err, "null argument");
+        // H arrives k x n (src/objErr.cpp:13); the context wants n x k column-major
+        const int64_t n = E->ncol;
+        std::vector<double> Ht((size_t)n * k);
+        for (int64_t c = 0; c < n; ++c)
+            for (int f = 0; f < k; ++f) Ht[(size_t)f * n + c] = H[(size_t)c * k + f];
+        lgr_inmf_args a;
+        memset(&a, 0, sizeof(a));
+        a.d = 1;
+        a.k = k;
+        a.niter = 0;
+        a.m = E->nrow;
+        a.E = E;
+        a.lambda = &lambda;
+        a.Winit = W;
+        const double* vs[1] = {V};
+        const double* hs[1] = {Ht.data()};
+        a.Vinit = vs;
+        a.Hinit = hs;
+        a.device = device;
+        a.world = 1;
+        lgr_ctx* raw = nullptr;
+        create(&a, &raw);
+        std::unique_ptr<lgr_ctx> c(raw);
+        *err = objective(c.get());
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// liger_b200 -- shared declarations of the CUDA implementation (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/liger_b200.h"
+
+namespace lgr {
+
+// ---------------------------------------------------------------------------------------------
+// error handling: C++ exceptions inside the library, converted to status codes at the C ABI.
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define LGR_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ::lgr::Error(LGR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +  \
+                                                 " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+#define LGR_REQUIRE(cond, msg)                                          \
+    do {                                                                \
+        if (!(cond)) throw ::lgr::Error(LGR_ERR_INVALID, std::string(msg)); \
+    } while (0)
+
+// RAII device buffer
+template <typename T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    explicit DBuf(size_t n_) { alloc(n_); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) {
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+            if (e != cudaSuccess) {
+                p = nullptr; n = 0;
+                throw Error(LGR_ERR_ALLOC, std::string("cudaMalloc of ") + std::to_string(n_ * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
+            }
+        }
+    }
+    void zero(cudaStream_t st) { if (n) LGR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DBuf() { release(); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// device-side description of one dataset (one rank's cell shard of it)
+// ---------------------------------------------------------------------------------------------
+// Layout in HBM (all row strides are KP = 32 or 64 floats so that one factor row is one or two
+// 128-byte lines):
+//   X (stacked [E_i; P_i], rows = m + u_i) is held twice:
+//     * CSC   colptr[n+1], rowidx[nnz] (int32), val[nnz] (fp32)        -> K1  B = L^T X   (gather of L rows)
+//     * tiled CSR: cells are cut into tiles of TC; inside a tile entries are ordered by gene;
+//       tptr[ntiles*rows + 1], tcell[nnz] (uint16, cell index inside the tile), tval[nnz] (fp32)
+//                                                                   -> K2  R = X H     (gather of H rows)
+//   L = [W + V_i; U_i]  rows x KP fp32        H, B  n x KP fp32       masks n x uint64
+//   V64 rows x KP fp64 (V_i stacked over U_i) R rows x KP fp32        G KP x KP fp64
+struct DsDev {
+    int n;       // local cells
+    int rows;    // m + u
+    int m;       // shared rows
+    int u;       // unshared rows
+    int ntiles;  // cell tiles of TC
+    int ltx_blk_off;  // first flat block of this dataset in k_spmm_ltx
+    int xh_blk_off;   // first flat block (tile) in k_spmm_xh
+    int prep_blk_off; // first flat block in k_prep
+    const int* colptr;
+    const int* rowidx;
+    const float* val;
+    const int* tptr;
+    const unsigned short* tcell;
+    const float* tval;
+    float* L;
+    float* H;
+    float* B;
+    unsigned long long* hmask;
+    double* V;      // rows x KP
+    double* CtBv;   // rows x KP   rhs of the V/U solve
+    unsigned long long* vmask;
+    float* R;       // rows x KP   (inside the all-reduce arena)
+    double* G;      // KP x KP     H^T H (inside the all-reduce arena)
+    double* LtL;    // KP x KP     L~^T L~
+    double* VtV;    // KP x KP     V~^T V~
+    double lambda;
+    double sqnorm;  // ||[E;P]||_F^2 (global, after all-reduce)
+};
+
+// One batch of NNLS columns sharing a Gram matrix:  Gs = cA * A + cB * B  (A, B fp64 KP x KP, B may be null)
+struct NnlsGroup {
+    const double* gramA;
+    const double* gramB;
+    double cA, cB;
+    const void* rhs;            // T: ncols x ld  (column j at rhs + j*ld)
+    void* x;                    // T: ncols x ld
+    unsigned long long* mask;   // ncols, warm start in/out (never null)
+    int ncols;
+    int ld;
+    int blk_off;                // first flat column block
+    int pad;
+};
+
+struct Counters {
+    unsigned long long nnls_pivots;
+    unsigned long long nnls_unconverged;
+    unsigned long long nnls_bad_pivot;
+    unsigned long long nnls_spill;  // solves that used the global-memory factor scratch
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel launch wrappers (lgr_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+constexpr int LTX_CELLS_PER_BLOCK = 64;
+inline int prep_rows_per_block(int kp) { return 2048 / kp; }  // keeps k_prep's static smem < 48 KB
+
+struct NnlsConfig {
+    int threads;      // columns per CTA
+    int ps;           // largest passive-set size whose Cholesky factor lives in shared memory
+    size_t smem;
+    int grid_cap;     // persistent grid size
+    size_t scratch_elems_per_thread;
+};
+NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
+
+void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st);
+void launch_spmm_ltx(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st);
+void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st);
+void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_blocks, int k, int kp,
+                 const NnlsConfig& cfg, void* scratch, Counters* cnt, int cold_start, cudaStream_t st);
+void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st);
+void launch_wrhs(const DsDev* ds, int nds, int m, double* CtBw, double* Gsum, int k, int kp, cudaStream_t st);
+void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot, cudaStream_t st);
+size_t spmm_xh_smem(int kp, int tc);
+void kernels_init();  // opt-in shared memory attributes
+
+// layout / conversion kernels (lgr_layout.cu)
+void dev_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
+void dev_sumsq(const float* v, size_t n, double* out, cudaStream_t st);
+void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const int* pP, const int* iP,
+                   const float* vP, int m, int* pS, int* iS, float* vS, cudaStream_t st);
+void dev_build_tiled_csr(int n, int rows, int tc, const int* colptr, const int* rowidx, const float* val, size_t nnz,
+                         int* tptr, unsigned short* tcell, float* tval, cudaStream_t st);
+void dev_colmajor_to_padded(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);   // R m x k -> [row][KP]
+void dev_padded_to_colmajor(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);
+void dev_hpad_to_colmajor(const float* H, double* out, int n, int k, int kp, cudaStream_t st);          // [cell][KP] f32 -> n x k f64
+void dev_colmajor_to_hpad(const double* in, float* H, int n, int k, int kp, cudaStream_t st);
+void dev_mask_from_positive(const float* H, unsigned long long* mask, int n, int k, int kp, cudaStream_t st);
+
+}  // namespace lgr

@@ -1,0 +1,203 @@
+// liger_b200 -- one-time layout conversion on the device (upload path, not part of the timed ANLS loop).
+//   * fp64 -> fp32 value conversion, ||X||_F^2
+//   * stacking [E_i; P_i] for UINMF
+//   * the tiled-CSR copy of X used by k_spmm_xh (stable radix sort on the key  tile * rows + gene)
+//   * R (column-major fp64) <-> device (row-padded) factor layouts
+#include <cub/cub.cuh>
+
+#include "lgr_common.cuh"
+
+namespace lgr {
+
+__global__ void k_f64_to_f32(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i];
+}
+void dev_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st) {
+    if (!n) return;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    k_f64_to_f32<<<grid, 256, 0, st>>>(in, out, n);
+    LGR_CUDA(cudaGetLastError());
+}
+
+__global__ void k_sumsq(const float* __restrict__ v, size_t n, double* out) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double x = (double)v[i];
+        acc += x * x;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, sh[0]);
+}
+void dev_sumsq(const float* v, size_t n, double* out, cudaStream_t st) {
+    if (!n) return;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    k_sumsq<<<grid, 256, 0, st>>>(v, n, out);
+    LGR_CUDA(cudaGetLastError());
+}
+
+// stacked column j = E column j followed by P column j with row indices shifted by m
+__global__ void k_stack_ptr(int n, const int* pE, const int* pP, int* pS) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= n) pS[j] = pE[j] + pP[j];
+}
+__global__ void k_stack_fill(int n, const int* pE, const int* iE, const float* vE, const int* pP, const int* iP,
+                             const float* vP, int m, const int* pS, int* iS, float* vS) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const int be = pE[warp], ne = pE[warp + 1] - be, bp = pP[warp], np = pP[warp + 1] - bp, o = pS[warp];
+    for (int t = lane; t < ne; t += 32) {
+        iS[o + t] = iE[be + t];
+        vS[o + t] = vE[be + t];
+    }
+    for (int t = lane; t < np; t += 32) {
+        iS[o + ne + t] = iP[bp + t] + m;
+        vS[o + ne + t] = vP[bp + t];
+    }
+}
+void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const int* pP, const int* iP, const float* vP,
+                   int m, int* pS, int* iS, float* vS, cudaStream_t st) {
+    k_stack_ptr<<<(n + 1 + 255) / 256, 256, 0, st>>>(n, pE, pP, pS);
+    LGR_CUDA(cudaGetLastError());
+    if (n > 0) {
+        k_stack_fill<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(n, pE, iE, vE, pP, iP, vP, m, pS, iS, vS);
+        LGR_CUDA(cudaGetLastError());
+    }
+}
+
+// ---- tiled CSR ----------------------------------------------------------------------------------
+__global__ void k_tile_keys(int n, int rows, int tc, const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                            unsigned int* __restrict__ keys, unsigned int* __restrict__ perm,
+                            unsigned short* __restrict__ cell_local, int* __restrict__ counts) {
+    const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const int b = colptr[warp], e = colptr[warp + 1];
+    const unsigned int tile = (unsigned)(warp / tc);
+    const unsigned short cl = (unsigned short)(warp % tc);
+    for (int t = b + lane; t < e; t += 32) {
+        const unsigned int key = tile * (unsigned)rows + (unsigned)rowidx[t];
+        keys[t] = key;
+        perm[t] = (unsigned)t;
+        cell_local[t] = cl;
+        atomicAdd(&counts[key], 1);
+    }
+}
+__global__ void k_tile_gather(size_t nnz, const unsigned int* __restrict__ perm, const unsigned short* __restrict__ cell_local,
+                              const float* __restrict__ val, unsigned short* __restrict__ tcell, float* __restrict__ tval) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned int p = perm[i];
+        tcell[i] = cell_local[p];
+        tval[i] = val[p];
+    }
+}
+
+void dev_build_tiled_csr(int n, int rows, int tc, const int* colptr, const int* rowidx, const float* val, size_t nnz,
+                         int* tptr, unsigned short* tcell, float* tval, cudaStream_t st) {
+    const int ntiles = (n + tc - 1) / tc;
+    const size_t nkeys = (size_t)ntiles * rows;
+    LGR_REQUIRE(nkeys < (size_t)0x7fffffff, "tiled CSR: tiles x rows exceeds 2^31");
+    LGR_CUDA(cudaMemsetAsync(tptr, 0, (nkeys + 1) * sizeof(int), st));
+    if (nnz == 0 || n == 0) return;
+    unsigned int *keys = nullptr, *keys2 = nullptr, *perm = nullptr, *perm2 = nullptr;
+    unsigned short* cl = nullptr;
+    int* counts = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    LGR_CUDA(cudaMalloc(&keys, nnz * 4));
+    LGR_CUDA(cudaMalloc(&keys2, nnz * 4));
+    LGR_CUDA(cudaMalloc(&perm, nnz * 4));
+    LGR_CUDA(cudaMalloc(&perm2, nnz * 4));
+    LGR_CUDA(cudaMalloc(&cl, nnz * 2));
+    LGR_CUDA(cudaMalloc(&counts, (nkeys + 1) * sizeof(int)));
+    LGR_CUDA(cudaMemsetAsync(counts, 0, (nkeys + 1) * sizeof(int), st));
+    k_tile_keys<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(n, rows, tc, colptr, rowidx, keys, perm, cl,
+                                                                             counts);
+    LGR_CUDA(cudaGetLastError());
+    int bits = 1;
+    while (((size_t)1 << bits) < nkeys) ++bits;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, perm, perm2, (int)nnz, 0, bits, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, tptr, (int)(nkeys + 1), st);
+    if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
+    LGR_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    LGR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, perm, perm2, (int)nnz, 0, bits, st));
+    LGR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, tptr, (int)(nkeys + 1), st));
+    const int grid = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
+    k_tile_gather<<<grid, 256, 0, st>>>(nnz, perm2, cl, val, tcell, tval);
+    LGR_CUDA(cudaGetLastError());
+    LGR_CUDA(cudaStreamSynchronize(st));
+    cudaFree(keys);
+    cudaFree(keys2);
+    cudaFree(perm);
+    cudaFree(perm2);
+    cudaFree(cl);
+    cudaFree(counts);
+    cudaFree(tmp);
+}
+
+// ---- factor layout conversion -------------------------------------------------------------------
+__global__ void k_colmajor_to_padded(const double* __restrict__ in, double* __restrict__ out, int rows, int k, int kp) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * kp) return;
+    const int r = (int)(idx / kp), f = (int)(idx % kp);
+    out[idx] = f < k ? in[(size_t)f * rows + r] : 0.0;
+}
+__global__ void k_padded_to_colmajor(const double* __restrict__ in, double* __restrict__ out, int rows, int k, int kp) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * k) return;
+    const int f = (int)(idx / rows), r = (int)(idx % rows);
+    out[idx] = in[(size_t)r * kp + f];
+}
+__global__ void k_hpad_to_colmajor(const float* __restrict__ H, double* __restrict__ out, int n, int k, int kp) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * k) return;
+    const int f = (int)(idx / n), c = (int)(idx % n);
+    out[idx] = (double)H[(size_t)c * kp + f];
+}
+__global__ void k_colmajor_to_hpad(const double* __restrict__ in, float* __restrict__ H, int n, int k, int kp) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * kp) return;
+    const int c = (int)(idx / kp), f = (int)(idx % kp);
+    H[idx] = f < k ? (float)in[(size_t)f * n + c] : 0.f;
+}
+__global__ void k_mask_from_positive(const float* __restrict__ H, unsigned long long* __restrict__ mask, int n, int k, int kp) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    unsigned long long m = 0;
+    for (int f = 0; f < k; ++f)
+        if (H[(size_t)c * kp + f] > 0.f) m |= 1ull << f;
+    mask[c] = m;
+}
+#define LGR_GRID(total) (unsigned)(((size_t)(total) + 255) / 256)
+void dev_colmajor_to_padded(const double* in, double* out, int rows, int k, int kp, cudaStream_t st) {
+    if (!rows) return;
+    k_colmajor_to_padded<<<LGR_GRID((size_t)rows * kp), 256, 0, st>>>(in, out, rows, k, kp);
+    LGR_CUDA(cudaGetLastError());
+}
+void dev_padded_to_colmajor(const double* in, double* out, int rows, int k, int kp, cudaStream_t st) {
+    if (!rows) return;
+    k_padded_to_colmajor<<<LGR_GRID((size_t)rows * k), 256, 0, st>>>(in, out, rows, k, kp);
+    LGR_CUDA(cudaGetLastError());
+}
+void dev_hpad_to_colmajor(const float* H, double* out, int n, int k, int kp, cudaStream_t st) {
+    if (!n) return;
+    k_hpad_to_colmajor<<<LGR_GRID((size_t)n * k), 256, 0, st>>>(H, out, n, k, kp);
+    LGR_CUDA(cudaGetLastError());
+}
+void dev_colmajor_to_hpad(const double* in, float* H, int n, int k, int kp, cudaStream_t st) {
+    if (!n) return;
+    k_colmajor_to_hpad<<<LGR_GRID((size_t)n * kp), 256, 0, st>>>(in, H, n, k, kp);
+    LGR_CUDA(cudaGetLastError());
+}
+void dev_mask_from_positive(const float* H, unsigned long long* mask, int n, int k, int kp, cudaStream_t st) {
+    if (!n) return;
+    k_mask_from_positive<<<LGR_GRID(n), 256, 0, st>>>(H, mask, n, k, kp);
+    LGR_CUDA(cudaGetLastError());
+}
+
+}  // namespace lgr

@@ -1,0 +1,117 @@
+"""Mirror of the R wrappers around the native iNMF / UINMF calls.
+
+    run_inmf_list   <- .runINMF.list   (reference R/integration.R:370-461)
+    run_uinmf_list  <- .runUINMF.list  (reference R/integration.R:1254-1310)
+    runINMF / runUINMF: thin entry points over {name: scaleData} dicts mirroring
+                       runINMF.liger (R/integration.R:230-284) / runUINMF.liger (:1206-1250)
+
+Same argument names and meaning, same validation errors, same seeded initialisation
+(R's Mersenne-Twister stream; draw order W, V_1..V_d, H_1..H_d), same restart selection
+(best objErr; note `%||%` keeps restart 1's inits for later restarts, R/integration.R:413-428),
+same output orientation (H transposed to k x n_i, R/integration.R:453).
+"""
+import numpy as np
+
+from . import api
+
+
+def _r_matrix(rng, nrow, ncol):
+    # matrix(abs(runif(nrow*ncol, 0, 2)), nrow, ncol): column-major fill
+    return np.abs(rng.runif(nrow * ncol, 0.0, 2.0)).reshape((nrow, ncol), order="F")
+
+
+def run_inmf_list(objectList, k=20, lambda_=5.0, nIteration=30, nRandomStarts=1, HInit=None, WInit=None, VInit=None,
+                  seed=1, nCores=2, verbose=False, trajectory=False):
+    mats = list(objectList.values()) if isinstance(objectList, dict) else list(objectList)
+    names = list(objectList.keys()) if isinstance(objectList, dict) else None
+    m = mats[0].shape[0]
+    for x in mats:
+        if x.shape[0] != m:
+            raise ValueError("All datasets must share the same features (rows)")
+    n_list = [x.shape[1] for x in mats]
+    if min(n_list) < k:
+        raise ValueError(f"Number of factors (k={k}) should be less than the number of cells in the smallest "
+                         f"dataset ({min(n_list)}).")
+    if m < k:
+        raise ValueError(f"Number of factors (k={k}) should be less than the number of shared features ({m}).")
+    best = None
+    best_seed = seed
+    for i in range(nRandomStarts):
+        rng = api.RRandom(seed + i)
+        if WInit is None:
+            WInit = _r_matrix(rng, m, k)
+        if VInit is None:
+            VInit = [_r_matrix(rng, m, k) for _ in mats]
+        if HInit is None:
+            HInit = [_r_matrix(rng, n, k) for n in n_list]
+        out = api.inmf(mats, k=k, lambda_=lambda_, niter=nIteration, Hinit=HInit, Vinit=VInit, Winit=WInit,
+                       nCores=nCores, verbose=verbose, trajectory=trajectory)
+        if best is None or out["objErr"] < best["objErr"]:
+            best = out
+            best_seed = seed + i
+    res = dict(best)
+    res["H"] = [h.T.copy(order="F") for h in best["H"]]   # k x n_i
+    res["bestSeed"] = best_seed
+    if names is not None:
+        res["H"] = dict(zip(names, res["H"]))
+        res["V"] = dict(zip(names, res["V"]))
+    return res
+
+
+def run_uinmf_list(objectList, unsharedList, k=20, lambda_=5.0, nIteration=30, nRandomStarts=1, seed=1, nCores=2,
+                   verbose=False, trajectory=False):
+    mats = list(objectList.values()) if isinstance(objectList, dict) else list(objectList)
+    names = list(objectList.keys()) if isinstance(objectList, dict) else None
+    uns = [unsharedList.get(nm) for nm in names] if isinstance(unsharedList, dict) else list(unsharedList)
+    m = mats[0].shape[0]
+    n_list = [x.shape[1] for x in mats]
+    if min(n_list) < k:
+        raise ValueError(f"Number of factors (k={k}) should be less than the number of cells in the smallest "
+                         f"dataset ({min(n_list)}).")
+    if all(u is None for u in uns):
+        raise ValueError("No scaled data for unshared feature found. Run `selectGenes()` with "
+                         "`useUnsharedDatasets` specified, and then `scaleNotCenter()`.")
+    u_list = [0 if u is None else u.shape[0] for u in uns]
+    best = None
+    best_seed = None
+    for i in range(nRandomStarts):
+        seed = seed + i            # cumulative, as in R/integration.R:1283
+        rng = api.RRandom(seed)
+        W0 = _r_matrix(rng, m, k)
+        V0 = [_r_matrix(rng, m, k) for _ in mats]
+        U0 = [(_r_matrix(rng, u, k) if u > 0 else None) for u in u_list]
+        _ = [rng.runif(n * k, 0.0, 2.0) for n in n_list]      # H draws (unused: H is solved first)
+        out = api.uinmf(mats, uns, k=k, lambda_=lambda_, niter=nIteration, nCores=nCores, verbose=verbose,
+                        Winit=W0, Vinit=V0, Uinit=U0, trajectory=trajectory)
+        if best is None or out["objErr"] < best["objErr"]:
+            best = out
+            best_seed = seed
+    res = dict(best)
+    res["H"] = [h.T.copy(order="F") for h in best["H"]]
+    res["bestSeed"] = best_seed
+    if names is not None:
+        res["H"] = dict(zip(names, res["H"]))
+        res["V"] = dict(zip(names, res["V"]))
+        res["U"] = {nm: u for nm, u in zip(names, res["U"]) if u is not None}
+    return res
+
+
+def runINMF(scaleData, k=20, lambda_=5.0, nIteration=30, nRandomStarts=1, HInit=None, WInit=None, VInit=None, seed=1,
+            nCores=2, verbose=False):
+    """runINMF.liger on a {dataset: scaleData} dict: returns dict(W, H={...k x n_i}, V={...}, objErr,
+    uns=dict(factorization=dict(k, lambda)))  (R/integration.R:230-284)."""
+    if any(v is None for v in scaleData.values()):
+        raise ValueError("Scaled data not available. Run `scaleNotCenter()` first.")
+    out = run_inmf_list(scaleData, k, lambda_, nIteration, nRandomStarts, HInit, WInit, VInit, seed, nCores, verbose)
+    out["uns"] = {"factorization": {"k": k, "lambda": lambda_}}
+    return out
+
+
+def runUINMF(scaleData, scaleUnsharedData, k=20, lambda_=5.0, nIteration=30, nRandomStarts=1, seed=1, nCores=2,
+             verbose=False):
+    """runUINMF.liger on dicts of scaleData / scaleUnsharedData (R/integration.R:1206-1250)."""
+    if any(v is None for v in scaleData.values()):
+        raise ValueError("Scaled data not available. Run `scaleNotCenter()` first.")
+    out = run_uinmf_list(scaleData, scaleUnsharedData, k, lambda_, nIteration, nRandomStarts, seed, nCores, verbose)
+    out["uns"] = {"factorization": {"k": k, "lambda": lambda_}}
+    return out
