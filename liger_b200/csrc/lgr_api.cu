@@ -95,9 +95,11 @@ struct lgr_ctx {
     DBuf<DsDev> ds_dev;
     DBuf<double> W, CtBw, Gsum, Garena, gram_arena, objbuf, sq;
     DBuf<unsigned long long> wmask;
-    DBuf<float> Bbuf, Rarena, scratchF;
-    DBuf<double> scratchD;
+    DBuf<float> Bbuf, Rarena;
+    DBuf<double> ctc_arena;   // per NNLS group: CtC and CtC^-1 (2 x KP x KP fp64), groups = H_0..H_d-1, V_0..V_d-1, W
+    DBuf<int> ok_arena;
     DBuf<NnlsGroup> grpH, grpV, grpW;
+    DBuf<GramSpec> specH, specV, specW;
     DBuf<Counters> counters;
     NnlsConfig cfgF{}, cfgD{};
     int blocksH = 0, blocksV = 0, blocksW = 0, ltx_blocks = 0, xh_tiles = 0, prep_blocks = 0, max_rows = 0;
@@ -248,7 +250,14 @@ void run_objective(lgr_ctx* c, double* slot) {
 
 void iterate(lgr_ctx* c, int niter, double* traj_host) {
     const bool traj = traj_host != nullptr;
-    const int cold = (c->flags & LGR_FLAG_COLD_START) ? 1 : 0;
+    int cold = (c->flags & LGR_FLAG_COLD_START) ? 1 : 0;
+    const bool hist = getenv("LGR_NNLS_HIST") != nullptr;
+    if (hist) {
+        cold |= 2;
+        if (atoi(getenv("LGR_NNLS_HIST")) == 2) cold |= 4;  // histogram of final passive-set sizes instead
+        c->counters.zero(c->st);
+    }
+    if (getenv("LGR_NNLS_NO_DUAL")) cold |= 8;
     if (traj) c->objbuf.alloc((size_t)niter + 1);
     c->kt.begin_loop();
     c->tm.kernel_launches = 0;
@@ -263,8 +272,12 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             launch_spmm_ltx(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->st);
         }
         {
+            Timed t(c, "k_gram_inv");
+            launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
+        }
+        {
             Timed t(c, "k_nnls_H");
-            launch_nnls(false, c->grpH.p, c->d, c->blocksH, c->k, c->kp, c->cfgF, c->scratchF.p, c->counters.p, cold, c->st);
+            launch_nnls(false, c->grpH.p, c->d, c->blocksH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
         }
         c->h_valid = true;
         // ---- sufficient statistics of the V / W solves ----
@@ -275,8 +288,12 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             launch_vrhs(c->ds_dev.p, c->d, c->W.p, c->k, c->kp, c->max_rows, c->st);
         }
         {
+            Timed t(c, "k_gram_inv");
+            launch_gram_inv(c->specV.p, c->d, c->k, c->kp, c->st);
+        }
+        {
             Timed t(c, "k_nnls_V");
-            launch_nnls(true, c->grpV.p, c->d, c->blocksV, c->k, c->kp, c->cfgD, c->scratchD.p, c->counters.p, cold, c->st);
+            launch_nnls(true, c->grpV.p, c->d, c->blocksV, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
         }
         // ---- W: new V_i ----
         {
@@ -284,8 +301,12 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             launch_wrhs(c->ds_dev.p, c->d, c->m, c->CtBw.p, c->Gsum.p, c->k, c->kp, c->st);
         }
         {
+            Timed t(c, "k_gram_inv");
+            launch_gram_inv(c->specW.p, 1, c->k, c->kp, c->st);
+        }
+        {
             Timed t(c, "k_nnls_W");
-            launch_nnls(true, c->grpW.p, 1, c->blocksW, c->k, c->kp, c->cfgD, c->scratchD.p, c->counters.p, cold, c->st);
+            launch_nnls(true, c->grpW.p, 1, c->blocksW, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
         }
     }
     if (traj && niter > 0) {
@@ -302,6 +323,11 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         LGR_CUDA(cudaMemcpy(traj_host, c->objbuf.p, (size_t)niter * sizeof(double), cudaMemcpyDeviceToHost));
     Counters cn;
     LGR_CUDA(cudaMemcpy(&cn, c->counters.p, sizeof(cn), cudaMemcpyDeviceToHost));
+    if (hist) {
+        fprintf(stderr, "[lgr] nnls pivots/column histogram:");
+        for (int b = 0; b < 40; ++b) fprintf(stderr, " %llu", cn.hist[b]);
+        fprintf(stderr, "  spill=%llu bad=%llu\n", cn.nnls_spill, cn.nnls_bad_pivot);
+    }
     c->tm.nnls_pivots = (int64_t)cn.nnls_pivots;
     c->tm.nnls_unconverged = (int64_t)cn.nnls_unconverged;
 }
@@ -379,8 +405,9 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         LGR_REQUIRE(E.ncol >= 1 && E.ncol < (int64_t)0x7fffffff, "E[i].ncol out of range");
         LGR_REQUIRE(E.colptr && (E.colptr[E.ncol] == 0 || (E.rowidx && E.values)), "E[i] has null arrays");
         D.n_full = (int)E.ncol;
-        D.c0 = (int)((int64_t)D.n_full * c->rank / c->world);
-        const int c1 = (int)((int64_t)D.n_full * (c->rank + 1) / c->world);
+        const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
+        D.c0 = local ? 0 : (int)((int64_t)D.n_full * c->rank / c->world);
+        const int c1 = local ? D.n_full : (int)((int64_t)D.n_full * (c->rank + 1) / c->world);
         D.n = c1 - D.c0;
         D.lambda = a->lambda[i];
         D.u = 0;
@@ -447,10 +474,14 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     // device-side dataset table + NNLS groups
     c->cfgF = nnls_config(k, kp, false, c->num_sms);
     c->cfgD = nnls_config(k, kp, true, c->num_sms);
-    if (c->cfgF.scratch_elems_per_thread)
-        c->scratchF.alloc((size_t)c->cfgF.grid_cap * c->cfgF.threads * c->cfgF.scratch_elems_per_thread);
-    if (c->cfgD.scratch_elems_per_thread)
-        c->scratchD.alloc((size_t)c->cfgD.grid_cap * c->cfgD.threads * c->cfgD.scratch_elems_per_thread);
+    const int ngrp = 2 * c->d + 1;
+    const size_t kk = (size_t)kp * kp;
+    c->ctc_arena.alloc((size_t)ngrp * 2 * kk);
+    c->ctc_arena.zero(c->st);
+    c->ok_arena.alloc((size_t)ngrp);
+    c->ok_arena.zero(c->st);
+    auto ctc = [&](int gi) { return c->ctc_arena.p + (size_t)gi * 2 * kk; };
+    std::vector<GramSpec> sH(c->d), sV(c->d), sW(1);
     c->ds_host.resize(c->d);
     std::vector<NnlsGroup> gH(c->d), gV(c->d), gW(1);
     int ltx = 0, xh = 0, prep = 0, bH = 0, bV = 0;
@@ -490,13 +521,16 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.lambda = D.lambda;
         h.sqnorm = sq[i];
         // H solve: CtC = LtL + lambda VtV, rhs = B (fp32), x = H
-        gH[i] = NnlsGroup{h.LtL, h.VtV, 1.0, D.lambda, h.B, h.H, h.hmask, D.n, kp, bH, 0};
+        sH[i] = GramSpec{h.LtL, h.VtV, 1.0, D.lambda, ctc(i), ctc(i) + kk, c->ok_arena.p + i};
+        gH[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, h.H, h.hmask, D.n, kp, bH, 0};
         bH += (D.n + c->cfgF.threads - 1) / c->cfgF.threads;
         // V/U solve: CtC = (1 + lambda) G_i, rhs = CtBv (fp64), x = V
-        gV[i] = NnlsGroup{h.G, nullptr, 1.0 + D.lambda, 0.0, h.CtBv, h.V, h.vmask, D.rows, kp, bV, 0};
+        sV[i] = GramSpec{h.G, nullptr, 1.0 + D.lambda, 0.0, ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i};
+        gV[i] = NnlsGroup{ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i, h.CtBv, h.V, h.vmask, D.rows, kp, bV, 0};
         bV += (D.rows + c->cfgD.threads - 1) / c->cfgD.threads;
     }
-    gW[0] = NnlsGroup{c->Gsum.p, nullptr, 1.0, 0.0, c->CtBw.p, c->W.p, c->wmask.p, m, kp, 0, 0};
+    sW[0] = GramSpec{c->Gsum.p, nullptr, 1.0, 0.0, ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d};
+    gW[0] = NnlsGroup{ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d, c->CtBw.p, c->W.p, c->wmask.p, m, kp, 0, 0};
     c->ltx_blocks = ltx;
     c->xh_tiles = xh;
     c->prep_blocks = prep;
@@ -507,6 +541,12 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->grpH.alloc((size_t)c->d);
     c->grpV.alloc((size_t)c->d);
     c->grpW.alloc(1);
+    c->specH.alloc((size_t)c->d);
+    c->specV.alloc((size_t)c->d);
+    c->specW.alloc(1);
+    LGR_CUDA(cudaMemcpyAsync(c->specH.p, sH.data(), sizeof(GramSpec) * c->d, cudaMemcpyHostToDevice, c->st));
+    LGR_CUDA(cudaMemcpyAsync(c->specV.p, sV.data(), sizeof(GramSpec) * c->d, cudaMemcpyHostToDevice, c->st));
+    LGR_CUDA(cudaMemcpyAsync(c->specW.p, sW.data(), sizeof(GramSpec), cudaMemcpyHostToDevice, c->st));
     LGR_CUDA(cudaMemcpyAsync(c->ds_dev.p, c->ds_host.data(), sizeof(DsDev) * c->d, cudaMemcpyHostToDevice, c->st));
     LGR_CUDA(cudaMemcpyAsync(c->grpH.p, gH.data(), sizeof(NnlsGroup) * c->d, cudaMemcpyHostToDevice, c->st));
     LGR_CUDA(cudaMemcpyAsync(c->grpV.p, gV.data(), sizeof(NnlsGroup) * c->d, cudaMemcpyHostToDevice, c->st));
@@ -748,13 +788,16 @@ int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* 
             LGR_CUDA(cudaMemcpyAsync(dB.p, CtB, (size_t)k * ncols * sizeof(double), cudaMemcpyHostToDevice, st));
             dev_colmajor_to_padded(dG.p, dGp.p, k, k, kp, st);  // symmetric: layout orientation is irrelevant
             NnlsConfig cfg = nnls_config(k, kp, true, prop.multiProcessorCount);
-            DBuf<double> scratch;
-            if (cfg.scratch_elems_per_thread)
-                scratch.alloc((size_t)cfg.grid_cap * cfg.threads * cfg.scratch_elems_per_thread);
-            NnlsGroup g{dGp.p, nullptr, 1.0, 0.0, dB.p, dX.p, mask.p, (int)ncols, k, 0, 0};
+            DBuf<double> ctc((size_t)2 * kp * kp);
+            DBuf<int> ok(1);
+            DBuf<GramSpec> spec(1);
+            GramSpec sp{dGp.p, nullptr, 1.0, 0.0, ctc.p, ctc.p + (size_t)kp * kp, ok.p};
+            LGR_CUDA(cudaMemcpyAsync(spec.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, st));
+            launch_gram_inv(spec.p, 1, k, kp, st);
+            NnlsGroup g{ctc.p, ctc.p + (size_t)kp * kp, ok.p, dB.p, dX.p, mask.p, (int)ncols, k, 0, 0};
             LGR_CUDA(cudaMemcpyAsync(grp.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
             const int blocks = (int)((ncols + cfg.threads - 1) / cfg.threads);
-            launch_nnls(true, grp.p, 1, blocks, k, kp, cfg, scratch.p, cnt.p, 1, st);
+            launch_nnls(true, grp.p, 1, blocks, k, kp, cfg, cnt.p, 1, st);
             LGR_CUDA(cudaMemcpyAsync(X, dX.p, (size_t)k * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
             LGR_CUDA(cudaStreamSynchronize(st));
         } catch (...) {

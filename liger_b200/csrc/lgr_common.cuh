@@ -107,11 +107,11 @@ struct DsDev {
     double sqnorm;  // ||[E;P]||_F^2 (global, after all-reduce)
 };
 
-// One batch of NNLS columns sharing a Gram matrix:  Gs = cA * A + cB * B  (A, B fp64 KP x KP, B may be null)
+// One batch of NNLS columns sharing a Gram matrix (gram / ginv / ok are produced by k_gram_inv)
 struct NnlsGroup {
-    const double* gramA;
-    const double* gramB;
-    double cA, cB;
+    const double* gram;         // KP x KP  CtC
+    const double* ginv;         // KP x KP  CtC^-1 (valid when *ok != 0)
+    const int* ok;
     const void* rhs;            // T: ncols x ld  (column j at rhs + j*ld)
     void* x;                    // T: ncols x ld
     unsigned long long* mask;   // ncols, warm start in/out (never null)
@@ -121,11 +121,22 @@ struct NnlsGroup {
     int pad;
 };
 
+// CtC = cA * A + cB * B (A, B fp64 KP x KP, B may be null) -> gram, ginv, ok
+struct GramSpec {
+    const double* A;
+    const double* B;
+    double cA, cB;
+    double* gram;
+    double* ginv;
+    int* ok;
+};
+
 struct Counters {
     unsigned long long nnls_pivots;
     unsigned long long nnls_unconverged;
     unsigned long long nnls_bad_pivot;
     unsigned long long nnls_spill;  // solves that used the global-memory factor scratch
+    unsigned long long hist[40];    // histogram of pivots per column (last bin: >= 39)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -136,18 +147,19 @@ inline int prep_rows_per_block(int kp) { return 2048 / kp; }  // keeps k_prep's 
 
 struct NnlsConfig {
     int threads;      // columns per CTA
-    int ps;           // largest passive-set size whose Cholesky factor lives in shared memory
+    int pool_elems;   // shared-memory pool for the per-column Cholesky factors
     size_t smem;
     int grid_cap;     // persistent grid size
-    size_t scratch_elems_per_thread;
 };
 NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
 
 void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st);
 void launch_spmm_ltx(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st);
 void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st);
+void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStream_t st);
 void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_blocks, int k, int kp,
-                 const NnlsConfig& cfg, void* scratch, Counters* cnt, int cold_start, cudaStream_t st);
+                 const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st);
+void nnls_init();
 void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st);
 void launch_wrhs(const DsDev* ds, int nds, int m, double* CtBw, double* Gsum, int k, int kp, cudaStream_t st);
 void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot, cudaStream_t st);

@@ -374,319 +374,6 @@ void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, in
         k_spmm_xh<64><<<total_tiles, XH_THREADS, smem, st>>>(ds, nds, k, tc);
     LGR_CUDA(cudaGetLastError());
 }
-
-// ------------------------------------------------------------------------------------------------
-// k_nnls: batched NNLS by block principal pivoting (Kim & Park 2011), one thread per column.
-//
-//   min_x>=0  1/2 x^T G x - b^T x   for every column b of a group that shares the k x k Gram G.
-//   Per column state (passive set F as a 64-bit mask, alpha/beta of the pivoting rule) lives in shared
-//   memory indexed by a column SLOT, so that after every pivot round the still-infeasible slots are
-//   compacted onto the low threads of the CTA (SIMT efficiency: warm-started columns finish after
-//   one solve and would otherwise idle their lanes).
-//   Each solve is a dense Cholesky of G_FF (p = |F|), left-looking, packed lower-triangular storage
-//   [element][slot] in shared memory (conflict-free); passive sets larger than PS spill the factor to
-//   a global scratch with the same layout.
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-struct Eps;
-template <>
-struct Eps<float> {
-    static __device__ float v() { return 1.1920929e-7f; }
-};
-template <>
-struct Eps<double> {
-    static __device__ double v() { return 2.220446049250313e-16; }
-};
-__device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
-
-// Solve G_FF x = b_F.  idx[t*IS] = t-th member of F (ascending); fac(e) = facp[e*FS].
-// On exit x[t*XS] (t < p) holds the solution in the compact order.  Returns false on a non-positive pivot.
-template <typename T>
-__device__ __forceinline__ bool chol_solve(int p, const unsigned char* idx, int IS, const T* __restrict__ Gs, int ldg,
-                                           const T* b, T* x, int XS, T* facp, int FS) {
-    bool ok = true;
-    for (int j = 0; j < p; ++j) {
-        const int gj = idx[j * IS];
-        const T* Gj = Gs + gj * ldg;
-        T* rowj = facp + (size_t)(j * (j + 1) / 2) * FS;
-        T d = Gj[gj];
-#pragma unroll 4
-        for (int t = 0; t < j; ++t) {
-            const T l = rowj[(size_t)t * FS];
-            d -= l * l;
-        }
-        T invd;
-        if (d > (T)0 && d > Gj[gj] * (Eps<T>::v() * (T)4)) {
-            invd = rsq(d);
-        } else {
-            invd = (T)0;  // numerically singular principal block: pin this coordinate to zero
-            ok = false;
-        }
-        rowj[(size_t)j * FS] = invd;
-        for (int i = j + 1; i < p; ++i) {
-            const int gi = idx[i * IS];
-            T* rowi = facp + (size_t)(i * (i + 1) / 2) * FS;
-            T sacc = Gj[gi];
-#pragma unroll 4
-            for (int t = 0; t < j; ++t) sacc -= rowi[(size_t)t * FS] * rowj[(size_t)t * FS];
-            rowi[(size_t)j * FS] = sacc * invd;
-        }
-    }
-    // forward substitution  z = L^-1 b_F
-    for (int j = 0; j < p; ++j) {
-        const T* rowj = facp + (size_t)(j * (j + 1) / 2) * FS;
-        T sacc = b[idx[j * IS] * XS];
-#pragma unroll 4
-        for (int t = 0; t < j; ++t) sacc -= rowj[(size_t)t * FS] * x[t * XS];
-        x[j * XS] = sacc * rowj[(size_t)j * FS];
-    }
-    // back substitution  x = L^-T z
-    for (int j = p - 1; j >= 0; --j) {
-        T sacc = x[j * XS];
-        for (int i = j + 1; i < p; ++i) sacc -= facp[((size_t)(i * (i + 1) / 2) + j) * FS] * x[i * XS];
-        x[j * XS] = sacc * facp[((size_t)(j * (j + 1) / 2) + j) * FS];
-    }
-    return ok;
-}
-
-template <typename T, int KP>
-__global__ void k_nnls(const NnlsGroup* __restrict__ groups, int ngroups, int total_blocks, int k, int PS,
-                       T* __restrict__ scratch, Counters* cnt, int cold_start) {
-    const int NT = blockDim.x;
-    const int XS = NT + 1;  // padded stride of the transposed rhs / solution tiles
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // carve-up (all sizes are multiples of 8 bytes)
-    T* Gs = reinterpret_cast<T*>(smem_raw);                      // KP*KP
-    T* bS = Gs + KP * KP;                                         // KP*XS
-    T* xS = bS + (size_t)KP * XS;                                 // KP*XS
-    T* facS = xS + (size_t)KP * XS;                               // tri(PS)*NT
-    unsigned long long* maskS = reinterpret_cast<unsigned long long*>(facS + (size_t)(PS * (PS + 1) / 2) * NT);
-    T* tolS = reinterpret_cast<T*>(maskS + NT);                   // NT
-    int* stateS = reinterpret_cast<int*>(tolS + NT);              // NT: alpha | beta<<8 | iter<<16
-    int* listS = stateS + NT;                                     // NT
-    int* list2S = listS + NT;                                     // NT
-    int* miscS = list2S + NT;                                     // [0]=nact
-    unsigned char* idxS = reinterpret_cast<unsigned char*>(miscS + 4);  // KP*NT
-
-    const int tid = threadIdx.x;
-    const unsigned long long kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
-    const int MAXIT = 4 * k + 16;
-    const size_t tri_full = (size_t)k * (k + 1) / 2;
-    T* myscratch = scratch ? scratch + ((size_t)blockIdx.x * NT) * tri_full : nullptr;
-
-    int cur_group = -1;
-    unsigned long long pivots_local = 0;
-    for (int blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
-        int g = 0;
-        while (g + 1 < ngroups && blk >= groups[g + 1].blk_off) ++g;
-        const NnlsGroup& grp = groups[g];
-        __syncthreads();  // previous block fully done with smem
-        if (g != cur_group) {
-            cur_group = g;
-            for (int e = tid; e < KP * KP; e += NT) {
-                const int a = e / KP, b = e % KP;
-                double v = 0.0;
-                if (a < k && b < k) {
-                    v = grp.cA * grp.gramA[e];
-                    if (grp.gramB) v += grp.cB * grp.gramB[e];
-                }
-                Gs[e] = (T)v;
-            }
-        }
-        const int col0 = (blk - grp.blk_off) * NT;
-        const int ncol = min(NT, grp.ncols - col0);
-        const T* __restrict__ rhs = reinterpret_cast<const T*>(grp.rhs) + (size_t)col0 * grp.ld;
-        T* __restrict__ xout = reinterpret_cast<T*>(grp.x) + (size_t)col0 * grp.ld;
-        const int ld = grp.ld;
-        // coalesced load of the rhs tile, transposed into bS[f][slot]
-        for (int e = tid; e < ncol * KP; e += NT) {
-            const int j = e / KP, f = e % KP;
-            bS[f * XS + j] = (f < k) ? rhs[(size_t)j * ld + f] : (T)0;
-        }
-        if (tid < ncol) {
-            maskS[tid] = cold_start ? 0ull : (grp.mask[col0 + tid] & kmask);
-            stateS[tid] = 3 | ((k + 1) << 8);
-            listS[tid] = tid;
-        }
-        if (tid == 0) miscS[0] = ncol;
-        __syncthreads();
-        if (tid < ncol) {
-            T bm = (T)0;
-            for (int f = 0; f < k; ++f) bm = fmax(bm, fabs(bS[f * XS + tid]));
-            tolS[tid] = bm * Eps<T>::v() * (T)8;
-        }
-        __syncthreads();
-
-        int nact = ncol;
-        int* cur = listS;
-        int* nxt = list2S;
-        while (nact > 0) {
-            bool notdone = false;
-            if (tid < nact) {
-                const int slot = cur[tid];
-                unsigned long long F = maskS[slot];
-                const int p = __popcll(F);
-                unsigned char* idx = idxS + slot;
-                {
-                    unsigned long long r = F;
-                    int t = 0;
-                    while (r) {
-                        idx[t * NT] = (unsigned char)(__ffsll((long long)r) - 1);
-                        r &= r - 1;
-                        ++t;
-                    }
-                }
-                const T* b = bS + slot;
-                T* x = xS + slot;
-                bool ok = true;
-                if (p > 0) {
-                    if (p <= PS) {
-                        ok = chol_solve<T>(p, idx, NT, Gs, KP, b, x, XS, facS + slot, NT);
-                    } else {
-                        ok = chol_solve<T>(p, idx, NT, Gs, KP, b, x, XS, myscratch + slot, NT);
-                        atomicAdd(&cnt->nnls_spill, 1ull);
-                    }
-                }
-                if (!ok) atomicAdd(&cnt->nnls_bad_pivot, 1ull);
-                // infeasible coordinates
-                const T tol = tolS[slot];
-                unsigned long long infeas = 0ull;
-                T xmax = (T)0;
-                for (int t = 0; t < p; ++t) xmax = fmax(xmax, fabs(x[t * XS]));
-                const T tolx = xmax * Eps<T>::v() * (T)8;
-                for (int t = 0; t < p; ++t)
-                    if (x[t * XS] < -tolx) infeas |= 1ull << idx[t * NT];
-                {
-                    unsigned long long A = (~F) & kmask;
-                    while (A) {
-                        const int j = __ffsll((long long)A) - 1;
-                        A &= A - 1;
-                        T y = -b[j * XS];
-                        const T* Gj = Gs + j * KP;
-                        for (int t = 0; t < p; ++t) y += Gj[idx[t * NT]] * x[t * XS];
-                        if (y < -tol) infeas |= 1ull << j;
-                    }
-                }
-                int st = stateS[slot];
-                int alpha = st & 0xff, beta = (st >> 8) & 0xff, iter = st >> 16;
-                if (infeas != 0ull && iter < MAXIT) {
-                    const int ninf = __popcll(infeas);
-                    unsigned long long flip;
-                    if (ninf < beta) {
-                        beta = ninf;
-                        alpha = 3;
-                        flip = infeas;
-                    } else if (alpha >= 1) {
-                        --alpha;
-                        flip = infeas;
-                    } else {
-                        flip = 1ull << (63 - __clzll((long long)infeas));
-                    }
-                    F ^= flip;
-                    ++iter;
-                    maskS[slot] = F;
-                    stateS[slot] = alpha | (beta << 8) | (iter << 16);
-                    notdone = true;
-                    ++pivots_local;
-                } else {
-                    if (infeas != 0ull) atomicAdd(&cnt->nnls_unconverged, 1ull);
-                    // expand the compact solution over b's slot (b is no longer needed)
-                    T* out = bS + slot;
-                    T keep[1];
-                    (void)keep;
-                    // x is compact in xS; write zeros then scatter
-                    for (int f = 0; f < KP; ++f) out[f * XS] = (T)0;
-                    for (int t = 0; t < p; ++t) {
-                        const T v = x[t * XS];
-                        out[idx[t * NT] * XS] = v > (T)0 ? v : (T)0;
-                    }
-                }
-            }
-            // compaction of the unfinished slots (order-preserving, ballot + warp prefix)
-            __syncthreads();
-            {
-                const unsigned bal = __ballot_sync(0xffffffffu, notdone);
-                const int lane = tid & 31, warp = tid >> 5;
-                int* wcount = miscS + 0;  // reuse after reading nact (all threads hold nact in a register)
-                __shared__ int wsum[32];
-                if (lane == 0) wsum[warp] = __popc(bal);
-                __syncthreads();
-                int base = 0, total = 0;
-                const int nw = (NT + 31) >> 5;
-                for (int w = 0; w < nw; ++w) {
-                    const int cw = wsum[w];
-                    if (w < warp) base += cw;
-                    total += cw;
-                }
-                if (notdone) nxt[base + __popc(bal & ((1u << lane) - 1u))] = cur[tid];
-                (void)wcount;
-                nact = total;
-                __syncthreads();
-                int* tmp = cur;
-                cur = nxt;
-                nxt = tmp;
-            }
-        }
-        // coalesced store of the solution tile + masks
-        for (int e = tid; e < ncol * KP; e += NT) {
-            const int j = e / KP, f = e % KP;
-            if (f < k) xout[(size_t)j * ld + f] = bS[f * XS + j];
-        }
-        if (tid < ncol) grp.mask[col0 + tid] = maskS[tid];
-    }
-    if (pivots_local) atomicAdd(&cnt->nnls_pivots, pivots_local);
-}
-
-static size_t nnls_smem_bytes(int kp, int nt, int ps, size_t tsize) {
-    size_t b = 0;
-    b += (size_t)kp * kp * tsize;
-    b += 2 * (size_t)kp * (nt + 1) * tsize;
-    b += (size_t)(ps * (ps + 1) / 2) * nt * tsize;
-    b += (size_t)nt * 8;          // masks
-    b += (size_t)nt * tsize;      // tol
-    b += 3 * (size_t)nt * 4 + 16; // state, lists, misc
-    b += (size_t)kp * nt;         // idx
-    return (b + 15) & ~(size_t)15;
-}
-
-NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms) {
-    NnlsConfig c{};
-    const size_t ts = is_double ? 8 : 4;
-    c.threads = is_double ? 64 : 128;
-    const size_t budget = is_double ? 160 * 1024 : 110 * 1024;  // fp32: two CTAs per SM
-    int ps = k;
-    while (ps > 4 && nnls_smem_bytes(kp, c.threads, ps, ts) > budget) --ps;
-    c.ps = ps;
-    c.smem = nnls_smem_bytes(kp, c.threads, ps, ts);
-    const int per_sm = (int)((226 * 1024) / (c.smem + 1024));
-    c.grid_cap = num_sms * (per_sm > 0 ? per_sm : 1);
-    c.scratch_elems_per_thread = (ps < k) ? (size_t)k * (k + 1) / 2 : 0;
-    return c;
-}
-
-void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_blocks, int k, int kp,
-                 const NnlsConfig& cfg, void* scratch, Counters* cnt, int cold_start, cudaStream_t st) {
-    if (total_blocks <= 0) return;
-    const int grid = total_blocks < cfg.grid_cap ? total_blocks : cfg.grid_cap;
-    if (is_double) {
-        if (kp == 32)
-            k_nnls<double, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.ps,
-                                                                     (double*)scratch, cnt, cold_start);
-        else
-            k_nnls<double, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.ps,
-                                                                     (double*)scratch, cnt, cold_start);
-    } else {
-        if (kp == 32)
-            k_nnls<float, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.ps,
-                                                                    (float*)scratch, cnt, cold_start);
-        else
-            k_nnls<float, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.ps,
-                                                                    (float*)scratch, cnt, cold_start);
-    }
-    LGR_CUDA(cudaGetLastError());
-}
-
 // ------------------------------------------------------------------------------------------------
 // right-hand sides of the V/U and W solves (fp64; tiny)
 //   CtBv_i[g][:] = R_i[g][:] - G_i W[g][:]  (g < m),  R_i[g][:]  (unshared rows)      R/cINMF.R:488
@@ -794,11 +481,8 @@ void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot,
 }
 
 void kernels_init() {
+    nnls_init();
     const int maxs = 227 * 1024 - 1024;  // static smem of the kernels counts against the 227 KB limit
-    LGR_CUDA(cudaFuncSetAttribute(k_nnls<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    LGR_CUDA(cudaFuncSetAttribute(k_nnls<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    LGR_CUDA(cudaFuncSetAttribute(k_nnls<double, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    LGR_CUDA(cudaFuncSetAttribute(k_nnls<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
 }
