@@ -1,0 +1,122 @@
+"""CPU suite: the oracle against the reference's own golden vectors / known answers."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import rel
+from oracle import inmf_oracle as orc
+from oracle import c_oracle
+
+
+def test_r_rng_known_answer():
+    # set.seed(1); runif(3)  
+    u = orc.RRandom(1).runif(3)
+    assert np.allclose(u, [0.2655087, 0.3721239, 0.5728534], atol=5e-8)
+    # the product's host RNG (C++) is the same stream
+    import liger_b200
+    v = liger_b200.RRandom(1).runif(1000, 0, 2)
+    w = orc.RRandom(1).runif(1000, 0, 2)
+    assert np.array_equal(v, w)
+    assert np.array_equal(liger_b200.RRandom(12345).runif(700), orc.RRandom(12345).runif(700))
+
+
+def test_preprocessing_known_answers(pbmc):
+    g = pbmc["golden"]
+    # tests/testthat/test_preprocessing.R:184,190,262-263
+    assert int(g["n_union"]) == 173 and int(g["n_intersection"]) == 161
+    assert abs(float(g["kat_ctrl_3_5"]) - 0.4693316) < 1e-6
+    assert abs(float(g["kat_stim_7_9"]) - 2.360295) < 1e-6
+    E = pbmc["Es"][0].toarray()
+    assert abs(E[2, 4] - 0.4693316) < 1e-6
+    assert pbmc["Es"][0].shape == (173, 300) and pbmc["Es"][1].shape == (173, 300)
+
+
+def test_oracle_reproduces_reference_golden_factors(pbmc):
+    """data/pbmcPlot.rda = runINMF(pbmc, k=20, lambda=5, nIteration=30, seed=1) (R/data.R:8-18)."""
+    g = pbmc["golden"]
+    out = orc.run_inmf_list(pbmc["Es"], k=20, lam=5.0, niter=30, seed=1, trajectory=True)
+    rows = g["golden_rows"]
+    assert rel(out["W"][rows], g["golden_W"]) < 1e-12
+    for i, n in enumerate(pbmc["names"]):
+        assert rel(out["V"][i][rows], g[f"golden_V_{n}"]) < 1e-12
+        assert rel(out["H"][i], g[f"golden_H_{n}"]) < 1e-12
+        assert np.array_equal(out["H"][i] == 0, g[f"golden_H_{n}"] == 0)
+    traj = np.array(out["traj"])
+    assert np.all(np.diff(traj) < 0)
+    # objective trajectory recorded in SURVEY Appendix E
+    assert np.allclose(traj[:5], [61343.051026, 43772.982015, 40131.427700, 38763.763611, 38062.001197], rtol=1e-9)
+    assert abs(out["objErr"] - 36105.069129349) < 1e-6
+
+
+def test_reference_test_config_k10_niter2(pbmc):
+    # tests/testthat/test_factorization.R:49: runIntegration(pbmc, k = 10, nIteration = 2)
+    out = orc.run_inmf_list(pbmc["Es"], k=10, lam=5.0, niter=2, seed=1, trajectory=True)
+    assert np.allclose(out["traj"], [66551.145423, 49910.681818], rtol=1e-9)
+    assert out["W"].shape == (173, 10) and out["H"][0].shape == (10, 300) and out["V"][1].shape == (173, 10)
+
+
+def test_bmmc_trajectory(bmmc):
+    W0, V0, _, _ = orc.seeded_init(1, 135, 20, [340, 340])
+    out = orc.inmf(bmmc["Es"], 20, 5.0, 30, W0, V0, trajectory=True)
+    t = np.array(out["traj"])
+    assert np.allclose(t[[0, 1, 2, 29]], [76619.413, 67245.834, 63243.201, 58526.508], rtol=2e-8)
+    assert np.all(np.diff(t) < 0)
+
+
+def test_bpp_against_lawson_hanson():
+    rng = np.random.default_rng(7)
+    for k in (5, 20, 33):
+        C = rng.random((3 * k, k))
+        G = C.T @ C
+        B = C.T @ (rng.random((3 * k, 40)) - 0.3)
+        X = orc.bppnnls_prod(G, B)
+        for j in range(B.shape[1]):
+            x = orc.nnls_lawson_hanson(G, B[:, j])
+            assert np.allclose(X[:, j], x, atol=1e-9)
+        # KKT
+        Y = G @ X - B
+        assert X.min() >= 0 and Y[X == 0].min() > -1e-9 and np.abs(Y[X > 0]).max() < 1e-8
+
+
+def test_c_oracle_matches_numpy_oracle(pbmc):
+    W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    a = c_oracle.inmf(pbmc["Es"], 20, 5.0, 8, W0, V0, trajectory=True)
+    b = orc.inmf(pbmc["Es"], 20, 5.0, 8, W0, V0, trajectory=True)
+    assert rel(a["W"], b["W"]) < 1e-11
+    for x, y in zip(a["H"] + a["V"], b["H"] + b["V"]):
+        assert rel(x, y) < 1e-11
+    assert np.allclose(a["traj"], b["traj"], rtol=1e-12)
+    rng = np.random.default_rng(3)
+    C = rng.random((80, 30))
+    G, B = C.T @ C, C.T @ rng.random((80, 257))
+    assert rel(c_oracle.bppnnls_prod(G, B), orc.bppnnls_prod(G, B)) < 1e-12
+
+
+def test_uinmf_oracle_monotone_and_stacked_equivalence(pbmc):
+    Es = [E[:150] for E in pbmc["Es"]]
+    Ps = [pbmc["Es"][0][150:], None]           # only the first dataset carries unshared features
+    W0, V0, U0, _ = orc.seeded_init(3, 150, 20, [300, 300], [23, 0])
+    b = orc.uinmf(Es, Ps, 20, [5.0, 2.0], 10, W0, V0, U0, trajectory=True)
+    assert np.all(np.diff(b["traj"]) < 0)
+    a = c_oracle.inmf(Es, 20, [5.0, 2.0], 10, W0, V0, Ps=Ps, Uinit=U0, trajectory=True)
+    assert rel(a["W"], b["W"]) < 1e-11 and rel(a["U"][0], b["U"][0]) < 1e-11 and a["U"][1] is None
+    assert abs(a["objErr"] - b["objErr"]) < 1e-7 * b["objErr"]
+
+
+def test_objerr_formula_against_direct_norm(pbmc):
+    rng = np.random.default_rng(1)
+    E = pbmc["Es"][0]
+    W, V, H = rng.random((173, 7)), rng.random((173, 7)), rng.random((7, 300))
+    direct = np.linalg.norm(E.toarray() - (W + V) @ H) ** 2 + 3.5 * np.linalg.norm(V @ H) ** 2
+    assert abs(orc.objerr_i(H, W, V, E, 3.5) - direct) < 1e-8 * direct
+
+
+def test_synthetic_generator():
+    from liger_b200 import synthetic as syn
+    Es, Ps = syn.make_numpy(2, 1200, 400, 12, u=50, block=500)
+    for E, P in zip(Es, Ps):
+        assert E.shape == (400, 1200) and P.shape == (50, 1200)
+        assert 0.03 < E.nnz / (400 * 1200) < 0.07
+        assert E.data.min() > 0
+        ss = np.asarray(E.multiply(E).sum(axis=1)).ravel() / (1200 - 1)
+        assert np.allclose(ss[ss > 0], 1.0)
