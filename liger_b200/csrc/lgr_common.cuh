@@ -117,7 +117,7 @@ struct NnlsGroup {
     unsigned long long* mask;   // ncols, warm start in/out (never null)
     int ncols;
     int ld;
-    int blk_off;                // first flat column block
+    int blk_off;                // first flat CTA tile of this group
     int pad;
 };
 
@@ -146,18 +146,20 @@ constexpr int LTX_CELLS_PER_BLOCK = 64;
 inline int prep_rows_per_block(int kp) { return 2048 / kp; }  // keeps k_prep's static smem < 48 KB
 
 struct NnlsConfig {
-    int threads;      // columns per CTA
-    int pool_elems;   // shared-memory pool for the per-column Cholesky factors
+    int threads;      // threads per CTA (warps x 32; every warp owns 32 columns at a time)
+    int pool_elems;   // per-warp shared-memory pool for the per-column Cholesky factors
     size_t smem;
     int grid_cap;     // persistent grid size
+    int ct_cols;      // default columns per CTA tile
 };
+int nnls_tile_cols(const NnlsConfig& cfg, long long total_cols, int num_sms);
 NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
 
 void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st);
 void launch_spmm_ltx(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st);
 void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st);
 void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStream_t st);
-void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_blocks, int k, int kp,
+void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_tiles, int ct_cols, int k, int kp,
                  const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st);
 void nnls_init();
 void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st);

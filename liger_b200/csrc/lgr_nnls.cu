@@ -101,21 +101,21 @@ void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------------
-// Solve M_II z = r_I by Cholesky (left-looking, packed lower-triangular factor in the pool).
-//   idx[t*IS]   t-th member of the index set I (ascending)
-//   M           k x k symmetric matrix in shared memory (row stride ldm)
-//   r[f*RS]     right-hand side indexed by factor id
+// Solve M_II z = r_I by Cholesky (left-looking, packed lower-triangular factor in the warp's pool).
+//   idx[t*32]   t-th member of the index set I (ascending), one byte per entry, [t][lane]
+//   M           k x k symmetric matrix in shared memory (row stride MST)
+//   r[f*33]     right-hand side indexed by factor id, [f][lane] tile (stride 33)
 //   fac[e*FS]   packed factor, e = i(i+1)/2 + j;  the diagonal stores 1/L_jj
-//   z[t*FS]     solution in compact order (same stride as the factor: it lives in the pool)
+//   z[t*FS]     solution in compact order (lives in the pool right after the factor)
 // A non-positive pivot pins that coordinate to zero (numerically singular principal block).
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ bool chol_solve(int n, const unsigned char* idx, int IS, const T* __restrict__ M, int ldm,
-                                           const T* r, int RS, T* fac, T* z, int FS) {
+template <typename T, int MST>
+__device__ __forceinline__ bool chol_solve(int n, const unsigned char* idx, const T* __restrict__ M, const T* r, T* fac,
+                                           T* z, const int FS) {
     bool ok = true;
     for (int j = 0; j < n; ++j) {
-        const int gj = idx[j * IS];
-        const T* Mj = M + gj * ldm;
+        const int gj = idx[j * 32];
+        const T* Mj = M + gj * MST;
         T* rowj = fac + (j * (j + 1) / 2) * FS;
         T d = Mj[gj];
 #pragma unroll 4
@@ -131,12 +131,11 @@ __device__ __forceinline__ bool chol_solve(int n, const unsigned char* idx, int 
             ok = false;
         }
         rowj[j * FS] = invd;
-        // rows below, two at a time (shares the loads of row j, doubles the ILP of the FMA chain)
         int i = j + 1;
-        for (; i + 1 < n; i += 2) {
+        for (; i + 1 < n; i += 2) {  // two rows at a time: shares row j, doubles the ILP of the FMA chain
             T* r0 = fac + (i * (i + 1) / 2) * FS;
-            T* r1 = fac + ((i + 1) * (i + 2) / 2) * FS;
-            T s0 = Mj[idx[i * IS]], s1 = Mj[idx[(i + 1) * IS]];
+            T* r1 = r0 + (i + 1) * FS;
+            T s0 = Mj[idx[i * 32]], s1 = Mj[idx[(i + 1) * 32]];
 #pragma unroll 2
             for (int t = 0; t < j; ++t) {
                 const T l = rowj[t * FS];
@@ -148,7 +147,7 @@ __device__ __forceinline__ bool chol_solve(int n, const unsigned char* idx, int 
         }
         if (i < n) {
             T* r0 = fac + (i * (i + 1) / 2) * FS;
-            T s0 = Mj[idx[i * IS]];
+            T s0 = Mj[idx[i * 32]];
 #pragma unroll 4
             for (int t = 0; t < j; ++t) s0 -= r0[t * FS] * rowj[t * FS];
             r0[j * FS] = s0 * invd;
@@ -156,337 +155,290 @@ __device__ __forceinline__ bool chol_solve(int n, const unsigned char* idx, int 
     }
     for (int j = 0; j < n; ++j) {  // forward substitution
         const T* rowj = fac + (j * (j + 1) / 2) * FS;
-        T s = r[idx[j * IS] * RS];
+        T s = r[idx[j * 32] * 33];
 #pragma unroll 4
         for (int t = 0; t < j; ++t) s -= rowj[t * FS] * z[t * FS];
         z[j * FS] = s * rowj[j * FS];
     }
     for (int j = n - 1; j >= 0; --j) {  // back substitution
         T s = z[j * FS];
-        for (int i = j + 1; i < n; ++i) s -= fac[((i * (i + 1) / 2) + j) * FS] * z[i * FS];
+        const T* col = fac + ((j + 1) * (j + 2) / 2 + j) * FS;  // element (j+1, j)
+        for (int i = j + 1; i < n; ++i) {
+            s -= col[0] * z[i * FS];
+            col += (i + 1) * FS;
+        }
         z[j * FS] = s * fac[((j * (j + 1) / 2) + j) * FS];
     }
     return ok;
 }
 
+// shared-memory carve-up (host and device must agree)
 struct NnlsSmem {
-    // byte offsets of the carve-up (host and device must agree)
-    size_t G, P, b, u, x, pool, mask, tol, state, listA, listB, sorted, bins, wmeta, size, idx, total;
+    size_t G, P, warp0, per_warp, b, u, pool, idx, total;
 };
-
-__host__ __device__ inline NnlsSmem nnls_layout(int kp, int nt, int pool_elems, size_t ts) {
+__host__ __device__ inline NnlsSmem nnls_layout(int kp, int nwarps, int pool_elems, size_t ts) {
     NnlsSmem L;
+    const size_t mst = (size_t)kp + 4;  // row stride of G / P: = 4 (mod 32) words -> conflict-free 128-bit row reads
     size_t o = 0;
     auto take = [&](size_t bytes) {
         const size_t at = o;
         o += (bytes + 15) & ~(size_t)15;
         return at;
     };
-    L.G = take((size_t)kp * kp * ts);
-    L.P = take((size_t)kp * kp * ts);
-    L.b = take((size_t)kp * (nt + 1) * ts);
-    L.u = take((size_t)kp * (nt + 1) * ts);
-    L.x = take((size_t)kp * (nt + 1) * ts);
-    L.pool = take((size_t)pool_elems * ts);
-    L.mask = take((size_t)nt * 8);
-    L.tol = take((size_t)nt * ts);
-    L.state = take((size_t)nt * 4);
-    L.listA = take((size_t)nt * 4);
-    L.listB = take((size_t)nt * 4);
-    L.sorted = take((size_t)nt * 4);
-    L.bins = take((size_t)(kp + 2) * 4 * 2);
-    L.wmeta = take((size_t)(nt / 32 + 1) * 4 * 4);
-    L.size = take((size_t)nt);
-    L.idx = take((size_t)kp * nt);
-    L.total = o;
+    L.G = take((size_t)kp * mst * ts);
+    L.P = take((size_t)kp * mst * ts);
+    L.warp0 = o;
+    size_t w = 0;
+    auto wtake = [&](size_t bytes) {
+        const size_t at = w;
+        w += (bytes + 15) & ~(size_t)15;
+        return at;
+    };
+    L.b = wtake((size_t)kp * 33 * ts);
+    L.u = wtake((size_t)kp * 33 * ts);
+    L.pool = wtake((size_t)pool_elems * ts);
+    L.idx = wtake((size_t)kp * 32);
+    L.per_warp = w;
+    L.total = o + (size_t)nwarps * w;
     return L;
 }
 
+// One pivot round of one column (executed by the lane that owns it).  Returns true when the column stays active.
 template <typename T, int KP>
-__global__ void k_nnls(const NnlsGroup* __restrict__ groups, int ngroups, int total_blocks, int k, int pool_elems,
-                       Counters* cnt, int flags) {
-    const int NT = blockDim.x;
-    const int NW = NT >> 5;
-    const int XS = NT + 1;  // padded stride of the transposed [factor][slot] tiles
+__device__ __forceinline__ bool nnls_round(const int k, const unsigned long long kmask, const int dual_ok, const int MAXIT,
+                                           const T* __restrict__ Gs, const T* __restrict__ Ps, T* bcol, const T* ucol,
+                                           unsigned char* idx, T* fac, const int FS, unsigned long long& F, int& state,
+                                           const T tol, Counters* cnt, unsigned long long& pivots, const int hist_mode) {
+    constexpr int MST = KP + 4;
+    const int p = __popcll(F);
+    const bool dual = dual_ok && (k - p) < p;
+    const int s = dual ? (k - p) : p;
+    {
+        unsigned long long r = dual ? ((~F) & kmask) : F;
+        int t = 0;
+        while (r) {
+            idx[t * 32] = (unsigned char)(__ffsll((long long)r) - 1);
+            r &= r - 1;
+            ++t;
+        }
+    }
+    T* z = fac + (s * (s + 1) / 2) * FS;
+    bool ok = true;
+    if (s > 0) ok = chol_solve<T, MST>(s, idx, dual ? Ps : Gs, dual ? ucol : bcol, fac, z, FS);
+    if (!ok) atomicAdd(&cnt->nnls_bad_pivot, 1ull);
+
+    // all k entries of  x = u - P_:A z  (dual)  or  y = G_:F x_F - b  (primal)  with register accumulators
+    T acc[KP];
+    const T* init = dual ? ucol : bcol;
+#pragma unroll
+    for (int f = 0; f < KP; ++f) acc[f] = init[f * 33];
+    if (!dual) {
+#pragma unroll
+        for (int f = 0; f < KP; ++f) acc[f] = -acc[f];
+    }
+    const T* Mat = dual ? Ps : Gs;
+    const T sgn = dual ? (T)-1 : (T)1;
+    for (int t = 0; t < s; ++t) {
+        const T zt = sgn * z[t * FS];
+        const T* row = Mat + idx[t * 32] * MST;
+#pragma unroll
+        for (int f = 0; f < KP; ++f) acc[f] = fma(zt, row[f], acc[f]);
+    }
+    unsigned long long infeas = 0ull;
+    if (dual) {
+        // y_A = -z >= 0 required ; x_F = acc_F >= 0 required
+        for (int t = 0; t < s; ++t)
+            if (z[t * FS] > tol) infeas |= 1ull << idx[t * 32];
+        T xmax = (T)0;
+#pragma unroll
+        for (int f = 0; f < KP; ++f)
+            if ((F >> f) & 1ull) xmax = fmax(xmax, fabs(acc[f]));
+        const T tolx = xmax * Eps<T>::v() * (T)8;
+#pragma unroll
+        for (int f = 0; f < KP; ++f)
+            if (((F >> f) & 1ull) && acc[f] < -tolx) infeas |= 1ull << f;
+    } else {
+        T xmax = (T)0;
+        for (int t = 0; t < s; ++t) xmax = fmax(xmax, fabs(z[t * FS]));
+        const T tolx = xmax * Eps<T>::v() * (T)8;
+        for (int t = 0; t < s; ++t)
+            if (z[t * FS] < -tolx) infeas |= 1ull << idx[t * 32];
+        const unsigned long long A = (~F) & kmask;
+#pragma unroll
+        for (int f = 0; f < KP; ++f)
+            if (((A >> f) & 1ull) && acc[f] < -tol) infeas |= 1ull << f;
+    }
+    int alpha = state & 0xff, beta = (state >> 8) & 0xff, iter = state >> 16;
+    if (infeas != 0ull && iter < MAXIT) {
+        const int ninf = __popcll(infeas);
+        unsigned long long flip;
+        if (ninf < beta) {
+            beta = ninf;
+            alpha = 3;
+            flip = infeas;
+        } else if (alpha >= 1) {
+            --alpha;
+            flip = infeas;
+        } else {
+            flip = 1ull << (63 - __clzll((long long)infeas));
+        }
+        F ^= flip;
+        state = alpha | (beta << 8) | ((iter + 1) << 16);
+        ++pivots;
+        return true;
+    }
+    if (infeas != 0ull) atomicAdd(&cnt->nnls_unconverged, 1ull);
+    if (hist_mode) atomicAdd(&cnt->hist[hist_mode == 2 ? (p < 39 ? p : 39) : (iter < 39 ? iter : 39)], 1ull);
+    // final x, expanded by factor id, over b's column of the tile (b is no longer needed)
+    if (dual) {
+#pragma unroll
+        for (int f = 0; f < KP; ++f) {
+            T v = acc[f];
+            if (!((F >> f) & 1ull) || !(v > (T)0)) v = (T)0;
+            bcol[f * 33] = v;
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < KP; ++f) bcol[f * 33] = (T)0;
+        for (int t = 0; t < s; ++t) {
+            const T v = z[t * FS];
+            bcol[idx[t * 32] * 33] = v > (T)0 ? v : (T)0;
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_nnls: persistent CTAs; a CTA takes "CTA tiles" (ct_cols columns of one group, so G / P are loaded once per
+// tile) and its warps pull 32-column warp tiles from a shared counter.  Inside a warp tile every lane owns one
+// column from load to store; the warp iterates pivot rounds until all its columns are done -- there is no
+// CTA-wide barrier inside a tile, so slow columns only delay their own warp.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int KP>
+__global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ groups, int ngroups, int total_tiles,
+                                                 int ct_cols, int k, int pool_elems, Counters* cnt, int flags) {
+    constexpr int MST = KP + 4;
+    const int NW = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const NnlsSmem L = nnls_layout(KP, NT, pool_elems, sizeof(T));
+    const NnlsSmem L = nnls_layout(KP, NW, pool_elems, sizeof(T));
     T* Gs = reinterpret_cast<T*>(smem_raw + L.G);
     T* Ps = reinterpret_cast<T*>(smem_raw + L.P);
-    T* bS = reinterpret_cast<T*>(smem_raw + L.b);
-    T* uS = reinterpret_cast<T*>(smem_raw + L.u);
-    T* xS = reinterpret_cast<T*>(smem_raw + L.x);
-    T* pool = reinterpret_cast<T*>(smem_raw + L.pool);
-    unsigned long long* maskS = reinterpret_cast<unsigned long long*>(smem_raw + L.mask);
-    T* tolS = reinterpret_cast<T*>(smem_raw + L.tol);
-    int* stateS = reinterpret_cast<int*>(smem_raw + L.state);  // alpha | beta << 8 | iter << 16
-    int* listA = reinterpret_cast<int*>(smem_raw + L.listA);
-    int* listB = reinterpret_cast<int*>(smem_raw + L.listB);
-    int* sorted = reinterpret_cast<int*>(smem_raw + L.sorted);
-    int* bins = reinterpret_cast<int*>(smem_raw + L.bins);     // [0..KP+1] counts, [KP+2..] starts
-    int* wmeta = reinterpret_cast<int*>(smem_raw + L.wmeta);   // per warp: offset, lanes, tri ; [4*NW] = nact
-    unsigned char* sizeS = smem_raw + L.size;
-    unsigned char* idxS = smem_raw + L.idx;
-    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* wbase = smem_raw + L.warp0 + (size_t)warp * L.per_warp;
+    T* bS = reinterpret_cast<T*>(wbase + L.b);     // [f][lane], stride 33
+    T* uS = reinterpret_cast<T*>(wbase + L.u);
+    T* pool = reinterpret_cast<T*>(wbase + L.pool);
+    unsigned char* idxS = wbase + L.idx;           // [t][lane]
+    __shared__ int next_wt;
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
     const bool cold_start = (flags & 1) != 0;
-    const bool want_hist = (flags & 2) != 0;
-    const bool hist_p = (flags & 4) != 0;
+    const int hist_mode = (flags & 2) ? ((flags & 4) ? 2 : 1) : 0;
     const bool no_dual = (flags & 8) != 0;
     const unsigned long long kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
     const int MAXIT = 4 * k + 16;
+    const int share = pool_elems / 32;  // pool elements per lane in the regular [e][lane] layout
 
-    int cur_group = -1;
-    int dual_ok = 0;
     unsigned long long pivots_local = 0;
-    for (int blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int g = 0;
-        while (g + 1 < ngroups && blk >= groups[g + 1].blk_off) ++g;
+        while (g + 1 < ngroups && tile >= groups[g + 1].blk_off) ++g;
         const NnlsGroup grp = groups[g];
-        __syncthreads();  // previous tile fully consumed
-        if (g != cur_group) {
-            cur_group = g;
-            dual_ok = no_dual ? 0 : *grp.ok;
-            for (int e = tid; e < KP * KP; e += NT) {
-                Gs[e] = (T)grp.gram[e];
-                Ps[e] = (T)grp.ginv[e];
-            }
+        __syncthreads();  // every warp is done with the previous tile (G / P / counter may change)
+        const int dual_ok = no_dual ? 0 : *grp.ok;
+        for (int e = tid; e < KP * KP; e += blockDim.x) {
+            const int a = e / KP, b = e % KP;
+            Gs[a * MST + b] = (T)grp.gram[e];
+            Ps[a * MST + b] = (T)grp.ginv[e];
         }
-        const int col0 = (blk - grp.blk_off) * NT;
-        const int ncol = min(NT, grp.ncols - col0);
-        const int ld = grp.ld;
-        const T* __restrict__ rhs = reinterpret_cast<const T*>(grp.rhs) + (size_t)col0 * ld;
-        T* __restrict__ xout = reinterpret_cast<T*>(grp.x) + (size_t)col0 * ld;
-        for (int e = tid; e < ncol * KP; e += NT) {  // coalesced load, transposed into bS[f][slot]
-            const int j = e / KP, f = e % KP;
-            bS[f * XS + j] = (f < k) ? rhs[(size_t)j * ld + f] : (T)0;
-        }
-        if (tid < ncol) {
-            maskS[tid] = cold_start ? 0ull : (grp.mask[col0 + tid] & kmask);
-            stateS[tid] = 3 | ((k + 1) << 8);
-            listA[tid] = tid;
-        }
+        if (tid == 0) next_wt = 0;
         __syncthreads();
-        if (tid < ncol) {
-            const T* b = bS + tid;
-            T bm = (T)0;
-            for (int f = 0; f < k; ++f) bm = fmax(bm, fabs(b[f * XS]));
-            tolS[tid] = bm * Eps<T>::v() * (T)8;
-            if (dual_ok) {  // u = P b : register accumulators, broadcast shared-memory reads of P
-                for (int a0 = 0; a0 < k; a0 += 16) {
-                    T acc[16];
+        const int tcol0 = (tile - grp.blk_off) * ct_cols;
+        const int tcols = min(ct_cols, grp.ncols - tcol0);
+        const int nwt = (tcols + 31) >> 5;
+        const int ld = grp.ld;
+        for (;;) {
+            int wt = 0;
+            if (lane == 0) wt = atomicAdd(&next_wt, 1);
+            wt = __shfl_sync(0xffffffffu, wt, 0);
+            if (wt >= nwt) break;
+            const int col0 = tcol0 + wt * 32;
+            const int ncol = min(32, tcol0 + tcols - col0);
+            const T* __restrict__ rhs = reinterpret_cast<const T*>(grp.rhs) + (size_t)col0 * ld;
+            T* __restrict__ xout = reinterpret_cast<T*>(grp.x) + (size_t)col0 * ld;
+            // coalesced load of the 32-column rhs tile, transposed into bS[f][column]
+            for (int e = lane; e < ncol * KP; e += 32) {
+                const int j = e / KP, f = e % KP;
+                bS[f * 33 + j] = (f < k) ? rhs[(size_t)j * ld + f] : (T)0;
+            }
+            __syncwarp();
+            const bool valid = lane < ncol;
+            unsigned long long F = 0ull;
+            int state = 3 | ((k + 1) << 8);
+            T tol = (T)0;
+            T* bcol = bS + lane;
+            T* ucol = uS + lane;
+            if (valid) {
+                if (!cold_start) F = grp.mask[col0 + lane] & kmask;
+                T bm = (T)0;
 #pragma unroll
-                    for (int a = 0; a < 16; ++a) acc[a] = (T)0;
+                for (int f = 0; f < KP; ++f) bm = fmax(bm, fabs(bcol[f * 33]));
+                tol = bm * Eps<T>::v() * (T)8;
+                if (dual_ok) {  // u = P b : register accumulators, broadcast shared-memory reads of P
+                    T acc[KP];
+#pragma unroll
+                    for (int f = 0; f < KP; ++f) acc[f] = (T)0;
                     for (int t = 0; t < k; ++t) {
-                        const T bt = b[t * XS];
-                        const T* Pt = Ps + t * KP + a0;
+                        const T bt = bcol[t * 33];
+                        const T* Pt = Ps + t * MST;
 #pragma unroll
-                        for (int a = 0; a < 16; ++a) acc[a] = fma(Pt[a], bt, acc[a]);
+                        for (int f = 0; f < KP; ++f) acc[f] = fma(Pt[f], bt, acc[f]);
                     }
 #pragma unroll
-                    for (int a = 0; a < 16; ++a)
-                        if (a0 + a < k) uS[(a0 + a) * XS + tid] = acc[a];
+                    for (int f = 0; f < KP; ++f) ucol[f * 33] = acc[f];
                 }
             }
-        }
-
-        int nact = ncol;
-        int* cur = listA;
-        int* nxt = listB;
-        while (nact > 0) {
-            // ---- 1. size of every active slot's solve, counting sort by size ----
-            for (int e = tid; e < 2 * (KP + 2); e += NT) bins[e] = 0;
-            __syncthreads();
-            int myslot = -1, mysize = 0, myrank = 0;
-            if (tid < nact) {
-                myslot = cur[tid];
-                const int p = __popcll(maskS[myslot]);
-                const int q = k - p;
-                mysize = (dual_ok && q < p) ? q : p;
-                sizeS[myslot] = (unsigned char)mysize;
-                myrank = atomicAdd(&bins[mysize], 1);
-            }
-            __syncthreads();
-            if (warp == 0) {  // exclusive prefix over the KP + 1 size bins
-                int carry = 0;
-                for (int base = 0; base < KP + 1; base += 32) {
-                    const int i = base + lane;
-                    const int v = (i < KP + 1) ? bins[i] : 0;
-                    int incl = v;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const int n = __shfl_up_sync(0xffffffffu, incl, off);
-                        if (lane >= off) incl += n;
-                    }
-                    if (i < KP + 1) bins[KP + 2 + i] = carry + incl - v;
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
-                }
-            }
-            __syncthreads();
-            if (tid < nact) sorted[bins[KP + 2 + mysize] + myrank] = myslot;
-            __syncthreads();
-            // ---- 2. pool allocation per warp (sorted ascending: the warp's largest size is its last slot) ----
-            if (tid == 0) {
-                int used = 0;
-                for (int w = 0; w < NW; ++w) {
-                    const int first = w * 32;
-                    int lanes = 0, need = 1, off = used;
-                    if (first < nact) {
-                        const int last = min(first + 32, nact) - 1;
-                        const int smax = sizeS[sorted[last]];
-                        need = smax * (smax + 1) / 2 + smax;  // factor + compact solution
-                        if (need < 1) need = 1;
-                        lanes = min(last - first + 1, (pool_elems - used) / need);
-                        used += lanes * need;
-                    }
-                    wmeta[w * 4 + 0] = off;
-                    wmeta[w * 4 + 1] = lanes;
-                    wmeta[w * 4 + 2] = need;
-                }
-            }
-            __syncthreads();
-            // ---- 3. one pivot round for every slot that got pool space ----
-            bool keep = false;  // stays in the active list (not finished, or deferred for lack of pool space)
-            if (tid < nact) {
-                const int slot = sorted[tid];
-                const int wl = wmeta[warp * 4 + 1];
-                if (lane >= wl) {
-                    keep = true;  // deferred to the next pass
-                } else {
-                    const int s = sizeS[slot];
-                    T* fac = pool + wmeta[warp * 4 + 0] + lane;
-                    const int FS = wl;
-                    unsigned long long F = maskS[slot];
+            bool active = valid;
+            while (__any_sync(0xffffffffu, active)) {
+                int need = 0;
+                if (active) {
                     const int p = __popcll(F);
-                    const bool dual = dual_ok && (k - p) < p;
-                    unsigned char* idx = idxS + slot;
-                    {
-                        unsigned long long r = dual ? ((~F) & kmask) : F;
-                        int t = 0;
-                        while (r) {
-                            idx[t * NT] = (unsigned char)(__ffsll((long long)r) - 1);
-                            r &= r - 1;
-                            ++t;
-                        }
-                    }
-                    T* z = fac + (size_t)(s * (s + 1) / 2) * FS;  // compact solution right after the factor
-                    const T* b = bS + slot;
-                    const T tol = tolS[slot];
-                    unsigned long long infeas = 0ull;
-                    bool ok = true;
-                    if (!dual) {
-                        if (s > 0) ok = chol_solve<T>(s, idx, NT, Gs, KP, b, XS, fac, z, FS);
-                        T xmax = (T)0;
-                        for (int t = 0; t < s; ++t) xmax = fmax(xmax, fabs(z[t * FS]));
-                        const T tolx = xmax * Eps<T>::v() * (T)8;
-                        for (int t = 0; t < s; ++t)
-                            if (z[t * FS] < -tolx) infeas |= 1ull << idx[t * NT];
-                        unsigned long long A = (~F) & kmask;
-                        while (A) {
-                            const int j = __ffsll((long long)A) - 1;
-                            A &= A - 1;
-                            T y = -b[j * XS];
-                            const T* Gj = Gs + j * KP;
-                            for (int t = 0; t < s; ++t) y = fma(Gj[idx[t * NT]], z[t * FS], y);
-                            if (y < -tol) infeas |= 1ull << j;
-                        }
-                    } else {
-                        const T* u = uS + slot;
-                        T* x = xS + slot;
-                        if (s > 0) ok = chol_solve<T>(s, idx, NT, Ps, KP, u, XS, fac, z, FS);
-                        // y_A = -z ; infeasible where y_A < 0  <=>  z > 0
-                        for (int t = 0; t < s; ++t)
-                            if (z[t * FS] > tol) infeas |= 1ull << idx[t * NT];
-                        // x_F = u_F - P_FA z
-                        T xmax = (T)0;
-                        unsigned long long Fb = F;
-                        while (Fb) {
-                            const int f = __ffsll((long long)Fb) - 1;
-                            Fb &= Fb - 1;
-                            T xf = u[f * XS];
-                            const T* Pf = Ps + f * KP;
-                            for (int t = 0; t < s; ++t) xf = fma(-Pf[idx[t * NT]], z[t * FS], xf);
-                            x[f * XS] = xf;
-                            xmax = fmax(xmax, fabs(xf));
-                        }
-                        const T tolx = xmax * Eps<T>::v() * (T)8;
-                        Fb = F;
-                        while (Fb) {
-                            const int f = __ffsll((long long)Fb) - 1;
-                            Fb &= Fb - 1;
-                            if (x[f * XS] < -tolx) infeas |= 1ull << f;
-                        }
-                    }
-                    if (!ok) atomicAdd(&cnt->nnls_bad_pivot, 1ull);
-                    const int st = stateS[slot];
-                    int alpha = st & 0xff, beta = (st >> 8) & 0xff, iter = st >> 16;
-                    if (infeas != 0ull && iter < MAXIT) {
-                        const int ninf = __popcll(infeas);
-                        unsigned long long flip;
-                        if (ninf < beta) {
-                            beta = ninf;
-                            alpha = 3;
-                            flip = infeas;
-                        } else if (alpha >= 1) {
-                            --alpha;
-                            flip = infeas;
-                        } else {
-                            flip = 1ull << (63 - __clzll((long long)infeas));
-                        }
-                        maskS[slot] = F ^ flip;
-                        stateS[slot] = alpha | (beta << 8) | ((iter + 1) << 16);
-                        keep = true;
-                        ++pivots_local;
-                    } else {
-                        if (infeas != 0ull) atomicAdd(&cnt->nnls_unconverged, 1ull);
-                        if (want_hist) atomicAdd(&cnt->hist[hist_p ? (p < 39 ? p : 39) : (iter < 39 ? iter : 39)], 1ull);
-                        // final x, expanded by factor id, over b's slot (b is no longer needed)
-                        T* out = bS + slot;
-                        if (!dual) {
-                            for (int f = 0; f < KP; ++f) out[f * XS] = (T)0;
-                            for (int t = 0; t < s; ++t) {
-                                const T v = z[t * FS];
-                                out[idx[t * NT] * XS] = v > (T)0 ? v : (T)0;
-                            }
-                        } else {
-                            const T* x = xS + slot;
-                            for (int f = 0; f < KP; ++f) {
-                                T v = (T)0;
-                                if ((F >> f) & 1ull) {
-                                    v = x[f * XS];
-                                    if (!(v > (T)0)) v = (T)0;
-                                }
-                                out[f * XS] = v;
-                            }
-                        }
-                    }
+                    const int s = (dual_ok && (k - p) < p) ? (k - p) : p;
+                    need = s * (s + 1) / 2 + s;
                 }
-            }
-            // ---- 4. order-preserving compaction of the slots that stay active ----
-            {
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) wsum[warp] = __popc(bal);
-                __syncthreads();
-                int base = 0, total = 0;
-                for (int w = 0; w < NW; ++w) {
-                    const int cw = wsum[w];
-                    if (w < warp) base += cw;
-                    total += cw;
+                const bool regular = active && need <= share;
+                if (regular)
+                    active = nnls_round<T, KP>(k, kmask, dual_ok, MAXIT, Gs, Ps, bcol, ucol, idxS + lane, pool + lane, 32,
+                                               F, state, tol, cnt, pivots_local, hist_mode);
+                // columns whose factor does not fit the per-lane share (only without the dual side, or k > 32):
+                // a few lanes at a time over the whole warp pool
+                unsigned big = __ballot_sync(0xffffffffu, active && !regular && need > share);
+                while (big) {
+                    __syncwarp();
+                    int maxneed = need;
+                    if (!((big >> lane) & 1u)) maxneed = 0;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) maxneed = max(maxneed, __shfl_xor_sync(0xffffffffu, maxneed, off));
+                    int fit = pool_elems / maxneed;
+                    if (fit < 1) fit = 1;
+                    if (fit > 32) fit = 32;
+                    const int rank = __popc(big & ((1u << lane) - 1u));
+                    const bool mine = ((big >> lane) & 1u) && rank < fit;
+                    if (mine)
+                        active = nnls_round<T, KP>(k, kmask, dual_ok, MAXIT, Gs, Ps, bcol, ucol, idxS + lane, pool + rank,
+                                                   fit, F, state, tol, cnt, pivots_local, hist_mode);
+                    big &= ~__ballot_sync(0xffffffffu, mine);
                 }
-                if (keep) nxt[base + __popc(bal & ((1u << lane) - 1u))] = sorted[tid];
-                nact = total;
-                __syncthreads();
-                int* tmp = cur;
-                cur = nxt;
-                nxt = tmp;
+                __syncwarp();
             }
+            // coalesced store of the solution tile + passive sets
+            __syncwarp();
+            for (int e = lane; e < ncol * KP; e += 32) {
+                const int j = e / KP, f = e % KP;
+                if (f < k) xout[(size_t)j * ld + f] = bS[f * 33 + j];
+            }
+            if (valid) grp.mask[col0 + lane] = F;
+            __syncwarp();
         }
-        for (int e = tid; e < ncol * KP; e += NT) {  // coalesced store of the solution tile
-            const int j = e / KP, f = e % KP;
-            if (f < k) xout[(size_t)j * ld + f] = bS[f * XS + j];
-        }
-        if (tid < ncol) grp.mask[col0 + tid] = maskS[tid];
     }
     if (pivots_local) atomicAdd(&cnt->nnls_pivots, pivots_local);
 }
@@ -494,42 +446,45 @@ __global__ void k_nnls(const NnlsGroup* __restrict__ groups, int ngroups, int to
 NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms) {
     NnlsConfig c{};
     const size_t ts = is_double ? 8 : 4;
-    if (kp == 32) {
-        c.threads = is_double ? 64 : 128;
-    } else {
-        c.threads = is_double ? 32 : 64;
-    }
-    // pool: must hold at least one column at the worst-case size (primal-only fallback: s = k)
-    const int worst = k * (k + 1) / 2 + k;
-    const int half = (k / 2 + 1);
-    const int typical = half * (half + 1) / 2 + half;            // dual/primal split: s <= k/2
-    int pool = typical * c.threads / 2;                           // half the columns at the largest usual size
-    if (pool < 2 * worst) pool = 2 * worst;
-    const size_t fixed = nnls_layout(kp, c.threads, 0, ts).total;
-    const size_t limit = 100 * 1024;                              // two CTAs per SM
-    if (fixed + (size_t)pool * ts > limit && fixed + (size_t)2 * worst * ts <= limit)
-        pool = (int)((limit - fixed) / ts);
+    const int worst = k * (k + 1) / 2 + k;                 // primal-only fallback: s = k
+    const int half = k / 2 + 1;
+    const int typical = half * (half + 1) / 2 + half;      // with the dual side: s <= k/2
+    int pool = 32 * typical;
+    if (pool < worst) pool = worst;
+    const size_t limit = 226 * 1024;
+    int nw = 8;
+    while (nw > 1 && nnls_layout(kp, nw, pool, ts).total > limit) --nw;
+    while (nnls_layout(kp, nw, pool, ts).total > limit && pool > worst) pool -= 32;
+    c.threads = nw * 32;
     c.pool_elems = pool;
-    c.smem = nnls_layout(kp, c.threads, pool, ts).total;
-    const int per_sm = (int)((226 * 1024) / (c.smem + 1024));
-    c.grid_cap = num_sms * (per_sm > 0 ? per_sm : 1);
+    c.smem = nnls_layout(kp, nw, pool, ts).total;
+    c.grid_cap = num_sms;
+    c.ct_cols = 1024;
     return c;
 }
 
-void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_blocks, int k, int kp,
+int nnls_tile_cols(const NnlsConfig& cfg, long long total_cols, int num_sms) {
+    // columns per CTA tile: large enough to amortise the G / P load, small enough to fill the machine
+    int ct = cfg.ct_cols;
+    while (ct > cfg.threads && total_cols / ct < 2LL * num_sms) ct >>= 1;
+    if (ct < cfg.threads) ct = cfg.threads;
+    return ct;
+}
+
+void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_tiles, int ct_cols, int k, int kp,
                  const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st) {
-    if (total_blocks <= 0) return;
-    const int grid = total_blocks < cfg.grid_cap ? total_blocks : cfg.grid_cap;
+    if (total_tiles <= 0) return;
+    const int grid = total_tiles < cfg.grid_cap ? total_tiles : cfg.grid_cap;
     if (is_double) {
         if (kp == 32)
-            k_nnls<double, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.pool_elems, cnt, flags);
+            k_nnls<double, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
         else
-            k_nnls<double, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.pool_elems, cnt, flags);
+            k_nnls<double, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
     } else {
         if (kp == 32)
-            k_nnls<float, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.pool_elems, cnt, flags);
+            k_nnls<float, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
         else
-            k_nnls<float, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_blocks, k, cfg.pool_elems, cnt, flags);
+            k_nnls<float, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
     }
     LGR_CUDA(cudaGetLastError());
 }
