@@ -447,18 +447,27 @@ NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms) {
     NnlsConfig c{};
     const size_t ts = is_double ? 8 : 4;
     const int worst = k * (k + 1) / 2 + k;                 // primal-only fallback: s = k
-    const int half = k / 2 + 1;
-    const int typical = half * (half + 1) / 2 + half;      // with the dual side: s <= k/2
-    int pool = 32 * typical;
+    // per-lane share sized for systems of `cls` unknowns (larger ones run a few lanes at a time over the whole pool)
+    int cls = k / 2 + 1;
+    if (const char* e = getenv("LGR_NNLS_POOL_S")) cls = atoi(e);
+    if (cls < 2) cls = 2;
+    if (cls > k) cls = k;
+    int pool = 32 * (cls * (cls + 1) / 2 + cls);
     if (pool < worst) pool = worst;
-    const size_t limit = 226 * 1024;
     int nw = 8;
+    if (const char* e = getenv("LGR_NNLS_WARPS")) nw = atoi(e);
+    if (nw < 1) nw = 1;
+    if (nw > 8) nw = 8;
+    const size_t limit = 226 * 1024;
     while (nw > 1 && nnls_layout(kp, nw, pool, ts).total > limit) --nw;
     while (nnls_layout(kp, nw, pool, ts).total > limit && pool > worst) pool -= 32;
     c.threads = nw * 32;
     c.pool_elems = pool;
     c.smem = nnls_layout(kp, nw, pool, ts).total;
-    c.grid_cap = num_sms;
+    int per_sm = (int)(limit / (c.smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * c.threads > 512) per_sm = 512 / c.threads > 0 ? 512 / c.threads : 1;   // register budget
+    c.grid_cap = num_sms * per_sm;
     c.ct_cols = 1024;
     return c;
 }
