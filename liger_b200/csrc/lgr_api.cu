@@ -73,9 +73,10 @@ struct Dataset {
     int n_full = 0, n = 0, c0 = 0, rows = 0, u = 0;
     size_t nnz = 0;
     double lambda = 0.0;
-    DBuf<int> colptr, rowidx, tptr;
-    DBuf<float> val, tval, L, H;
-    DBuf<unsigned short> tcell;
+    DBuf<int> colptr, rowidx, tptr8, cptr8;
+    DBuf<float> val, tval, cval, L, H;
+    DBuf<unsigned short> tcell, crow;
+    int ngt = 1;
     DBuf<unsigned long long> hmask, vmask;
     DBuf<double> V, CtBv;
     size_t b_off = 0, r_off = 0;
@@ -87,7 +88,7 @@ struct Dataset {
 using namespace lgr;
 
 struct lgr_ctx {
-    int d = 0, k = 0, kp = 32, m = 0, device = 0, rank = 0, world = 1, tc = 1024, num_sms = 148;
+    int d = 0, k = 0, kp = 32, m = 0, device = 0, rank = 0, world = 1, tc = 1024, cb = 512, gt = 1024, num_sms = 148;
     uint32_t flags = 0;
     cudaStream_t st = nullptr;
     std::vector<Dataset> ds;
@@ -269,7 +270,7 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         // ---- H phase ----
         {
             Timed t(c, "k_spmm_ltx");
-            launch_spmm_ltx(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->st);
+            launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->st);
         }
         {
             Timed t(c, "k_gram_inv");
@@ -380,6 +381,15 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     LGR_CUDA(cudaEventCreate(&c->evA));
     LGR_CUDA(cudaEventCreate(&c->evB));
     c->tc = c->kp == 32 ? 1024 : 512;
+    c->cb = c->kp == 32 ? 512 : 256;
+    {   // gene tiles of at most 1024 (512) rows, balanced
+        const int gmax = c->kp == 32 ? 1024 : 512;
+        int maxrows = (int)a->m;
+        if (a->P)
+            for (int i = 0; i < a->d; ++i) maxrows = std::max<int>(maxrows, (int)(a->m + a->P[i].nrow));
+        const int nt = (maxrows + gmax - 1) / gmax;
+        c->gt = (maxrows + nt - 1) / nt;
+    }
     if (const char* e = getenv("LGR_TC")) {
         const int v = atoi(e);
         if (v >= 32 && v <= 65536 && (size_t)v * c->kp * 4 <= 200 * 1024) c->tc = v;
@@ -396,6 +406,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
 
     const int k = c->k, kp = c->kp, m = c->m;
     c->ds.resize(c->d);
+    c->sq.alloc((size_t)c->d);
+    c->sq.zero(c->st);
     size_t b_total = 0, r_total = 0;
     int max_rows = 0;
     for (int i = 0; i < c->d; ++i) {
@@ -435,10 +447,16 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
             LGR_CUDA(cudaStreamSynchronize(c->st));
         }
         const int ntiles = (D.n + c->tc - 1) / c->tc;
-        D.tptr.alloc((size_t)ntiles * D.rows + 1);
-        D.tcell.alloc(D.nnz);
-        D.tval.alloc(D.nnz);
-        dev_build_tiled_csr(D.n, D.rows, c->tc, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr.p, D.tcell.p, D.tval.p, c->st);
+        (void)ntiles;
+        // the two padded tile formats of X (lgr_spmm.cu); the plain CSC upload is dropped afterwards
+        dev_build_padded(1, D.n, D.rows, c->tc, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.tval, c->st);
+        D.ngt = (D.rows + c->gt - 1) / c->gt;
+        dev_build_padded(0, D.n, D.rows, c->gt, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.cval, c->st);
+        dev_sumsq(D.val.p, D.nnz, c->sq.p + i, c->st);
+        LGR_CUDA(cudaStreamSynchronize(c->st));
+        D.colptr.release();
+        D.rowidx.release();
+        D.val.release();
         D.L.alloc((size_t)D.rows * kp);
         D.H.alloc((size_t)std::max(D.n, 1) * kp);
         D.H.zero(c->st);
@@ -463,9 +481,6 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->Gsum.alloc((size_t)kp * kp);
     c->wmask.alloc((size_t)m);
     c->counters.alloc(1);
-    c->sq.alloc((size_t)c->d);
-    c->sq.zero(c->st);
-    for (int i = 0; i < c->d; ++i) dev_sumsq(c->ds[i].val.p, c->ds[i].nnz, c->sq.p + i, c->st);
     if (c->world > 1) nccl_allreduce_sum_f64(c->comm, c->sq.p, (size_t)c->d, c->st);
     std::vector<double> sq((size_t)c->d);
     LGR_CUDA(cudaMemcpyAsync(sq.data(), c->sq.p, sq.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
@@ -508,15 +523,19 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.ltx_blk_off = ltx;
         h.xh_blk_off = xh;
         h.prep_blk_off = prep;
-        ltx += (D.n + LTX_CELLS_PER_BLOCK - 1) / LTX_CELLS_PER_BLOCK;
+        ltx += (D.n + c->cb - 1) / c->cb;
         xh += h.ntiles;
         prep += (D.rows + rb - 1) / rb;
         h.colptr = D.colptr.p;
         h.rowidx = D.rowidx.p;
         h.val = D.val.p;
-        h.tptr = D.tptr.p;
+        h.cptr8 = D.cptr8.p;
+        h.crow = D.crow.p;
+        h.cval = D.cval.p;
+        h.tptr8 = D.tptr8.p;
         h.tcell = D.tcell.p;
         h.tval = D.tval.p;
+        h.ngt = D.ngt;
         h.L = D.L.p;
         h.H = D.H.p;
         h.B = c->Bbuf.p + D.b_off;

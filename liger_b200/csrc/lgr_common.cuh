@@ -89,9 +89,14 @@ struct DsDev {
     const int* colptr;
     const int* rowidx;
     const float* val;
-    const int* tptr;
-    const unsigned short* tcell;
+    const int* cptr8;            // gene-tiled CSC (padded to 8): [ngt * n + 1] segment starts in groups of 8
+    const unsigned short* crow;  // row inside the gene tile
+    const float* cval;
+    const int* tptr8;            // cell-tiled CSR (padded to 8): [ntiles * rows + 1]
+    const unsigned short* tcell; // cell inside the cell tile
     const float* tval;
+    int ngt;                     // gene tiles
+    int pad0;
     float* L;
     float* H;
     float* B;
@@ -156,7 +161,10 @@ int nnls_tile_cols(const NnlsConfig& cfg, long long total_cols, int num_sms);
 NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
 
 void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st);
-void launch_spmm_ltx(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st);
+void launch_spmm_ltx_gather(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st);
+void launch_spmm_ltx_tiled(const DsDev* ds, int nds, int total_blocks, int kp, int cb, int gt, cudaStream_t st);
+size_t spmm_ltx_smem(int kp, int cb, int gt);
+void spmm_init();
 void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st);
 void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStream_t st);
 void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_tiles, int ct_cols, int k, int kp,
@@ -173,8 +181,8 @@ void dev_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
 void dev_sumsq(const float* v, size_t n, double* out, cudaStream_t st);
 void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const int* pP, const int* iP,
                    const float* vP, int m, int* pS, int* iS, float* vS, cudaStream_t st);
-void dev_build_tiled_csr(int n, int rows, int tc, const int* colptr, const int* rowidx, const float* val, size_t nnz,
-                         int* tptr, unsigned short* tcell, float* tval, cudaStream_t st);
+void dev_build_padded(int mode, int n, int rows, int tile, const int* colptr, const int* rowidx, const float* val,
+                      size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<float>& oval, cudaStream_t st);
 void dev_colmajor_to_padded(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);   // R m x k -> [row][KP]
 void dev_padded_to_colmajor(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);
 void dev_hpad_to_colmajor(const float* H, double* out, int n, int k, int kp, cudaStream_t st);          // [cell][KP] f32 -> n x k f64

@@ -9,72 +9,9 @@
 #include <cooperative_groups.h>
 
 #include "lgr_common.cuh"
+#include "lgr_ptx.cuh"
 
 namespace lgr {
-
-// ------------------------------------------------------------------------------------------------
-// small PTX helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ float4 ldg_nc4(const float4* p) {
-    float4 r;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-// streaming loads for the sparse arrays: read once, do not pollute L1
-__device__ __forceinline__ int ldg_stream(const int* p) {
-    int r;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float ldg_stream(const float* p) {
-    float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ unsigned short ldg_stream(const unsigned short* p) {
-    unsigned short r;
-    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-
-template <typename DS>
-__device__ __forceinline__ int find_ds(const DS* ds, int nds, int blk, int DS::*off) {
-    int i = 0;
-    while (i + 1 < nds && blk >= ds[i + 1].*off) ++i;
-    return i;
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_prep: L~ rows + partial Grams.  One CTA = PREP_ROWS_PER_BLOCK rows of one dataset.
@@ -189,7 +126,7 @@ __global__ void __launch_bounds__(256) k_spmm_ltx(const DsDev* __restrict__ ds, 
     }
 }
 
-void launch_spmm_ltx(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st) {
+void launch_spmm_ltx_gather(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st) {
     if (total_blocks <= 0) return;
     if (kp == 32)
         k_spmm_ltx<32><<<total_blocks, 256, 0, st>>>(ds, nds);
@@ -198,182 +135,6 @@ void launch_spmm_ltx(const DsDev* ds, int nds, int total_blocks, int kp, cudaStr
     LGR_CUDA(cudaGetLastError());
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_spmm_xh: one CTA = one cell tile (TC cells) of one dataset.
-//   phase 0: the tile's H rows (TC x KP fp32, contiguous in HBM) are staged in shared memory by one
-//            TMA bulk copy (cp.async.bulk + mbarrier).
-//   phase 1: warp per gene: R[g][:] += sum_{c in tile, x_gc != 0} x_gc * Hs[c][:]   (gather from smem,
-//            quarter-warp per non-zero), one vector RED (red.global.add.v4.f32) per (gene, tile).
-//   phase 2: G += Hs^T Hs  (4x4 register patches over the upper triangle, fp64 atomics per CTA).
-// ------------------------------------------------------------------------------------------------
-constexpr int XH_THREADS = 512;
-
-size_t spmm_xh_smem(int kp, int tc) {
-    const int np = kp / 4;
-    const int npatch = np * (np + 1) / 2;
-    const int ncg = XH_THREADS / npatch > 0 ? XH_THREADS / npatch : 1;
-    return (size_t)tc * kp * sizeof(float) + (size_t)ncg * npatch * 16 * sizeof(float) + 64;
-}
-
-template <int KP>
-__global__ void __launch_bounds__(XH_THREADS) k_spmm_xh(const DsDev* __restrict__ ds, int nds, int k, int TC) {
-    constexpr int LPN = KP / 4;
-    constexpr int NPI = 32 / LPN;
-    constexpr int NP = KP / 4;                 // 4-wide patches per side
-    constexpr int NPATCH = NP * (NP + 1) / 2;  // upper-triangular patches
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* Hs = reinterpret_cast<float*>(smem_raw);
-    float* red = Hs + (size_t)TC * KP;
-    const int ncg = (XH_THREADS / NPATCH) > 0 ? (XH_THREADS / NPATCH) : 1;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(red + (size_t)ncg * NPATCH * 16);
-
-    const int i = find_ds(ds, nds, (int)blockIdx.x, &DsDev::xh_blk_off);
-    const DsDev& D = ds[i];
-    const int tile = (int)blockIdx.x - D.xh_blk_off;
-    const int c0 = tile * TC;
-    const int ncell = min(TC, D.n - c0);
-    const int rows = D.rows;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)ncell * KP * sizeof(float);
-        mbar_expect_tx(bar, bytes);
-        const char* src = reinterpret_cast<const char*>(D.H + (size_t)c0 * KP);
-        char* dst = reinterpret_cast<char*>(Hs);
-        for (uint32_t off = 0; off < bytes; off += 32768u) {
-            const uint32_t nb = min(32768u, bytes - off);
-            bulk_g2s(dst + off, src + off, nb, bar);
-        }
-    }
-    mbar_wait(bar, 0);
-
-    // ---- phase 1: R += X_tile * Hs ----
-    {
-        const int q = lane / LPN, s = lane % LPN;
-        const int* __restrict__ tptr = D.tptr + (size_t)tile * rows;
-        const unsigned short* __restrict__ tcell = D.tcell;
-        const float* __restrict__ tval = D.tval;
-        const float4* Hs4 = reinterpret_cast<const float4*>(Hs);
-        for (int g0 = warp * 32; g0 < rows; g0 += nwarps * 32) {
-            // lane holds the segment bounds of gene g0 + lane (coalesced), broadcast per gene below
-            const int gl = g0 + lane;
-            int pb = 0, pe = 0;
-            if (gl < rows) {
-                pb = __ldg(tptr + gl);
-                pe = __ldg(tptr + gl + 1);
-            }
-            const int ng = min(32, rows - g0);
-            for (int gg = 0; gg < ng; ++gg) {
-                const int beg = __shfl_sync(0xffffffffu, pb, gg);
-                const int end = __shfl_sync(0xffffffffu, pe, gg);
-                if (beg == end) continue;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int base = beg; base < end; base += 32) {
-                    const int e = base + lane;
-                    int cc = 0;
-                    float v = 0.f;
-                    if (e < end) {
-                        cc = (int)ldg_stream(tcell + e);
-                        v = ldg_stream(tval + e);
-                    }
-                    const int cnt = min(32, end - base);
-#pragma unroll
-                    for (int stp = 0; stp < LPN; ++stp) {
-                        const int t = stp * NPI + q;
-                        const int c = __shfl_sync(0xffffffffu, cc, t);
-                        const float vv = __shfl_sync(0xffffffffu, v, t);
-                        if (stp * NPI < cnt) {
-                            const float4 h = Hs4[c * LPN + s];
-                            acc.x = fmaf(vv, h.x, acc.x);
-                            acc.y = fmaf(vv, h.y, acc.y);
-                            acc.z = fmaf(vv, h.z, acc.z);
-                            acc.w = fmaf(vv, h.w, acc.w);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int off = LPN; off < 32; off <<= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
-                    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
-                }
-                if (q == 0) red_add_v4(D.R + (size_t)(g0 + gg) * KP + s * 4, acc);
-            }
-        }
-    }
-
-    // ---- phase 2: G += Hs^T Hs over this tile ----
-    {
-        const int t = threadIdx.x;
-        const int cg = t / NPATCH, pt = t % NPATCH;
-        int pi = 0, pj = 0;
-        {  // decode upper-triangular patch index: pt -> (pi <= pj)
-            int rem = pt;
-            while (rem >= NP - pi) {
-                rem -= NP - pi;
-                ++pi;
-            }
-            pj = pi + rem;
-        }
-        float a[4][4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) a[x][y] = 0.f;
-        const float4* Hs4 = reinterpret_cast<const float4*>(Hs);
-        if (cg < ncg) {
-            for (int c = cg; c < ncell; c += ncg) {
-                const float4 u = Hs4[c * NP + pi];
-                const float4 v = Hs4[c * NP + pj];
-                const float uu[4] = {u.x, u.y, u.z, u.w};
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) a[x][y] = fmaf(uu[x], vv[y], a[x][y]);
-            }
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) red[((size_t)cg * NPATCH + pt) * 16 + x * 4 + y] = a[x][y];
-        }
-        __syncthreads();
-        // reduce over cell groups, one thread per (patch, element); fp64 atomics into G (symmetric fill)
-        for (int e = t; e < NPATCH * 16; e += blockDim.x) {
-            const int p = e / 16, xy = e % 16, x = xy / 4, y = xy % 4;
-            double sum = 0.0;
-            for (int g = 0; g < ncg; ++g) sum += (double)red[((size_t)g * NPATCH + p) * 16 + xy];
-            int ppi = 0, rem = p;
-            while (rem >= NP - ppi) {
-                rem -= NP - ppi;
-                ++ppi;
-            }
-            const int ppj = ppi + rem;
-            const int fa = ppi * 4 + x, fb = ppj * 4 + y;
-            if (fa < k && fb < k) {
-                if (ppi == ppj) {
-                    atomicAdd(&D.G[fa * KP + fb], sum);  // diagonal patch holds the full 4x4 block
-                } else {
-                    atomicAdd(&D.G[fa * KP + fb], sum);
-                    atomicAdd(&D.G[fb * KP + fa], sum);
-                }
-            }
-        }
-    }
-}
-
-void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st) {
-    if (total_tiles <= 0) return;
-    const size_t smem = spmm_xh_smem(kp, tc);
-    if (kp == 32)
-        k_spmm_xh<32><<<total_tiles, XH_THREADS, smem, st>>>(ds, nds, k, tc);
-    else
-        k_spmm_xh<64><<<total_tiles, XH_THREADS, smem, st>>>(ds, nds, k, tc);
-    LGR_CUDA(cudaGetLastError());
-}
 // ------------------------------------------------------------------------------------------------
 // right-hand sides of the V/U and W solves (fp64; tiny)
 //   CtBv_i[g][:] = R_i[g][:] - G_i W[g][:]  (g < m),  R_i[g][:]  (unshared rows)      R/cINMF.R:488
@@ -482,9 +243,8 @@ void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot,
 
 void kernels_init() {
     nnls_init();
+    spmm_init();
     const int maxs = 227 * 1024 - 1024;  // static smem of the kernels counts against the 227 KB limit
-    LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
 }
 
 }  // namespace lgr

@@ -71,73 +71,97 @@ void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const i
     }
 }
 
-// ---- tiled CSR ----------------------------------------------------------------------------------
-__global__ void k_tile_keys(int n, int rows, int tc, const int* __restrict__ colptr, const int* __restrict__ rowidx,
-                            unsigned int* __restrict__ keys, unsigned int* __restrict__ perm,
-                            unsigned short* __restrict__ cell_local, int* __restrict__ counts) {
+// ---- padded tile formats (see lgr_spmm.cu) ---------------------------------------------------------
+//   mode 0, gene-tiled CSC: key = (row / tile) * n + col ,  loc = row % tile      (k_spmm_ltx_tiled)
+//   mode 1, cell-tiled CSR: key = (col / tile) * rows + row, loc = col % tile      (k_spmm_xh)
+// Entries are stably sorted by key (so the minor index stays ascending inside a segment) and every segment is
+// padded with (loc 0, value 0) entries to a multiple of 8; ptr8[key] is the segment start in groups of 8.
+__global__ void k_tile_keys(int mode, int n, int rows, int tile, const int* __restrict__ colptr,
+                            const int* __restrict__ rowidx, unsigned int* __restrict__ keys,
+                            unsigned int* __restrict__ perm, unsigned short* __restrict__ loc, int* __restrict__ counts) {
     const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (warp >= n) return;
     const int b = colptr[warp], e = colptr[warp + 1];
-    const unsigned int tile = (unsigned)(warp / tc);
-    const unsigned short cl = (unsigned short)(warp % tc);
     for (int t = b + lane; t < e; t += 32) {
-        const unsigned int key = tile * (unsigned)rows + (unsigned)rowidx[t];
+        const int r = rowidx[t];
+        unsigned int key;
+        unsigned short l;
+        if (mode == 0) {
+            key = (unsigned)(r / tile) * (unsigned)n + (unsigned)warp;
+            l = (unsigned short)(r % tile);
+        } else {
+            key = (unsigned)(warp / tile) * (unsigned)rows + (unsigned)r;
+            l = (unsigned short)(warp % tile);
+        }
         keys[t] = key;
         perm[t] = (unsigned)t;
-        cell_local[t] = cl;
+        loc[t] = l;
         atomicAdd(&counts[key], 1);
     }
 }
-__global__ void k_tile_gather(size_t nnz, const unsigned int* __restrict__ perm, const unsigned short* __restrict__ cell_local,
-                              const float* __restrict__ val, unsigned short* __restrict__ tcell, float* __restrict__ tval) {
+__global__ void k_pad_counts(size_t nkeys, const int* __restrict__ counts, int* __restrict__ groups) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nkeys; i += (size_t)gridDim.x * blockDim.x)
+        groups[i] = i < nkeys ? (counts[i] + 7) >> 3 : 0;
+}
+__global__ void k_tile_scatter(size_t nnz, const unsigned int* __restrict__ keys_sorted, const unsigned int* __restrict__ perm,
+                               const int* __restrict__ segstart, const int* __restrict__ ptr8,
+                               const unsigned short* __restrict__ loc, const float* __restrict__ val,
+                               unsigned short* __restrict__ oloc, float* __restrict__ oval) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned int p = perm[i];
-        tcell[i] = cell_local[p];
-        tval[i] = val[p];
+        const unsigned int key = keys_sorted[i], p = perm[i];
+        const size_t dst = (size_t)ptr8[key] * 8 + (i - (size_t)segstart[key]);
+        oloc[dst] = loc[p];
+        oval[dst] = val[p];
     }
 }
 
-void dev_build_tiled_csr(int n, int rows, int tc, const int* colptr, const int* rowidx, const float* val, size_t nnz,
-                         int* tptr, unsigned short* tcell, float* tval, cudaStream_t st) {
-    const int ntiles = (n + tc - 1) / tc;
-    const size_t nkeys = (size_t)ntiles * rows;
-    LGR_REQUIRE(nkeys < (size_t)0x7fffffff, "tiled CSR: tiles x rows exceeds 2^31");
-    LGR_CUDA(cudaMemsetAsync(tptr, 0, (nkeys + 1) * sizeof(int), st));
-    if (nnz == 0 || n == 0) return;
-    unsigned int *keys = nullptr, *keys2 = nullptr, *perm = nullptr, *perm2 = nullptr;
-    unsigned short* cl = nullptr;
-    int* counts = nullptr;
-    void* tmp = nullptr;
-    size_t tmp_bytes = 0, scan_bytes = 0;
-    LGR_CUDA(cudaMalloc(&keys, nnz * 4));
-    LGR_CUDA(cudaMalloc(&keys2, nnz * 4));
-    LGR_CUDA(cudaMalloc(&perm, nnz * 4));
-    LGR_CUDA(cudaMalloc(&perm2, nnz * 4));
-    LGR_CUDA(cudaMalloc(&cl, nnz * 2));
-    LGR_CUDA(cudaMalloc(&counts, (nkeys + 1) * sizeof(int)));
-    LGR_CUDA(cudaMemsetAsync(counts, 0, (nkeys + 1) * sizeof(int), st));
-    k_tile_keys<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(n, rows, tc, colptr, rowidx, keys, perm, cl,
-                                                                             counts);
+void dev_build_padded(int mode, int n, int rows, int tile, const int* colptr, const int* rowidx, const float* val,
+                      size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<float>& oval, cudaStream_t st) {
+    LGR_REQUIRE(tile >= 1 && tile <= 65536, "tile size must fit a 16-bit local index");
+    const size_t nmajor = mode == 0 ? (size_t)(rows + tile - 1) / tile : (size_t)(n + tile - 1) / tile;
+    const size_t nkeys = nmajor * (size_t)(mode == 0 ? n : rows);
+    LGR_REQUIRE(nkeys < (size_t)0x7fffffff, "tiled format: tiles x minor dimension exceeds 2^31");
+    ptr8.alloc(nkeys + 1);
+    ptr8.zero(st);
+    if (nnz == 0 || n == 0) {
+        oloc.alloc(8);
+        oval.alloc(8);
+        oloc.zero(st);
+        oval.zero(st);
+        return;
+    }
+    DBuf<unsigned int> keys(nnz), keys2(nnz), perm(nnz), perm2(nnz);
+    DBuf<unsigned short> loc(nnz);
+    DBuf<int> counts(nkeys + 1), segstart(nkeys + 1), groups(nkeys + 1);
+    counts.zero(st);
+    k_tile_keys<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(mode, n, rows, tile, colptr, rowidx, keys.p, perm.p,
+                                                                             loc.p, counts.p);
     LGR_CUDA(cudaGetLastError());
     int bits = 1;
     while (((size_t)1 << bits) < nkeys) ++bits;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, perm, perm2, (int)nnz, 0, bits, st);
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, tptr, (int)(nkeys + 1), st);
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys2.p, perm.p, perm2.p, (int)nnz, 0, bits, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts.p, segstart.p, (int)(nkeys + 1), st);
     if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
-    LGR_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    LGR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, perm, perm2, (int)nnz, 0, bits, st));
-    LGR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, tptr, (int)(nkeys + 1), st));
-    const int grid = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
-    k_tile_gather<<<grid, 256, 0, st>>>(nnz, perm2, cl, val, tcell, tval);
+    DBuf<unsigned char> tmp(tmp_bytes);
+    LGR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, perm.p, perm2.p, (int)nnz, 0, bits, st));
+    LGR_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.p, segstart.p, (int)(nkeys + 1), st));
+    const int grid = (int)std::min<size_t>((nkeys + 256) / 256, 148 * 16);
+    k_pad_counts<<<grid, 256, 0, st>>>(nkeys, counts.p, groups.p);
+    LGR_CUDA(cudaGetLastError());
+    LGR_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, groups.p, ptr8.p, (int)(nkeys + 1), st));
+    int total_groups = 0;
+    LGR_CUDA(cudaMemcpyAsync(&total_groups, ptr8.p + nkeys, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LGR_CUDA(cudaStreamSynchronize(st));
+    const size_t padded = (size_t)total_groups * 8 + 8;
+    oloc.alloc(padded);
+    oval.alloc(padded);
+    oloc.zero(st);
+    oval.zero(st);
+    const int grid2 = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
+    k_tile_scatter<<<grid2, 256, 0, st>>>(nnz, keys2.p, perm2.p, segstart.p, ptr8.p, loc.p, val, oloc.p, oval.p);
     LGR_CUDA(cudaGetLastError());
     LGR_CUDA(cudaStreamSynchronize(st));
-    cudaFree(keys);
-    cudaFree(keys2);
-    cudaFree(perm);
-    cudaFree(perm2);
-    cudaFree(cl);
-    cudaFree(counts);
-    cudaFree(tmp);
 }
 
 // ---- factor layout conversion -------------------------------------------------------------------

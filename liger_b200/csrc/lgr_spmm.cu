@@ -1,0 +1,308 @@
+// liger_b200 -- the two sparse contractions of an ANLS iteration (sm_100a), both as shared-memory GATHERS:
+//
+//   k_spmm_ltx_tiled   B = L~^T X   (rhs of the H solve, reference R/cINMF.R:480)
+//       X in "gene-tiled CSC": genes are cut into tiles of GT rows whose L~ rows (GT x KP fp32) fit in shared
+//       memory; inside a gene tile the entries are ordered by cell.  One CTA owns a block of CB cells, walks the
+//       gene tiles, stages each L~ tile with one TMA bulk copy and accumulates the partial B rows in shared memory.
+//   k_spmm_xh          R = X H  and  G = H^T H   (statistics of the V / W solves, R/cINMF.R:486-488,497-499)
+//       X in "cell-tiled CSR": cells are cut into tiles of TC whose H rows (TC x KP fp32, contiguous in HBM) are
+//       staged by one TMA bulk copy; inside a cell tile the entries are ordered by gene.  Warps own genes, gather
+//       H rows, and issue one vector RED (red.global.add.v4.f32) per (gene, tile).
+//
+// Both formats pad every (tile, minor) segment to a multiple of 8 entries (u16 local index + fp32 value, zero padded)
+// so that a quarter-warp fetches its 8 entries with three aligned 128-bit loads and then issues, per non-zero,
+// one 128-bit shared-memory load and four FFMAs: ~2 warp instructions and one shared-memory wavefront per non-zero.
+#include "lgr_common.cuh"
+#include "lgr_ptx.cuh"
+
+namespace lgr {
+
+// acc += sum_j val_j * tile[loc_j][4s..4s+3]   for the 8 entries of one group (cells: 8 x u16, vals: 8 x f32)
+template <int LPN>
+__device__ __forceinline__ void gather8(float4& acc, const uint4 cells, const float4 v0, const float4 v1,
+                                        const float4* __restrict__ tile4, const int s) {
+    const unsigned cw[4] = {cells.x, cells.y, cells.z, cells.w};
+    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const unsigned c = (j & 1) ? (cw[j >> 1] >> 16) : (cw[j >> 1] & 0xffffu);
+        const float4 h = tile4[c * LPN + s];
+        acc.x = fmaf(vv[j], h.x, acc.x);
+        acc.y = fmaf(vv[j], h.y, acc.y);
+        acc.z = fmaf(vv[j], h.z, acc.z);
+        acc.w = fmaf(vv[j], h.w, acc.w);
+    }
+}
+
+// One padded segment [beg, end) (units: groups of 8 entries).  The NPI lane-groups of the warp take groups
+// beg + q, beg + q + NPI, ...; the next group's loads are issued before the current one is consumed.
+template <int KP>
+__device__ __forceinline__ float4 gather_segment(const int beg, const int end, const unsigned short* __restrict__ loc,
+                                                 const float* __restrict__ val, const float4* __restrict__ tile4,
+                                                 const int q, const int s) {
+    constexpr int LPN = KP / 4;
+    constexpr int NPI = 32 / LPN;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int g = beg + q;
+    uint4 cells = make_uint4(0, 0, 0, 0);
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (g < end) {
+        cells = ldg_stream4(loc + (size_t)g * 8);
+        const uint4 a = ldg_stream4(val + (size_t)g * 8), b = ldg_stream4(val + (size_t)g * 8 + 4);
+        v0 = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+        v1 = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
+    }
+    while (g < end) {
+        const int gn = g + NPI;
+        uint4 ncells = make_uint4(0, 0, 0, 0);
+        uint4 na = ncells, nb = ncells;
+        if (gn < end) {
+            ncells = ldg_stream4(loc + (size_t)gn * 8);
+            na = ldg_stream4(val + (size_t)gn * 8);
+            nb = ldg_stream4(val + (size_t)gn * 8 + 4);
+        }
+        gather8<LPN>(acc, cells, v0, v1, tile4, s);
+        cells = ncells;
+        v0 = make_float4(__uint_as_float(na.x), __uint_as_float(na.y), __uint_as_float(na.z), __uint_as_float(na.w));
+        v1 = make_float4(__uint_as_float(nb.x), __uint_as_float(nb.y), __uint_as_float(nb.z), __uint_as_float(nb.w));
+        g = gn;
+    }
+#pragma unroll
+    for (int off = LPN; off < 32; off <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_spmm_ltx_tiled
+// ------------------------------------------------------------------------------------------------
+constexpr int LTX_THREADS = 1024;
+
+size_t spmm_ltx_smem(int kp, int cb, int gt) { return (size_t)(cb + gt) * kp * sizeof(float) + 64; }
+
+template <int KP>
+__global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* __restrict__ ds, int nds, int CB, int GT) {
+    constexpr int LPN = KP / 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* Ls = reinterpret_cast<float*>(smem_raw);             // GT x KP
+    float* Bp = Ls + (size_t)GT * KP;                            // CB x KP partial rows of B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Bp + (size_t)CB * KP);
+    const int i = find_ds(ds, nds, (int)blockIdx.x, &DsDev::ltx_blk_off);
+    const DsDev& D = ds[i];
+    const int n = D.n, rows = D.rows, ngt = D.ngt;
+    const int c0 = ((int)blockIdx.x - D.ltx_blk_off) * CB;
+    const int ncell = min(CB, n - c0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int q = lane / LPN, s = lane % LPN;
+    const float4* Ls4 = reinterpret_cast<const float4*>(Ls);
+    float4* Bp4 = reinterpret_cast<float4*>(Bp);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    // each warp owns a contiguous run of cells of the block (contiguous entries in HBM)
+    const int cpw = (ncell + nwarps - 1) / nwarps;
+    const int w0 = min(warp * cpw, ncell), w1 = min(w0 + cpw, ncell);
+    for (int gt = 0; gt < ngt; ++gt) {
+        __syncthreads();  // everyone is done reading the previous L~ tile (and sees the barrier init)
+        if (threadIdx.x == 0) {
+            const int r0 = gt * GT;
+            const uint32_t bytes = (uint32_t)min(GT, rows - r0) * KP * sizeof(float);
+            mbar_expect_tx(bar, bytes);
+            const char* src = reinterpret_cast<const char*>(D.L + (size_t)r0 * KP);
+            char* dst = reinterpret_cast<char*>(Ls);
+            for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
+        }
+        const int* __restrict__ ptr = D.cptr8 + (size_t)gt * n + c0;
+        mbar_wait(bar, (uint32_t)(gt & 1));
+        for (int cb = w0; cb < w1; cb += 32) {
+            const int nc = min(32, w1 - cb);
+            int pb = 0, pe = 0;  // lane j holds the segment bounds of cell cb + j
+            if (lane <= nc) pb = __ldg(ptr + cb + lane);
+            pe = __shfl_down_sync(0xffffffffu, pb, 1);
+            if (lane == 31 && nc == 32) pe = __ldg(ptr + cb + 32);
+            for (int j = 0; j < nc; ++j) {
+                const int beg = __shfl_sync(0xffffffffu, pb, j), end = __shfl_sync(0xffffffffu, pe, j);
+                float4 acc = gather_segment<KP>(beg, end, D.crow, D.cval, Ls4, q, s);
+                if (q == 0) {
+                    float4* dst = Bp4 + (size_t)(cb + j) * LPN + s;
+                    if (gt > 0) {
+                        const float4 o = *dst;
+                        acc.x += o.x;
+                        acc.y += o.y;
+                        acc.z += o.z;
+                        acc.w += o.w;
+                    }
+                    *dst = acc;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float4* __restrict__ out = reinterpret_cast<float4*>(D.B) + (size_t)c0 * LPN;
+    for (int e = threadIdx.x; e < ncell * LPN; e += blockDim.x) out[e] = Bp4[e];
+}
+
+void launch_spmm_ltx_tiled(const DsDev* ds, int nds, int total_blocks, int kp, int cb, int gt, cudaStream_t st) {
+    if (total_blocks <= 0) return;
+    const size_t smem = spmm_ltx_smem(kp, cb, gt);
+    if (kp == 32)
+        k_spmm_ltx_tiled<32><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
+    else
+        k_spmm_ltx_tiled<64><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
+    LGR_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_spmm_xh
+// ------------------------------------------------------------------------------------------------
+constexpr int XH_THREADS = 1024;
+constexpr int XH_MAX_CG = 14;  // cell groups of the H^T H phase (bounds its reduction scratch)
+
+static int xh_ncg(int kp) {
+    const int np = kp / 4, npatch = np * (np + 1) / 2;
+    int ncg = XH_THREADS / npatch;
+    if (ncg < 1) ncg = 1;
+    if (ncg > XH_MAX_CG) ncg = XH_MAX_CG;
+    return ncg;
+}
+size_t spmm_xh_smem(int kp, int tc) {
+    const int np = kp / 4, npatch = np * (np + 1) / 2;
+    return (size_t)tc * kp * sizeof(float) + (size_t)xh_ncg(kp) * npatch * 16 * sizeof(float) + 64;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(XH_THREADS, 1) k_spmm_xh(const DsDev* __restrict__ ds, int nds, int k, int TC, int ncg) {
+    constexpr int LPN = KP / 4;
+    constexpr int NP = KP / 4;                 // 4-wide patches per side
+    constexpr int NPATCH = NP * (NP + 1) / 2;  // upper-triangular patches
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* Hs = reinterpret_cast<float*>(smem_raw);
+    float* red = Hs + (size_t)TC * KP;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + (size_t)ncg * NPATCH * 16);
+    __shared__ int next_blk;
+
+    const int i = find_ds(ds, nds, (int)blockIdx.x, &DsDev::xh_blk_off);
+    const DsDev& D = ds[i];
+    const int tile = (int)blockIdx.x - D.xh_blk_off;
+    const int c0 = tile * TC;
+    const int ncell = min(TC, D.n - c0);
+    const int rows = D.rows;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        next_blk = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)ncell * KP * sizeof(float);
+        mbar_expect_tx(bar, bytes);
+        const char* src = reinterpret_cast<const char*>(D.H + (size_t)c0 * KP);
+        char* dst = reinterpret_cast<char*>(Hs);
+        for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
+    }
+    mbar_wait(bar, 0);
+
+    // ---- phase 1: R += X_tile * Hs ; warps pull blocks of 32 genes ----
+    {
+        const int q = lane / LPN, s = lane % LPN;
+        const int* __restrict__ tptr = D.tptr8 + (size_t)tile * rows;
+        const float4* Hs4 = reinterpret_cast<const float4*>(Hs);
+        const int nblk = (rows + 31) >> 5;
+        for (;;) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&next_blk, 1);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= nblk) break;
+            const int g0 = b * 32;
+            const int ng = min(32, rows - g0);
+            int pb = 0;
+            if (lane <= ng) pb = __ldg(tptr + g0 + lane);
+            int pe = __shfl_down_sync(0xffffffffu, pb, 1);
+            if (lane == 31) pe = __ldg(tptr + min(g0 + 32, rows));
+            for (int gg = 0; gg < ng; ++gg) {
+                const int beg = __shfl_sync(0xffffffffu, pb, gg), end = __shfl_sync(0xffffffffu, pe, gg);
+                if (beg == end) continue;
+                const float4 acc = gather_segment<KP>(beg, end, D.tcell, D.tval, Hs4, q, s);
+                if (q == 0) red_add_v4(D.R + (size_t)(g0 + gg) * KP + s * 4, acc);
+            }
+        }
+    }
+
+    // ---- phase 2: G += Hs^T Hs over this tile (4x4 register patches of the upper triangle) ----
+    {
+        const int t = threadIdx.x;
+        const int cg = t / NPATCH, pt = t % NPATCH;
+        int pi = 0, pj = 0;
+        {
+            int rem = pt;
+            while (rem >= NP - pi) {
+                rem -= NP - pi;
+                ++pi;
+            }
+            pj = pi + rem;
+        }
+        const float4* Hs4 = reinterpret_cast<const float4*>(Hs);
+        if (cg < ncg) {
+            float a[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) a[x][y] = 0.f;
+            for (int c = cg; c < ncell; c += ncg) {
+                const float4 u = Hs4[c * NP + pi];
+                const float4 v = Hs4[c * NP + pj];
+                const float uu[4] = {u.x, u.y, u.z, u.w};
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) a[x][y] = fmaf(uu[x], vv[y], a[x][y]);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) red[((size_t)cg * NPATCH + pt) * 16 + x * 4 + y] = a[x][y];
+        }
+        __syncthreads();
+        for (int e = t; e < NPATCH * 16; e += blockDim.x) {
+            const int p = e / 16, xy = e % 16, x = xy / 4, y = xy % 4;
+            double sum = 0.0;
+            for (int g = 0; g < ncg; ++g) sum += (double)red[((size_t)g * NPATCH + p) * 16 + xy];
+            int ppi = 0, rem = p;
+            while (rem >= NP - ppi) {
+                rem -= NP - ppi;
+                ++ppi;
+            }
+            const int ppj = ppi + rem;
+            const int fa = ppi * 4 + x, fb = ppj * 4 + y;
+            if (fa < k && fb < k) {
+                atomicAdd(&D.G[fa * KP + fb], sum);
+                if (ppi != ppj) atomicAdd(&D.G[fb * KP + fa], sum);  // a diagonal patch already holds both triangles
+            }
+        }
+    }
+}
+
+void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st) {
+    if (total_tiles <= 0) return;
+    const size_t smem = spmm_xh_smem(kp, tc);
+    const int ncg = xh_ncg(kp);
+    if (kp == 32)
+        k_spmm_xh<32><<<total_tiles, XH_THREADS, smem, st>>>(ds, nds, k, tc, ncg);
+    else
+        k_spmm_xh<64><<<total_tiles, XH_THREADS, smem, st>>>(ds, nds, k, tc, ncg);
+    LGR_CUDA(cudaGetLastError());
+}
+
+void spmm_init() {
+    const int maxs = 227 * 1024 - 1024;
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+}
+
+}  // namespace lgr
