@@ -34,47 +34,58 @@ __device__ __forceinline__ void gather8(float4& acc, const uint4 cells, const fl
     }
 }
 
-// One padded segment [beg, end) (units: groups of 8 entries).  The NPI lane-groups of the warp take groups
-// beg + q, beg + q + NPI, ...; the next group's loads are issued before the current one is consumed.
-template <int KP>
-__device__ __forceinline__ float4 gather_segment(const int beg, const int end, const unsigned short* __restrict__ loc,
-                                                 const float* __restrict__ val, const float4* __restrict__ tile4,
-                                                 const int q, const int s) {
+struct Group8 {
+    uint4 cells;
+    float4 v0, v1;
+};
+__device__ __forceinline__ Group8 load_group(const unsigned short* __restrict__ loc, const float* __restrict__ val, int g,
+                                             bool pred) {
+    Group8 r;
+    r.cells = make_uint4(0, 0, 0, 0);
+    r.v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.v1 = r.v0;
+    if (pred) {
+        r.cells = __ldg(reinterpret_cast<const uint4*>(loc + (size_t)g * 8));
+        r.v0 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8));
+        r.v1 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8 + 4));
+    }
+    return r;
+}
+
+// A lane-group (KP/4 lanes) walks the contiguous stream of 8-entry groups of the segments [sa, sb): every group is
+// one 128-bit load of local indices, two of values (prefetched one group ahead), then per non-zero one 128-bit
+// shared-memory load of the staged factor row and four FFMAs.  At a segment end the 32 (64) sums the lane-group
+// holds are the complete output row, so there is no cross-lane reduction; `store(seg, acc, nonempty)` consumes them.
+template <int KP, typename Store>
+__device__ __forceinline__ void gather_stream(const int* __restrict__ ptr8, const int sa, const int sb,
+                                              const unsigned short* __restrict__ loc, const float* __restrict__ val,
+                                              const float4* __restrict__ tile4, const int s, Store store) {
     constexpr int LPN = KP / 4;
-    constexpr int NPI = 32 / LPN;
+    if (sa >= sb) return;
+    int seg = sa;
+    int g = __ldg(ptr8 + sa);
+    const int gend = __ldg(ptr8 + sb);
+    int segend = __ldg(ptr8 + sa + 1);
+    int nsegend = (seg + 2 <= sb) ? __ldg(ptr8 + seg + 2) : gend;
+    Group8 cur = load_group(loc, val, g, g < gend);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int g = beg + q;
-    uint4 cells = make_uint4(0, 0, 0, 0);
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (g < end) {
-        cells = ldg_stream4(loc + (size_t)g * 8);
-        const uint4 a = ldg_stream4(val + (size_t)g * 8), b = ldg_stream4(val + (size_t)g * 8 + 4);
-        v0 = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-        v1 = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
-    }
-    while (g < end) {
-        const int gn = g + NPI;
-        uint4 ncells = make_uint4(0, 0, 0, 0);
-        uint4 na = ncells, nb = ncells;
-        if (gn < end) {
-            ncells = ldg_stream4(loc + (size_t)gn * 8);
-            na = ldg_stream4(val + (size_t)gn * 8);
-            nb = ldg_stream4(val + (size_t)gn * 8 + 4);
+    bool nonempty = false;
+    while (seg < sb) {
+        if (g < segend) {
+            const Group8 nx = load_group(loc, val, g + 1, g + 1 < gend);
+            gather8<LPN>(acc, cur.cells, cur.v0, cur.v1, tile4, s);
+            cur = nx;
+            ++g;
+            nonempty = true;
+        } else {
+            store(seg, acc, nonempty);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            nonempty = false;
+            ++seg;
+            segend = nsegend;
+            nsegend = (seg + 2 <= sb) ? __ldg(ptr8 + seg + 2) : gend;
         }
-        gather8<LPN>(acc, cells, v0, v1, tile4, s);
-        cells = ncells;
-        v0 = make_float4(__uint_as_float(na.x), __uint_as_float(na.y), __uint_as_float(na.z), __uint_as_float(na.w));
-        v1 = make_float4(__uint_as_float(nb.x), __uint_as_float(nb.y), __uint_as_float(nb.z), __uint_as_float(nb.w));
-        g = gn;
     }
-#pragma unroll
-    for (int off = LPN; off < 32; off <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
-    }
-    return acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -116,27 +127,23 @@ __global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* 
         }
         const int* __restrict__ ptr = D.cptr8 + (size_t)gt * n + c0;
         mbar_wait(bar, (uint32_t)(gt & 1));
-        for (int cb = w0; cb < w1; cb += 32) {
-            const int nc = min(32, w1 - cb);
-            int pb = 0, pe = 0;  // lane j holds the segment bounds of cell cb + j
-            if (lane <= nc) pb = __ldg(ptr + cb + lane);
-            pe = __shfl_down_sync(0xffffffffu, pb, 1);
-            if (lane == 31 && nc == 32) pe = __ldg(ptr + cb + 32);
-            for (int j = 0; j < nc; ++j) {
-                const int beg = __shfl_sync(0xffffffffu, pb, j), end = __shfl_sync(0xffffffffu, pe, j);
-                float4 acc = gather_segment<KP>(beg, end, D.crow, D.cval, Ls4, q, s);
-                if (q == 0) {
-                    float4* dst = Bp4 + (size_t)(cb + j) * LPN + s;
-                    if (gt > 0) {
-                        const float4 o = *dst;
-                        acc.x += o.x;
-                        acc.y += o.y;
-                        acc.z += o.z;
-                        acc.w += o.w;
-                    }
-                    *dst = acc;
+        {
+            // the warp's cells [w0, w1) are split into contiguous runs, one per lane-group
+            const int nq = 32 / LPN;
+            const int per = (w1 - w0 + nq - 1) / nq;
+            const int sa = min(w0 + q * per, w1), sb = min(sa + per, w1);
+            const bool first = gt == 0;
+            gather_stream<KP>(ptr, sa, sb, D.crow, D.cval, Ls4, s, [&](int cell, float4 acc, bool) {
+                float4* dst = Bp4 + (size_t)cell * LPN + s;
+                if (!first) {
+                    const float4 o = *dst;
+                    acc.x += o.x;
+                    acc.y += o.y;
+                    acc.z += o.z;
+                    acc.w += o.w;
                 }
-            }
+                *dst = acc;
+            });
         }
     }
     __syncthreads();
@@ -218,16 +225,13 @@ __global__ void __launch_bounds__(XH_THREADS, 1) k_spmm_xh(const DsDev* __restri
             if (b >= nblk) break;
             const int g0 = b * 32;
             const int ng = min(32, rows - g0);
-            int pb = 0;
-            if (lane <= ng) pb = __ldg(tptr + g0 + lane);
-            int pe = __shfl_down_sync(0xffffffffu, pb, 1);
-            if (lane == 31) pe = __ldg(tptr + min(g0 + 32, rows));
-            for (int gg = 0; gg < ng; ++gg) {
-                const int beg = __shfl_sync(0xffffffffu, pb, gg), end = __shfl_sync(0xffffffffu, pe, gg);
-                if (beg == end) continue;
-                const float4 acc = gather_segment<KP>(beg, end, D.tcell, D.tval, Hs4, q, s);
-                if (q == 0) red_add_v4(D.R + (size_t)(g0 + gg) * KP + s * 4, acc);
-            }
+            const int nq = 32 / LPN;
+            const int per = (ng + nq - 1) / nq;
+            const int sa = min(g0 + q * per, g0 + ng), sb = min(sa + per, g0 + ng);
+            float* __restrict__ R = D.R;
+            gather_stream<KP>(tptr, sa, sb, D.tcell, D.tval, Hs4, s, [&](int gene, float4 acc, bool nonempty) {
+                if (nonempty) red_add_v4(R + (size_t)gene * KP + s * 4, acc);
+            });
         }
     }
 
