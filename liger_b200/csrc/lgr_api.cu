@@ -103,7 +103,7 @@ struct lgr_ctx {
     DBuf<GramSpec> specH, specV, specW;
     DBuf<Counters> counters;
     NnlsConfig cfgF{}, cfgD{};
-    int blocksH = 0, blocksV = 0, blocksW = 0, ctH = 0, ctV = 0, ctW = 0, ltx_blocks = 0, xh_tiles = 0, prep_blocks = 0, max_rows = 0;
+    long long colsH = 0, colsV = 0; int ltx_blocks = 0, xh_tiles = 0, prep_blocks = 0, max_rows = 0;
     size_t N_local = 0;
     NcclComm* comm = nullptr;
     bool stats_valid = false;  // R / G arenas hold the statistics of the current H
@@ -278,7 +278,7 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         }
         {
             Timed t(c, "k_nnls_H");
-            launch_nnls(false, c->grpH.p, c->d, c->blocksH, c->ctH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
+            launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
         }
         c->h_valid = true;
         // ---- sufficient statistics of the V / W solves ----
@@ -294,7 +294,7 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         }
         {
             Timed t(c, "k_nnls_V");
-            launch_nnls(true, c->grpV.p, c->d, c->blocksV, c->ctV, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
+            launch_nnls(true, c->grpV.p, c->d, c->colsV, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
         }
         // ---- W: new V_i ----
         {
@@ -307,7 +307,7 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         }
         {
             Timed t(c, "k_nnls_W");
-            launch_nnls(true, c->grpW.p, 1, c->blocksW, c->ctW, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
+            launch_nnls(true, c->grpW.p, 1, (long long)c->m, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
         }
     }
     if (traj && niter > 0) {
@@ -499,17 +499,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     std::vector<GramSpec> sH(c->d), sV(c->d), sW(1);
     c->ds_host.resize(c->d);
     std::vector<NnlsGroup> gH(c->d), gV(c->d), gW(1);
-    int ltx = 0, xh = 0, prep = 0, bH = 0, bV = 0;
-    {
-        long long totH = 0, totV = 0;
-        for (int i = 0; i < c->d; ++i) {
-            totH += c->ds[i].n;
-            totV += c->ds[i].rows;
-        }
-        c->ctH = nnls_tile_cols(c->cfgF, totH, c->num_sms);
-        c->ctV = nnls_tile_cols(c->cfgD, totV, c->num_sms);
-        c->ctW = nnls_tile_cols(c->cfgD, m, c->num_sms);
-    }
+    int ltx = 0, xh = 0, prep = 0;
+    long long bH = 0, bV = 0;
     const int rb = prep_rows_per_block(kp);
     for (int i = 0; i < c->d; ++i) {
         Dataset& D = c->ds[i];
@@ -551,21 +542,20 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.sqnorm = sq[i];
         // H solve: CtC = LtL + lambda VtV, rhs = B (fp32), x = H
         sH[i] = GramSpec{h.LtL, h.VtV, 1.0, D.lambda, ctc(i), ctc(i) + kk, c->ok_arena.p + i};
-        gH[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, h.H, h.hmask, D.n, kp, bH, 0};
-        bH += (D.n + c->ctH - 1) / c->ctH;
+        gH[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, h.H, h.hmask, D.n, kp, bH};
+        bH += D.n;
         // V/U solve: CtC = (1 + lambda) G_i, rhs = CtBv (fp64), x = V
         sV[i] = GramSpec{h.G, nullptr, 1.0 + D.lambda, 0.0, ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i};
-        gV[i] = NnlsGroup{ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i, h.CtBv, h.V, h.vmask, D.rows, kp, bV, 0};
-        bV += (D.rows + c->ctV - 1) / c->ctV;
+        gV[i] = NnlsGroup{ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i, h.CtBv, h.V, h.vmask, D.rows, kp, bV};
+        bV += D.rows;
     }
     sW[0] = GramSpec{c->Gsum.p, nullptr, 1.0, 0.0, ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d};
-    gW[0] = NnlsGroup{ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d, c->CtBw.p, c->W.p, c->wmask.p, m, kp, 0, 0};
+    gW[0] = NnlsGroup{ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d, c->CtBw.p, c->W.p, c->wmask.p, m, kp, 0};
     c->ltx_blocks = ltx;
     c->xh_tiles = xh;
     c->prep_blocks = prep;
-    c->blocksH = bH;
-    c->blocksV = bV;
-    c->blocksW = (m + c->ctW - 1) / c->ctW;
+    c->colsH = bH;
+    c->colsV = bV;
     c->ds_dev.alloc((size_t)c->d);
     c->grpH.alloc((size_t)c->d);
     c->grpV.alloc((size_t)c->d);
@@ -823,11 +813,9 @@ int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* 
             GramSpec sp{dGp.p, nullptr, 1.0, 0.0, ctc.p, ctc.p + (size_t)kp * kp, ok.p};
             LGR_CUDA(cudaMemcpyAsync(spec.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, st));
             launch_gram_inv(spec.p, 1, k, kp, st);
-            NnlsGroup g{ctc.p, ctc.p + (size_t)kp * kp, ok.p, dB.p, dX.p, mask.p, (int)ncols, k, 0, 0};
+            NnlsGroup g{ctc.p, ctc.p + (size_t)kp * kp, ok.p, dB.p, dX.p, mask.p, (int)ncols, k, 0};
             LGR_CUDA(cudaMemcpyAsync(grp.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
-            const int ct = nnls_tile_cols(cfg, ncols, prop.multiProcessorCount);
-            const int blocks = (int)((ncols + ct - 1) / ct);
-            launch_nnls(true, grp.p, 1, blocks, ct, k, kp, cfg, cnt.p, 1, st);
+            launch_nnls(true, grp.p, 1, (long long)ncols, k, kp, cfg, cnt.p, 1, st);
             LGR_CUDA(cudaMemcpyAsync(X, dX.p, (size_t)k * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
             LGR_CUDA(cudaStreamSynchronize(st));
         } catch (...) {

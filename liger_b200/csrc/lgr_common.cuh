@@ -122,8 +122,7 @@ struct NnlsGroup {
     unsigned long long* mask;   // ncols, warm start in/out (never null)
     int ncols;
     int ld;
-    int blk_off;                // first flat CTA tile of this group
-    int pad;
+    long long col_off;          // first column of this group in the launch's flat column range
 };
 
 // CtC = cA * A + cB * B (A, B fp64 KP x KP, B may be null) -> gram, ginv, ok
@@ -157,7 +156,6 @@ struct NnlsConfig {
     int grid_cap;     // persistent grid size
     int ct_cols;      // default columns per CTA tile
 };
-int nnls_tile_cols(const NnlsConfig& cfg, long long total_cols, int num_sms);
 NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
 
 void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st);
@@ -167,7 +165,7 @@ size_t spmm_ltx_smem(int kp, int cb, int gt);
 void spmm_init();
 void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st);
 void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStream_t st);
-void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_tiles, int ct_cols, int k, int kp,
+void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp,
                  const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st);
 void nnls_init();
 void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st);

@@ -17,6 +17,8 @@
 //     [element][lane] (bank-conflict free).  Slots are counting-sorted by s every round so that the lanes
 //     of a warp do similar work, and finished slots are compacted away (SIMT efficiency).
 //   * if G is numerically singular (dead factor) the group falls back to primal-only solves.
+#include <type_traits>
+
 #include "lgr_common.cuh"
 
 namespace lgr {
@@ -309,14 +311,51 @@ __device__ __forceinline__ bool nnls_round(const int k, const unsigned long long
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_nnls: persistent CTAs; a CTA takes "CTA tiles" (ct_cols columns of one group, so G / P are loaded once per
-// tile) and its warps pull 32-column warp tiles from a shared counter.  Inside a warp tile every lane owns one
-// column from load to store; the warp iterates pivot rounds until all its columns are done -- there is no
-// CTA-wide barrier inside a tile, so slow columns only delay their own warp.
+// k_nnls: persistent CTAs.  The columns of all groups form one flat range that is split evenly over the CTAs; a CTA
+// walks its range group by group (G / P are loaded once per group, so a CTA reloads them at most a few times).
+// Inside a group's chunk every LANE owns one column from load to store and claims the next column from a shared
+// counter as soon as its current one is solved ("lane refill"): there is no barrier of any kind between columns,
+// so a column that needs several pivot rounds delays nobody, and the warp stays full until the chunk runs dry.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int KP>
-__global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ groups, int ngroups, int total_tiles,
-                                                 int ct_cols, int k, int pool_elems, Counters* cnt, int flags) {
+__device__ __forceinline__ void load_row(const T* __restrict__ r, T* bcol, int k, int ld) {
+    if (ld == KP) {  // padded row, 16-byte aligned: vector loads
+        constexpr int VEC = 16 / sizeof(T);
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+        const V* rv = reinterpret_cast<const V*>(r);
+#pragma unroll
+        for (int i = 0; i < KP / VEC; ++i) {
+            const V v = rv[i];
+            const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) bcol[(i * VEC + j) * 33] = e[j];
+        }
+    } else {
+        for (int f = 0; f < KP; ++f) bcol[f * 33] = f < k ? r[f] : (T)0;
+    }
+}
+template <typename T, int KP>
+__device__ __forceinline__ void store_row(T* __restrict__ x, const T* bcol, int k, int ld) {
+    if (ld == KP) {
+        constexpr int VEC = 16 / sizeof(T);
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+        V* xv = reinterpret_cast<V*>(x);
+#pragma unroll
+        for (int i = 0; i < KP / VEC; ++i) {
+            V v;
+            T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) e[j] = bcol[(i * VEC + j) * 33];
+            xv[i] = v;
+        }
+    } else {
+        for (int f = 0; f < k; ++f) x[f] = bcol[f * 33];
+    }
+}
+
+template <typename T, int KP>
+__global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ groups, int ngroups, long long total_cols,
+                                                 int k, int pool_elems, Counters* cnt, int flags) {
     constexpr int MST = KP + 4;
     const int NW = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -329,7 +368,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
     T* uS = reinterpret_cast<T*>(wbase + L.u);
     T* pool = reinterpret_cast<T*>(wbase + L.pool);
     unsigned char* idxS = wbase + L.idx;           // [t][lane]
-    __shared__ int next_wt;
+    __shared__ int next_col;
 
     const bool cold_start = (flags & 1) != 0;
     const int hist_mode = (flags & 2) ? ((flags & 4) ? 2 : 1) : 0;
@@ -337,107 +376,118 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
     const unsigned long long kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
     const int MAXIT = 4 * k + 16;
     const int share = pool_elems / 32;  // pool elements per lane in the regular [e][lane] layout
+    T* bcol = bS + lane;
+    T* ucol = uS + lane;
 
+    // this CTA's slice of the flat column range
+    long long per = (total_cols + gridDim.x - 1) / gridDim.x;
+    per = (per + 31) & ~31LL;
+    long long pos = (long long)blockIdx.x * per;
+    const long long stop = pos + per < total_cols ? pos + per : total_cols;
     unsigned long long pivots_local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    while (pos < stop) {
         int g = 0;
-        while (g + 1 < ngroups && tile >= groups[g + 1].blk_off) ++g;
+        while (g + 1 < ngroups && pos >= groups[g + 1].col_off) ++g;
         const NnlsGroup grp = groups[g];
-        __syncthreads();  // every warp is done with the previous tile (G / P / counter may change)
+        const long long gend = grp.col_off + grp.ncols;
+        const int c0 = (int)(pos - grp.col_off);
+        const int ccols = (int)((stop < gend ? stop : gend) - pos);
+        pos += ccols;
+        __syncthreads();  // every warp is done with the previous chunk (G / P / counter change)
         const int dual_ok = no_dual ? 0 : *grp.ok;
         for (int e = tid; e < KP * KP; e += blockDim.x) {
             const int a = e / KP, b = e % KP;
             Gs[a * MST + b] = (T)grp.gram[e];
             Ps[a * MST + b] = (T)grp.ginv[e];
         }
-        if (tid == 0) next_wt = 0;
+        if (tid == 0) next_col = 0;
         __syncthreads();
-        const int tcol0 = (tile - grp.blk_off) * ct_cols;
-        const int tcols = min(ct_cols, grp.ncols - tcol0);
-        const int nwt = (tcols + 31) >> 5;
         const int ld = grp.ld;
+        const T* __restrict__ rhs = reinterpret_cast<const T*>(grp.rhs) + (size_t)c0 * ld;
+        T* __restrict__ xout = reinterpret_cast<T*>(grp.x) + (size_t)c0 * ld;
+        unsigned long long* __restrict__ masks = grp.mask + c0;
+
+        bool active = false, exhausted = false;
+        int col = 0;
+        unsigned long long F = 0ull;
+        int state = 0;
+        T tol = (T)0;
         for (;;) {
-            int wt = 0;
-            if (lane == 0) wt = atomicAdd(&next_wt, 1);
-            wt = __shfl_sync(0xffffffffu, wt, 0);
-            if (wt >= nwt) break;
-            const int col0 = tcol0 + wt * 32;
-            const int ncol = min(32, tcol0 + tcols - col0);
-            const T* __restrict__ rhs = reinterpret_cast<const T*>(grp.rhs) + (size_t)col0 * ld;
-            T* __restrict__ xout = reinterpret_cast<T*>(grp.x) + (size_t)col0 * ld;
-            // coalesced load of the 32-column rhs tile, transposed into bS[f][column]
-            for (int e = lane; e < ncol * KP; e += 32) {
-                const int j = e / KP, f = e % KP;
-                bS[f * 33 + j] = (f < k) ? rhs[(size_t)j * ld + f] : (T)0;
-            }
-            __syncwarp();
-            const bool valid = lane < ncol;
-            unsigned long long F = 0ull;
-            int state = 3 | ((k + 1) << 8);
-            T tol = (T)0;
-            T* bcol = bS + lane;
-            T* ucol = uS + lane;
-            if (valid) {
-                if (!cold_start) F = grp.mask[col0 + lane] & kmask;
-                T bm = (T)0;
+            // ---- refill: idle lanes claim the next columns of the chunk ----
+            const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
+            if (want) {
+                const int leader = __ffs((int)want) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&next_col, __popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!active && !exhausted) {
+                    const int c = base + __popc(want & ((1u << lane) - 1u));
+                    if (c >= ccols) {
+                        exhausted = true;
+                    } else {
+                        col = c;
+                        load_row<T, KP>(rhs + (size_t)c * ld, bcol, k, ld);
+                        F = cold_start ? 0ull : (masks[c] & kmask);
+                        state = 3 | ((k + 1) << 8);
+                        T bm = (T)0;
 #pragma unroll
-                for (int f = 0; f < KP; ++f) bm = fmax(bm, fabs(bcol[f * 33]));
-                tol = bm * Eps<T>::v() * (T)8;
-                if (dual_ok) {  // u = P b : register accumulators, broadcast shared-memory reads of P
-                    T acc[KP];
+                        for (int f = 0; f < KP; ++f) bm = fmax(bm, fabs(bcol[f * 33]));
+                        tol = bm * Eps<T>::v() * (T)8;
+                        if (dual_ok) {  // u = P b : register accumulators, broadcast shared-memory reads of P
+                            T acc[KP];
 #pragma unroll
-                    for (int f = 0; f < KP; ++f) acc[f] = (T)0;
-                    for (int t = 0; t < k; ++t) {
-                        const T bt = bcol[t * 33];
-                        const T* Pt = Ps + t * MST;
+                            for (int f = 0; f < KP; ++f) acc[f] = (T)0;
+                            for (int t = 0; t < k; ++t) {
+                                const T bt = bcol[t * 33];
+                                const T* Pt = Ps + t * MST;
 #pragma unroll
-                        for (int f = 0; f < KP; ++f) acc[f] = fma(Pt[f], bt, acc[f]);
+                                for (int f = 0; f < KP; ++f) acc[f] = fma(Pt[f], bt, acc[f]);
+                            }
+#pragma unroll
+                            for (int f = 0; f < KP; ++f) ucol[f * 33] = acc[f];
+                        }
+                        active = true;
                     }
-#pragma unroll
-                    for (int f = 0; f < KP; ++f) ucol[f * 33] = acc[f];
                 }
             }
-            bool active = valid;
-            while (__any_sync(0xffffffffu, active)) {
-                int need = 0;
-                if (active) {
-                    const int p = __popcll(F);
-                    const int s = (dual_ok && (k - p) < p) ? (k - p) : p;
-                    need = s * (s + 1) / 2 + s;
-                }
-                const bool regular = active && need <= share;
-                if (regular)
-                    active = nnls_round<T, KP>(k, kmask, dual_ok, MAXIT, Gs, Ps, bcol, ucol, idxS + lane, pool + lane, 32,
-                                               F, state, tol, cnt, pivots_local, hist_mode);
-                // columns whose factor does not fit the per-lane share (only without the dual side, or k > 32):
-                // a few lanes at a time over the whole warp pool
-                unsigned big = __ballot_sync(0xffffffffu, active && !regular && need > share);
-                while (big) {
-                    __syncwarp();
-                    int maxneed = need;
-                    if (!((big >> lane) & 1u)) maxneed = 0;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) maxneed = max(maxneed, __shfl_xor_sync(0xffffffffu, maxneed, off));
-                    int fit = pool_elems / maxneed;
-                    if (fit < 1) fit = 1;
-                    if (fit > 32) fit = 32;
-                    const int rank = __popc(big & ((1u << lane) - 1u));
-                    const bool mine = ((big >> lane) & 1u) && rank < fit;
-                    if (mine)
-                        active = nnls_round<T, KP>(k, kmask, dual_ok, MAXIT, Gs, Ps, bcol, ucol, idxS + lane, pool + rank,
-                                                   fit, F, state, tol, cnt, pivots_local, hist_mode);
-                    big &= ~__ballot_sync(0xffffffffu, mine);
-                }
+            if (!__any_sync(0xffffffffu, active)) break;
+            // ---- one pivot round for every active lane ----
+            int need = 0;
+            if (active) {
+                const int p = __popcll(F);
+                const int s = (dual_ok && (k - p) < p) ? (k - p) : p;
+                need = s * (s + 1) / 2 + s;
+            }
+            bool still = active;
+            const bool regular = active && need <= share;
+            if (regular)
+                still = nnls_round<T, KP>(k, kmask, dual_ok, MAXIT, Gs, Ps, bcol, ucol, idxS + lane, pool + lane, 32, F, state,
+                                          tol, cnt, pivots_local, hist_mode);
+            // columns whose factor does not fit the per-lane share (only without the dual side, or k > 32):
+            // a few lanes at a time over the whole warp pool
+            unsigned big = __ballot_sync(0xffffffffu, active && !regular);
+            while (big) {
                 __syncwarp();
+                int maxneed = ((big >> lane) & 1u) ? need : 0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) maxneed = max(maxneed, __shfl_xor_sync(0xffffffffu, maxneed, off));
+                int fit = pool_elems / maxneed;
+                if (fit < 1) fit = 1;
+                if (fit > 32) fit = 32;
+                const int rank = __popc(big & ((1u << lane) - 1u));
+                const bool mine = ((big >> lane) & 1u) && rank < fit;
+                if (mine)
+                    still = nnls_round<T, KP>(k, kmask, dual_ok, MAXIT, Gs, Ps, bcol, ucol, idxS + lane, pool + rank, fit, F,
+                                              state, tol, cnt, pivots_local, hist_mode);
+                big &= ~__ballot_sync(0xffffffffu, mine);
             }
-            // coalesced store of the solution tile + passive sets
             __syncwarp();
-            for (int e = lane; e < ncol * KP; e += 32) {
-                const int j = e / KP, f = e % KP;
-                if (f < k) xout[(size_t)j * ld + f] = bS[f * 33 + j];
+            // ---- solved columns leave: the lane writes its own row (full 128-byte lines) and its passive set ----
+            if (active && !still) {
+                store_row<T, KP>(xout + (size_t)col * ld, bcol, k, ld);
+                masks[col] = F;
             }
-            if (valid) grp.mask[col0 + lane] = F;
-            __syncwarp();
+            active = still;
         }
     }
     if (pivots_local) atomicAdd(&cnt->nnls_pivots, pivots_local);
@@ -472,28 +522,21 @@ NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms) {
     return c;
 }
 
-int nnls_tile_cols(const NnlsConfig& cfg, long long total_cols, int num_sms) {
-    // columns per CTA tile: large enough to amortise the G / P load, small enough to fill the machine
-    int ct = cfg.ct_cols;
-    while (ct > cfg.threads && total_cols / ct < 2LL * num_sms) ct >>= 1;
-    if (ct < cfg.threads) ct = cfg.threads;
-    return ct;
-}
-
-void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, int total_tiles, int ct_cols, int k, int kp,
+void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp,
                  const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st) {
-    if (total_tiles <= 0) return;
-    const int grid = total_tiles < cfg.grid_cap ? total_tiles : cfg.grid_cap;
+    if (total_cols <= 0) return;
+    long long want = (total_cols + cfg.threads - 1) / cfg.threads;   // at least one column per lane
+    const int grid = (int)(want < cfg.grid_cap ? want : cfg.grid_cap);
     if (is_double) {
         if (kp == 32)
-            k_nnls<double, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<double, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
         else
-            k_nnls<double, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<double, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
     } else {
         if (kp == 32)
-            k_nnls<float, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<float, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
         else
-            k_nnls<float, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_tiles, ct_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<float, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
     }
     LGR_CUDA(cudaGetLastError());
 }
