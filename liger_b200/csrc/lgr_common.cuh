@@ -154,7 +154,8 @@ struct NnlsConfig {
     int pool_elems;   // per-warp shared-memory pool for the per-column Cholesky factors
     size_t smem;
     int grid_cap;     // persistent grid size
-    int ct_cols;      // default columns per CTA tile
+    int ct_cols;      // (unused)
+    int ctas_per_sm;
 };
 NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
 

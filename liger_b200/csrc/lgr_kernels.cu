@@ -140,70 +140,88 @@ void launch_spmm_ltx_gather(const DsDev* ds, int nds, int total_blocks, int kp, 
 //   CtBv_i[g][:] = R_i[g][:] - G_i W[g][:]  (g < m),  R_i[g][:]  (unshared rows)      R/cINMF.R:488
 //   CtBw[g][:]   = sum_i ( R_i[g][:] - G_i V_i[g][:] ),  Gsum = sum_i G_i               R/cINMF.R:497-499
 // ------------------------------------------------------------------------------------------------
+// One CTA = RHS_ROWS feature rows x KP factors; G_i and the W / V_i rows are staged in shared memory.
+constexpr int RHS_ROWS = 8;
+
 template <int KP>
-__global__ void k_vrhs(const DsDev* __restrict__ ds, const double* __restrict__ W, int k) {
+__global__ void __launch_bounds__(RHS_ROWS* KP) k_vrhs(const DsDev* __restrict__ ds, const double* __restrict__ W, int k) {
     const DsDev& D = ds[blockIdx.y];
-    __shared__ double Gs[KP * KP];
-    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) Gs[e] = D.G[e];
+    __shared__ double Gs[KP][KP + 1];
+    __shared__ double Ws[RHS_ROWS][KP];
+    const int r0 = blockIdx.x * RHS_ROWS;
+    if (r0 >= D.rows) return;
+    const int f = threadIdx.x % KP, rl = threadIdx.x / KP, g = r0 + rl;
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) Gs[e / KP][e % KP] = D.G[e];
+    Ws[rl][f] = (g < D.m) ? W[(size_t)g * KP + f] : 0.0;
     __syncthreads();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = idx / KP, f = idx % KP;
     if (g >= D.rows) return;
     double v = 0.0;
     if (f < k) {
-        v = (double)D.R[(size_t)g * KP + f];
-        if (g < D.m) {
-            const double* w = W + (size_t)g * KP;
-            double acc = 0.0;
-            for (int f2 = 0; f2 < k; ++f2) acc = fma(Gs[f * KP + f2], w[f2], acc);
-            v -= acc;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int f2 = 0;
+        for (; f2 + 3 < k; f2 += 4) {
+            a0 = fma(Gs[f][f2], Ws[rl][f2], a0);
+            a1 = fma(Gs[f][f2 + 1], Ws[rl][f2 + 1], a1);
+            a2 = fma(Gs[f][f2 + 2], Ws[rl][f2 + 2], a2);
+            a3 = fma(Gs[f][f2 + 3], Ws[rl][f2 + 3], a3);
         }
+        for (; f2 < k; ++f2) a0 = fma(Gs[f][f2], Ws[rl][f2], a0);
+        v = (double)D.R[(size_t)g * KP + f] - ((a0 + a1) + (a2 + a3));
     }
     D.CtBv[(size_t)g * KP + f] = v;
 }
 
 void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st) {
-    dim3 grid((unsigned)(((size_t)max_rows * kp + 255) / 256), (unsigned)nds);
+    dim3 grid((unsigned)((max_rows + RHS_ROWS - 1) / RHS_ROWS), (unsigned)nds);
     if (kp == 32)
-        k_vrhs<32><<<grid, 256, 0, st>>>(ds, W, k);
+        k_vrhs<32><<<grid, RHS_ROWS * 32, 0, st>>>(ds, W, k);
     else
-        k_vrhs<64><<<grid, 256, 0, st>>>(ds, W, k);
+        k_vrhs<64><<<grid, RHS_ROWS * 64, 0, st>>>(ds, W, k);
     LGR_CUDA(cudaGetLastError());
 }
 
 template <int KP>
-__global__ void k_wrhs(const DsDev* __restrict__ ds, int nds, int m, double* __restrict__ CtBw, double* __restrict__ Gsum,
-                       int k) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0) {
-        for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
-            double s = 0.0;
-            for (int i = 0; i < nds; ++i) s += ds[i].G[e];
-            Gsum[e] = s;
-        }
-    }
-    const int g = idx / KP, f = idx % KP;
-    if (g >= m) return;
+__global__ void __launch_bounds__(RHS_ROWS* KP) k_wrhs(const DsDev* __restrict__ ds, int nds, int m, double* __restrict__ CtBw,
+                                                       double* __restrict__ Gsum, int k) {
+    __shared__ double Gs[KP][KP + 1];
+    __shared__ double Vs[RHS_ROWS][KP];
+    const int r0 = blockIdx.x * RHS_ROWS;
+    const int f = threadIdx.x % KP, rl = threadIdx.x / KP, g = r0 + rl;
     double v = 0.0;
-    if (f < k) {
-        for (int i = 0; i < nds; ++i) {
-            const DsDev& D = ds[i];
-            const double* vi = D.V + (size_t)g * KP;
-            const double* Gi = D.G + (size_t)f * KP;
-            double acc = 0.0;
-            for (int f2 = 0; f2 < k; ++f2) acc = fma(Gi[f2], vi[f2], acc);
-            v += (double)D.R[(size_t)g * KP + f] - acc;
+    for (int i = 0; i < nds; ++i) {
+        const DsDev& D = ds[i];
+        __syncthreads();
+        for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) Gs[e / KP][e % KP] = D.G[e];
+        Vs[rl][f] = (g < m) ? D.V[(size_t)g * KP + f] : 0.0;
+        __syncthreads();
+        if (g < m && f < k) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int f2 = 0;
+            for (; f2 + 3 < k; f2 += 4) {
+                a0 = fma(Gs[f][f2], Vs[rl][f2], a0);
+                a1 = fma(Gs[f][f2 + 1], Vs[rl][f2 + 1], a1);
+                a2 = fma(Gs[f][f2 + 2], Vs[rl][f2 + 2], a2);
+                a3 = fma(Gs[f][f2 + 3], Vs[rl][f2 + 3], a3);
+            }
+            for (; f2 < k; ++f2) a0 = fma(Gs[f][f2], Vs[rl][f2], a0);
+            v += (double)D.R[(size_t)g * KP + f] - ((a0 + a1) + (a2 + a3));
+        }
+        if (blockIdx.x == 0) {  // Gsum = sum_i G_i (accumulated by block 0 while it walks the datasets)
+            for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+                const double prev = (i == 0) ? 0.0 : Gsum[e];
+                Gsum[e] = prev + Gs[e / KP][e % KP];
+            }
         }
     }
-    CtBw[(size_t)g * KP + f] = v;
+    if (g < m) CtBw[(size_t)g * KP + f] = (f < k) ? v : 0.0;
 }
 
 void launch_wrhs(const DsDev* ds, int nds, int m, double* CtBw, double* Gsum, int k, int kp, cudaStream_t st) {
-    const unsigned grid = (unsigned)(((size_t)m * kp + 255) / 256);
+    const unsigned grid = (unsigned)((m + RHS_ROWS - 1) / RHS_ROWS);
     if (kp == 32)
-        k_wrhs<32><<<grid, 256, 0, st>>>(ds, nds, m, CtBw, Gsum, k);
+        k_wrhs<32><<<grid, RHS_ROWS * 32, 0, st>>>(ds, nds, m, CtBw, Gsum, k);
     else
-        k_wrhs<64><<<grid, 256, 0, st>>>(ds, nds, m, CtBw, Gsum, k);
+        k_wrhs<64><<<grid, RHS_ROWS * 64, 0, st>>>(ds, nds, m, CtBw, Gsum, k);
     LGR_CUDA(cudaGetLastError());
 }
 

@@ -41,13 +41,13 @@ __device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
 // pivoting), ok = 0 when a pivot collapses (then the NNLS kernel uses primal solves only).
 // ------------------------------------------------------------------------------------------------
 template <int KP>
-__global__ void __launch_bounds__(128) k_gram_inv(const GramSpec* __restrict__ specs, int k) {
+__global__ void __launch_bounds__(1024) k_gram_inv(const GramSpec* __restrict__ specs, int k) {
     const GramSpec sp = specs[blockIdx.x];
     __shared__ double M[KP][KP + 1];
     __shared__ double colbuf[KP];
-    __shared__ double piv_s;
     __shared__ int ok_s;
     const int tid = threadIdx.x;
+    constexpr int EPT = KP * KP / 1024 > 0 ? KP * KP / 1024 : 1;  // elements per thread (1 for KP=32, 4 for KP=64)
     for (int e = tid; e < KP * KP; e += blockDim.x) {
         const int a = e / KP, b = e % KP;
         double v = 0.0;
@@ -62,27 +62,29 @@ __global__ void __launch_bounds__(128) k_gram_inv(const GramSpec* __restrict__ s
     __syncthreads();
     double maxdiag = 0.0;
     for (int a = 0; a < k; ++a) maxdiag = fmax(maxdiag, M[a][a]);
-    __syncthreads();
     for (int c = 0; c < k; ++c) {  // in-place Gauss-Jordan, SPD => no pivoting
-        if (tid == 0) {
-            const double p = M[c][c];
-            if (!(p > 1e-11 * maxdiag)) ok_s = 0;
-            piv_s = p;
-        }
-        for (int r = tid; r < k; r += blockDim.x) colbuf[r] = M[r][c];
         __syncthreads();
-        if (!ok_s) break;
-        const double ip = 1.0 / piv_s;
-        for (int col = tid; col < k; col += blockDim.x) M[c][col] = (col == c) ? ip : M[c][col] * ip;
-        __syncthreads();
-        for (int e = tid; e < k * k; e += blockDim.x) {
-            const int r = e / k, col = e % k;
-            if (r == c) continue;
-            const double base = (col == c) ? 0.0 : M[r][col];
-            M[r][col] = base - colbuf[r] * M[c][col];
+        const double piv = M[c][c];
+        if (tid < KP) colbuf[tid] = M[tid][c];
+        if (!(piv > 1e-11 * maxdiag)) {
+            if (tid == 0) ok_s = 0;
+            break;   // uniform: every thread reads the same pivot
         }
         __syncthreads();
+        const double ip = 1.0 / piv;
+        if (tid < KP) M[c][tid] = (tid == c) ? ip : M[c][tid] * ip;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int e = tid + j * 1024;
+            const int r = e / KP, col = e % KP;
+            if (r != c && r < k && col < k) {
+                const double base = (col == c) ? 0.0 : M[r][col];
+                M[r][col] = base - colbuf[r] * M[c][col];
+            }
+        }
     }
+    __syncthreads();
     const int ok = ok_s;
     for (int e = tid; e < KP * KP; e += blockDim.x) {
         const int a = e / KP, b = e % KP;
@@ -96,9 +98,9 @@ __global__ void __launch_bounds__(128) k_gram_inv(const GramSpec* __restrict__ s
 void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStream_t st) {
     if (nspecs <= 0) return;
     if (kp == 32)
-        k_gram_inv<32><<<nspecs, 128, 0, st>>>(specs, k);
+        k_gram_inv<32><<<nspecs, 1024, 0, st>>>(specs, k);
     else
-        k_gram_inv<64><<<nspecs, 128, 0, st>>>(specs, k);
+        k_gram_inv<64><<<nspecs, 1024, 0, st>>>(specs, k);
     LGR_CUDA(cudaGetLastError());
 }
 
@@ -518,6 +520,7 @@ NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms) {
     if (per_sm < 1) per_sm = 1;
     if (per_sm * c.threads > 512) per_sm = 512 / c.threads > 0 ? 512 / c.threads : 1;   // register budget
     c.grid_cap = num_sms * per_sm;
+    c.ctas_per_sm = per_sm;
     c.ct_cols = 1024;
     return c;
 }
@@ -525,18 +528,24 @@ NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms) {
 void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp,
                  const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st) {
     if (total_cols <= 0) return;
-    long long want = (total_cols + cfg.threads - 1) / cfg.threads;   // at least one column per lane
+    // small launches (the V_i / W solves): fewer warps per CTA so that the columns spread over all SMs
+    const int num_sms = cfg.grid_cap / (cfg.ctas_per_sm > 0 ? cfg.ctas_per_sm : 1);
+    int nw = cfg.threads / 32;
+    while (nw > 1 && total_cols < (long long)num_sms * nw * 32) nw >>= 1;
+    const int threads = nw * 32;
+    const size_t smem = nnls_layout(kp, nw, cfg.pool_elems, is_double ? 8 : 4).total;
+    long long want = (total_cols + threads - 1) / threads;   // at least one column per lane
     const int grid = (int)(want < cfg.grid_cap ? want : cfg.grid_cap);
     if (is_double) {
         if (kp == 32)
-            k_nnls<double, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<double, 32><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
         else
-            k_nnls<double, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<double, 64><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
     } else {
         if (kp == 32)
-            k_nnls<float, 32><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<float, 32><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
         else
-            k_nnls<float, 64><<<grid, cfg.threads, cfg.smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
+            k_nnls<float, 64><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);
     }
     LGR_CUDA(cudaGetLastError());
 }
