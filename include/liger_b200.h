@@ -162,6 +162,9 @@ LGR_API const char* lgr_last_error(void);
 LGR_API int lgr_device_count(void);
 LGR_API int lgr_version(void);                      /* major * 1000 + minor */
 LGR_API int lgr_nccl_unique_id(void* out128);       /* rank 0 calls this and ships the 128 bytes to the others */
+/* page-locked host memory for callers that want full-speed PCIe copies of their inputs / outputs (optional) */
+LGR_API void* lgr_host_alloc(size_t bytes);
+LGR_API void lgr_host_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -59,7 +59,8 @@ EXPORTS = [
     "lgr_inmf", "lgr_uinmf", "lgr_bppnnls_prod", "lgr_objerr_i", "lgr_ctx_create", "lgr_ctx_reset",
     "lgr_ctx_iterate", "lgr_ctx_objective", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
     "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
-    "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id",
+    "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id", "lgr_host_alloc",
+    "lgr_host_free",
 ]
 
 
@@ -98,6 +99,10 @@ def lib():
     L.lgr_r_free.argtypes = [C.c_void_p]
     L.lgr_r_free.restype = None
     L.lgr_nccl_unique_id.argtypes = [C.c_void_p]
+    L.lgr_host_alloc.argtypes = [C.c_size_t]
+    L.lgr_host_alloc.restype = C.c_void_p
+    L.lgr_host_free.argtypes = [C.c_void_p]
+    L.lgr_host_free.restype = None
     _lib = L
     return L
 

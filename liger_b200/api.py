@@ -30,6 +30,44 @@ def _dp(a):
     return a.ctypes.data_as(c_double_p)
 
 
+class _Pinned:
+    """Owner of one page-locked host allocation (lgr_host_alloc); numpy arrays are views of it.  Freed blocks go
+    back to a small cache (cudaHostAlloc costs ~0.4 ms per MB), mirroring the library's device memory pool."""
+    _cache = {}
+    _cached_bytes = 0
+    _CACHE_LIMIT = 4 << 30
+
+    def __init__(self, nbytes):
+        self.nbytes = max(int(nbytes), 1)
+        free = _Pinned._cache.get(self.nbytes)
+        if free:
+            self.ptr = free.pop()
+            _Pinned._cached_bytes -= self.nbytes
+        else:
+            self.ptr = _ffi.lib().lgr_host_alloc(self.nbytes)
+            if not self.ptr:
+                raise MemoryError("lgr_host_alloc failed")
+
+    def __del__(self):
+        try:
+            if _Pinned._cached_bytes + self.nbytes <= _Pinned._CACHE_LIMIT:
+                _Pinned._cache.setdefault(self.nbytes, []).append(self.ptr)
+                _Pinned._cached_bytes += self.nbytes
+            else:
+                _ffi.lib().lgr_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """Fortran-ordered array in page-locked host memory (full-speed D2H for the outputs); NOT zero-initialised."""
+    n = int(np.prod(shape))
+    own = _Pinned(n * np.dtype(dtype).itemsize)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(own.ptr)
+    buf._lgr_owner = own        # the ctypes buffer (base of the array) keeps the allocation alive
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order="F")
+
+
 class _Csc:
     """Keeps the numpy buffers of one dgCMatrix-like input alive and exposes an lgr_csc view."""
 
@@ -120,11 +158,14 @@ class _Args:
 
 
 class _Out:
-    def __init__(self, args, want_passive=False, traj=False):
+    def __init__(self, args, want_passive=False, traj=False, pinned=False):
         d, k, m = args.d, args.k, args.m
         self.W = np.zeros((m, k), order="F")
         self.V = [np.zeros((m, k), order="F") for _ in range(d)]
-        self.H = [np.zeros((n, k), order="F") for n in args.n]
+        if pinned:
+            self.H = [pinned_empty((n, k)) for n in args.n]     # every entry is written by the library
+        else:
+            self.H = [np.zeros((n, k), order="F") for n in args.n]
         self.U = [np.zeros((u, k), order="F") if u > 0 else None for u in args.u]
         self.Varr = (c_double_p * d)(*[_dp(v) for v in self.V])
         self.Harr = (c_double_p * d)(*[_dp(h) for h in self.H])
@@ -151,7 +192,7 @@ class _Out:
 
 
 def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
-         trajectory=False, device=-1, return_passive=False, cold_start=False):
+         trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False):
     """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
 
     objectList: list of scipy CSC matrices (genes x cells; the `scaleData` of each dataset).
@@ -165,7 +206,7 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
                          "use liger_b200.integration.run_inmf_list for the seeded initialisation)")
     flags = (_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0)
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device)
-    o = _Out(a, want_passive=return_passive, traj=trajectory)
+    o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs)
     _ffi.check(_ffi.lib().lgr_inmf(C.byref(a.struct), C.byref(o.struct)))
     res = {"H": o.H, "V": o.V, "W": o.W, "objErr": float(o.struct.objErr), "timings": o.timings()}
     if trajectory:

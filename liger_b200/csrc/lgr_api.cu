@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <mutex>
 
@@ -16,6 +17,10 @@ namespace lgr {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+cudaStream_t& alloc_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
 
 namespace {
 
@@ -87,7 +92,19 @@ struct Dataset {
 
 using namespace lgr;
 
+// declared first in lgr_ctx => destroyed last, after every stream-ordered buffer has been freed on it
+struct StreamHolder {
+    cudaStream_t s = nullptr;
+    ~StreamHolder() {
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
+    }
+};
+
 struct lgr_ctx {
+    StreamHolder stream_holder;
     int d = 0, k = 0, kp = 32, m = 0, device = 0, rank = 0, world = 1, tc = 1024, cb = 512, gt = 1024, num_sms = 148;
     uint32_t flags = 0;
     cudaStream_t st = nullptr;
@@ -119,11 +136,23 @@ struct lgr_ctx {
         if (ev1) cudaEventDestroy(ev1);
         if (evA) cudaEventDestroy(evA);
         if (evB) cudaEventDestroy(evB);
-        if (st) cudaStreamDestroy(st);
     }
 };
 
 namespace {
+
+// wall-clock trace of the host-side phases (LGR_TRACE=1)
+struct Trace {
+    bool on = getenv("LGR_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lgr trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 struct Timed {
     lgr_ctx* c;
@@ -357,6 +386,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     LGR_REQUIRE(a->E && a->lambda, "E and lambda are required");
     LGR_REQUIRE(a->niter >= 0, "niter must be >= 0");
     LGR_REQUIRE(a->world >= 1 && a->rank >= 0 && a->rank < a->world, "bad rank/world");
+    Trace tr;
     std::unique_ptr<lgr_ctx> c(new lgr_ctx);
     c->d = a->d;
     c->k = a->k;
@@ -376,6 +406,15 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     static std::once_flag once;
     std::call_once(once, [] { kernels_init(); });
     LGR_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    c->stream_holder.s = c->st;
+    AllocStreamScope alloc_scope(c->st);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;  // keep freed blocks cached for the next call
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     LGR_CUDA(cudaEventCreate(&c->ev0));
     LGR_CUDA(cudaEventCreate(&c->ev1));
     LGR_CUDA(cudaEventCreate(&c->evA));
@@ -431,8 +470,10 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         }
         D.rows = m + D.u;
         max_rows = std::max(max_rows, D.rows);
+        if (i == 0) tr.mark("ctx setup");
         if (!P) {
             upload_csc(E, D.c0, c1, D.colptr, D.rowidx, D.val, D.nnz, c->st);
+            tr.mark("upload_csc");
         } else {
             DBuf<int> pE, iE, pP, iP;
             DBuf<float> vE, vP;
@@ -450,8 +491,10 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         (void)ntiles;
         // the two padded tile formats of X (lgr_spmm.cu); the plain CSC upload is dropped afterwards
         dev_build_padded(1, D.n, D.rows, c->tc, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.tval, c->st);
+        tr.mark("build cell-tiled CSR");
         D.ngt = (D.rows + c->gt - 1) / c->gt;
         dev_build_padded(0, D.n, D.rows, c->gt, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.cval, c->st);
+        tr.mark("build gene-tiled CSC");
         dev_sumsq(D.val.p, D.nnz, c->sq.p + i, c->st);
         LGR_CUDA(cudaStreamSynchronize(c->st));
         D.colptr.release();
@@ -572,7 +615,9 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     LGR_CUDA(cudaMemcpyAsync(c->grpW.p, gW.data(), sizeof(NnlsGroup), cudaMemcpyHostToDevice, c->st));
     LGR_CUDA(cudaStreamSynchronize(c->st));
 
+    tr.mark("tables + allocs");
     set_inits(c.get(), a->Winit, a->Vinit, a->Uinit);
+    tr.mark("set_inits");
     if (a->Hinit) {
         for (int i = 0; i < c->d; ++i) {
             Dataset& D = c->ds[i];
@@ -599,6 +644,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
 }
 
 void download(lgr_ctx* c, lgr_inmf_out* o) {
+    Trace tr;
     cudaEvent_t u0, u1;
     LGR_CUDA(cudaEventCreate(&u0));
     LGR_CUDA(cudaEventCreate(&u1));
@@ -624,6 +670,7 @@ void download(lgr_ctx* c, lgr_inmf_out* o) {
             LGR_CUDA(cudaMemcpyAsync(o->U[i], tmp.p, (size_t)D.u * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
             LGR_CUDA(cudaStreamSynchronize(c->st));
         }
+        if (i == 0) tr.mark("download W,V");
         if (o->H && o->H[i] && D.n > 0) {
             DBuf<double> tmp((size_t)D.n * k);
             dev_hpad_to_colmajor(D.H.p, tmp.p, D.n, k, kp, c->st);
@@ -638,6 +685,7 @@ void download(lgr_ctx* c, lgr_inmf_out* o) {
             LGR_CUDA(cudaStreamSynchronize(c->st));
         }
     }
+    tr.mark("download rest (H)");
     LGR_CUDA(cudaEventRecord(u1, c->st));
     LGR_CUDA(cudaStreamSynchronize(c->st));
     float ms = 0.f;
@@ -680,6 +728,7 @@ int run_oneshot(const lgr_inmf_args* args, lgr_inmf_out* out, bool need_unshared
         lgr_ctx* raw = nullptr;
         create(args, &raw);
         std::unique_ptr<lgr_ctx> c(raw);
+        AllocStreamScope alloc_scope(c->st);
         iterate(c.get(), args->niter, (args->flags & LGR_FLAG_TRAJECTORY) ? out->obj_traj : nullptr);
         out->objErr = objective(c.get());
         download(c.get(), out);
@@ -723,6 +772,7 @@ int lgr_ctx_reset(lgr_ctx* c, const double* Winit, const double* const* Vinit, c
     return guarded([&] {
         LGR_REQUIRE(c, "null ctx");
         LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
         set_inits(c, Winit, Vinit, Uinit);
     });
 }
@@ -730,6 +780,7 @@ int lgr_ctx_iterate(lgr_ctx* c, int32_t niter, double* obj_traj) {
     return guarded([&] {
         LGR_REQUIRE(c && niter >= 0, "bad argument");
         LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
         iterate(c, niter, obj_traj);
     });
 }
@@ -737,6 +788,7 @@ int lgr_ctx_objective(lgr_ctx* c, double* obj) {
     return guarded([&] {
         LGR_REQUIRE(c && obj, "bad argument");
         LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
         *obj = objective(c);
     });
 }
@@ -744,6 +796,7 @@ int lgr_ctx_download(lgr_ctx* c, lgr_inmf_out* out) {
     return guarded([&] {
         LGR_REQUIRE(c && out, "bad argument");
         LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
         download(c, out);
     });
 }
@@ -779,6 +832,20 @@ void lgr_ctx_destroy(lgr_ctx* c) {
     delete c;
 }
 
+void* lgr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 1;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+void lgr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* CtB, double* X, int32_t device) {
     return guarded([&] {
         check_device();
@@ -796,6 +863,7 @@ int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* 
         const int kp = k <= 32 ? 32 : 64;
         cudaStream_t st;
         LGR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        AllocStreamScope alloc_scope(st);
         try {
             DBuf<double> dG((size_t)k * k), dGp((size_t)kp * kp), dB((size_t)k * ncols), dX((size_t)k * ncols);
             DBuf<unsigned long long> mask((size_t)ncols);
@@ -853,6 +921,7 @@ int lgr_objerr_i(int32_t k, const double* H, const double* W, const double* V, c
         lgr_ctx* raw = nullptr;
         create(&a, &raw);
         std::unique_ptr<lgr_ctx> c(raw);
+        AllocStreamScope alloc_scope(c->st);
         *err = objective(c.get());
     });
 }

@@ -35,33 +35,45 @@ void set_last_error(const std::string& msg);
         if (!(cond)) throw ::lgr::Error(LGR_ERR_INVALID, std::string(msg)); \
     } while (0)
 
+// Stream the RAII buffers below allocate / free on (stream-ordered allocation from the device's default memory
+// pool: no device-wide synchronisation, and the pool keeps freed blocks for the next call).
+cudaStream_t& alloc_stream();
+struct AllocStreamScope {
+    cudaStream_t prev;
+    explicit AllocStreamScope(cudaStream_t s) : prev(alloc_stream()) { alloc_stream() = s; }
+    ~AllocStreamScope() { alloc_stream() = prev; }
+};
+
 // RAII device buffer
 template <typename T>
 struct DBuf {
     T* p = nullptr;
     size_t n = 0;
+    cudaStream_t st = nullptr;
     DBuf() {}
     explicit DBuf(size_t n_) { alloc(n_); }
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
-    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
     DBuf& operator=(DBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
         return *this;
     }
     void alloc(size_t n_) {
         release();
         n = n_;
         if (n) {
-            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+            st = alloc_stream();
+            cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), st);
             if (e != cudaSuccess) {
                 p = nullptr; n = 0;
-                throw Error(LGR_ERR_ALLOC, std::string("cudaMalloc of ") + std::to_string(n_ * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
+                cudaGetLastError();
+                throw Error(LGR_ERR_ALLOC, std::string("cudaMallocAsync of ") + std::to_string(n_ * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
             }
         }
     }
-    void zero(cudaStream_t st) { if (n) LGR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void zero(cudaStream_t s) { if (n) LGR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; n = 0; }
     ~DBuf() { release(); }
 };
 

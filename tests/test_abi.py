@@ -18,7 +18,7 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     from liger_b200 import _ffi
     syms = _declared_symbols()
-    assert len(syms) >= 20
+    assert len(syms) >= 22
     assert sorted(_ffi.EXPORTS) == syms
     lib = ctypes.CDLL(_ffi.LIB_PATH)
     for s in syms:
