@@ -29,6 +29,7 @@ CONFIGS = {
     "C3": dict(d=8, n_per=125000, m=2000, k=30, density=0.05),     # BASELINE.json configs[2], the metric's config
     "C3s": dict(d=8, n_per=12500, m=2000, k=30, density=0.05),     # 1/10 sample (cpu legs, smoke runs)
     "C4": dict(d=16, n_per=250000, m=3000, k=50, density=0.05),    # configs[3] (8-GPU shape; per-GPU shard = 1/8)
+    "C4s": dict(d=16, n_per=31250, m=3000, k=50, density=0.05),    # one GPU's 1/8 cell shard of C4
     "tiny": dict(d=2, n_per=3000, m=500, k=20, density=0.05),
 }
 LAMBDA = 5.0
@@ -102,6 +103,24 @@ class ClockSampler:
                     pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
+    of this same command (profiles/r*_traffic.json, written by scripts/make_profiles.py); None if not captured."""
+    import glob
+    alias = {"k_nnls_H": "k_nnls<float", "k_spmm_ltx": "k_spmm_ltx_tiled", "k_spmm_xh": "k_spmm_xh"}
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files or kernel not in alias:
+        return None
+    try:
+        t = json.load(open(files[-1]))
+        for name, v in t.items():
+            if name.startswith(alias[kernel]):
+                return float(v)
+    except Exception:
+        pass
+    return None
 
 
 def algorithmic_bytes(cfg, nnz_total, n_total):
@@ -262,7 +281,8 @@ def main():
         bytes_launch = ab.get(dom)
         ach = (bytes_launch / (per_launch_ms * 1e-3) / 1e9) if bytes_launch else None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (ach / hbm_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / hbm_peak) if ach else None,
+                    "traffic": ncu_traffic(dom) if args.config == "C3" else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": per_launch_ms,
                     "iteration": {"algorithmic_bytes": ab["iteration"],
                                   "achieved": ab["iteration"] / (loop_ms * 1e-3 / args.steps) / 1e9,

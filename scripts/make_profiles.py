@@ -1,0 +1,59 @@
+"""Turns gpurun_out ncu artefacts into the committed summaries under profiles/ (developer tool).
+
+    python scripts/make_profiles.py r01
+"""
+import csv, io, json, os, subprocess, sys, collections
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = "profiles"
+os.makedirs(out, exist_ok=True)
+# ---- launch list -> per-kernel share of the step ----
+rows = [r for r in csv.reader(open(f"gpurun_out/{tag}_launches.csv")) if len(r) > 5]
+hdr = rows[0]
+ik, iv, im = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+agg = collections.OrderedDict()
+for r in rows[1:]:
+    if r[im] != "gpu__time_duration.sum":
+        continue
+    name = r[ik].split("(")[0].replace("void ", "").replace("lgr::", "")
+    t = float(r[iv].replace(",", ""))
+    a = agg.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += t
+unit = rows[1][hdr.index("Metric Unit")]
+tot = sum(v[1] for v in agg.values())
+with open(f"{out}/{tag}_launches_summary.txt", "w") as f:
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e (C3, first 400 launches)\n")
+    f.write(f"# per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  unit: {unit}\n")
+    f.write(f"{'kernel':60s} {'launches':>8s} {'total':>14s} {'share':>7s} {'avg':>12s}\n")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"{k:60s} {n:8d} {t:14.1f} {t / tot * 100:6.1f}% {t / n:12.1f}\n")
+print(open(f"{out}/{tag}_launches_summary.txt").read())
+# ---- full capture -> raw metrics of the top kernels ----
+raw = subprocess.run(["ncu", "-i", f"gpurun_out/{tag}_top3.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__cycles_elapsed.max"]
+traffic = {}
+with open(f"{out}/{tag}_top_kernels_ncu.txt", "w") as f:
+    f.write("# ncu --set full --clock-control none --import-source on, python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e (C3)\n")
+    for r in rows[2:]:
+        for w in want:
+            if w in hdr:
+                i = hdr.index(w)
+                f.write(f"{w} = {r[i]} {units[i]}\n")
+        def num(name):
+            i = hdr.index(name); v = float(r[i].replace(",", "")); u = units[i]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        kn = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
+        traffic[kn] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        f.write(f"dram traffic per launch = {traffic[kn] / 1e6:.1f} MB\n---\n")
+json.dump(traffic, open(f"{out}/{tag}_traffic.json", "w"), indent=1)
+print(open(f"{out}/{tag}_top_kernels_ncu.txt").read())
