@@ -490,10 +490,10 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         const int ntiles = (D.n + c->tc - 1) / c->tc;
         (void)ntiles;
         // the two padded tile formats of X (lgr_spmm.cu); the plain CSC upload is dropped afterwards
-        dev_build_padded(1, D.n, D.rows, c->tc, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.tval, c->st);
+        dev_build_padded(1, D.n, D.rows, c->tc, kp / 4, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.tval, c->st);
         tr.mark("build cell-tiled CSR");
         D.ngt = (D.rows + c->gt - 1) / c->gt;
-        dev_build_padded(0, D.n, D.rows, c->gt, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.cval, c->st);
+        dev_build_padded(0, D.n, D.rows, c->gt, kp / 4, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.cval, c->st);
         tr.mark("build gene-tiled CSC");
         dev_sumsq(D.val.p, D.nnz, c->sq.p + i, c->st);
         LGR_CUDA(cudaStreamSynchronize(c->st));

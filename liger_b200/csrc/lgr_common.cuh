@@ -192,8 +192,9 @@ void dev_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
 void dev_sumsq(const float* v, size_t n, double* out, cudaStream_t st);
 void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const int* pP, const int* iP,
                    const float* vP, int m, int* pS, int* iS, float* vS, cudaStream_t st);
-void dev_build_padded(int mode, int n, int rows, int tile, const int* colptr, const int* rowidx, const float* val,
-                      size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<float>& oval, cudaStream_t st);
+void dev_build_padded(int mode, int n, int rows, int tile, int scale, const int* colptr, const int* rowidx,
+                      const float* val, size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<float>& oval,
+                      cudaStream_t st);
 void dev_colmajor_to_padded(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);   // R m x k -> [row][KP]
 void dev_padded_to_colmajor(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);
 void dev_hpad_to_colmajor(const float* H, double* out, int n, int k, int kp, cudaStream_t st);          // [cell][KP] f32 -> n x k f64

@@ -76,7 +76,7 @@ void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const i
 //   mode 1, cell-tiled CSR: key = (col / tile) * rows + row, loc = col % tile      (k_spmm_xh)
 // Entries are stably sorted by key (so the minor index stays ascending inside a segment) and every segment is
 // padded with (loc 0, value 0) entries to a multiple of 8; ptr8[key] is the segment start in groups of 8.
-__global__ void k_tile_keys(int mode, int n, int rows, int tile, const int* __restrict__ colptr,
+__global__ void k_tile_keys(int mode, int n, int rows, int tile, int scale, const int* __restrict__ colptr,
                             const int* __restrict__ rowidx, unsigned int* __restrict__ keys,
                             unsigned int* __restrict__ perm, unsigned short* __restrict__ loc, int* __restrict__ counts) {
     const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
@@ -88,10 +88,10 @@ __global__ void k_tile_keys(int mode, int n, int rows, int tile, const int* __re
         unsigned short l;
         if (mode == 0) {
             key = (unsigned)(r / tile) * (unsigned)n + (unsigned)warp;
-            l = (unsigned short)(r % tile);
+            l = (unsigned short)((r % tile) * scale);
         } else {
             key = (unsigned)(warp / tile) * (unsigned)rows + (unsigned)r;
-            l = (unsigned short)(warp % tile);
+            l = (unsigned short)((warp % tile) * scale);
         }
         keys[t] = key;
         perm[t] = (unsigned)t;
@@ -115,9 +115,11 @@ __global__ void k_tile_scatter(size_t nnz, const unsigned int* __restrict__ keys
     }
 }
 
-void dev_build_padded(int mode, int n, int rows, int tile, const int* colptr, const int* rowidx, const float* val,
-                      size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<float>& oval, cudaStream_t st) {
-    LGR_REQUIRE(tile >= 1 && tile <= 65536, "tile size must fit a 16-bit local index");
+void dev_build_padded(int mode, int n, int rows, int tile, int scale, const int* colptr, const int* rowidx,
+                      const float* val, size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<float>& oval,
+                      cudaStream_t st) {
+    // local indices are stored pre-scaled by `scale` (= KP/4, the float4 slots per staged row)
+    LGR_REQUIRE(tile >= 1 && (long long)tile * scale <= 65536, "tile size x KP/4 must fit a 16-bit local index");
     const size_t nmajor = mode == 0 ? (size_t)(rows + tile - 1) / tile : (size_t)(n + tile - 1) / tile;
     const size_t nkeys = nmajor * (size_t)(mode == 0 ? n : rows);
     LGR_REQUIRE(nkeys < (size_t)0x7fffffff, "tiled format: tiles x minor dimension exceeds 2^31");
@@ -134,7 +136,7 @@ void dev_build_padded(int mode, int n, int rows, int tile, const int* colptr, co
     DBuf<unsigned short> loc(nnz);
     DBuf<int> counts(nkeys + 1), segstart(nkeys + 1), groups(nkeys + 1);
     counts.zero(st);
-    k_tile_keys<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(mode, n, rows, tile, colptr, rowidx, keys.p, perm.p,
+    k_tile_keys<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(mode, n, rows, tile, scale, colptr, rowidx, keys.p, perm.p,
                                                                              loc.p, counts.p);
     LGR_CUDA(cudaGetLastError());
     int bits = 1;

@@ -17,16 +17,17 @@
 
 namespace lgr {
 
-// acc += sum_j val_j * tile[loc_j][4s..4s+3]   for the 8 entries of one group (cells: 8 x u16, vals: 8 x f32)
-template <int LPN>
+// acc += sum_j val_j * tile[loc_j / LPN][4s..4s+3]   for the 8 entries of one group.
+// Local indices are stored PRE-SCALED by LPN (= float4 slots per staged row) and `tile4s` already points at this
+// lane's 16-byte slot, so the shared-memory address of a non-zero is one mask/shift plus one LEA.
 __device__ __forceinline__ void gather8(float4& acc, const uint4 cells, const float4 v0, const float4 v1,
-                                        const float4* __restrict__ tile4, const int s) {
+                                        const float4* __restrict__ tile4s) {
     const unsigned cw[4] = {cells.x, cells.y, cells.z, cells.w};
     const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const unsigned c = (j & 1) ? (cw[j >> 1] >> 16) : (cw[j >> 1] & 0xffffu);
-        const float4 h = tile4[c * LPN + s];
+        const float4 h = tile4s[c];
         acc.x = fmaf(vv[j], h.x, acc.x);
         acc.y = fmaf(vv[j], h.y, acc.y);
         acc.z = fmaf(vv[j], h.z, acc.z);
@@ -38,54 +39,69 @@ struct Group8 {
     uint4 cells;
     float4 v0, v1;
 };
-__device__ __forceinline__ Group8 load_group(const unsigned short* __restrict__ loc, const float* __restrict__ val, int g,
-                                             bool pred) {
+__device__ __forceinline__ Group8 load_group(const unsigned short* __restrict__ loc, const float* __restrict__ val, int g) {
     Group8 r;
-    r.cells = make_uint4(0, 0, 0, 0);
-    r.v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    r.v1 = r.v0;
-    if (pred) {
-        r.cells = __ldg(reinterpret_cast<const uint4*>(loc + (size_t)g * 8));
-        r.v0 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8));
-        r.v1 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8 + 4));
-    }
+    r.cells = __ldg(reinterpret_cast<const uint4*>(loc + (size_t)g * 8));
+    r.v0 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8));
+    r.v1 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8 + 4));
     return r;
 }
 
 // A lane-group (KP/4 lanes) walks the contiguous stream of 8-entry groups of the segments [sa, sb): every group is
-// one 128-bit load of local indices, two of values (prefetched one group ahead), then per non-zero one 128-bit
-// shared-memory load of the staged factor row and four FFMAs.  At a segment end the 32 (64) sums the lane-group
-// holds are the complete output row, so there is no cross-lane reduction; `store(seg, acc, nonempty)` consumes them.
+// one 128-bit load of local indices, two of values (prefetched one group ahead, two register buffers in ping-pong),
+// then per non-zero one 128-bit shared-memory load of the staged factor row and four FFMAs.  At a segment end the
+// 32 (64) sums the lane-group holds are the complete output row, so there is no cross-lane reduction;
+// `store(seg, acc, nonempty)` consumes them.
 template <int KP, typename Store>
 __device__ __forceinline__ void gather_stream(const int* __restrict__ ptr8, const int sa, const int sb,
                                               const unsigned short* __restrict__ loc, const float* __restrict__ val,
                                               const float4* __restrict__ tile4, const int s, Store store) {
-    constexpr int LPN = KP / 4;
-    if (sa >= sb) return;
+    const float4* __restrict__ tile4s = tile4 + s;
     int seg = sa;
-    int g = __ldg(ptr8 + sa);
-    const int gend = __ldg(ptr8 + sb);
-    int segend = __ldg(ptr8 + sa + 1);
-    int nsegend = (seg + 2 <= sb) ? __ldg(ptr8 + seg + 2) : gend;
-    Group8 cur = load_group(loc, val, g, g < gend);
+    int g = 0, gend = 0, segend = 0, nsegend = 0;
+    if (sa < sb) {
+        g = __ldg(ptr8 + sa);
+        gend = __ldg(ptr8 + sb);
+        segend = __ldg(ptr8 + sa + 1);
+        nsegend = (sa + 2 <= sb) ? __ldg(ptr8 + sa + 2) : gend;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool nonempty = false;
-    while (seg < sb) {
-        if (g < segend) {
-            const Group8 nx = load_group(loc, val, g + 1, g + 1 < gend);
-            gather8<LPN>(acc, cur.cells, cur.v0, cur.v1, tile4, s);
-            cur = nx;
-            ++g;
-            nonempty = true;
-        } else {
-            store(seg, acc, nonempty);
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            nonempty = false;
-            ++seg;
-            segend = nsegend;
-            nsegend = (seg + 2 <= sb) ? __ldg(ptr8 + seg + 2) : gend;
-        }
+    const int glast = gend > 0 ? gend - 1 : 0;   // prefetches are clamped, never predicated
+    bool alive = g < gend;
+    if (!alive)
+        for (; seg < sb; ++seg) store(seg, acc, false);   // nothing but empty segments
+    Group8 a = load_group(loc, val, alive ? g : 0), b;
+    // One group per step and per live lane-group.  The warp-wide vote at the top of every step is the reconvergence
+    // point: lane-groups whose segments end at different places fall back into lockstep immediately.
+#define LGR_GATHER_STEP(CUR, NXT)                                                          \
+    if (alive) {                                                                           \
+        while (g >= segend) { /* close the segments that end before this group */          \
+            store(seg, acc, nonempty);                                                     \
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);                                         \
+            nonempty = false;                                                              \
+            ++seg;                                                                         \
+            segend = nsegend;                                                              \
+            nsegend = (seg + 2 <= sb) ? __ldg(ptr8 + seg + 2) : gend;                      \
+        }                                                                                  \
+        NXT = load_group(loc, val, min(g + 1, glast));                                     \
+        gather8(acc, CUR.cells, CUR.v0, CUR.v1, tile4s);                                   \
+        nonempty = true;                                                                   \
+        if (++g >= gend) { /* stream exhausted: close the current and the trailing empty segments */ \
+            for (; seg < sb; ++seg) {                                                      \
+                store(seg, acc, nonempty);                                                 \
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);                                     \
+                nonempty = false;                                                          \
+            }                                                                              \
+            alive = false;                                                                 \
+        }                                                                                  \
     }
+    while (__any_sync(0xffffffffu, alive)) {
+        LGR_GATHER_STEP(a, b)
+        if (!__any_sync(0xffffffffu, alive)) break;
+        LGR_GATHER_STEP(b, a)
+    }
+#undef LGR_GATHER_STEP
 }
 
 // ------------------------------------------------------------------------------------------------
