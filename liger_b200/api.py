@@ -112,7 +112,7 @@ class _Args:
         if unsharedList is not None:
             ps = []
             for i, p in enumerate(unsharedList):
-                if p is None or p.shape[0] == 0:
+                if p is None or (p.shape[0] if hasattr(p, "shape") else p[3][0]) == 0:
                     ps.append(lgr_csc(0, self.n[i], None, None, None, 0, 0))
                 else:
                     self.P[i] = _Csc(p, keep_f32)

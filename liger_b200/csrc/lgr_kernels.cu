@@ -232,14 +232,17 @@ void launch_wrhs(const DsDev* ds, int nds, int m, double* CtBw, double* Gsum, in
 // ------------------------------------------------------------------------------------------------
 template <int KP>
 __global__ void __launch_bounds__(256) k_objective(const DsDev* __restrict__ ds, int k, double* obj) {
-    const DsDev& D = ds[blockIdx.x];
+    const DsDev& D = ds[blockIdx.y];
     double acc = 0.0;
     const size_t tot = (size_t)D.rows * KP;
-    for (size_t e = threadIdx.x; e < tot; e += blockDim.x) acc += (double)D.L[e] * (double)D.R[e];
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x)
+        acc += (double)D.L[e] * (double)D.R[e];
     acc *= -2.0;
-    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
-        const int a = e / KP, b = e % KP;
-        if (a < k && b < k) acc += (D.LtL[a * KP + b] + D.lambda * D.VtV[a * KP + b]) * D.G[b * KP + a];
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+            const int a = e / KP, b = e % KP;
+            if (a < k && b < k) acc += (D.LtL[a * KP + b] + D.lambda * D.VtV[a * KP + b]) * D.G[b * KP + a];
+        }
     }
     __shared__ double sh[256];
     sh[threadIdx.x] = acc;
@@ -248,14 +251,15 @@ __global__ void __launch_bounds__(256) k_objective(const DsDev* __restrict__ ds,
         if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) atomicAdd(obj, sh[0] + D.sqnorm);
+    if (threadIdx.x == 0) atomicAdd(obj, sh[0] + (blockIdx.x == 0 ? D.sqnorm : 0.0));
 }
 
 void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot, cudaStream_t st) {
+    dim3 grid(16, (unsigned)nds);
     if (kp == 32)
-        k_objective<32><<<nds, 256, 0, st>>>(ds, k, obj_slot);
+        k_objective<32><<<grid, 256, 0, st>>>(ds, k, obj_slot);
     else
-        k_objective<64><<<nds, 256, 0, st>>>(ds, k, obj_slot);
+        k_objective<64><<<grid, 256, 0, st>>>(ds, k, obj_slot);
     LGR_CUDA(cudaGetLastError());
 }
 

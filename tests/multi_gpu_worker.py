@@ -1,0 +1,49 @@
+"""Worker for tests/test_gpu_multi.py: one rank per GPU, cell-sharded iNMF through the C ABI (world = WORLD_SIZE)."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import liger_b200  # noqa: E402
+from oracle import inmf_oracle as orc  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pbmc_golden.npz"))
+    Es = [sp.csc_matrix((g[f"scale_{n}_data"], g[f"scale_{n}_indices"], g[f"scale_{n}_indptr"]),
+                        shape=tuple(g[f"scale_{n}_shape"])) for n in ("ctrl", "stim")]
+    W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(liger_b200.nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    nccl_id = bytes(idt.cpu().numpy().tobytes())
+    mode = sys.argv[1]
+    if mode == "slice":      # every rank passes the FULL matrices; the library takes its column range
+        ctx = liger_b200.Context(Es, 20, 5.0, W0, V0, device=local, rank=rank, world=world, nccl_id=nccl_id)
+        lo = [0, 0]
+    else:                    # every rank passes only its own cells (LGR_FLAG_LOCAL_SHARD)
+        rng_ = [(E.shape[1] * rank // world, E.shape[1] * (rank + 1) // world) for E in Es]
+        Xs = [E[:, a:b].tocsc() for E, (a, b) in zip(Es, rng_)]
+        ctx = liger_b200.Context(Xs, 20, 5.0, W0, V0, device=local, rank=rank, world=world, nccl_id=nccl_id, flags=0x8)
+        lo = [a for a, _ in rng_]
+    traj = ctx.iterate(10, trajectory=True)
+    res = ctx.download()
+    obj = ctx.objective()
+    ctx.close()
+    np.savez(os.path.join(sys.argv[2], f"{mode}_rank{rank}.npz"), W=res["W"], V0=res["V"][0], V1=res["V"][1],
+             H0=res["H"][0], H1=res["H"][1], traj=traj, obj=obj, lo=np.array(lo))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
