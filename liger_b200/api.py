@@ -192,7 +192,7 @@ class _Out:
 
 
 def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
-         trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False):
+         trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False, tensor_u=False):
     """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
 
     objectList: list of scipy CSC matrices (genes x cells; the `scaleData` of each dataset).
@@ -204,7 +204,8 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
     if Winit is None or Vinit is None:
         raise ValueError("liger_b200.inmf needs explicit Winit/Vinit (rliger's .runINMF.list always passes them; "
                          "use liger_b200.integration.run_inmf_list for the seeded initialisation)")
-    flags = (_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0)
+    flags = ((_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0) |
+             (_ffi.FLAG_TENSOR_U if tensor_u else 0))
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device)
     o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs)
     _ffi.check(_ffi.lib().lgr_inmf(C.byref(a.struct), C.byref(o.struct)))

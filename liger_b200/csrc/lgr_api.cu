@@ -113,7 +113,10 @@ struct lgr_ctx {
     DBuf<DsDev> ds_dev;
     DBuf<double> W, CtBw, Gsum, Garena, gram_arena, objbuf, sq;
     DBuf<unsigned long long> wmask;
-    DBuf<float> Bbuf, Rarena;
+    DBuf<float> Bbuf, Ubuf, Rarena;
+    DBuf<NnlsGroup> grpT;      // tensor-core U = B P launch (tile offsets)
+    long long tilesT = 0;
+    bool use_tc = false;
     DBuf<double> ctc_arena;   // per NNLS group: CtC and CtC^-1 (2 x KP x KP fp64), groups = H_0..H_d-1, V_0..V_d-1, W
     DBuf<int> ok_arena;
     DBuf<NnlsGroup> grpH, grpV, grpW;
@@ -304,6 +307,10 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         {
             Timed t(c, "k_gram_inv");
             launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
+        }
+        if (c->use_tc) {
+            Timed t(c, "k_pb_tc");
+            launch_pb_tc(c->grpT.p, c->d, c->tilesT, c->kp, c->num_sms, c->st);
         }
         {
             Timed t(c, "k_nnls_H");
@@ -516,6 +523,9 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->max_rows = max_rows;
     c->N_local = b_total / kp;
     c->Bbuf.alloc(std::max<size_t>(b_total, 1));
+    c->use_tc = (c->flags & LGR_FLAG_TENSOR_U) != 0;
+    if (const char* e = getenv("LGR_TC_U")) c->use_tc = atoi(e) != 0;
+    if (c->use_tc) c->Ubuf.alloc(std::max<size_t>(b_total, 1));
     c->Rarena.alloc(r_total);
     c->Garena.alloc((size_t)c->d * kp * kp);
     c->gram_arena.alloc((size_t)2 * c->d * kp * kp);
@@ -541,7 +551,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     auto ctc = [&](int gi) { return c->ctc_arena.p + (size_t)gi * 2 * kk; };
     std::vector<GramSpec> sH(c->d), sV(c->d), sW(1);
     c->ds_host.resize(c->d);
-    std::vector<NnlsGroup> gH(c->d), gV(c->d), gW(1);
+    std::vector<NnlsGroup> gH(c->d), gV(c->d), gW(1), gT(c->d);
+    long long tT = 0;
     int ltx = 0, xh = 0, prep = 0;
     long long bH = 0, bV = 0;
     const int rb = prep_rows_per_block(kp);
@@ -585,15 +596,19 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.sqnorm = sq[i];
         // H solve: CtC = LtL + lambda VtV, rhs = B (fp32), x = H
         sH[i] = GramSpec{h.LtL, h.VtV, 1.0, D.lambda, ctc(i), ctc(i) + kk, c->ok_arena.p + i};
-        gH[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, h.H, h.hmask, D.n, kp, bH};
+        const float* upre = c->use_tc ? c->Ubuf.p + D.b_off : nullptr;
+        gH[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, upre, h.H, h.hmask, D.n, kp, bH};
+        gT[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, nullptr, c->use_tc ? (void*)(c->Ubuf.p + D.b_off) : nullptr,
+                          nullptr, D.n, kp, tT};
+        tT += (D.n + 127) / 128;
         bH += D.n;
         // V/U solve: CtC = (1 + lambda) G_i, rhs = CtBv (fp64), x = V
         sV[i] = GramSpec{h.G, nullptr, 1.0 + D.lambda, 0.0, ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i};
-        gV[i] = NnlsGroup{ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i, h.CtBv, h.V, h.vmask, D.rows, kp, bV};
+        gV[i] = NnlsGroup{ctc(c->d + i), ctc(c->d + i) + kk, c->ok_arena.p + c->d + i, h.CtBv, nullptr, h.V, h.vmask, D.rows, kp, bV};
         bV += D.rows;
     }
     sW[0] = GramSpec{c->Gsum.p, nullptr, 1.0, 0.0, ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d};
-    gW[0] = NnlsGroup{ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d, c->CtBw.p, c->W.p, c->wmask.p, m, kp, 0};
+    gW[0] = NnlsGroup{ctc(2 * c->d), ctc(2 * c->d) + kk, c->ok_arena.p + 2 * c->d, c->CtBw.p, nullptr, c->W.p, c->wmask.p, m, kp, 0};
     c->ltx_blocks = ltx;
     c->xh_tiles = xh;
     c->prep_blocks = prep;
@@ -603,6 +618,9 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->grpH.alloc((size_t)c->d);
     c->grpV.alloc((size_t)c->d);
     c->grpW.alloc(1);
+    c->grpT.alloc((size_t)c->d);
+    c->tilesT = tT;
+    LGR_CUDA(cudaMemcpyAsync(c->grpT.p, gT.data(), sizeof(NnlsGroup) * c->d, cudaMemcpyHostToDevice, c->st));
     c->specH.alloc((size_t)c->d);
     c->specV.alloc((size_t)c->d);
     c->specW.alloc(1);
@@ -881,7 +899,7 @@ int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* 
             GramSpec sp{dGp.p, nullptr, 1.0, 0.0, ctc.p, ctc.p + (size_t)kp * kp, ok.p};
             LGR_CUDA(cudaMemcpyAsync(spec.p, &sp, sizeof(sp), cudaMemcpyHostToDevice, st));
             launch_gram_inv(spec.p, 1, k, kp, st);
-            NnlsGroup g{ctc.p, ctc.p + (size_t)kp * kp, ok.p, dB.p, dX.p, mask.p, (int)ncols, k, 0};
+            NnlsGroup g{ctc.p, ctc.p + (size_t)kp * kp, ok.p, dB.p, nullptr, dX.p, mask.p, (int)ncols, k, 0};
             LGR_CUDA(cudaMemcpyAsync(grp.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
             launch_nnls(true, grp.p, 1, (long long)ncols, k, kp, cfg, cnt.p, 1, st);
             LGR_CUDA(cudaMemcpyAsync(X, dX.p, (size_t)k * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));

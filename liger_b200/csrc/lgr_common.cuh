@@ -130,6 +130,7 @@ struct NnlsGroup {
     const double* ginv;         // KP x KP  CtC^-1 (valid when *ok != 0)
     const int* ok;
     const void* rhs;            // T: ncols x ld  (column j at rhs + j*ld)
+    const void* u;              // optional T: ncols x ld, u_j = CtC^-1 rhs_j precomputed on the tensor cores (lgr_tc.cu)
     void* x;                    // T: ncols x ld
     unsigned long long* mask;   // ncols, warm start in/out (never null)
     int ncols;
@@ -181,6 +182,8 @@ void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStrea
 void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp,
                  const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st);
 void nnls_init();
+void launch_pb_tc(const NnlsGroup* groups, int ngroups, long long total_tiles, int kp, int num_sms, cudaStream_t st);
+void tc_init();
 void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st);
 void launch_wrhs(const DsDev* ds, int nds, int m, double* CtBw, double* Gsum, int k, int kp, cudaStream_t st);
 void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot, cudaStream_t st);

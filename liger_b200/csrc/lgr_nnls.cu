@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
         const T* __restrict__ rhs = reinterpret_cast<const T*>(grp.rhs) + (size_t)c0 * ld;
         T* __restrict__ xout = reinterpret_cast<T*>(grp.x) + (size_t)c0 * ld;
         unsigned long long* __restrict__ masks = grp.mask + c0;
+        const T* __restrict__ upre = grp.u ? reinterpret_cast<const T*>(grp.u) + (size_t)c0 * ld : nullptr;
 
         bool active = false, exhausted = false;
         int col = 0;
@@ -435,7 +436,9 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
 #pragma unroll
                         for (int f = 0; f < KP; ++f) bm = fmax(bm, fabs(bcol[f * 33]));
                         tol = bm * Eps<T>::v() * (T)8;
-                        if (dual_ok) {  // u = P b : register accumulators, broadcast shared-memory reads of P
+                        if (dual_ok && upre) {   // u = P b was formed on the tensor cores (k_pb_tc)
+                            load_row<T, KP>(upre + (size_t)c * ld, ucol, k, ld);
+                        } else if (dual_ok) {  // u = P b : register accumulators, broadcast shared-memory reads of P
                             T acc[KP];
 #pragma unroll
                             for (int f = 0; f < KP; ++f) acc[f] = (T)0;

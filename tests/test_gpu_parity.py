@@ -250,6 +250,24 @@ def test_context_api_and_properties():
     assert abs(traj[-1] - ref["objErr"]) < TOL_OBJ * ref["objErr"]
 
 
+def test_tensor_core_u_path(pbmc):
+    """LGR_FLAG_TENSOR_U: u = CtC^-1 b on tcgen05 tensor cores (3xTF32 split, TMEM accumulators) -- same factors."""
+    import liger_b200
+    from liger_b200 import synthetic as syn
+    W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    a = liger_b200.inmf(pbmc["Es"], k=20, niter=30, Winit=W0, Vinit=V0, tensor_u=True, trajectory=True)
+    ref = orc.inmf(pbmc["Es"], 20, 5.0, 30, W0, V0, trajectory=True)
+    _check(a, ref)
+    assert np.max(np.abs(a["traj"] - np.array(ref["traj"])) / np.array(ref["traj"])) < TOL_OBJ
+    assert rel(a["W"], ref["W"]) < 1e-4                      # 3xTF32 keeps ~2^-21 per product
+    # k > 32 (two 128-byte lines per row, N = 64 MMA) and ragged tiles (n not a multiple of 128)
+    Es, _ = syn.make_numpy(2, 333, 150, 8, block=500, seed=5)
+    W0, V0, _, _ = orc.seeded_init(2, 150, 40, [333, 333])
+    b = liger_b200.inmf(Es, k=40, lambda_=2.5, niter=6, Winit=W0, Vinit=V0, tensor_u=True)
+    refb = c_oracle.inmf(Es, 40, 2.5, 6, W0, V0)
+    _check(b, refb)
+
+
 def test_float32_values_input(pbmc):
     import liger_b200
     W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
