@@ -314,7 +314,14 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         }
         {
             Timed t(c, "k_nnls_H");
-            launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
+            // fp32, k <= 32: register-resident solver; groups with a singular Gram fall through to k_nnls (flag 16)
+            static const bool no_reg = getenv("LGR_NNLS_NO_REG") != nullptr;
+            if (!no_reg && !c->use_tc && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
+                launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, cold, c->st);
+                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold | 16, c->st);
+            } else {
+                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
+            }
         }
         c->h_valid = true;
         // ---- sufficient statistics of the V / W solves ----

@@ -265,6 +265,7 @@ void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot,
 
 void kernels_init() {
     nnls_init();
+    nnls_reg_init();
     spmm_init();
     tc_init();
     const int maxs = 227 * 1024 - 1024;  // static smem of the kernels counts against the 227 KB limit

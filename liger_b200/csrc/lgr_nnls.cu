@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
         const int c0 = (int)(pos - grp.col_off);
         const int ccols = (int)((stop < gend ? stop : gend) - pos);
         pos += ccols;
+        if ((flags & 16) && *grp.ok != 0) continue;   // this launch only mops up the groups k_nnls_reg skipped (CTA-uniform)
         __syncthreads();  // every warp is done with the previous chunk (G / P / counter change)
         const int dual_ok = no_dual ? 0 : *grp.ok;
         for (int e = tid; e < KP * KP; e += blockDim.x) {

@@ -1,0 +1,360 @@
+// liger_b200 -- register-resident block-principal-pivoting NNLS for the H solves (fp32, k <= 32).
+// Same problem and pivoting rule as lgr_nnls.cu (reference: RcppPlanc::bppnnls_prod, call site R/cINMF.R:481);
+// different execution plan:
+//
+//   * one thread per column, a lane refills itself as soon as its column is solved (no barrier between columns);
+//   * every pivot round solves the KKT system from the smaller side (primal G_FF or dual P_AA, P = G^-1 from
+//     k_gram_inv), so the per-column system has s = min(|F|, k-|F|) <= 16 unknowns;
+//   * the s x s principal block is gathered into REGISTERS, padded to a compile-time size SMAX in {8,12,16} with
+//     identity rows (index 32 addresses a padding row/column of the staged matrix whose only non-zero is a unit
+//     diagonal), and factorised by a fully unrolled Cholesky: no shared-memory traffic, no data-dependent loop
+//     bounds, no divergence inside a warp.  SMAX is chosen per warp and per round from the largest s of its lanes;
+//   * the k-vector products (x = u - P_:A y_A, y = G_:F x_F - b) are dense 32x32 products against the solution
+//     expanded by factor id: the matrix rows are then warp-uniform, i.e. broadcast 128-bit shared-memory reads
+//     (one wavefront per four FMAs' worth of operands) instead of per-lane row gathers (bank conflicts);
+//   * u = P b is formed lazily, only for columns that actually take the dual side.
+//
+// Groups whose Gram is numerically singular (no inverse: *ok == 0) are left to k_nnls (lgr_nnls.cu), which is
+// launched right after this kernel restricted to exactly those groups.
+#include "lgr_common.cuh"
+
+namespace lgr {
+namespace {
+
+constexpr int RKP = 32;          // padded factor count handled here
+constexpr int RMST = 36;         // row stride of the staged matrices (words)
+constexpr int RROWS = 33;        // 32 rows + the padding row
+constexpr int RCOL = 33 * 32;    // words of one [row][lane] column tile (33 rows)
+constexpr float REPS = 1.1920929e-7f;
+
+__host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+struct RegSmem {
+    size_t G, P, warp0, per_warp, total;
+};
+__host__ __device__ inline RegSmem reg_layout(int nwarps) {
+    RegSmem L;
+    L.G = 0;
+    L.P = (size_t)RROWS * RMST * 4;
+    L.warp0 = 2 * L.P;
+    L.per_warp = (size_t)3 * RCOL * 4;   // b, u, z tiles
+    L.total = L.warp0 + (size_t)nwarps * L.per_warp;
+    return L;
+}
+
+// One pivot round of one column with the principal block padded to SMAX.  Returns true while the column is active.
+template <int SMAX>
+__device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, const bool dual, const int s, const uint32_t S,
+                                          const float* __restrict__ Mat, const float* bcol, const float* ucol, float* zcol,
+                                          uint32_t& F, int& state, const float tol, const int MAXIT, Counters* cnt,
+                                          unsigned long long& pivots, float4* __restrict__ xrow) {
+    constexpr int N = SMAX * (SMAX + 1) / 2;
+    int idx[SMAX];
+    {
+        uint32_t r = S;
+#pragma unroll
+        for (int t = 0; t < SMAX; ++t) {
+            idx[t] = r ? (__ffs((int)r) - 1) : 32;
+            r &= r - 1;
+        }
+    }
+    float A[N];
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) {
+        const float* rowp = Mat + idx[i] * RMST;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j)
+            if (j <= i) A[tri(i, j)] = rowp[idx[j]];
+    }
+    // left-looking Cholesky, factor in place, diagonal holds 1/L_jj; a collapsed pivot pins the coordinate to zero
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        const float orig = A[tri(j, j)];
+        float d = orig;
+#pragma unroll
+        for (int t = 0; t < SMAX; ++t)
+            if (t < j) d = fmaf(-A[tri(j, t)], A[tri(j, t)], d);
+        float invd = 0.f;
+        if (d > orig * (REPS * 4.f))
+            invd = rsqrtf(d);
+        else
+            ok = false;
+        A[tri(j, j)] = invd;
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) {
+            if (i > j) {
+                float a = A[tri(i, j)];
+#pragma unroll
+                for (int t = 0; t < SMAX; ++t)
+                    if (t < j) a = fmaf(-A[tri(i, t)], A[tri(j, t)], a);
+                A[tri(i, j)] = a * invd;
+            }
+        }
+    }
+    if (!ok) atomicAdd(&cnt->nnls_bad_pivot, 1ull);
+    const float* rhs = dual ? ucol : bcol;
+    float z[SMAX];
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        float v = rhs[idx[j] * 32];
+#pragma unroll
+        for (int t = 0; t < SMAX; ++t)
+            if (t < j) v = fmaf(-A[tri(j, t)], z[t], v);
+        z[j] = v * A[tri(j, j)];
+    }
+#pragma unroll
+    for (int j = SMAX - 1; j >= 0; --j) {
+        float v = z[j];
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i)
+            if (i > j) v = fmaf(-A[tri(i, j)], z[i], v);
+        z[j] = v * A[tri(j, j)];
+    }
+    // infeasible coordinates of the solved side; expand the (signed) solution by factor id
+    uint32_t infeas = 0u;
+    float zmax = 0.f;
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t) zmax = fmaxf(zmax, fabsf(z[t]));
+    const float tolz = dual ? tol : zmax * (REPS * 8.f);
+    const float sgn = dual ? -1.f : 1.f;   // dual: y_A = -z must be >= 0 ; primal: x_F = z must be >= 0
+#pragma unroll
+    for (int g = 0; g < RKP; ++g) zcol[g * 32] = 0.f;
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t) {
+        if (t < s) {
+            if (sgn * z[t] < -tolz) infeas |= 1u << idx[t];
+            zcol[idx[t] * 32] = sgn * z[t];
+        }
+    }
+    // dense product against the expanded vector: acc = u - P zs (dual, zs = -(-z) ... see sign below) or G zs - b
+    float acc[RKP];
+#pragma unroll
+    for (int f = 0; f < RKP; ++f) acc[f] = dual ? ucol[f * 32] : -bcol[f * 32];
+    // dual:   x = u - P_:A z = u + P_:A (sgn z)      primal: y = G_:F z - b = -b + G_:F (sgn z)
+    for (int g = 0; g < k; ++g) {
+        const float zg = zcol[g * 32];
+        const float4* row = reinterpret_cast<const float4*>(Mat + g * RMST);
+#pragma unroll
+        for (int c = 0; c < RKP / 4; ++c) {
+            const float4 mrow = row[c];
+            acc[4 * c + 0] = fmaf(zg, mrow.x, acc[4 * c + 0]);
+            acc[4 * c + 1] = fmaf(zg, mrow.y, acc[4 * c + 1]);
+            acc[4 * c + 2] = fmaf(zg, mrow.z, acc[4 * c + 2]);
+            acc[4 * c + 3] = fmaf(zg, mrow.w, acc[4 * c + 3]);
+        }
+    }
+    if (dual) {
+        float xmax = 0.f;
+#pragma unroll
+        for (int f = 0; f < RKP; ++f)
+            if ((F >> f) & 1u) xmax = fmaxf(xmax, fabsf(acc[f]));
+        const float tolx = xmax * (REPS * 8.f);
+#pragma unroll
+        for (int f = 0; f < RKP; ++f)
+            if (((F >> f) & 1u) && acc[f] < -tolx) infeas |= 1u << f;
+    } else {
+        const uint32_t Aset = (~F) & kmask;
+#pragma unroll
+        for (int f = 0; f < RKP; ++f)
+            if (((Aset >> f) & 1u) && acc[f] < -tol) infeas |= 1u << f;
+    }
+    int alpha = state & 0xff, beta = (state >> 8) & 0xff, iter = state >> 16;
+    if (infeas != 0u && iter < MAXIT) {
+        const int ninf = __popc(infeas);
+        uint32_t flip;
+        if (ninf < beta) {
+            beta = ninf;
+            alpha = 3;
+            flip = infeas;
+        } else if (alpha >= 1) {
+            --alpha;
+            flip = infeas;
+        } else {
+            flip = 1u << (31 - __clz((int)infeas));
+        }
+        F ^= flip;
+        state = alpha | (beta << 8) | ((iter + 1) << 16);
+        ++pivots;
+        return true;
+    }
+    if (infeas != 0u) atomicAdd(&cnt->nnls_unconverged, 1ull);
+    // final x straight from registers: full 128-byte row
+    if (dual) {
+#pragma unroll
+        for (int f = 0; f < RKP; ++f)
+            if (!((F >> f) & 1u) || !(acc[f] > 0.f)) acc[f] = 0.f;
+    } else {
+#pragma unroll
+        for (int f = 0; f < RKP; ++f) acc[f] = fmaxf(zcol[f * 32], 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < RKP / 4; ++c) xrow[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+    return false;
+}
+
+__global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict__ groups, int ngroups, long long total_cols,
+                                                     int k, Counters* cnt, int flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NW = blockDim.x >> 5;
+    const RegSmem L = reg_layout(NW);
+    float* Gs = reinterpret_cast<float*>(smem_raw + L.G);
+    float* Ps = reinterpret_cast<float*>(smem_raw + L.P);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* wbase = reinterpret_cast<float*>(smem_raw + L.warp0 + (size_t)warp * L.per_warp);
+    float* bcol = wbase + lane;            // [f][lane], 33 rows (row 32 = 0: rhs of the padding unknowns)
+    float* ucol = wbase + RCOL + lane;
+    float* zcol = wbase + 2 * RCOL + lane;
+    __shared__ int next_col;
+
+    const bool cold_start = (flags & 1) != 0;
+    const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+    const int MAXIT = 4 * k + 16;
+    bcol[32 * 32] = 0.f;
+    ucol[32 * 32] = 0.f;
+    zcol[32 * 32] = 0.f;
+
+    long long per = (total_cols + gridDim.x - 1) / gridDim.x;
+    per = (per + 31) & ~31LL;
+    long long pos = (long long)blockIdx.x * per;
+    const long long stop = pos + per < total_cols ? pos + per : total_cols;
+    unsigned long long pivots_local = 0;
+    while (pos < stop) {
+        int g = 0;
+        while (g + 1 < ngroups && pos >= groups[g + 1].col_off) ++g;
+        const NnlsGroup grp = groups[g];
+        const long long gend = grp.col_off + grp.ncols;
+        const int c0 = (int)(pos - grp.col_off);
+        const int ccols = (int)((stop < gend ? stop : gend) - pos);
+        pos += ccols;
+        if (*grp.ok == 0) continue;   // singular Gram: k_nnls takes this group (CTA-uniform)
+        __syncthreads();
+        for (int e = tid; e < RROWS * RMST; e += blockDim.x) {
+            const int a = e / RMST, b = e % RMST;
+            float gv = 0.f, pv = 0.f;
+            if (a < RKP && b < RKP) {
+                gv = (float)grp.gram[a * RKP + b];
+                pv = (float)grp.ginv[a * RKP + b];
+            } else if (a == 32 && b == 32) {
+                gv = 1.f;
+                pv = 1.f;
+            }
+            Gs[e] = gv;
+            Ps[e] = pv;
+        }
+        if (tid == 0) next_col = 0;
+        __syncthreads();
+        const float* __restrict__ rhs = reinterpret_cast<const float*>(grp.rhs) + (size_t)c0 * RKP;
+        float* __restrict__ xout = reinterpret_cast<float*>(grp.x) + (size_t)c0 * RKP;
+        unsigned long long* __restrict__ masks = grp.mask + c0;
+
+        bool active = false, exhausted = false, have_u = false;
+        int col = 0, state = 0;
+        uint32_t F = 0u;
+        float tol = 0.f;
+        for (;;) {
+            const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
+            if (want) {
+                const int leader = __ffs((int)want) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&next_col, __popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!active && !exhausted) {
+                    const int c = base + __popc(want & ((1u << lane) - 1u));
+                    if (c >= ccols) {
+                        exhausted = true;
+                    } else {
+                        col = c;
+                        const float4* rv = reinterpret_cast<const float4*>(rhs + (size_t)c * RKP);
+                        float bm = 0.f;
+#pragma unroll
+                        for (int i = 0; i < RKP / 4; ++i) {
+                            const float4 v = __ldg(rv + i);
+                            bcol[(4 * i + 0) * 32] = v.x;
+                            bcol[(4 * i + 1) * 32] = v.y;
+                            bcol[(4 * i + 2) * 32] = v.z;
+                            bcol[(4 * i + 3) * 32] = v.w;
+                            bm = fmaxf(bm, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                        }
+                        F = cold_start ? 0u : ((uint32_t)masks[c] & kmask);
+                        state = 3 | ((k + 1) << 8);
+                        tol = bm * (REPS * 8.f);
+                        have_u = false;
+                        active = true;
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) break;
+            int s = 0;
+            bool dual = false;
+            uint32_t S = 0u;
+            if (active) {
+                const int p = __popc(F);
+                dual = (k - p) < p;
+                S = dual ? ((~F) & kmask) : F;
+                s = dual ? (k - p) : p;
+                if (dual && !have_u) {   // u = P b, once per column, broadcast reads of P
+                    float acc[RKP];
+#pragma unroll
+                    for (int f = 0; f < RKP; ++f) acc[f] = 0.f;
+                    for (int t = 0; t < k; ++t) {
+                        const float bt = bcol[t * 32];
+                        const float4* row = reinterpret_cast<const float4*>(Ps + t * RMST);
+#pragma unroll
+                        for (int c = 0; c < RKP / 4; ++c) {
+                            const float4 mrow = row[c];
+                            acc[4 * c + 0] = fmaf(bt, mrow.x, acc[4 * c + 0]);
+                            acc[4 * c + 1] = fmaf(bt, mrow.y, acc[4 * c + 1]);
+                            acc[4 * c + 2] = fmaf(bt, mrow.z, acc[4 * c + 2]);
+                            acc[4 * c + 3] = fmaf(bt, mrow.w, acc[4 * c + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int f = 0; f < RKP; ++f) ucol[f * 32] = acc[f];
+                    have_u = true;
+                }
+            }
+            const int smax = __reduce_max_sync(0xffffffffu, s);
+            bool still = false;
+            if (active) {
+                const float* Mat = dual ? Ps : Gs;
+                float4* xrow = reinterpret_cast<float4*>(xout + (size_t)col * RKP);
+                if (smax <= 8)
+                    still = round_reg<8>(k, kmask, dual, s, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                else if (smax <= 12)
+                    still = round_reg<12>(k, kmask, dual, s, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                else
+                    still = round_reg<16>(k, kmask, dual, s, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                if (!still) masks[col] = (unsigned long long)F;
+            }
+            active = still;
+        }
+    }
+    if (pivots_local) atomicAdd(&cnt->nnls_pivots, pivots_local);
+}
+
+}  // namespace
+
+bool nnls_reg_supported(int k, int kp) { return kp == 32 && k <= 32; }
+
+void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
+                     cudaStream_t st) {
+    if (total_cols <= 0) return;
+    int nw = 8;
+    if (const char* e = getenv("LGR_NNLS_REG_WARPS")) nw = atoi(e);
+    if (nw < 1) nw = 1;
+    if (nw > 8) nw = 8;
+    while (nw > 1 && total_cols < (long long)num_sms * nw * 32) nw >>= 1;
+    const int threads = nw * 32;
+    const size_t smem = reg_layout(nw).total;
+    long long want = (total_cols + threads - 1) / threads;
+    const int grid = (int)(want < num_sms ? want : num_sms);
+    k_nnls_reg<<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, flags);
+    LGR_CUDA(cudaGetLastError());
+}
+
+void nnls_reg_init() {
+    LGR_CUDA(cudaFuncSetAttribute(k_nnls_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+}
+
+}  // namespace lgr
