@@ -80,7 +80,7 @@ struct Dataset {
     double lambda = 0.0;
     DBuf<int> colptr, rowidx, tptr8, cptr8;
     DBuf<float> val, tval, cval, L, H;
-    DBuf<unsigned short> tcell, crow;
+    DBuf<unsigned int> tcell, crow;
     int ngt = 1;
     DBuf<unsigned long long> hmask, vmask;
     DBuf<double> V, CtBv;
@@ -316,7 +316,7 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             Timed t(c, "k_nnls_H");
             // fp32, k <= 32: register-resident solver; groups with a singular Gram fall through to k_nnls (flag 16)
             static const bool no_reg = getenv("LGR_NNLS_NO_REG") != nullptr;
-            if (!no_reg && !c->use_tc && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
+            if (!no_reg && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
                 launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, cold, c->st);
                 launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold | 16, c->st);
             } else {
@@ -504,10 +504,10 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         const int ntiles = (D.n + c->tc - 1) / c->tc;
         (void)ntiles;
         // the two padded tile formats of X (lgr_spmm.cu); the plain CSC upload is dropped afterwards
-        dev_build_padded(1, D.n, D.rows, c->tc, kp / 4, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.tval, c->st);
+        dev_build_padded(1, D.n, D.rows, c->tc, kp / 4, 0, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.tval, c->st);
         tr.mark("build cell-tiled CSR");
         D.ngt = (D.rows + c->gt - 1) / c->gt;
-        dev_build_padded(0, D.n, D.rows, c->gt, kp / 4, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.cval, c->st);
+        dev_build_padded(0, D.n, D.rows, c->gt, kp / 4, c->cb, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.cval, c->st);
         tr.mark("build gene-tiled CSC");
         dev_sumsq(D.val.p, D.nnz, c->sq.p + i, c->st);
         LGR_CUDA(cudaStreamSynchronize(c->st));

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
     __shared__ int next_col;
 
     const bool cold_start = (flags & 1) != 0;
+    const bool sync_rounds = (flags & 32) != 0;   // CTA-wide round barrier: the warps walk the unrolled code together (I-cache)
     const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
     const int MAXIT = 4 * k + 16;
     bcol[32 * 32] = 0.f;
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         const float* __restrict__ rhs = reinterpret_cast<const float*>(grp.rhs) + (size_t)c0 * RKP;
         float* __restrict__ xout = reinterpret_cast<float*>(grp.x) + (size_t)c0 * RKP;
         unsigned long long* __restrict__ masks = grp.mask + c0;
+        const float* __restrict__ upre = grp.u ? reinterpret_cast<const float*>(grp.u) + (size_t)c0 * RKP : nullptr;
 
         bool active = false, exhausted = false, have_u = false;
         int col = 0, state = 0;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, active)) break;
+            if (sync_rounds ? !__syncthreads_or(active) : !__any_sync(0xffffffffu, active)) break;
             int s = 0;
             bool dual = false;
             uint32_t S = 0u;
@@ -293,6 +295,18 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 dual = (k - p) < p;
                 S = dual ? ((~F) & kmask) : F;
                 s = dual ? (k - p) : p;
+                if (dual && !have_u && upre) {   // u = P b was formed on the tensor cores (k_pb_tc)
+                    const float4* uv = reinterpret_cast<const float4*>(upre + (size_t)col * RKP);
+#pragma unroll
+                    for (int i = 0; i < RKP / 4; ++i) {
+                        const float4 v = __ldg(uv + i);
+                        ucol[(4 * i + 0) * 32] = v.x;
+                        ucol[(4 * i + 1) * 32] = v.y;
+                        ucol[(4 * i + 2) * 32] = v.z;
+                        ucol[(4 * i + 3) * 32] = v.w;
+                    }
+                    have_u = true;
+                }
                 if (dual && !have_u) {   // u = P b, once per column, broadcast reads of P
                     float acc[RKP];
 #pragma unroll
@@ -349,7 +363,8 @@ void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols,
     const size_t smem = reg_layout(nw).total;
     long long want = (total_cols + threads - 1) / threads;
     const int grid = (int)(want < num_sms ? want : num_sms);
-    k_nnls_reg<<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, flags);
+    static const bool sync_rounds = getenv("LGR_NNLS_REG_NOSYNC") == nullptr;
+    k_nnls_reg<<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, flags | (sync_rounds ? 32 : 0));
     LGR_CUDA(cudaGetLastError());
 }
 

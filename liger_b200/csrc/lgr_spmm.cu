@@ -9,25 +9,39 @@
 //       staged by one TMA bulk copy; inside a cell tile the entries are ordered by gene.  Warps own genes, gather
 //       H rows, and issue one vector RED (red.global.add.v4.f32) per (gene, tile).
 //
-// Both formats pad every (tile, minor) segment to a multiple of 8 entries (u16 local index + fp32 value, zero padded)
-// so that a quarter-warp fetches its 8 entries with three aligned 128-bit loads and then issues, per non-zero,
-// one 128-bit shared-memory load and four FFMAs: ~2 warp instructions and one shared-memory wavefront per non-zero.
+// Both formats pad every (tile, minor) segment to a multiple of 8 entries (32-bit pre-scaled local index + fp32 value,
+// zero padded) and tag word 0 of every group of 8 with the group's output row (lgr_layout.cu).  The stream of a CTA is
+// therefore a flat, self-describing list of groups that is cut into EQUAL contiguous ranges, one per lane-group
+// (KP/4 lanes = one staged row per 128-bit shared-memory load): uniform trip counts, no votes, no pointer walks.
+// Per group: four 128-bit loads (prefetched one group ahead), then per non-zero one LEA, one 128-bit shared-memory
+// load and four FFMAs; a change of the tag flushes the lane-group's 4 sums (the complete output row slice).
 #include "lgr_common.cuh"
 #include "lgr_ptx.cuh"
 
 namespace lgr {
 
-// acc += sum_j val_j * tile[loc_j / LPN][4s..4s+3]   for the 8 entries of one group.
-// Local indices are stored PRE-SCALED by LPN (= float4 slots per staged row) and `tile4s` already points at this
-// lane's 16-byte slot, so the shared-memory address of a non-zero is one mask/shift plus one LEA.
-__device__ __forceinline__ void gather8(float4& acc, const uint4 cells, const float4 v0, const float4 v1,
-                                        const float4* __restrict__ tile4s) {
-    const unsigned cw[4] = {cells.x, cells.y, cells.z, cells.w};
-    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+struct Group8 {
+    uint4 i0, i1;
+    float4 v0, v1;
+};
+__device__ __forceinline__ Group8 load_group(const unsigned int* __restrict__ loc, const float* __restrict__ val, int g) {
+    Group8 r;
+    const uint4* li = reinterpret_cast<const uint4*>(loc + (size_t)g * 8);
+    const float4* vi = reinterpret_cast<const float4*>(val + (size_t)g * 8);
+    r.i0 = __ldg(li);
+    r.i1 = __ldg(li + 1);
+    r.v0 = __ldg(vi);
+    r.v1 = __ldg(vi + 1);
+    return r;
+}
+
+// acc += sum_j val_j * tile[idx_j][4s..4s+3]; `tile4s` already points at this lane's 16-byte slot of row 0.
+__device__ __forceinline__ void gather8(float4& acc, const Group8& G, const float4* __restrict__ tile4s) {
+    const unsigned c[8] = {G.i0.x & 0x3fffu, G.i0.y, G.i0.z, G.i0.w, G.i1.x, G.i1.y, G.i1.z, G.i1.w};
+    const float vv[8] = {G.v0.x, G.v0.y, G.v0.z, G.v0.w, G.v1.x, G.v1.y, G.v1.z, G.v1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const unsigned c = (j & 1) ? (cw[j >> 1] >> 16) : (cw[j >> 1] & 0xffffu);
-        const float4 h = tile4s[c];
+        const float4 h = tile4s[c[j]];
         acc.x = fmaf(vv[j], h.x, acc.x);
         acc.y = fmaf(vv[j], h.y, acc.y);
         acc.z = fmaf(vv[j], h.z, acc.z);
@@ -35,73 +49,35 @@ __device__ __forceinline__ void gather8(float4& acc, const uint4 cells, const fl
     }
 }
 
-struct Group8 {
-    uint4 cells;
-    float4 v0, v1;
-};
-__device__ __forceinline__ Group8 load_group(const unsigned short* __restrict__ loc, const float* __restrict__ val, int g) {
-    Group8 r;
-    r.cells = __ldg(reinterpret_cast<const uint4*>(loc + (size_t)g * 8));
-    r.v0 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8));
-    r.v1 = __ldg(reinterpret_cast<const float4*>(val + (size_t)g * 8 + 4));
-    return r;
-}
-
-// A lane-group (KP/4 lanes) walks the contiguous stream of 8-entry groups of the segments [sa, sb): every group is
-// one 128-bit load of local indices, two of values (prefetched one group ahead, two register buffers in ping-pong),
-// then per non-zero one 128-bit shared-memory load of the staged factor row and four FFMAs.  At a segment end the
-// 32 (64) sums the lane-group holds are the complete output row, so there is no cross-lane reduction;
-// `store(seg, acc, nonempty)` consumes them.
-template <int KP, typename Store>
-__device__ __forceinline__ void gather_stream(const int* __restrict__ ptr8, const int sa, const int sb,
-                                              const unsigned short* __restrict__ loc, const float* __restrict__ val,
-                                              const float4* __restrict__ tile4, const int s, Store store) {
-    const float4* __restrict__ tile4s = tile4 + s;
-    int seg = sa;
-    int g = 0, gend = 0, segend = 0, nsegend = 0;
-    if (sa < sb) {
-        g = __ldg(ptr8 + sa);
-        gend = __ldg(ptr8 + sb);
-        segend = __ldg(ptr8 + sa + 1);
-        nsegend = (sa + 2 <= sb) ? __ldg(ptr8 + sa + 2) : gend;
-    }
+// One lane-group consumes the groups [g, gend) of the stream; `trips` is the warp-uniform loop count (>= gend - g)
+// and `glast` the last group the prefetch may touch.  flush(row, acc, edge): `edge` is set for the first and the
+// last flush of the range, whose segments may continue in a neighbouring range.
+template <typename Flush>
+__device__ __forceinline__ void gather_range(const unsigned int* __restrict__ loc, const float* __restrict__ val, int g,
+                                             const int gend, const int trips, const int glast,
+                                             const float4* __restrict__ tile4s, Flush flush) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool nonempty = false;
-    const int glast = gend > 0 ? gend - 1 : 0;   // prefetches are clamped, never predicated
-    bool alive = g < gend;
-    if (!alive)
-        for (; seg < sb; ++seg) store(seg, acc, false);   // nothing but empty segments
-    Group8 a = load_group(loc, val, alive ? g : 0), b;
-    // One group per step and per live lane-group.  The warp-wide vote at the top of every step is the reconvergence
-    // point: lane-groups whose segments end at different places fall back into lockstep immediately.
-#define LGR_GATHER_STEP(CUR, NXT)                                                          \
-    if (alive) {                                                                           \
-        while (g >= segend) { /* close the segments that end before this group */          \
-            store(seg, acc, nonempty);                                                     \
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);                                         \
-            nonempty = false;                                                              \
-            ++seg;                                                                         \
-            segend = nsegend;                                                              \
-            nsegend = (seg + 2 <= sb) ? __ldg(ptr8 + seg + 2) : gend;                      \
-        }                                                                                  \
-        NXT = load_group(loc, val, min(g + 1, glast));                                     \
-        gather8(acc, CUR.cells, CUR.v0, CUR.v1, tile4s);                                   \
-        nonempty = true;                                                                   \
-        if (++g >= gend) { /* stream exhausted: close the current and the trailing empty segments */ \
-            for (; seg < sb; ++seg) {                                                      \
-                store(seg, acc, nonempty);                                                 \
-                acc = make_float4(0.f, 0.f, 0.f, 0.f);                                     \
-                nonempty = false;                                                          \
-            }                                                                              \
-            alive = false;                                                                 \
-        }                                                                                  \
+    const bool any = g < gend;
+    Group8 cur = load_group(loc, val, min(g, glast));
+    unsigned seg = cur.i0.x >> 14;
+    bool first = true;
+#pragma unroll 2
+    for (int i = 0; i < trips; ++i) {
+        const Group8 nxt = load_group(loc, val, min(g + 1, glast));
+        if (g < gend) {
+            const unsigned t = cur.i0.x >> 14;
+            if (t != seg) {
+                flush(seg, acc, first);
+                first = false;
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                seg = t;
+            }
+            gather8(acc, cur, tile4s);
+        }
+        cur = nxt;
+        ++g;
     }
-    while (__any_sync(0xffffffffu, alive)) {
-        LGR_GATHER_STEP(a, b)
-        if (!__any_sync(0xffffffffu, alive)) break;
-        LGR_GATHER_STEP(b, a)
-    }
-#undef LGR_GATHER_STEP
+    if (any) flush(seg, acc, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -128,11 +104,10 @@ __global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* 
     const float4* Ls4 = reinterpret_cast<const float4*>(Ls);
     float4* Bp4 = reinterpret_cast<float4*>(Bp);
     if (threadIdx.x == 0) mbar_init(bar, 1);
-    // each warp owns a contiguous run of cells of the block (contiguous entries in HBM)
-    const int cpw = (ncell + nwarps - 1) / nwarps;
-    const int w0 = min(warp * cpw, ncell), w1 = min(w0 + cpw, ncell);
+    for (int e = threadIdx.x; e < ncell * LPN; e += blockDim.x) Bp4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nq = 32 / LPN, NQ = nwarps * nq, qid = warp * nq + q;
     for (int gt = 0; gt < ngt; ++gt) {
-        __syncthreads();  // everyone is done reading the previous L~ tile (and sees the barrier init)
+        __syncthreads();  // everyone is done reading the previous L~ tile (and sees the barrier init / the zeroed Bp)
         if (threadIdx.x == 0) {
             const int r0 = gt * GT;
             const uint32_t bytes = (uint32_t)min(GT, rows - r0) * KP * sizeof(float);
@@ -141,26 +116,29 @@ __global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* 
             char* dst = reinterpret_cast<char*>(Ls);
             for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
         }
+        // this (gene tile, cell block)'s groups, cut into NQ equal ranges
         const int* __restrict__ ptr = D.cptr8 + (size_t)gt * n + c0;
+        const int G0 = __ldg(ptr), G1 = __ldg(ptr + ncell);
+        const int per = (G1 - G0 + NQ - 1) / NQ;
+        const int g = min(G0 + qid * per, G1), gend = min(g + per, G1);
         mbar_wait(bar, (uint32_t)(gt & 1));
-        {
-            // the warp's cells [w0, w1) are split into contiguous runs, one per lane-group
-            const int nq = 32 / LPN;
-            const int per = (w1 - w0 + nq - 1) / nq;
-            const int sa = min(w0 + q * per, w1), sb = min(sa + per, w1);
-            const bool first = gt == 0;
-            gather_stream<KP>(ptr, sa, sb, D.crow, D.cval, Ls4, s, [&](int cell, float4 acc, bool) {
-                float4* dst = Bp4 + (size_t)cell * LPN + s;
-                if (!first) {
-                    const float4 o = *dst;
-                    acc.x += o.x;
-                    acc.y += o.y;
-                    acc.z += o.z;
-                    acc.w += o.w;
-                }
-                *dst = acc;
-            });
-        }
+        gather_range(D.crow, D.cval, g, gend, per, max(G1 - 1, 0), Ls4 + s, [&](unsigned cell, float4 acc, bool edge) {
+            float* dst = Bp + (size_t)cell * KP + s * 4;
+            if (edge) {   // the segment may be shared with the neighbouring range
+                atomicAdd(dst + 0, acc.x);
+                atomicAdd(dst + 1, acc.y);
+                atomicAdd(dst + 2, acc.z);
+                atomicAdd(dst + 3, acc.w);
+            } else {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                float4 o = *d4;
+                o.x += acc.x;
+                o.y += acc.y;
+                o.z += acc.z;
+                o.w += acc.w;
+                *d4 = o;
+            }
+        });
     }
     __syncthreads();
     float4* __restrict__ out = reinterpret_cast<float4*>(D.B) + (size_t)c0 * LPN;
@@ -204,7 +182,6 @@ __global__ void __launch_bounds__(XH_THREADS, 1) k_spmm_xh(const DsDev* __restri
     float* Hs = reinterpret_cast<float*>(smem_raw);
     float* red = Hs + (size_t)TC * KP;
     uint64_t* bar = reinterpret_cast<uint64_t*>(red + (size_t)ncg * NPATCH * 16);
-    __shared__ int next_blk;
 
     const int i = find_ds(ds, nds, (int)blockIdx.x, &DsDev::xh_blk_off);
     const DsDev& D = ds[i];
@@ -214,10 +191,7 @@ __global__ void __launch_bounds__(XH_THREADS, 1) k_spmm_xh(const DsDev* __restri
     const int rows = D.rows;
     const int lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        next_blk = 0;
-    }
+    if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bytes = (uint32_t)ncell * KP * sizeof(float);
@@ -228,27 +202,18 @@ __global__ void __launch_bounds__(XH_THREADS, 1) k_spmm_xh(const DsDev* __restri
     }
     mbar_wait(bar, 0);
 
-    // ---- phase 1: R += X_tile * Hs ; warps pull blocks of 32 genes ----
+    // ---- phase 1: R += X_tile * Hs ; the tile's groups are cut into equal ranges, one per lane-group ----
     {
         const int q = lane / LPN, s = lane % LPN;
+        const int nq = 32 / LPN, NQ = (int)(blockDim.x >> 5) * nq, qid = (int)(threadIdx.x >> 5) * nq + q;
         const int* __restrict__ tptr = D.tptr8 + (size_t)tile * rows;
+        const int G0 = __ldg(tptr), G1 = __ldg(tptr + rows);
+        const int per = (G1 - G0 + NQ - 1) / NQ;
+        const int g = min(G0 + qid * per, G1), gend = min(g + per, G1);
         const float4* Hs4 = reinterpret_cast<const float4*>(Hs);
-        const int nblk = (rows + 31) >> 5;
-        for (;;) {
-            int b = 0;
-            if (lane == 0) b = atomicAdd(&next_blk, 1);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= nblk) break;
-            const int g0 = b * 32;
-            const int ng = min(32, rows - g0);
-            const int nq = 32 / LPN;
-            const int per = (ng + nq - 1) / nq;
-            const int sa = min(g0 + q * per, g0 + ng), sb = min(sa + per, g0 + ng);
-            float* __restrict__ R = D.R;
-            gather_stream<KP>(tptr, sa, sb, D.tcell, D.tval, Hs4, s, [&](int gene, float4 acc, bool nonempty) {
-                if (nonempty) red_add_v4(R + (size_t)gene * KP + s * 4, acc);
-            });
-        }
+        float* __restrict__ R = D.R;
+        gather_range(D.tcell, D.tval, g, gend, per, max(G1 - 1, 0), Hs4 + s,
+                     [&](unsigned gene, float4 acc, bool) { red_add_v4(R + (size_t)gene * KP + s * 4, acc); });
     }
 
     // ---- phase 2: G += Hs^T Hs over this tile (4x4 register patches of the upper triangle) ----
