@@ -26,6 +26,7 @@ constexpr int RMST = 36;         // row stride of the staged matrices (words)
 constexpr int RROWS = 33;        // 32 rows + the padding row
 constexpr int RCOL = 33 * 32;    // words of one [row][lane] column tile (33 rows)
 constexpr float REPS = 1.1920929e-7f;
+constexpr int RSUB = 8192;       // columns ordered (by system size) and solved per pass of a CTA
 
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
@@ -44,7 +45,8 @@ __host__ __device__ inline RegSmem reg_layout(int nwarps) {
 
 // One pivot round of one column with the principal block padded to SMAX.  Returns true while the column is active.
 template <int SMAX>
-__device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, const bool dual, const int s, const uint32_t S,
+__device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, const bool dual, const int s, const int smax,
+                                          const uint32_t S,
                                           const float* __restrict__ Mat, const float* bcol, const float* ucol, float* zcol,
                                           uint32_t& F, int& state, const float tol, const int MAXIT, Counters* cnt,
                                           unsigned long long& pivots, float4* __restrict__ xrow) {
@@ -132,16 +134,35 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
 #pragma unroll
     for (int f = 0; f < RKP; ++f) acc[f] = dual ? ucol[f * 32] : -bcol[f * 32];
     // dual:   x = u - P_:A z = u + P_:A (sgn z)      primal: y = G_:F z - b = -b + G_:F (sgn z)
-    for (int g = 0; g < k; ++g) {
-        const float zg = zcol[g * 32];
-        const float4* row = reinterpret_cast<const float4*>(Mat + g * RMST);
+    if (SMAX <= 8) {
+        // few unknowns: gather the s rows of the matrix (per-lane rows, some bank conflicts, but only s of them)
 #pragma unroll
-        for (int c = 0; c < RKP / 4; ++c) {
-            const float4 mrow = row[c];
-            acc[4 * c + 0] = fmaf(zg, mrow.x, acc[4 * c + 0]);
-            acc[4 * c + 1] = fmaf(zg, mrow.y, acc[4 * c + 1]);
-            acc[4 * c + 2] = fmaf(zg, mrow.z, acc[4 * c + 2]);
-            acc[4 * c + 3] = fmaf(zg, mrow.w, acc[4 * c + 3]);
+        for (int t = 0; t < SMAX; ++t) {
+            if (t < smax) {   // warp-uniform
+                const float zt = sgn * z[t];
+                const float4* row = reinterpret_cast<const float4*>(Mat + idx[t] * RMST);
+#pragma unroll
+                for (int c = 0; c < RKP / 4; ++c) {
+                    const float4 mrow = row[c];
+                    acc[4 * c + 0] = fmaf(zt, mrow.x, acc[4 * c + 0]);
+                    acc[4 * c + 1] = fmaf(zt, mrow.y, acc[4 * c + 1]);
+                    acc[4 * c + 2] = fmaf(zt, mrow.z, acc[4 * c + 2]);
+                    acc[4 * c + 3] = fmaf(zt, mrow.w, acc[4 * c + 3]);
+                }
+            }
+        }
+    } else {
+        for (int g = 0; g < k; ++g) {
+            const float zg = zcol[g * 32];
+            const float4* row = reinterpret_cast<const float4*>(Mat + g * RMST);
+#pragma unroll
+            for (int c = 0; c < RKP / 4; ++c) {
+                const float4 mrow = row[c];
+                acc[4 * c + 0] = fmaf(zg, mrow.x, acc[4 * c + 0]);
+                acc[4 * c + 1] = fmaf(zg, mrow.y, acc[4 * c + 1]);
+                acc[4 * c + 2] = fmaf(zg, mrow.z, acc[4 * c + 2]);
+                acc[4 * c + 3] = fmaf(zg, mrow.w, acc[4 * c + 3]);
+            }
         }
     }
     if (dual) {
@@ -206,6 +227,8 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
     float* ucol = wbase + RCOL + lane;
     float* zcol = wbase + 2 * RCOL + lane;
     __shared__ int next_col;
+    __shared__ int hist[18];
+    __shared__ unsigned short order[RSUB];
 
     const bool cold_start = (flags & 1) != 0;
     const bool sync_rounds = (flags & 32) != 0;   // CTA-wide round barrier: the warps walk the unrolled code together (I-cache)
@@ -243,12 +266,42 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
             Gs[e] = gv;
             Ps[e] = pv;
         }
-        if (tid == 0) next_col = 0;
         __syncthreads();
-        const float* __restrict__ rhs = reinterpret_cast<const float*>(grp.rhs) + (size_t)c0 * RKP;
-        float* __restrict__ xout = reinterpret_cast<float*>(grp.x) + (size_t)c0 * RKP;
-        unsigned long long* __restrict__ masks = grp.mask + c0;
-        const float* __restrict__ upre = grp.u ? reinterpret_cast<const float*>(grp.u) + (size_t)c0 * RKP : nullptr;
+        const float* __restrict__ rhs_g = reinterpret_cast<const float*>(grp.rhs) + (size_t)c0 * RKP;
+        float* __restrict__ xout_g = reinterpret_cast<float*>(grp.x) + (size_t)c0 * RKP;
+        unsigned long long* __restrict__ masks_g = grp.mask + c0;
+        const float* __restrict__ upre_g = grp.u ? reinterpret_cast<const float*>(grp.u) + (size_t)c0 * RKP : nullptr;
+      for (int sub0 = 0; sub0 < ccols; sub0 += RSUB) {
+        // ---- order this sub-chunk's columns by the size of the system their warm start implies (largest first):
+        //      the lanes of a warp then solve systems of similar size and the small templates are actually used ----
+        const int nsub = min(RSUB, ccols - sub0);
+        const float* __restrict__ rhs = rhs_g + (size_t)sub0 * RKP;
+        float* __restrict__ xout = xout_g + (size_t)sub0 * RKP;
+        unsigned long long* __restrict__ masks = masks_g + sub0;
+        const float* __restrict__ upre = upre_g ? upre_g + (size_t)sub0 * RKP : nullptr;
+        __syncthreads();   // previous sub-chunk fully drained (order[] / counters are reused)
+        if (tid < 18) hist[tid] = 0;
+        __syncthreads();
+        for (int c = tid; c < nsub; c += blockDim.x) {
+            const int p = cold_start ? 0 : __popc((uint32_t)masks[c] & kmask);
+            atomicAdd(&hist[16 - min(p, k - p)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int b = 0; b < 17; ++b) {
+                const int h = hist[b];
+                hist[b] = run;
+                run += h;
+            }
+            next_col = 0;
+        }
+        __syncthreads();
+        for (int c = tid; c < nsub; c += blockDim.x) {
+            const int p = cold_start ? 0 : __popc((uint32_t)masks[c] & kmask);
+            order[atomicAdd(&hist[16 - min(p, k - p)], 1)] = (unsigned short)c;
+        }
+        __syncthreads();
 
         bool active = false, exhausted = false, have_u = false;
         int col = 0, state = 0;
@@ -262,10 +315,11 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 if (lane == leader) base = atomicAdd(&next_col, __popc(want));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (!active && !exhausted) {
-                    const int c = base + __popc(want & ((1u << lane) - 1u));
-                    if (c >= ccols) {
+                    const int ci = base + __popc(want & ((1u << lane) - 1u));
+                    if (ci >= nsub) {
                         exhausted = true;
                     } else {
+                        const int c = order[ci];
                         col = c;
                         const float4* rv = reinterpret_cast<const float4*>(rhs + (size_t)c * RKP);
                         float bm = 0.f;
@@ -334,15 +388,16 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 const float* Mat = dual ? Ps : Gs;
                 float4* xrow = reinterpret_cast<float4*>(xout + (size_t)col * RKP);
                 if (smax <= 8)
-                    still = round_reg<8>(k, kmask, dual, s, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                    still = round_reg<8>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
                 else if (smax <= 12)
-                    still = round_reg<12>(k, kmask, dual, s, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                    still = round_reg<12>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
                 else
-                    still = round_reg<16>(k, kmask, dual, s, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                    still = round_reg<16>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
                 if (!still) masks[col] = (unsigned long long)F;
             }
             active = still;
         }
+      }
     }
     if (pivots_local) atomicAdd(&cnt->nnls_pivots, pivots_local);
 }
@@ -369,7 +424,7 @@ void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols,
 }
 
 void nnls_reg_init() {
-    LGR_CUDA(cudaFuncSetAttribute(k_nnls_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    LGR_CUDA(cudaFuncSetAttribute(k_nnls_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_layout(8).total));
 }
 
 }  // namespace lgr
