@@ -21,24 +21,29 @@
 namespace lgr {
 namespace {
 
+constexpr int RSUB = 4096;       // columns ordered (by system size) and solved per pass of a CTA
 constexpr int RKP = 32;          // padded factor count handled here
 constexpr int RMST = 36;         // row stride of the staged matrices (words)
 constexpr int RROWS = 33;        // 32 rows + the padding row
-constexpr int RCOL = 33 * 32;    // words of one [row][lane] column tile (33 rows)
+constexpr int RCOL = 33 * 32;    // words of the z tile: [row][lane], 33 rows
+constexpr int RBUF = 9 * 32 * 4;  // words of one b / u staging tile: [16-byte chunk][lane], 8 chunks + a zero chunk (padding unknowns)
 constexpr float REPS = 1.1920929e-7f;
-constexpr int RSUB = 8192;       // columns ordered (by system size) and solved per pass of a CTA
 
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+// word offset of element f of a lane's row in a [chunk][lane] staging tile (relative to the lane's chunk 0)
+__device__ __forceinline__ int bw(int f) { return (f >> 2) * 128 + (f & 3); }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct RegSmem {
-    size_t G, P, warp0, per_warp, total;
+    size_t G, P, fmask, warp0, per_warp, total;
 };
 __host__ __device__ inline RegSmem reg_layout(int nwarps) {
     RegSmem L;
     L.G = 0;
     L.P = (size_t)RROWS * RMST * 4;
-    L.warp0 = 2 * L.P;
-    L.per_warp = (size_t)3 * RCOL * 4;   // b, u, z tiles
+    L.fmask = 2 * L.P;
+    L.warp0 = L.fmask + (size_t)RSUB * 4;
+    L.per_warp = (size_t)(4 * RBUF + RCOL) * 4;   // 2 x (b, u) staging tiles (double buffered), z tile
     L.total = L.warp0 + (size_t)nwarps * L.per_warp;
     return L;
 }
@@ -99,7 +104,7 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
     float z[SMAX];
 #pragma unroll
     for (int j = 0; j < SMAX; ++j) {
-        float v = rhs[idx[j] * 32];
+        float v = rhs[bw(idx[j])];
 #pragma unroll
         for (int t = 0; t < SMAX; ++t)
             if (t < j) v = fmaf(-A[tri(j, t)], z[t], v);
@@ -131,8 +136,18 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
     }
     // dense product against the expanded vector: acc = u - P zs (dual, zs = -(-z) ... see sign below) or G zs - b
     float acc[RKP];
+    {
+        const float4* src = reinterpret_cast<const float4*>(rhs);
+        const float sg0 = dual ? 1.f : -1.f;
 #pragma unroll
-    for (int f = 0; f < RKP; ++f) acc[f] = dual ? ucol[f * 32] : -bcol[f * 32];
+        for (int c = 0; c < RKP / 4; ++c) {
+            const float4 v = src[c * 32];
+            acc[4 * c + 0] = sg0 * v.x;
+            acc[4 * c + 1] = sg0 * v.y;
+            acc[4 * c + 2] = sg0 * v.z;
+            acc[4 * c + 3] = sg0 * v.w;
+        }
+    }
     // dual:   x = u - P_:A z = u + P_:A (sgn z)      primal: y = G_:F z - b = -b + G_:F (sgn z)
     if (SMAX <= 8) {
         // few unknowns: gather the s rows of the matrix (per-lane rows, some bank conflicts, but only s of them)
@@ -165,20 +180,30 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
             }
         }
     }
-    if (dual) {
-        float xmax = 0.f;
+    // sign tests over all 32 coordinates with four independent chains, masked by the set afterwards.  In the dual case
+    // acc is x on every coordinate (x_A = u_A - P_AA z = 0 up to rounding), so the unmasked maximum scales the tolerance.
+    {
+        float thr = tol;
+        if (dual) {
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
 #pragma unroll
-        for (int f = 0; f < RKP; ++f)
-            if ((F >> f) & 1u) xmax = fmaxf(xmax, fabsf(acc[f]));
-        const float tolx = xmax * (REPS * 8.f);
+            for (int f = 0; f < RKP; f += 4) {
+                m0 = fmaxf(m0, fabsf(acc[f]));
+                m1 = fmaxf(m1, fabsf(acc[f + 1]));
+                m2 = fmaxf(m2, fabsf(acc[f + 2]));
+                m3 = fmaxf(m3, fabsf(acc[f + 3]));
+            }
+            thr = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * (REPS * 8.f);
+        }
+        uint32_t n0 = 0u, n1 = 0u, n2 = 0u, n3 = 0u;
 #pragma unroll
-        for (int f = 0; f < RKP; ++f)
-            if (((F >> f) & 1u) && acc[f] < -tolx) infeas |= 1u << f;
-    } else {
-        const uint32_t Aset = (~F) & kmask;
-#pragma unroll
-        for (int f = 0; f < RKP; ++f)
-            if (((Aset >> f) & 1u) && acc[f] < -tol) infeas |= 1u << f;
+        for (int f = 0; f < RKP; f += 4) {
+            n0 |= (acc[f] < -thr) ? (1u << f) : 0u;
+            n1 |= (acc[f + 1] < -thr) ? (2u << f) : 0u;
+            n2 |= (acc[f + 2] < -thr) ? (4u << f) : 0u;
+            n3 |= (acc[f + 3] < -thr) ? (8u << f) : 0u;
+        }
+        infeas |= ((n0 | n1) | (n2 | n3)) & (dual ? F : ((~F) & kmask));
     }
     int alpha = state & 0xff, beta = (state >> 8) & 0xff, iter = state >> 16;
     if (infeas != 0u && iter < MAXIT) {
@@ -223,19 +248,20 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
     float* Ps = reinterpret_cast<float*>(smem_raw + L.P);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* wbase = reinterpret_cast<float*>(smem_raw + L.warp0 + (size_t)warp * L.per_warp);
-    float* bcol = wbase + lane;            // [f][lane], 33 rows (row 32 = 0: rhs of the padding unknowns)
-    float* ucol = wbase + RCOL + lane;
-    float* zcol = wbase + 2 * RCOL + lane;
+    // staging tiles: buffer q of b at wbase + q*2*RBUF, of u at wbase + (q*2+1)*RBUF; this lane's chunk 0 at + lane*4
+    float* stage = wbase + lane * 4;
+    float* zcol = wbase + 4 * RBUF + lane;
     __shared__ int next_col;
     __shared__ int hist[18];
     __shared__ unsigned short order[RSUB];
+    uint32_t* fmask = reinterpret_cast<uint32_t*>(smem_raw + L.fmask);   // warm-start passive sets of the pass
 
     const bool cold_start = (flags & 1) != 0;
     const bool sync_rounds = (flags & 32) != 0;   // CTA-wide round barrier: the warps walk the unrolled code together (I-cache)
     const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
     const int MAXIT = 4 * k + 16;
-    bcol[32 * 32] = 0.f;
-    ucol[32 * 32] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(stage + q * RBUF + 8 * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
     zcol[32 * 32] = 0.f;
 
     long long per = (total_cols + gridDim.x - 1) / gridDim.x;
@@ -283,7 +309,9 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         if (tid < 18) hist[tid] = 0;
         __syncthreads();
         for (int c = tid; c < nsub; c += blockDim.x) {
-            const int p = cold_start ? 0 : __popc((uint32_t)masks[c] & kmask);
+            const uint32_t f0 = cold_start ? 0u : ((uint32_t)masks[c] & kmask);
+            fmask[c] = f0;
+            const int p = __popc(f0);
             atomicAdd(&hist[16 - min(p, k - p)], 1);
         }
         __syncthreads();
@@ -293,54 +321,91 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 const int h = hist[b];
                 hist[b] = run;
                 run += h;
+                if (b == 7) hist[17] = run;   // columns whose system has more than 8 unknowns
             }
             next_col = 0;
         }
         __syncthreads();
         for (int c = tid; c < nsub; c += blockDim.x) {
-            const int p = cold_start ? 0 : __popc((uint32_t)masks[c] & kmask);
+            const int p = __popc(fmask[c]);
             order[atomicAdd(&hist[16 - min(p, k - p)], 1)] = (unsigned short)c;
         }
         __syncthreads();
 
+        // round barrier only while the big unrolled templates dominate (they do not fit the instruction cache: the
+        // warps then walk the code together); a pass of mostly small systems runs barrier-free
+        const bool sync_pass = sync_rounds && hist[17] * 4 > nsub;
         bool active = false, exhausted = false, have_u = false;
-        int col = 0, state = 0;
+        int col = 0, state = 0, nxt = -1;
         uint32_t F = 0u;
         float tol = 0.f;
-        for (;;) {
-            const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
-            if (want) {
-                const int leader = __ffs((int)want) - 1;
+        // every lane keeps ONE column reserved ahead of the one it is solving, and prefetches that column's b (and u)
+        // row -- exactly one 128-byte line each -- into L1 while it works: the refill then finds its operands on chip
+        int cur = 0;   // staging buffer of the column being solved; the reserved column streams into cur ^ 1
+        auto claim = [&](bool wants, int into) {
+            const unsigned w = __ballot_sync(0xffffffffu, wants);
+            int got = -1;
+            if (w) {
+                const int leader = __ffs((int)w) - 1;
                 int base = 0;
-                if (lane == leader) base = atomicAdd(&next_col, __popc(want));
+                if (lane == leader) base = atomicAdd(&next_col, __popc(w));
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (!active && !exhausted) {
-                    const int ci = base + __popc(want & ((1u << lane) - 1u));
-                    if (ci >= nsub) {
-                        exhausted = true;
-                    } else {
-                        const int c = order[ci];
-                        col = c;
-                        const float4* rv = reinterpret_cast<const float4*>(rhs + (size_t)c * RKP);
-                        float bm = 0.f;
+                if (wants) {
+                    const int ci = base + __popc(w & ((1u << lane) - 1u));
+                    if (ci < nsub) {
+                        got = order[ci];
+                        const uint32_t db = smem_addr(stage + into * 2 * RBUF);
+                        const float* gb = rhs + (size_t)got * RKP;
 #pragma unroll
-                        for (int i = 0; i < RKP / 4; ++i) {
-                            const float4 v = __ldg(rv + i);
-                            bcol[(4 * i + 0) * 32] = v.x;
-                            bcol[(4 * i + 1) * 32] = v.y;
-                            bcol[(4 * i + 2) * 32] = v.z;
-                            bcol[(4 * i + 3) * 32] = v.w;
-                            bm = fmaxf(bm, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                        for (int i = 0; i < RKP / 4; ++i)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(db + i * 512), "l"(gb + 4 * i) : "memory");
+                        if (upre) {
+                            const float* gu = upre + (size_t)got * RKP;
+#pragma unroll
+                            for (int i = 0; i < RKP / 4; ++i)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(db + RBUF * 4 + i * 512), "l"(gu + 4 * i)
+                                             : "memory");
                         }
-                        F = cold_start ? 0u : ((uint32_t)masks[c] & kmask);
-                        state = 3 | ((k + 1) << 8);
-                        tol = bm * (REPS * 8.f);
-                        have_u = false;
-                        active = true;
                     }
                 }
             }
-            if (sync_rounds ? !__syncthreads_or(active) : !__any_sync(0xffffffffu, active)) break;
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return got;
+        };
+        nxt = claim(true, 0);
+        cur = 1;   // the first refill flips to buffer 0
+        for (;;) {
+            const bool refill = !active && !exhausted;
+            int c = -1;
+            if (refill) {
+                c = nxt;
+                if (c < 0) exhausted = true;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");   // the reserved column's rows have landed (issued a round ago)
+            if (c >= 0) cur ^= 1;
+            {
+                const bool wants = refill && c >= 0;
+                const int got = claim(wants, cur ^ 1);
+                if (wants) nxt = got;
+            }
+            const float* bcol = stage + cur * 2 * RBUF;
+            float* ucol = stage + cur * 2 * RBUF + RBUF;
+            if (c >= 0) {
+                col = c;
+                const float4* b4 = reinterpret_cast<const float4*>(bcol);
+                float bm = 0.f;
+#pragma unroll
+                for (int i = 0; i < RKP / 4; ++i) {
+                    const float4 v = b4[i * 32];
+                    bm = fmaxf(bm, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                }
+                F = fmask[c];
+                state = 3 | ((k + 1) << 8);
+                tol = bm * (REPS * 8.f);
+                have_u = upre != nullptr;   // u = P b from the tensor cores arrived with b
+                active = true;
+            }
+            if (sync_pass ? !__syncthreads_or(active) : !__any_sync(0xffffffffu, active)) break;
             int s = 0;
             bool dual = false;
             uint32_t S = 0u;
@@ -349,24 +414,12 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 dual = (k - p) < p;
                 S = dual ? ((~F) & kmask) : F;
                 s = dual ? (k - p) : p;
-                if (dual && !have_u && upre) {   // u = P b was formed on the tensor cores (k_pb_tc)
-                    const float4* uv = reinterpret_cast<const float4*>(upre + (size_t)col * RKP);
-#pragma unroll
-                    for (int i = 0; i < RKP / 4; ++i) {
-                        const float4 v = __ldg(uv + i);
-                        ucol[(4 * i + 0) * 32] = v.x;
-                        ucol[(4 * i + 1) * 32] = v.y;
-                        ucol[(4 * i + 2) * 32] = v.z;
-                        ucol[(4 * i + 3) * 32] = v.w;
-                    }
-                    have_u = true;
-                }
                 if (dual && !have_u) {   // u = P b, once per column, broadcast reads of P
                     float acc[RKP];
 #pragma unroll
                     for (int f = 0; f < RKP; ++f) acc[f] = 0.f;
                     for (int t = 0; t < k; ++t) {
-                        const float bt = bcol[t * 32];
+                        const float bt = bcol[bw(t)];
                         const float4* row = reinterpret_cast<const float4*>(Ps + t * RMST);
 #pragma unroll
                         for (int c = 0; c < RKP / 4; ++c) {
@@ -378,7 +431,8 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                         }
                     }
 #pragma unroll
-                    for (int f = 0; f < RKP; ++f) ucol[f * 32] = acc[f];
+                    for (int c4 = 0; c4 < RKP / 4; ++c4)
+                        reinterpret_cast<float4*>(ucol)[c4 * 32] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
                     have_u = true;
                 }
             }
