@@ -190,35 +190,66 @@ void check_device() {
 }
 
 // upload one CSC block's local column range [c0, c1) as fp32 device CSC
-void upload_csc(const lgr_csc& M, int c0, int c1, DBuf<int>& colptr, DBuf<int>& rowidx, DBuf<float>& val, size_t& nnz,
-                cudaStream_t st) {
-    const int n = c1 - c0;
-    std::vector<int> p((size_t)n + 1);
-    const int base = M.colptr[c0];
-    for (int j = 0; j <= n; ++j) {
-        const int v = M.colptr[c0 + j] - base;
-        LGR_REQUIRE(v >= 0 && (j == 0 || v >= p[j - 1]), "CSC column pointers must be non-decreasing");
-        p[j] = v;
-    }
-    nnz = (size_t)p[n];
-    colptr.alloc((size_t)n + 1);
-    LGR_CUDA(cudaMemcpyAsync(colptr.p, p.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    LGR_CUDA(cudaStreamSynchronize(st));  // p is a stack-owned staging vector
-    rowidx.alloc(nnz);
-    val.alloc(nnz);
-    if (nnz) {
-        LGR_CUDA(cudaMemcpyAsync(rowidx.p, M.rowidx + base, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
-        if (M.value_dtype == LGR_F32) {
-            LGR_CUDA(cudaMemcpyAsync(val.p, static_cast<const float*>(M.values) + base, nnz * sizeof(float),
-                                     cudaMemcpyHostToDevice, st));
-        } else {
-            DBuf<double> tmp(nnz);
-            LGR_CUDA(cudaMemcpyAsync(tmp.p, static_cast<const double*>(M.values) + base, nnz * sizeof(double),
-                                     cudaMemcpyHostToDevice, st));
-            dev_f64_to_f32(tmp.p, val.p, nnz, st);
-            LGR_CUDA(cudaStreamSynchronize(st));
+// Upload of one CSC block in two phases so that the PCIe copies of ALL blocks are queued on a copy stream up front
+// and overlap the layout construction of the earlier blocks on the compute stream:
+//   stage_csc   validates / rebases the column pointers on the host, allocates, enqueues the H2D copies on `cs`
+//   finish_csc  (compute stream, after the block's copy event) converts fp64 values to fp32
+struct CopyStream {
+    cudaStream_t s = nullptr;
+    CopyStream() { LGR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+    ~CopyStream() {
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
         }
     }
+};
+struct StagedCsc {
+    int base = 0;             // first entry of the shard in the caller's arrays (column pointers are rebased on the device)
+    DBuf<int> colptr, rowidx;
+    DBuf<float> val;
+    DBuf<double> val64;
+    size_t nnz = 0;
+    cudaEvent_t done = nullptr;
+    ~StagedCsc() {
+        if (done) cudaEventDestroy(done);
+    }
+};
+void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs) {
+    const int n = c1 - c0;
+    const int base = M.colptr[c0];
+    for (int j = 1; j <= n; ++j)
+        LGR_REQUIRE(M.colptr[c0 + j] >= M.colptr[c0 + j - 1], "CSC column pointers must be non-decreasing");
+    S.base = base;
+    S.nnz = (size_t)(M.colptr[c0 + n] - base);
+    S.colptr.alloc((size_t)n + 1);
+    S.rowidx.alloc(S.nnz);
+    S.val.alloc(S.nnz);
+    if (S.nnz && M.value_dtype != LGR_F32) S.val64.alloc(S.nnz);
+    LGR_CUDA(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    // the buffers were allocated in stream order on the allocation stream: the copy stream must not run ahead of it
+    cudaEvent_t alloc_done;
+    LGR_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+    LGR_CUDA(cudaEventRecord(alloc_done, alloc_stream()));
+    LGR_CUDA(cudaStreamWaitEvent(cs, alloc_done, 0));
+    LGR_CUDA(cudaEventDestroy(alloc_done));
+    // straight from the caller's array (no pageable staging vector: that would serialise the host with the copy stream)
+    LGR_CUDA(cudaMemcpyAsync(S.colptr.p, M.colptr + c0, ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, cs));
+    if (S.nnz) {
+        LGR_CUDA(cudaMemcpyAsync(S.rowidx.p, M.rowidx + base, S.nnz * sizeof(int), cudaMemcpyHostToDevice, cs));
+        if (M.value_dtype == LGR_F32)
+            LGR_CUDA(cudaMemcpyAsync(S.val.p, static_cast<const float*>(M.values) + base, S.nnz * sizeof(float),
+                                     cudaMemcpyHostToDevice, cs));
+        else
+            LGR_CUDA(cudaMemcpyAsync(S.val64.p, static_cast<const double*>(M.values) + base, S.nnz * sizeof(double),
+                                     cudaMemcpyHostToDevice, cs));
+    }
+    LGR_CUDA(cudaEventRecord(S.done, cs));
+}
+void finish_csc(StagedCsc& S, cudaStream_t st) {
+    LGR_CUDA(cudaStreamWaitEvent(st, S.done, 0));
+    if (S.base != 0) dev_add_int(S.colptr.p, S.colptr.n, -S.base, st);
+    if (S.nnz && S.val64.p) dev_f64_to_f32(S.val64.p, S.val.p, S.nnz, st);
 }
 
 void upload_factor(const double* host, double* dev_padded, int rows, int k, int kp, cudaStream_t st) {
@@ -463,6 +494,32 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->sq.zero(c->st);
     size_t b_total = 0, r_total = 0;
     int max_rows = 0;
+    tr.mark("ctx setup");
+    // ---- pass 1: validate, then queue every H2D copy on the copy stream ----
+    std::vector<StagedCsc> stagedE(c->d), stagedP(c->d);
+    CopyStream cstream;
+    for (int i = 0; i < c->d; ++i) {
+        const lgr_csc& E = a->E[i];
+        LGR_REQUIRE(E.nrow == a->m, "every E[i] must have m rows");
+        LGR_REQUIRE(E.ncol >= 1 && E.ncol < (int64_t)0x7fffffff, "E[i].ncol out of range");
+        LGR_REQUIRE(E.colptr && (E.colptr[E.ncol] == 0 || (E.rowidx && E.values)), "E[i] has null arrays");
+        const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
+        const int n_full = (int)E.ncol;
+        const int s0 = local ? 0 : (int)((int64_t)n_full * c->rank / c->world);
+        const int s1 = local ? n_full : (int)((int64_t)n_full * (c->rank + 1) / c->world);
+        tr.mark("validate");
+        stage_csc(E, s0, s1, stagedE[i], cstream.s);
+        tr.mark("stage_csc");
+        if (a->P && a->P[i].nrow > 0) {
+            LGR_REQUIRE(a->P[i].ncol == E.ncol, "P[i] must have the same cells as E[i]");
+            LGR_REQUIRE(a->P[i].nrow < (1 << 30), "P[i].nrow out of range");
+            LGR_REQUIRE(a->P[i].colptr && (a->P[i].colptr[a->P[i].ncol] == 0 || (a->P[i].rowidx && a->P[i].values)),
+                        "P[i] has null arrays");
+            stage_csc(a->P[i], s0, s1, stagedP[i], cstream.s);
+        }
+    }
+    tr.mark("stage H2D copies");
+    // ---- pass 2: per dataset, wait for its copy and build the device layouts (the later copies keep streaming) ----
     for (int i = 0; i < c->d; ++i) {
         Dataset& D = c->ds[i];
         const lgr_csc& E = a->E[i];
@@ -484,22 +541,24 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         }
         D.rows = m + D.u;
         max_rows = std::max(max_rows, D.rows);
-        if (i == 0) tr.mark("ctx setup");
+        StagedCsc& SE = stagedE[i];
+        StagedCsc& SP = stagedP[i];
         if (!P) {
-            upload_csc(E, D.c0, c1, D.colptr, D.rowidx, D.val, D.nnz, c->st);
-            tr.mark("upload_csc");
+            finish_csc(SE, c->st);
+            D.colptr = std::move(SE.colptr);
+            D.rowidx = std::move(SE.rowidx);
+            D.val = std::move(SE.val);
+            D.nnz = SE.nnz;
+            tr.mark("finish_csc");
         } else {
-            DBuf<int> pE, iE, pP, iP;
-            DBuf<float> vE, vP;
-            size_t nE = 0, nP = 0;
-            upload_csc(E, D.c0, c1, pE, iE, vE, nE, c->st);
-            upload_csc(*P, D.c0, c1, pP, iP, vP, nP, c->st);
-            D.nnz = nE + nP;
+            finish_csc(SE, c->st);
+            finish_csc(SP, c->st);
+            D.nnz = SE.nnz + SP.nnz;
             D.colptr.alloc((size_t)D.n + 1);
             D.rowidx.alloc(D.nnz);
             D.val.alloc(D.nnz);
-            dev_stack_csc(D.n, pE.p, iE.p, vE.p, pP.p, iP.p, vP.p, m, D.colptr.p, D.rowidx.p, D.val.p, c->st);
-            LGR_CUDA(cudaStreamSynchronize(c->st));
+            dev_stack_csc(D.n, SE.colptr.p, SE.rowidx.p, SE.val.p, SP.colptr.p, SP.rowidx.p, SP.val.p, m, D.colptr.p, D.rowidx.p,
+                          D.val.p, c->st);
         }
         const int ntiles = (D.n + c->tc - 1) / c->tc;
         (void)ntiles;
@@ -527,6 +586,9 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         D.r_off = r_total;
         r_total += (size_t)D.rows * kp;
     }
+    LGR_CUDA(cudaStreamSynchronize(cstream.s));
+    stagedE.clear();
+    stagedP.clear();
     c->max_rows = max_rows;
     c->N_local = b_total / kp;
     c->Bbuf.alloc(std::max<size_t>(b_total, 1));

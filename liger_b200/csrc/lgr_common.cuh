@@ -197,6 +197,7 @@ void kernels_init();  // opt-in shared memory attributes
 
 // layout / conversion kernels (lgr_layout.cu)
 void dev_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
+void dev_add_int(int* p, size_t n, int delta, cudaStream_t st);
 void dev_sumsq(const float* v, size_t n, double* out, cudaStream_t st);
 void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const int* pP, const int* iP,
                    const float* vP, int m, int* pS, int* iS, float* vS, cudaStream_t st);

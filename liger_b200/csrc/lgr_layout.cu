@@ -42,6 +42,15 @@ void dev_sumsq(const float* v, size_t n, double* out, cudaStream_t st) {
     LGR_CUDA(cudaGetLastError());
 }
 
+__global__ void k_add_int(int* __restrict__ p, size_t n, int delta) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] += delta;
+}
+void dev_add_int(int* p, size_t n, int delta, cudaStream_t st) {
+    if (!n) return;
+    k_add_int<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(p, n, delta);
+    LGR_CUDA(cudaGetLastError());
+}
+
 // stacked column j = E column j followed by P column j with row indices shifted by m
 __global__ void k_stack_ptr(int n, const int* pE, const int* pP, int* pS) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
