@@ -98,7 +98,8 @@ typedef struct lgr_inmf_args {
     int32_t rank;   /* cell-shard rank of this process, 0 when world == 1 */
     int32_t world;  /* number of processes sharing the factorisation (one GPU each) */
     int32_t reserved;
-    const void* nccl_unique_id; /* 128 bytes from lgr_nccl_unique_id() (same on all ranks); NULL if world == 1 */
+    const void* nccl_unique_id; /* 128 bytes from lgr_nccl_unique_id() (same on all ranks); NULL if world == 1.
+                                   Passing the SAME id again reuses the cached communicator (no ncclCommInitRank). */
     /* optional: polled between iterations; non-zero return aborts with LGR_ERR_INTERRUPT */
     int (*interrupt)(void* user);
     void* interrupt_user;

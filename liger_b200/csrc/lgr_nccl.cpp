@@ -7,6 +7,9 @@
 
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
+#include <string.h>
 
 #include "lgr_common.cuh"
 
@@ -60,11 +63,22 @@ void nccl_unique_id(void* out128) {
     check(api().GetUniqueId(&id), "ncclGetUniqueId");
     memcpy(out128, &id, sizeof(id));
 }
+// Communicators are cached per process, keyed by (unique id, rank, world): ncclCommInitRank costs ~0.3 s, so a caller
+// that passes the SAME unique id to successive lgr_inmf / lgr_uinmf / lgr_ctx_create calls (one per session, like an R
+// session would) pays for it once.  A new id makes a new communicator.  Cached communicators live until process exit.
 NcclComm* nccl_init(const void* id128, int rank, int world) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::string, NcclComm*>> cache;
+    std::string key(static_cast<const char*>(id128), sizeof(ncclUniqueId));
+    key += ":" + std::to_string(rank) + "/" + std::to_string(world);
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& kv : cache)
+        if (kv.first == key) return kv.second;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     NcclComm* c = new NcclComm;
     check(api().CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
+    cache.emplace_back(key, c);
     return c;
 }
 void nccl_allreduce_sum_f32(NcclComm* c, float* buf, size_t n, cudaStream_t st) {
@@ -75,9 +89,5 @@ void nccl_allreduce_sum_f64(NcclComm* c, double* buf, size_t n, cudaStream_t st)
 }
 void nccl_group_start() { check(api().GroupStart(), "ncclGroupStart"); }
 void nccl_group_end() { check(api().GroupEnd(), "ncclGroupEnd"); }
-void nccl_destroy(NcclComm* c) {
-    if (!c) return;
-    api().CommDestroy(c->comm);
-    delete c;
-}
+void nccl_destroy(NcclComm*) {}   // cached communicators are released at process exit
 }  // namespace lgr
