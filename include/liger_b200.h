@@ -74,6 +74,8 @@ typedef struct lgr_csc {
 #define LGR_FLAG_PINNED_IO 0x4u   /* caller promises host buffers are page-locked (faster copies) */
 #define LGR_FLAG_TENSOR_U 0x10u   /* form u = CtC^-1 b of the H solve on the tensor cores (tcgen05, 3xTF32 split) instead
                                      of fp32 FMAs inside the NNLS kernel; same results to ~1e-5, measured slower at k=30 */
+#define LGR_FLAG_LEGACY_NNLS 0x20u /* verification only: run the H solves with the shared-memory-factor NNLS kernel
+                                     (lgr_nnls.cu) instead of the register-resident one (lgr_nnls_reg.cu, k <= 32) */
 #define LGR_FLAG_LOCAL_SHARD 0x8u /* world > 1: E/P already hold only THIS rank's cells (one process per GPU, each
                                      with its own shard); without it every rank passes the full matrices and the
                                      library takes columns [n*rank/world, n*(rank+1)/world) */

@@ -193,7 +193,7 @@ class _Out:
 
 def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
          trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False, tensor_u=False,
-         rank=0, world=1, nccl_id=None, local_shard=False):
+         rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False):
     """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
 
     Multi-GPU (one process per GPU): pass `rank`, `world`, the `nccl_id` created by rank 0 (nccl_unique_id()) and
@@ -209,7 +209,8 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
         raise ValueError("liger_b200.inmf needs explicit Winit/Vinit (rliger's .runINMF.list always passes them; "
                          "use liger_b200.integration.run_inmf_list for the seeded initialisation)")
     flags = ((_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0) |
-             (_ffi.FLAG_TENSOR_U if tensor_u else 0) | (0x8 if (local_shard and world > 1) else 0))
+             (_ffi.FLAG_TENSOR_U if tensor_u else 0) | (0x8 if (local_shard and world > 1) else 0) |
+             (_ffi.FLAG_LEGACY_NNLS if legacy_nnls else 0))
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device, rank=rank, world=world,
               nccl_id=nccl_id)
     o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs)

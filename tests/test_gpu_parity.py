@@ -146,6 +146,41 @@ def test_inmf_synthetic_ragged(k, ns, m):
     assert np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"]) < TOL_OBJ
 
 
+def test_register_nnls_equals_shared_memory_nnls(pbmc):
+    """The two H-solve kernels (register-resident, lgr_nnls_reg.cu; shared-memory factor, lgr_nnls.cu) solve the same
+    strictly convex problems: same zero patterns away from degenerate coordinates, values to fp32 rounding."""
+    import liger_b200
+    W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    a = liger_b200.inmf(pbmc["Es"], k=20, niter=7, Winit=W0, Vinit=V0)
+    b = liger_b200.inmf(pbmc["Es"], k=20, niter=7, Winit=W0, Vinit=V0, legacy_nnls=True)
+    for x, y in zip(a["H"], b["H"]):
+        assert rel(x, y) < 1e-5
+        scale = y.max()
+        assert not np.any(((x == 0) & (y > 1e-5 * scale)) | ((y == 0) & (x > 1e-5 * scale)))
+    assert rel(a["W"], b["W"]) < 1e-5
+
+
+@pytest.mark.parametrize("k", [32, 31, 8])
+def test_register_nnls_full_width_and_dead_factor(k):
+    """k = 32 fills the padded factor row exactly (no spare padding column); a factor that is zero in W and every V_i
+    makes the H-solve Gram singular, which must route that dataset's columns to the fallback kernel, not to NaNs."""
+    import liger_b200
+    from liger_b200 import synthetic as syn
+    Es = [syn.make_numpy(1, n, 120, 8, block=500, seed=7 + i)[0][0] for i, n in enumerate((257, 64))]
+    W0, V0, _, _ = orc.seeded_init(3, 120, k, [257, 64])
+    out = liger_b200.inmf(Es, k=k, lambda_=5.0, niter=5, Winit=W0, Vinit=V0, trajectory=True)
+    ref = c_oracle.inmf(Es, k, 5.0, 5, W0, V0, trajectory=True)
+    _check(out, ref)
+    W1 = W0.copy()
+    V1 = [v.copy() for v in V0]
+    W1[:, 2] = 0.0
+    for v in V1:
+        v[:, 2] = 0.0
+    out = liger_b200.inmf(Es, k=k, lambda_=5.0, niter=1, Winit=W1, Vinit=V1)
+    assert all(np.isfinite(h).all() for h in out["H"]) and np.isfinite(out["W"]).all()
+    assert all(np.all(h[:, 2] == 0) for h in out["H"])          # the dead factor carries no loading after the H solve
+
+
 def test_inmf_cold_start_equals_warm_start(pbmc):
     import liger_b200
     W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
