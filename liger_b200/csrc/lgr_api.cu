@@ -80,7 +80,8 @@ struct Dataset {
     double lambda = 0.0;
     DBuf<int> colptr, rowidx, tptr8, cptr8;
     DBuf<float> val, tval, cval, L, H;
-    DBuf<unsigned int> tcell, crow;
+    DBuf<unsigned short> tcell, crow;
+    DBuf<unsigned int> ttag, ctag;
     int ngt = 1;
     DBuf<unsigned long long> hmask, vmask;
     DBuf<double> V, CtBv;
@@ -563,10 +564,10 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         const int ntiles = (D.n + c->tc - 1) / c->tc;
         (void)ntiles;
         // the two padded tile formats of X (lgr_spmm.cu); the plain CSC upload is dropped afterwards
-        dev_build_padded(1, D.n, D.rows, c->tc, kp / 4, 0, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.tval, c->st);
+        dev_build_padded(1, D.n, D.rows, c->tc, kp / 4, 0, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.ttag, D.tval, c->st);
         tr.mark("build cell-tiled CSR");
         D.ngt = (D.rows + c->gt - 1) / c->gt;
-        dev_build_padded(0, D.n, D.rows, c->gt, kp / 4, c->cb, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.cval, c->st);
+        dev_build_padded(0, D.n, D.rows, c->gt, kp / 4, c->cb, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.ctag, D.cval, c->st);
         tr.mark("build gene-tiled CSC");
         dev_sumsq(D.val.p, D.nnz, c->sq.p + i, c->st);
         LGR_CUDA(cudaStreamSynchronize(c->st));
@@ -645,9 +646,11 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.val = D.val.p;
         h.cptr8 = D.cptr8.p;
         h.crow = D.crow.p;
+        h.ctag = D.ctag.p;
         h.cval = D.cval.p;
         h.tptr8 = D.tptr8.p;
         h.tcell = D.tcell.p;
+        h.ttag = D.ttag.p;
         h.tval = D.tval.p;
         h.ngt = D.ngt;
         h.L = D.L.p;

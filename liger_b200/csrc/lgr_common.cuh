@@ -102,10 +102,12 @@ struct DsDev {
     const int* rowidx;
     const float* val;
     const int* cptr8;            // gene-tiled CSC (padded to 8): [ngt * n + 1] segment starts in groups of 8
-    const unsigned int* crow;    // (row inside the gene tile) * KP/4; word 0 of a group: | (cell % CB) << 14
+    const unsigned short* crow;  // (row inside the gene tile) * KP/4
+    const unsigned int* ctag;    // per group of 8: cell % CB
     const float* cval;
     const int* tptr8;            // cell-tiled CSR (padded to 8): [ntiles * rows + 1]
-    const unsigned int* tcell;   // (cell inside the cell tile) * KP/4; word 0 of a group: | gene << 14
+    const unsigned short* tcell; // (cell inside the cell tile) * KP/4
+    const unsigned int* ttag;    // per group of 8: gene
     const float* tval;
     int ngt;                     // gene tiles
     int pad0;
@@ -202,7 +204,8 @@ void dev_sumsq(const float* v, size_t n, double* out, cudaStream_t st);
 void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const int* pP, const int* iP,
                    const float* vP, int m, int* pS, int* iS, float* vS, cudaStream_t st);
 void dev_build_padded(int mode, int n, int rows, int tile, int scale, int tagmod, const int* colptr, const int* rowidx,
-                      const float* val, size_t nnz, DBuf<int>& ptr8, DBuf<unsigned int>& oloc, DBuf<float>& oval,
+                      const float* val, size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<unsigned int>& otag,
+                      DBuf<float>& oval,
                       cudaStream_t st);
 void dev_colmajor_to_padded(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);   // R m x k -> [row][KP]
 void dev_padded_to_colmajor(const double* in, double* out, int rows, int k, int kp, cudaStream_t st);

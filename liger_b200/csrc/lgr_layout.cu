@@ -85,9 +85,9 @@ void dev_stack_csc(int n, const int* pE, const int* iE, const float* vE, const i
 //   mode 1, cell-tiled CSR: key = (col / tile) * rows + row, loc = col % tile      (k_spmm_xh)
 // Entries are stably sorted by key (so the minor index stays ascending inside a segment) and every segment is
 // padded with (loc 0, value 0) entries to a multiple of 8; ptr8[key] is the segment start in groups of 8.
-// The stream is SELF-DESCRIBING: local indices are 32-bit words, pre-scaled by KP/4 (< 2^14), and word 0 of every
-// group of 8 carries in its upper 18 bits the group's output row (mode 0: cell % tagmod, mode 1: gene), so that a
-// consumer can be handed ANY contiguous range of groups without looking at ptr8.
+// The stream is SELF-DESCRIBING: besides the 16-bit local indices (pre-scaled by KP/4) and the fp32 values, every group
+// of 8 has a 32-bit tag = its output row (mode 0: cell % tagmod, mode 1: gene), so that a consumer can be handed ANY
+// contiguous range of groups without looking at ptr8.
 __global__ void k_tile_keys(int mode, int n, int rows, int tile, int scale, const int* __restrict__ colptr,
                             const int* __restrict__ rowidx, unsigned int* __restrict__ keys,
                             unsigned int* __restrict__ perm, unsigned short* __restrict__ loc, int* __restrict__ counts) {
@@ -118,25 +118,24 @@ __global__ void k_pad_counts(size_t nkeys, const int* __restrict__ counts, int* 
 __global__ void k_tile_scatter(size_t nnz, const unsigned int* __restrict__ keys_sorted, const unsigned int* __restrict__ perm,
                                const int* __restrict__ segstart, const int* __restrict__ ptr8,
                                const unsigned short* __restrict__ loc, const float* __restrict__ val,
-                               unsigned int minor, unsigned int tagmod, unsigned int* __restrict__ oloc,
-                               float* __restrict__ oval) {
+                               unsigned int minor, unsigned int tagmod, unsigned short* __restrict__ oloc,
+                               unsigned int* __restrict__ otag, float* __restrict__ oval) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (size_t)gridDim.x * blockDim.x) {
         const unsigned int key = keys_sorted[i], p = perm[i];
         const size_t off = i - (size_t)segstart[key];
         const size_t base = (size_t)ptr8[key] * 8;
-        const unsigned int tag = ((key % minor) % tagmod) << 14;
-        oloc[base + off] = (unsigned int)loc[p] | ((off & 7) == 0 ? tag : 0u);
+        oloc[base + off] = loc[p];
         oval[base + off] = val[p];
+        if ((off & 7) == 0) otag[(size_t)ptr8[key] + (off >> 3)] = (key % minor) % tagmod;
     }
 }
 
 void dev_build_padded(int mode, int n, int rows, int tile, int scale, int tagmod, const int* colptr, const int* rowidx,
-                      const float* val, size_t nnz, DBuf<int>& ptr8, DBuf<unsigned int>& oloc, DBuf<float>& oval,
-                      cudaStream_t st) {
+                      const float* val, size_t nnz, DBuf<int>& ptr8, DBuf<unsigned short>& oloc, DBuf<unsigned int>& otag,
+                      DBuf<float>& oval, cudaStream_t st) {
     // local indices are stored pre-scaled by `scale` (= KP/4, the float4 slots per staged row)
-    LGR_REQUIRE(tile >= 1 && (long long)tile * scale <= 16384, "tile size x KP/4 must fit a 14-bit local index");
-    LGR_REQUIRE(mode == 0 ? (tagmod >= 1 && tagmod <= (1 << 18)) : rows <= (1 << 18), "output-row tag must fit 18 bits");
-    if (mode == 1) tagmod = 1 << 18;
+    LGR_REQUIRE(tile >= 1 && (long long)tile * scale <= 65536, "tile size x KP/4 must fit a 16-bit local index");
+    if (mode == 1 || tagmod < 1) tagmod = 0x7fffffff;
     const size_t nmajor = mode == 0 ? (size_t)(rows + tile - 1) / tile : (size_t)(n + tile - 1) / tile;
     const size_t nkeys = nmajor * (size_t)(mode == 0 ? n : rows);
     LGR_REQUIRE(nkeys < (size_t)0x7fffffff, "tiled format: tiles x minor dimension exceeds 2^31");
@@ -145,8 +144,10 @@ void dev_build_padded(int mode, int n, int rows, int tile, int scale, int tagmod
     if (nnz == 0 || n == 0) {
         oloc.alloc(8);
         oval.alloc(8);
+        otag.alloc(1);
         oloc.zero(st);
         oval.zero(st);
+        otag.zero(st);
         return;
     }
     DBuf<unsigned int> keys(nnz), keys2(nnz), perm(nnz), perm2(nnz);
@@ -175,11 +176,13 @@ void dev_build_padded(int mode, int n, int rows, int tile, int scale, int tagmod
     const size_t padded = (size_t)total_groups * 8 + 8;
     oloc.alloc(padded);
     oval.alloc(padded);
+    otag.alloc((size_t)total_groups + 1);
     oloc.zero(st);
     oval.zero(st);
+    otag.zero(st);
     const int grid2 = (int)std::min<size_t>((nnz + 255) / 256, 148 * 16);
     k_tile_scatter<<<grid2, 256, 0, st>>>(nnz, keys2.p, perm2.p, segstart.p, ptr8.p, loc.p, val, (unsigned)(mode == 0 ? n : rows),
-                                         (unsigned)tagmod, oloc.p, oval.p);
+                                         (unsigned)tagmod, oloc.p, otag.p, oval.p);
     LGR_CUDA(cudaGetLastError());
     LGR_CUDA(cudaStreamSynchronize(st));
 }

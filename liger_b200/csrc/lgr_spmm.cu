@@ -9,11 +9,11 @@
 //       staged by one TMA bulk copy; inside a cell tile the entries are ordered by gene.  Warps own genes, gather
 //       H rows, and issue one vector RED (red.global.add.v4.f32) per (gene, tile).
 //
-// Both formats pad every (tile, minor) segment to a multiple of 8 entries (32-bit pre-scaled local index + fp32 value,
-// zero padded) and tag word 0 of every group of 8 with the group's output row (lgr_layout.cu).  The stream of a CTA is
+// Both formats pad every (tile, minor) segment to a multiple of 8 entries (16-bit pre-scaled local index + fp32 value,
+// zero padded) and keep one 32-bit tag per group of 8 = the group's output row (lgr_layout.cu).  The stream of a CTA is
 // therefore a flat, self-describing list of groups that is cut into EQUAL contiguous ranges, one per lane-group
 // (KP/4 lanes = one staged row per 128-bit shared-memory load): uniform trip counts, no votes, no pointer walks.
-// Per group: four 128-bit loads (prefetched one group ahead), then per non-zero one LEA, one 128-bit shared-memory
+// Per group: three 128-bit loads + the tag (prefetched one group ahead), then per non-zero ~2 ALU ops, one 128-bit shared-memory
 // load and four FFMAs; a change of the tag flushes the lane-group's 4 sums (the complete output row slice).
 #include "lgr_common.cuh"
 #include "lgr_ptx.cuh"
@@ -21,23 +21,25 @@
 namespace lgr {
 
 struct Group8 {
-    uint4 i0, i1;
-    float4 v0, v1;
+    uint4 i;        // 8 x 16-bit pre-scaled local indices
+    float4 v0, v1;  // 8 values
+    unsigned tag;   // output row of the group
 };
-__device__ __forceinline__ Group8 load_group(const unsigned int* __restrict__ loc, const float* __restrict__ val, int g) {
+__device__ __forceinline__ Group8 load_group(const unsigned short* __restrict__ loc, const unsigned int* __restrict__ tag,
+                                             const float* __restrict__ val, int g) {
     Group8 r;
-    const uint4* li = reinterpret_cast<const uint4*>(loc + (size_t)g * 8);
     const float4* vi = reinterpret_cast<const float4*>(val + (size_t)g * 8);
-    r.i0 = __ldg(li);
-    r.i1 = __ldg(li + 1);
+    r.i = __ldg(reinterpret_cast<const uint4*>(loc + (size_t)g * 8));
     r.v0 = __ldg(vi);
     r.v1 = __ldg(vi + 1);
+    r.tag = __ldg(tag + g);
     return r;
 }
 
 // acc += sum_j val_j * tile[idx_j][4s..4s+3]; `tile4s` already points at this lane's 16-byte slot of row 0.
 __device__ __forceinline__ void gather8(float4& acc, const Group8& G, const float4* __restrict__ tile4s) {
-    const unsigned c[8] = {G.i0.x & 0x3fffu, G.i0.y, G.i0.z, G.i0.w, G.i1.x, G.i1.y, G.i1.z, G.i1.w};
+    const unsigned c[8] = {G.i.x & 0xffffu, G.i.x >> 16, G.i.y & 0xffffu, G.i.y >> 16,
+                           G.i.z & 0xffffu, G.i.z >> 16, G.i.w & 0xffffu, G.i.w >> 16};
     const float vv[8] = {G.v0.x, G.v0.y, G.v0.z, G.v0.w, G.v1.x, G.v1.y, G.v1.z, G.v1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -53,19 +55,19 @@ __device__ __forceinline__ void gather8(float4& acc, const Group8& G, const floa
 // and `glast` the last group the prefetch may touch.  flush(row, acc, edge): `edge` is set for the first and the
 // last flush of the range, whose segments may continue in a neighbouring range.
 template <typename Flush>
-__device__ __forceinline__ void gather_range(const unsigned int* __restrict__ loc, const float* __restrict__ val, int g,
-                                             const int gend, const int trips, const int glast,
+__device__ __forceinline__ void gather_range(const unsigned short* __restrict__ loc, const unsigned int* __restrict__ tag,
+                                             const float* __restrict__ val, int g, const int gend, const int trips, const int glast,
                                              const float4* __restrict__ tile4s, Flush flush) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool any = g < gend;
-    Group8 cur = load_group(loc, val, min(g, glast));
-    unsigned seg = cur.i0.x >> 14;
+    Group8 cur = load_group(loc, tag, val, min(g, glast));
+    unsigned seg = cur.tag;
     bool first = true;
 #pragma unroll 2
     for (int i = 0; i < trips; ++i) {
-        const Group8 nxt = load_group(loc, val, min(g + 1, glast));
+        const Group8 nxt = load_group(loc, tag, val, min(g + 1, glast));
         if (g < gend) {
-            const unsigned t = cur.i0.x >> 14;
+            const unsigned t = cur.tag;
             if (t != seg) {
                 flush(seg, acc, first);
                 first = false;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* 
         const int per = (G1 - G0 + NQ - 1) / NQ;
         const int g = min(G0 + qid * per, G1), gend = min(g + per, G1);
         mbar_wait(bar, (uint32_t)(gt & 1));
-        gather_range(D.crow, D.cval, g, gend, per, max(G1 - 1, 0), Ls4 + s, [&](unsigned cell, float4 acc, bool edge) {
+        gather_range(D.crow, D.ctag, D.cval, g, gend, per, max(G1 - 1, 0), Ls4 + s, [&](unsigned cell, float4 acc, bool edge) {
             float* dst = Bp + (size_t)cell * KP + s * 4;
             if (edge) {   // the segment may be shared with the neighbouring range
                 atomicAdd(dst + 0, acc.x);
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(XH_THREADS, 1) k_spmm_xh(const DsDev* __restri
         const int g = min(G0 + qid * per, G1), gend = min(g + per, G1);
         const float4* Hs4 = reinterpret_cast<const float4*>(Hs);
         float* __restrict__ R = D.R;
-        gather_range(D.tcell, D.tval, g, gend, per, max(G1 - 1, 0), Hs4 + s,
+        gather_range(D.tcell, D.ttag, D.tval, g, gend, per, max(G1 - 1, 0), Hs4 + s,
                      [&](unsigned gene, float4 acc, bool) { red_add_v4(R + (size_t)gene * KP + s * 4, acc); });
     }
 
