@@ -313,3 +313,66 @@ def test_float32_values_input(pbmc):
     ctx.close()
     b = liger_b200.inmf(pbmc["Es"], k=20, niter=5, Winit=W0, Vinit=V0)
     assert rel(a["W"], b["W"]) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# optimizeNewK / optimizeNewLambda / optimizeNewData / optimizeSubset  (R/optimizeNewParam.R)
+# ----------------------------------------------------------------------------------------------
+def _fit_pair(pbmc, k=8, niter=3):
+    import liger_b200
+    from liger_b200 import integration
+    names = ["ctrl", "stim"]
+    data = dict(zip(names, pbmc["Es"]))
+    fit = integration.runINMF(data, k=k, lambda_=5.0, nIteration=niter, seed=1)
+    base = orc.run_inmf_list(pbmc["Es"], k=k, lam=5.0, niter=niter, seed=1)
+    ofit = {"W": base["W"], "V": base["V"], "H": base["H"], "lam": 5.0}
+    return names, data, fit, ofit
+
+
+def _cmp_fit(out, ref, names, tol=TOL_FACTOR):
+    assert rel(out["W"], ref["W"]) < tol
+    for i, n in enumerate(names):
+        assert rel(out["V"][n], ref["V"][i]) < tol
+        assert rel(out["H"][n], ref["H"][i]) < tol
+        assert pattern_mismatches(out["H"][n].T, ref["H"][i].T) == 0
+    assert abs(out["objErr"] - ref["objErr"]) / ref["objErr"] < TOL_OBJ
+
+
+@pytest.mark.parametrize("k_new", [11, 5, 8])
+def test_optimize_new_k(pbmc, k_new):
+    from liger_b200 import optimize
+    from oracle import optimize_oracle as oo
+    names, data, fit, ofit = _fit_pair(pbmc)
+    out = optimize.optimizeNewK(data, fit, kNew=k_new, nIteration=2, seed=1)
+    if k_new == 8:
+        assert out is fit           # test_factorization.R:106-107
+        return
+    ref = oo.optimize_new_k(pbmc["Es"], ofit, k_new, 2, seed=1)
+    assert out["W"].shape == (173, k_new) and out["uns"]["factorization"]["k"] == k_new
+    _cmp_fit(out, ref, names)
+
+
+def test_optimize_new_lambda_subset_and_data(pbmc):
+    from liger_b200 import optimize
+    from oracle import optimize_oracle as oo
+    names, data, fit, ofit = _fit_pair(pbmc)
+    msgs = []
+    out = optimize.optimizeNewLambda(data, fit, lambdaNew=4.0, nIteration=2, seed=1, warn=msgs.append)
+    assert msgs and "New lambda less than current lambda" in msgs[0]          # test_factorization.R:114-115
+    _cmp_fit(out, oo.optimize_new_lambda(pbmc["Es"], ofit, 4.0, 2, seed=1), names)
+    rng = np.random.default_rng(0)
+    idx = {"ctrl": np.sort(rng.choice(300, 150, replace=False)), "stim": np.sort(rng.choice(300, 150, replace=False))}
+    out = optimize.optimizeSubset(data, fit, idx, nIteration=2)
+    assert sum(h.shape[1] for h in out["H"].values()) == 300                  # test_factorization.R:119
+    _cmp_fit(out, oo.optimize_subset(pbmc["Es"], ofit, [idx["ctrl"], idx["stim"]], 2), names)
+    # new data as a new dataset inheriting ctrl's V (merge = FALSE), and appended to ctrl (merge = TRUE)
+    new = sp.csc_matrix(pbmc["Es"][0][:, ::2] * 1.5)
+    out = optimize.optimizeNewData(data, fit, {"ctrl2": new}, ["ctrl"], merge=False, nIteration=2)
+    ref = oo.optimize_new_data(pbmc["Es"], ofit, [new], [0], False, niter=2)
+    _cmp_fit(out, ref, names + ["ctrl2"])
+    merged = sp.hstack([pbmc["Es"][0], new]).tocsc()
+    out = optimize.optimizeNewData(data, fit, {"ctrl2": merged}, ["ctrl"], merge=True,
+                                   newCells={"ctrl2": np.arange(300, 450)}, nIteration=2)
+    ref = oo.optimize_new_data(pbmc["Es"], ofit, [merged], [0], True, new_cells=[np.arange(300, 450)], niter=2)
+    assert out["H"]["ctrl"].shape[1] == 450                                   # cells were added (cf. :127)
+    _cmp_fit(out, ref, names)

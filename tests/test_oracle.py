@@ -120,3 +120,26 @@ def test_synthetic_generator():
         assert E.data.min() > 0
         ss = np.asarray(E.multiply(E).sum(axis=1)).ravel() / (1200 - 1)
         assert np.allclose(ss[ss > 0], 1.0)
+
+
+def test_optimize_oracle_invariants(pbmc):
+    """oracle/optimize_oracle.py (R/optimizeNewParam.R): kNew == k is the identity, kNew < k keeps the factors with the
+    largest loading norms and starts exactly from them (niter = 0), kNew > k starts from a point that does not lose
+    to the old fit, a subset run starts from the subset's own H columns."""
+    from oracle import optimize_oracle as oo
+    Es = pbmc["Es"]
+    base = orc.run_inmf_list(Es, k=8, lam=5.0, niter=3, seed=1)
+    fit = {"W": base["W"], "V": base["V"], "H": base["H"], "lam": 5.0}
+    assert oo.optimize_new_k(Es, fit, 8, 2) is fit
+    down = oo.optimize_new_k(Es, fit, 5, 0)
+    assert down["W"].shape == (173, 5) and down["H"][0].shape == (5, 300)
+    cols = [int(np.argmin(np.abs(fit["W"] - down["W"][:, [j]]).sum(0))) for j in range(5)]
+    assert len(set(cols)) == 5 and np.allclose(fit["W"][:, cols], down["W"])
+    up0 = oo.optimize_new_k(Es, fit, 11, 0)
+    assert up0["W"].shape == (173, 11) and up0["objErr"] <= base["objErr"] * (1 + 1e-9)
+    assert min(x.min() for x in up0["H"]) >= 0 and up0["W"].min() >= 0
+    idx = [np.arange(0, 300, 3), np.arange(1, 300, 2)]
+    sub = oo.optimize_subset(Es, fit, idx, 0)
+    assert np.allclose(sub["H"][1], fit["H"][1][:, idx[1]])
+    lam2 = oo.optimize_new_lambda(Es, fit, 7.5, 2)
+    assert lam2["lam"] == 7.5 and lam2["W"].shape == (173, 8)
