@@ -141,6 +141,22 @@ LGR_API int lgr_bppnnls_prod(int32_t k, int64_t c, const double* CtC, const doub
 LGR_API int lgr_objerr_i(int32_t k, const double* H, const double* W, const double* V, const lgr_csc* E, double lambda,
                  int32_t device, double* err);
 
+/* ---- preprocessing that produces the path's input; FP64 on the device, HOST buffers --------
+   The matrix is a dgCMatrix: colptr (ncol + 1), rowidx (nnz), values (nnz doubles); outputs keep the pattern. */
+/* normalize.dgCMatrix (R/preprocess.R:592-608): out = x / colSums(x)[col]; colsums (ncol) may be NULL. */
+LGR_API int lgr_normalize_csc(int64_t ncol, const int32_t* colptr, const double* values, double* out, double* colsums,
+                              int32_t device);
+/* rowVars_sparse_rcpp(x, means, ncol) (src/data_processing.cpp:152-172) together with the Matrix::rowMeans that
+   feeds it (R/preprocess.R:1024): means_in may be NULL (then means = rowSums / ncol(x)); `ncol` is the divisor's
+   column count (the full matrix when x is a column chunk).  means_out / vars_out: nrow doubles, either may be NULL. */
+LGR_API int lgr_row_vars_sparse(int64_t nrow, int64_t ncol_x, const int32_t* colptr, const int32_t* rowidx,
+                                const double* values, const double* means_in, double ncol, double* means_out,
+                                double* vars_out, int32_t device);
+/* scaleNotCenter_byRow_rcpp (src/data_processing.cpp:42-58): out = x / sqrt(rowSums(x^2) / (ncol - 1)), 0 for rows
+   whose root mean square is 0; rms_out (nrow) may be NULL. */
+LGR_API int lgr_scale_not_center_by_row(int64_t nrow, int64_t ncol, const int32_t* colptr, const int32_t* rowidx,
+                                        const double* values, double* out, double* rms_out, int32_t device);
+
 /* ---- resident-handle API (data stays in HBM between calls; used by bench + multi-GPU hosts) ---- */
 typedef struct lgr_ctx lgr_ctx;
 LGR_API int lgr_ctx_create(const lgr_inmf_args* args, lgr_ctx** ctx); /* uploads E/P, builds device layouts, sets inits */

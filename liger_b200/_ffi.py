@@ -60,7 +60,7 @@ EXPORTS = [
     "lgr_ctx_iterate", "lgr_ctx_objective", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
     "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
     "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id", "lgr_host_alloc",
-    "lgr_host_free",
+    "lgr_host_free", "lgr_normalize_csc", "lgr_row_vars_sparse", "lgr_scale_not_center_by_row",
 ]
 
 
@@ -98,6 +98,11 @@ def lib():
     L.lgr_r_runif.restype = None
     L.lgr_r_free.argtypes = [C.c_void_p]
     L.lgr_r_free.restype = None
+    L.lgr_normalize_csc.argtypes = [C.c_int64, c_int32_p, c_double_p, c_double_p, c_double_p, C.c_int32]
+    L.lgr_row_vars_sparse.argtypes = [C.c_int64, C.c_int64, c_int32_p, c_int32_p, c_double_p, c_double_p, C.c_double,
+                                      c_double_p, c_double_p, C.c_int32]
+    L.lgr_scale_not_center_by_row.argtypes = [C.c_int64, C.c_int64, c_int32_p, c_int32_p, c_double_p, c_double_p,
+                                              c_double_p, C.c_int32]
     L.lgr_nccl_unique_id.argtypes = [C.c_void_p]
     L.lgr_host_alloc.argtypes = [C.c_size_t]
     L.lgr_host_alloc.restype = C.c_void_p

@@ -1017,3 +1017,102 @@ int lgr_objerr_i(int32_t k, const double* H, const double* W, const double* V, c
 }
 
 }  // extern "C"
+
+// ---- preprocessing scans (lgr_prep.cu) behind HOST buffers ------------------------------------------------------
+namespace {
+struct PrepStream {
+    cudaStream_t st = nullptr;
+    explicit PrepStream(int32_t device) {
+        check_device();
+        if (device >= 0) LGR_CUDA(cudaSetDevice(device));
+        LGR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    }
+    ~PrepStream() {
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    }
+};
+size_t check_csc(int64_t nrow, int64_t ncol, const int32_t* colptr, const int32_t* rowidx, const double* values) {
+    LGR_REQUIRE(ncol >= 0 && ncol < (int64_t)0x7fffffff && nrow >= 0 && nrow < (int64_t)0x7fffffff, "dimension out of range");
+    LGR_REQUIRE(colptr, "null column pointers");
+    LGR_REQUIRE(colptr[0] == 0, "colptr[0] must be 0");
+    for (int64_t j = 0; j < ncol; ++j) LGR_REQUIRE(colptr[j + 1] >= colptr[j], "CSC column pointers must be non-decreasing");
+    const size_t nnz = (size_t)colptr[ncol];
+    LGR_REQUIRE(nnz == 0 || values, "null values");
+    if (rowidx)
+        for (size_t t = 0; t < nnz; ++t) LGR_REQUIRE(rowidx[t] >= 0 && rowidx[t] < nrow, "row index out of range");
+    return nnz;
+}
+}  // namespace
+
+extern "C" {
+
+int lgr_normalize_csc(int64_t ncol, const int32_t* colptr, const double* values, double* out, double* colsums,
+                      int32_t device) {
+    return guarded([&] {
+        const size_t nnz = check_csc(1, ncol, colptr, nullptr, values);
+        LGR_REQUIRE(nnz == 0 || out, "null output");
+        if (ncol == 0) return;
+        PrepStream ps(device);
+        AllocStreamScope alloc_scope(ps.st);
+        DBuf<int> dp((size_t)ncol + 1);
+        DBuf<double> dx(std::max<size_t>(nnz, 1)), dout(std::max<size_t>(nnz, 1)), dcs((size_t)ncol);
+        LGR_CUDA(cudaMemcpyAsync(dp.p, colptr, ((size_t)ncol + 1) * sizeof(int), cudaMemcpyHostToDevice, ps.st));
+        if (nnz) LGR_CUDA(cudaMemcpyAsync(dx.p, values, nnz * sizeof(double), cudaMemcpyHostToDevice, ps.st));
+        prep_col_normalize((int)ncol, dp.p, dx.p, dout.p, dcs.p, ps.st);
+        if (nnz) LGR_CUDA(cudaMemcpyAsync(out, dout.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, ps.st));
+        if (colsums) LGR_CUDA(cudaMemcpyAsync(colsums, dcs.p, (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost, ps.st));
+        LGR_CUDA(cudaStreamSynchronize(ps.st));
+    });
+}
+
+int lgr_row_vars_sparse(int64_t nrow, int64_t ncol_x, const int32_t* colptr, const int32_t* rowidx, const double* values,
+                        const double* means_in, double ncol, double* means_out, double* vars_out, int32_t device) {
+    return guarded([&] {
+        LGR_REQUIRE(rowidx || (colptr && colptr[ncol_x >= 0 ? ncol_x : 0] == 0), "null row indices");
+        const size_t nnz = check_csc(nrow, ncol_x, colptr, rowidx, values);
+        if (nrow == 0) return;
+        PrepStream ps(device);
+        AllocStreamScope alloc_scope(ps.st);
+        DBuf<int> di(std::max<size_t>(nnz, 1));
+        DBuf<double> dx(std::max<size_t>(nnz, 1)), dm((size_t)nrow), dv((size_t)nrow), dc((size_t)nrow), dmi;
+        if (nnz) {
+            LGR_CUDA(cudaMemcpyAsync(di.p, rowidx, nnz * sizeof(int), cudaMemcpyHostToDevice, ps.st));
+            LGR_CUDA(cudaMemcpyAsync(dx.p, values, nnz * sizeof(double), cudaMemcpyHostToDevice, ps.st));
+        }
+        if (means_in) {
+            dmi.alloc((size_t)nrow);
+            LGR_CUDA(cudaMemcpyAsync(dmi.p, means_in, (size_t)nrow * sizeof(double), cudaMemcpyHostToDevice, ps.st));
+        }
+        prep_row_mean_var((int)nrow, (int)ncol_x, nnz, di.p, dx.p, means_in ? dmi.p : nullptr, ncol, dm.p, dv.p, dc.p, ps.st);
+        if (means_out) LGR_CUDA(cudaMemcpyAsync(means_out, dm.p, (size_t)nrow * sizeof(double), cudaMemcpyDeviceToHost, ps.st));
+        if (vars_out) LGR_CUDA(cudaMemcpyAsync(vars_out, dv.p, (size_t)nrow * sizeof(double), cudaMemcpyDeviceToHost, ps.st));
+        LGR_CUDA(cudaStreamSynchronize(ps.st));
+    });
+}
+
+int lgr_scale_not_center_by_row(int64_t nrow, int64_t ncol, const int32_t* colptr, const int32_t* rowidx,
+                                const double* values, double* out, double* rms_out, int32_t device) {
+    return guarded([&] {
+        LGR_REQUIRE(rowidx || (colptr && colptr[ncol >= 0 ? ncol : 0] == 0), "null row indices");
+        const size_t nnz = check_csc(nrow, ncol, colptr, rowidx, values);
+        LGR_REQUIRE(nnz == 0 || out, "null output");
+        if (nrow == 0) return;
+        PrepStream ps(device);
+        AllocStreamScope alloc_scope(ps.st);
+        DBuf<int> di(std::max<size_t>(nnz, 1));
+        DBuf<double> dx(std::max<size_t>(nnz, 1)), dout(std::max<size_t>(nnz, 1)), drms((size_t)nrow);
+        if (nnz) {
+            LGR_CUDA(cudaMemcpyAsync(di.p, rowidx, nnz * sizeof(int), cudaMemcpyHostToDevice, ps.st));
+            LGR_CUDA(cudaMemcpyAsync(dx.p, values, nnz * sizeof(double), cudaMemcpyHostToDevice, ps.st));
+        }
+        prep_scale_rows((int)nrow, (int)ncol, nnz, di.p, dx.p, dout.p, drms.p, ps.st);
+        if (nnz) LGR_CUDA(cudaMemcpyAsync(out, dout.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, ps.st));
+        if (rms_out) LGR_CUDA(cudaMemcpyAsync(rms_out, drms.p, (size_t)nrow * sizeof(double), cudaMemcpyDeviceToHost, ps.st));
+        LGR_CUDA(cudaStreamSynchronize(ps.st));
+    });
+}
+
+}  // extern "C"

@@ -213,4 +213,12 @@ void dev_hpad_to_colmajor(const float* H, double* out, int n, int k, int kp, cud
 void dev_colmajor_to_hpad(const double* in, float* H, int n, int k, int kp, cudaStream_t st);
 void dev_mask_from_positive(const float* H, unsigned long long* mask, int n, int k, int kp, cudaStream_t st);
 
+
+// preprocessing scans (lgr_prep.cu)
+void prep_col_normalize(int ncol, const int* colptr, const double* x, double* out, double* colsum, cudaStream_t st);
+void prep_row_mean_var(int nrow, int ncol_x, size_t nnz, const int* rowidx, const double* x, const double* means_in,
+                       double ncol, double* means_out, double* vars_out, double* scratch_count, cudaStream_t st);
+void prep_scale_rows(int nrow, int ncol, size_t nnz, const int* rowidx, const double* x, double* out, double* rms,
+                     cudaStream_t st);
+
 }  // namespace lgr

@@ -1,0 +1,132 @@
+// liger_b200 -- the native pieces of the preprocessing that produces the path's input (scaleData), on the device.
+// "the step immediately before the path".  Pure streaming scans over a CSC matrix (HBM bound):
+//
+//   k_col_normalize      x / colSums(x)[col]                 normalize.dgCMatrix        (R/preprocess.R:592-608)
+//   k_row_sum_count      rowSums, non-zeros per row          Matrix::rowMeans           (R/preprocess.R:1024)
+//   k_row_sqdev          sum_nz (x - mean_row)^2             rowVars_sparse_rcpp        (src/data_processing.cpp:152-172)
+//   k_row_sumsq          sum_nz x^2                          scaleNotCenter_byRow_rcpp  (src/data_processing.cpp:42-58)
+//   k_row_scale          x / sqrt(sumsq_row / (ncol - 1)), 0 where that is 0
+//
+// All arithmetic is FP64 like the reference.  Row reductions over a cell-major (CSC) matrix are scatters: they use
+// fire-and-forget fp64 `red.global.add` (one per non-zero; the row vectors live in L2).  Summation order differs from
+// the reference's serial loops, so results agree to ~1e-15 relative, not bitwise.
+#include "lgr_common.cuh"
+
+namespace lgr {
+
+// one warp per column: sum in fp64 (lane-strided, then a shuffle tree), then scale the column
+__global__ void __launch_bounds__(256) k_col_normalize(int ncol, const int* __restrict__ colptr, const double* __restrict__ x,
+                                                       double* __restrict__ out, double* __restrict__ colsum) {
+    const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= ncol) return;
+    const int b = colptr[warp], e = colptr[warp + 1];
+    double s = 0.0;
+    for (int t = b + lane; t < e; t += 32) s += x[t];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0 && colsum) colsum[warp] = s;
+    for (int t = b + lane; t < e; t += 32) out[t] = x[t] / s;
+}
+
+__global__ void __launch_bounds__(256) k_row_sum_count(size_t nnz, const int* __restrict__ rowidx, const double* __restrict__ x,
+                                                       double* __restrict__ rsum, double* __restrict__ rcount) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (size_t)gridDim.x * blockDim.x) {
+        const int r = rowidx[t];
+        atomicAdd(rsum + r, x[t]);
+        atomicAdd(rcount + r, 1.0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_row_sqdev(size_t nnz, const int* __restrict__ rowidx, const double* __restrict__ x,
+                                                   const double* __restrict__ means, double* __restrict__ acc) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (size_t)gridDim.x * blockDim.x) {
+        const int r = rowidx[t];
+        const double dlt = x[t] - means[r];
+        atomicAdd(acc + r, dlt * dlt);
+    }
+}
+
+// vars = (sqdev + (ncol_x - count) * mean^2) / (ncol - 1)      (src/data_processing.cpp:166-170)
+__global__ void k_row_var_finish(int nrow, double ncol_x, double ncol, const double* __restrict__ means,
+                                 const double* __restrict__ count, double* __restrict__ vars) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrow) return;
+    const double m2 = means[r] * means[r];
+    vars[r] = (vars[r] + (ncol_x - count[r]) * m2) / (ncol - 1.0);
+}
+
+__global__ void k_row_mean_finish(int nrow, double ncol_x, const double* __restrict__ rsum, double* __restrict__ means) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrow) means[r] = rsum[r] / ncol_x;
+}
+
+__global__ void __launch_bounds__(256) k_row_sumsq(size_t nnz, const int* __restrict__ rowidx, const double* __restrict__ x,
+                                                   double* __restrict__ ss) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (size_t)gridDim.x * blockDim.x) {
+        const double v = x[t];
+        atomicAdd(ss + rowidx[t], v * v);
+    }
+}
+
+__global__ void k_row_rms_finish(int nrow, double ncol, double* __restrict__ ss) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrow) ss[r] = sqrt(ss[r] / (ncol - 1.0));
+}
+
+__global__ void __launch_bounds__(256) k_row_scale(size_t nnz, const int* __restrict__ rowidx, const double* __restrict__ x,
+                                                   const double* __restrict__ rms, double* __restrict__ out) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (size_t)gridDim.x * blockDim.x) {
+        const double s = rms[rowidx[t]];
+        out[t] = (s == 0.0) ? 0.0 : x[t] / s;
+    }
+}
+
+static int stream_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16); }
+
+void prep_col_normalize(int ncol, const int* colptr, const double* x, double* out, double* colsum, cudaStream_t st) {
+    if (ncol <= 0) return;
+    k_col_normalize<<<(unsigned)(((size_t)ncol * 32 + 255) / 256), 256, 0, st>>>(ncol, colptr, x, out, colsum);
+    LGR_CUDA(cudaGetLastError());
+}
+
+// means_in == nullptr: means = rowSums / ncol_x are computed here.  means_out / vars_out: nrow doubles on the device.
+void prep_row_mean_var(int nrow, int ncol_x, size_t nnz, const int* rowidx, const double* x, const double* means_in,
+                       double ncol, double* means_out, double* vars_out, double* scratch_count, cudaStream_t st) {
+    if (nrow <= 0) return;
+    LGR_CUDA(cudaMemsetAsync(vars_out, 0, (size_t)nrow * sizeof(double), st));
+    LGR_CUDA(cudaMemsetAsync(scratch_count, 0, (size_t)nrow * sizeof(double), st));
+    LGR_CUDA(cudaMemsetAsync(means_out, 0, (size_t)nrow * sizeof(double), st));
+    const int rb = (nrow + 255) / 256;
+    if (nnz) {
+        k_row_sum_count<<<stream_grid(nnz), 256, 0, st>>>(nnz, rowidx, x, means_out, scratch_count);
+        LGR_CUDA(cudaGetLastError());
+    }
+    if (means_in)
+        LGR_CUDA(cudaMemcpyAsync(means_out, means_in, (size_t)nrow * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    else
+        k_row_mean_finish<<<rb, 256, 0, st>>>(nrow, (double)ncol_x, means_out, means_out);
+    if (nnz) {
+        k_row_sqdev<<<stream_grid(nnz), 256, 0, st>>>(nnz, rowidx, x, means_out, vars_out);
+        LGR_CUDA(cudaGetLastError());
+    }
+    k_row_var_finish<<<rb, 256, 0, st>>>(nrow, (double)ncol_x, ncol, means_out, scratch_count, vars_out);
+    LGR_CUDA(cudaGetLastError());
+}
+
+void prep_scale_rows(int nrow, int ncol, size_t nnz, const int* rowidx, const double* x, double* out, double* rms,
+                     cudaStream_t st) {
+    if (nrow <= 0) return;
+    LGR_CUDA(cudaMemsetAsync(rms, 0, (size_t)nrow * sizeof(double), st));
+    if (nnz) {
+        k_row_sumsq<<<stream_grid(nnz), 256, 0, st>>>(nnz, rowidx, x, rms);
+        LGR_CUDA(cudaGetLastError());
+    }
+    k_row_rms_finish<<<(nrow + 255) / 256, 256, 0, st>>>(nrow, (double)ncol, rms);
+    LGR_CUDA(cudaGetLastError());
+    if (nnz) {
+        k_row_scale<<<stream_grid(nnz), 256, 0, st>>>(nnz, rowidx, x, rms, out);
+        LGR_CUDA(cudaGetLastError());
+    }
+}
+
+}  // namespace lgr

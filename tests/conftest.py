@@ -31,7 +31,11 @@ def _csc(npz, name):
 @pytest.fixture(scope="session")
 def pbmc():
     g = np.load(os.path.join(GOLDEN, "pbmc_golden.npz"))
-    return {"Es": [_csc(g, "ctrl"), _csc(g, "stim")], "golden": g, "names": ("ctrl", "stim")}
+    r = np.load(os.path.join(GOLDEN, "pbmc_raw.npz"))
+    raws = [sp.csc_matrix((r[f"raw_{n}_data"], r[f"raw_{n}_indices"], r[f"raw_{n}_indptr"]), shape=tuple(r[f"raw_{n}_shape"]))
+            for n in ("ctrl", "stim")]
+    return {"Es": [_csc(g, "ctrl"), _csc(g, "stim")], "golden": g, "names": ("ctrl", "stim"), "raws": raws,
+            "genes": [list(r["genes_ctrl"]), list(r["genes_stim"])], "nUMI": [r["nUMI_ctrl"], r["nUMI_stim"]]}
 
 
 @pytest.fixture(scope="session")

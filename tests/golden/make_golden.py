@@ -57,6 +57,7 @@ def main():
         raws.append(sp.csc_matrix((x, i, p), shape=dim))
         genes.append(dn[0])
         numis.append(pb[nm]["nUMI"])
+    raws_pbmc, genes_pbmc, numis_pbmc = raws, genes, numis
     feats, scaled, sel = orc.default_pipeline(raws, genes, numis, combine="union")
     feats_int, _, _ = orc.default_pipeline(raws, genes, numis, combine="intersection")
     print("pbmc: selected", [len(s) for s in sel], "union", len(feats), "intersection", len(feats_int))
@@ -85,6 +86,14 @@ def main():
     store["golden_k"] = int(fac.value[0].value[0])
     store["golden_lambda"] = float(fac.value[1].value[0])
     np.savez_compressed(os.path.join(HERE, "pbmc_golden.npz"), **store)
+    # raw counts + gene names + nUMI of pbmc: inputs of the preprocessing parity tests (normalize / selectGenes /
+    # scaleNotCenter on the GPU against the known answers of tests/testthat/test_preprocessing.R:184,190,262-263)
+    rawstore = {}
+    for nm, r, g, u in zip(("ctrl", "stim"), raws_pbmc, genes_pbmc, numis_pbmc):
+        csc_pack(f"raw_{nm}", r, rawstore)
+        rawstore[f"genes_{nm}"] = np.array(g)
+        rawstore[f"nUMI_{nm}"] = np.asarray(u, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "pbmc_raw.npz"), **rawstore)
 
     # ---------------- bmmc: inputs only (config C2) ----------------
     _, bm = load_liger(f"{REF}/bmmc.rda", "bmmc")

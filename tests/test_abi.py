@@ -47,6 +47,12 @@ def test_no_cpu_fallback():
         liger_b200.bppnnls_prod(np.eye(3), np.ones((3, 2)))
     with pytest.raises(LigerB200Error):
         liger_b200.objErr_i(np.ones((5, 40)), np.ones((30, 5)), np.ones((30, 5)), E, 5.0)
+    from liger_b200 import preprocess as pp
+    for call in (lambda: pp.normalize(E), lambda: pp.rowMeansVars(E),
+                 lambda: pp.scaleNotCenter(E, [str(i) for i in range(30)], ["1", "2"])):
+        with pytest.raises(LigerB200Error) as e:
+            call()
+        assert e.value.code == 2
 
 
 def test_product_never_imports_the_oracle():

@@ -376,3 +376,59 @@ def test_optimize_new_lambda_subset_and_data(pbmc):
     ref = oo.optimize_new_data(pbmc["Es"], ofit, [merged], [0], True, new_cells=[np.arange(300, 450)], niter=2)
     assert out["H"]["ctrl"].shape[1] == 450                                   # cells were added (cf. :127)
     _cmp_fit(out, ref, names)
+
+
+# ----------------------------------------------------------------------------------------------
+# preprocessing feeding the path (normalize / selectGenes / scaleNotCenter), on the GPU
+# ----------------------------------------------------------------------------------------------
+def test_preprocessing_known_answers_on_gpu(pbmc):
+    """The reference's own known answers (tests/testthat/test_preprocessing.R:184,190,262-263): 173 (union) / 161
+    (intersection) variable genes, scaleData(ctrl)[3,5] = 0.4693316, scaleData(stim)[7,9] = 2.360295 (tol 1e-6);
+    and the regenerated scaleData equals the oracle's, which the golden iNMF factors were reproduced from."""
+    from liger_b200 import preprocess as pp
+    raws, genes, numis = pbmc["raws"], pbmc["genes"], pbmc["nUMI"]
+    norms = [pp.normalize(r) for r in raws]
+    for n, r in zip(norms, raws):
+        assert rel(n.toarray(), orc.normalize(r).toarray()) < 1e-14
+    feats, sel = pp.selectGenes(norms, genes, numis, combine="union")
+    assert len(feats) == 173
+    feats_i, _ = pp.selectGenes(norms, genes, numis, combine="intersection")
+    assert len(feats_i) == 161
+    scaled = [pp.scaleNotCenter(n, g, feats) for n, g in zip(norms, genes)]
+    assert abs(scaled[0][2, 4] - 0.4693316) < 1e-6
+    assert abs(scaled[1][6, 8] - 2.360295) < 1e-6
+    for s, e in zip(scaled, pbmc["Es"]):
+        assert s.shape == e.shape and (s != 0).nnz == (e != 0).nnz
+        assert rel(s.toarray(), e.toarray()) < 1e-13
+
+
+def test_preprocessing_edge_cases_on_gpu():
+    """empty rows (rms 0 -> stay 0), empty columns, a column chunk with the full-matrix divisor, one-cell rows."""
+    from liger_b200 import preprocess as pp
+    rng = np.random.default_rng(5)
+    x = sp.random(57, 211, 0.08, format="csc", random_state=3, data_rvs=lambda n: rng.integers(1, 9, n).astype(float))
+    x = sp.csc_matrix(x)
+    x[5, :] = 0
+    x[:, 7] = 0
+    x.eliminate_zeros()
+    keep = np.asarray(x.sum(axis=0)).ravel() > 0
+    n_gpu = pp.normalize(x[:, keep])
+    assert rel(n_gpu.toarray(), orc.normalize(x[:, keep]).toarray()) < 1e-14
+    m, v = pp.rowMeansVars(n_gpu)
+    dense = n_gpu.toarray()
+    assert np.allclose(m, dense.mean(axis=1), rtol=1e-13, atol=0)
+    assert np.allclose(v, dense.var(axis=1, ddof=1), rtol=1e-11, atol=1e-300)
+    # chunked use (src/data_processing.cpp:148-150): sums of per-chunk outputs with the full ncol
+    half = n_gpu.shape[1] // 2
+    v1 = pp.rowMeansVars(n_gpu[:, :half], ncol=n_gpu.shape[1], means=m)[1]
+    v2 = pp.rowMeansVars(n_gpu[:, half:], ncol=n_gpu.shape[1], means=m)[1]
+    ref1 = orc.row_vars_sparse(n_gpu[:, :half], m, n_gpu.shape[1]) + orc.row_vars_sparse(n_gpu[:, half:], m, n_gpu.shape[1])
+    assert np.allclose(v1 + v2, ref1, rtol=1e-12)
+    genes = [f"g{i}" for i in range(57)]
+    feats = genes[3:40]
+    s_gpu = pp.scaleNotCenter(n_gpu, genes, feats)
+    s_ref = orc.scale_not_center(n_gpu, genes, feats)
+    assert s_gpu.shape == s_ref.shape and rel(s_gpu.toarray(), s_ref.toarray()) < 1e-13
+    assert s_gpu[2, :].nnz == 0                   # the empty gene (row 5 of x) stays all-zero
+    with pytest.raises(ValueError):
+        pp.scaleNotCenter(n_gpu, genes, ["nope"])
