@@ -349,8 +349,8 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             // fp32, k <= 32: register-resident solver; groups with a singular Gram fall through to k_nnls (flag 16)
             static const bool no_reg = getenv("LGR_NNLS_NO_REG") != nullptr;
             if (!no_reg && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
-                launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, cold, c->st);
-                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold | 16, c->st);
+                launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->kp, c->num_sms, c->counters.p, cold, c->st);
+                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold | 16 | (c->kp > 32 ? 64 : 0), c->st);
             } else {
                 launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
             }

@@ -184,10 +184,11 @@ void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStrea
 void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp,
                  const NnlsConfig& cfg, Counters* cnt, int flags, cudaStream_t st);
 void nnls_init();
-// register-resident fp32 path (lgr_nnls_reg.cu): k <= 32; groups with a singular Gram are skipped (run launch_nnls with flag 16 after it)
+// register-resident fp32 path (lgr_nnls_reg.cu): k <= 62.  Groups with a singular Gram are skipped and columns whose
+// system exceeds 16 unknowns are flagged in their warm-start mask: run launch_nnls with flags 16 | 64 right after it
 bool nnls_reg_supported(int k, int kp);
-void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
-                     cudaStream_t st);
+void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp, int num_sms, Counters* cnt,
+                     int flags, cudaStream_t st);
 void nnls_reg_init();
 void launch_pb_tc(const NnlsGroup* groups, int ngroups, long long total_tiles, int kp, int num_sms, cudaStream_t st);
 void tc_init();

@@ -395,7 +395,11 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
         const int c0 = (int)(pos - grp.col_off);
         const int ccols = (int)((stop < gend ? stop : gend) - pos);
         pos += ccols;
-        if ((flags & 16) && *grp.ok != 0) continue;   // this launch only mops up the groups k_nnls_reg skipped (CTA-uniform)
+        // mop-up launch after k_nnls_reg (CTA-uniform): flag 16 = only the groups it skipped (singular Gram); with flag 64
+        // additionally, in the other groups, only the columns it flagged in their warm-start mask (bit 63: system too big
+        // for its register templates), continuing from the passive set it left there
+        const bool only_deferred = (flags & 64) && *grp.ok != 0;
+        if ((flags & 16) && *grp.ok != 0 && !only_deferred) continue;
         __syncthreads();  // every warp is done with the previous chunk (G / P / counter change)
         const int dual_ok = no_dual ? 0 : *grp.ok;
         for (int e = tid; e < KP * KP; e += blockDim.x) {
@@ -428,10 +432,12 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
                     const int c = base + __popc(want & ((1u << lane) - 1u));
                     if (c >= ccols) {
                         exhausted = true;
+                    } else if (only_deferred && !(masks[c] >> 63)) {
+                        // solved by k_nnls_reg: not ours; the lane claims again on the next trip
                     } else {
                         col = c;
                         load_row<T, KP>(rhs + (size_t)c * ld, bcol, k, ld);
-                        F = cold_start ? 0ull : (masks[c] & kmask);
+                        F = (cold_start && !only_deferred) ? 0ull : (masks[c] & kmask);
                         state = 3 | ((k + 1) << 8);
                         T bm = (T)0;
 #pragma unroll
@@ -456,7 +462,10 @@ __global__ void __launch_bounds__(256, 1) k_nnls(const NnlsGroup* __restrict__ g
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, active)) break;
+            if (!__any_sync(0xffffffffu, active)) {
+                if (__all_sync(0xffffffffu, exhausted)) break;
+                continue;   // lanes that skipped columns claim again
+            }
             // ---- one pivot round for every active lane ----
             int need = 0;
             if (active) {

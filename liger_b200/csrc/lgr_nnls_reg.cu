@@ -16,18 +16,35 @@
 //
 // Groups whose Gram is numerically singular (no inverse: *ok == 0) are left to k_nnls (lgr_nnls.cu), which is
 // launched right after this kernel restricted to exactly those groups.
+#include <type_traits>
+
 #include "lgr_common.cuh"
 
 namespace lgr {
 namespace {
 
-constexpr int RSUB = 4096;       // columns ordered (by system size) and solved per pass of a CTA
-constexpr int RKP = 32;          // padded factor count handled here
-constexpr int RMST = 36;         // row stride of the staged matrices (words)
-constexpr int RROWS = 33;        // 32 rows + the padding row
-constexpr int RCOL = 33 * 32;    // words of the z tile: [row][lane], 33 rows
-constexpr int RBUF = 9 * 32 * 4;  // words of one b / u staging tile: [16-byte chunk][lane], 8 chunks + a zero chunk (padding unknowns)
+constexpr int RSUB = 4096;       // columns ordered (by system size) and solved per pass of a CTA (KP = 32)
 constexpr float REPS = 1.1920929e-7f;
+constexpr unsigned long long DEFER_BIT = 1ull << 63;   // warm-start mask flag: "left to k_nnls" (needs k <= 62)
+
+// Sizes for a padded factor count KP (32 or 64): the staged matrices have KP + 1 rows (row KP = padding row whose only
+// non-zero is a unit diagonal) of stride KP + 4 words; the b / u staging tiles are [16-byte chunk][lane] with KP/4
+// chunks + a zero chunk (rhs of the padding unknowns); the z tile is [row][lane] with KP + 1 rows.
+template <int KP>
+struct RT {
+    static constexpr int MST = KP + 4;
+    static constexpr int ROWS = KP + 1;
+    static constexpr int COL = (KP + 1) * 32;
+    static constexpr int BUF = (KP / 4 + 1) * 32 * 4;
+    static constexpr int SUB = KP == 32 ? RSUB : 1024;
+    using Mask = typename std::conditional<KP == 32, uint32_t, unsigned long long>::type;
+};
+__device__ __forceinline__ int popc_m(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int popc_m(unsigned long long x) { return __popcll(x); }
+__device__ __forceinline__ int ffs_m(uint32_t x) { return __ffs((int)x); }
+__device__ __forceinline__ int ffs_m(unsigned long long x) { return __ffsll((long long)x); }
+__device__ __forceinline__ int top_m(uint32_t x) { return 31 - __clz((int)x); }
+__device__ __forceinline__ int top_m(unsigned long long x) { return 63 - __clzll((long long)x); }
 
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 // word offset of element f of a lane's row in a [chunk][lane] staging tile (relative to the lane's chunk 0)
@@ -37,31 +54,35 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 struct RegSmem {
     size_t G, P, fmask, warp0, per_warp, total;
 };
+template <int KP>
 __host__ __device__ inline RegSmem reg_layout(int nwarps) {
     RegSmem L;
     L.G = 0;
-    L.P = (size_t)RROWS * RMST * 4;
+    L.P = (size_t)RT<KP>::ROWS * RT<KP>::MST * 4;
     L.fmask = 2 * L.P;
-    L.warp0 = L.fmask + (size_t)RSUB * 4;
-    L.per_warp = (size_t)(4 * RBUF + RCOL) * 4;   // 2 x (b, u) staging tiles (double buffered), z tile
+    L.warp0 = L.fmask + (size_t)RT<KP>::SUB * sizeof(typename RT<KP>::Mask);
+    L.per_warp = (size_t)(4 * RT<KP>::BUF + RT<KP>::COL) * 4;   // 2 x (b, u) staging tiles (double buffered), z tile
     L.total = L.warp0 + (size_t)nwarps * L.per_warp;
     return L;
 }
 
 // One pivot round of one column with the principal block padded to SMAX.  Returns true while the column is active.
-template <int SMAX>
-__device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, const bool dual, const int s, const int smax,
-                                          const uint32_t S,
+template <int SMAX, int KP>
+__device__ __forceinline__ bool round_reg(const int k, const typename RT<KP>::Mask kmask, const bool dual, const int s,
+                                          const int smax, const typename RT<KP>::Mask S,
                                           const float* __restrict__ Mat, const float* bcol, const float* ucol, float* zcol,
-                                          uint32_t& F, int& state, const float tol, const int MAXIT, Counters* cnt,
+                                          typename RT<KP>::Mask& F, int& state, const float tol, const int MAXIT, Counters* cnt,
                                           unsigned long long& pivots, float4* __restrict__ xrow) {
+    using Mask = typename RT<KP>::Mask;
+    constexpr int RKP = KP, RMST = RT<KP>::MST;
+    constexpr Mask ONE = 1;
     constexpr int N = SMAX * (SMAX + 1) / 2;
     int idx[SMAX];
     {
-        uint32_t r = S;
+        Mask r = S;
 #pragma unroll
         for (int t = 0; t < SMAX; ++t) {
-            idx[t] = r ? (__ffs((int)r) - 1) : 32;
+            idx[t] = r ? (ffs_m(r) - 1) : RKP;
             r &= r - 1;
         }
     }
@@ -119,7 +140,7 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
         z[j] = v * A[tri(j, j)];
     }
     // infeasible coordinates of the solved side; expand the (signed) solution by factor id
-    uint32_t infeas = 0u;
+    Mask infeas = 0;
     float zmax = 0.f;
 #pragma unroll
     for (int t = 0; t < SMAX; ++t) zmax = fmaxf(zmax, fabsf(z[t]));
@@ -130,7 +151,7 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
 #pragma unroll
     for (int t = 0; t < SMAX; ++t) {
         if (t < s) {
-            if (sgn * z[t] < -tolz) infeas |= 1u << idx[t];
+            if (sgn * z[t] < -tolz) infeas |= ONE << idx[t];
             zcol[idx[t] * 32] = sgn * z[t];
         }
     }
@@ -195,20 +216,20 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
             }
             thr = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * (REPS * 8.f);
         }
-        uint32_t n0 = 0u, n1 = 0u, n2 = 0u, n3 = 0u;
+        Mask n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
         for (int f = 0; f < RKP; f += 4) {
-            n0 |= (acc[f] < -thr) ? (1u << f) : 0u;
-            n1 |= (acc[f + 1] < -thr) ? (2u << f) : 0u;
-            n2 |= (acc[f + 2] < -thr) ? (4u << f) : 0u;
-            n3 |= (acc[f + 3] < -thr) ? (8u << f) : 0u;
+            n0 |= (acc[f] < -thr) ? (ONE << f) : (Mask)0;
+            n1 |= (acc[f + 1] < -thr) ? (ONE << (f + 1)) : (Mask)0;
+            n2 |= (acc[f + 2] < -thr) ? (ONE << (f + 2)) : (Mask)0;
+            n3 |= (acc[f + 3] < -thr) ? (ONE << (f + 3)) : (Mask)0;
         }
         infeas |= ((n0 | n1) | (n2 | n3)) & (dual ? F : ((~F) & kmask));
     }
     int alpha = state & 0xff, beta = (state >> 8) & 0xff, iter = state >> 16;
-    if (infeas != 0u && iter < MAXIT) {
-        const int ninf = __popc(infeas);
-        uint32_t flip;
+    if (infeas != 0 && iter < MAXIT) {
+        const int ninf = popc_m(infeas);
+        Mask flip;
         if (ninf < beta) {
             beta = ninf;
             alpha = 3;
@@ -217,19 +238,19 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
             --alpha;
             flip = infeas;
         } else {
-            flip = 1u << (31 - __clz((int)infeas));
+            flip = ONE << top_m(infeas);
         }
         F ^= flip;
         state = alpha | (beta << 8) | ((iter + 1) << 16);
         ++pivots;
         return true;
     }
-    if (infeas != 0u) atomicAdd(&cnt->nnls_unconverged, 1ull);
+    if (infeas != 0) atomicAdd(&cnt->nnls_unconverged, 1ull);
     // final x straight from registers: full 128-byte row
     if (dual) {
 #pragma unroll
         for (int f = 0; f < RKP; ++f)
-            if (!((F >> f) & 1u) || !(acc[f] > 0.f)) acc[f] = 0.f;
+            if (!((F >> f) & ONE) || !(acc[f] > 0.f)) acc[f] = 0.f;
     } else {
 #pragma unroll
         for (int f = 0; f < RKP; ++f) acc[f] = fmaxf(zcol[f * 32], 0.f);
@@ -239,11 +260,15 @@ __device__ __forceinline__ bool round_reg(const int k, const uint32_t kmask, con
     return false;
 }
 
+template <int KP>
 __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict__ groups, int ngroups, long long total_cols,
                                                      int k, Counters* cnt, int flags) {
+    using Mask = typename RT<KP>::Mask;
+    constexpr int RKP = KP, RMST = RT<KP>::MST, RROWS = RT<KP>::ROWS, RBUF = RT<KP>::BUF, RSUBK = RT<KP>::SUB;
+    constexpr Mask ONE = 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NW = blockDim.x >> 5;
-    const RegSmem L = reg_layout(NW);
+    const RegSmem L = reg_layout<KP>(NW);
     float* Gs = reinterpret_cast<float*>(smem_raw + L.G);
     float* Ps = reinterpret_cast<float*>(smem_raw + L.P);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -253,16 +278,17 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
     float* zcol = wbase + 4 * RBUF + lane;
     __shared__ int next_col;
     __shared__ int hist[18];
-    __shared__ unsigned short order[RSUB];
-    uint32_t* fmask = reinterpret_cast<uint32_t*>(smem_raw + L.fmask);   // warm-start passive sets of the pass
+    __shared__ unsigned short order[RSUBK];
+    Mask* fmask = reinterpret_cast<Mask*>(smem_raw + L.fmask);   // warm-start passive sets of the pass
 
     const bool cold_start = (flags & 1) != 0;
     const bool sync_rounds = (flags & 32) != 0;   // CTA-wide round barrier: the warps walk the unrolled code together (I-cache)
-    const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+    const Mask kmask = (k >= (int)(8 * sizeof(Mask))) ? ~(Mask)0 : ((ONE << k) - ONE);
     const int MAXIT = 4 * k + 16;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(stage + q * RBUF + 8 * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
-    zcol[32 * 32] = 0.f;
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(stage + q * RBUF + (RKP / 4) * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+    zcol[RKP * 32] = 0.f;
 
     long long per = (total_cols + gridDim.x - 1) / gridDim.x;
     per = (per + 31) & ~31LL;
@@ -285,7 +311,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
             if (a < RKP && b < RKP) {
                 gv = (float)grp.gram[a * RKP + b];
                 pv = (float)grp.ginv[a * RKP + b];
-            } else if (a == 32 && b == 32) {
+            } else if (a == RKP && b == RKP) {
                 gv = 1.f;
                 pv = 1.f;
             }
@@ -297,10 +323,10 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         float* __restrict__ xout_g = reinterpret_cast<float*>(grp.x) + (size_t)c0 * RKP;
         unsigned long long* __restrict__ masks_g = grp.mask + c0;
         const float* __restrict__ upre_g = grp.u ? reinterpret_cast<const float*>(grp.u) + (size_t)c0 * RKP : nullptr;
-      for (int sub0 = 0; sub0 < ccols; sub0 += RSUB) {
+      for (int sub0 = 0; sub0 < ccols; sub0 += RSUBK) {
         // ---- order this sub-chunk's columns by the size of the system their warm start implies (largest first):
         //      the lanes of a warp then solve systems of similar size and the small templates are actually used ----
-        const int nsub = min(RSUB, ccols - sub0);
+        const int nsub = min(RSUBK, ccols - sub0);
         const float* __restrict__ rhs = rhs_g + (size_t)sub0 * RKP;
         float* __restrict__ xout = xout_g + (size_t)sub0 * RKP;
         unsigned long long* __restrict__ masks = masks_g + sub0;
@@ -309,10 +335,10 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         if (tid < 18) hist[tid] = 0;
         __syncthreads();
         for (int c = tid; c < nsub; c += blockDim.x) {
-            const uint32_t f0 = cold_start ? 0u : ((uint32_t)masks[c] & kmask);
+            const Mask f0 = cold_start ? (Mask)0 : ((Mask)masks[c] & kmask);
             fmask[c] = f0;
-            const int p = __popc(f0);
-            atomicAdd(&hist[16 - min(p, k - p)], 1);
+            const int p = popc_m(f0);
+            atomicAdd(&hist[16 - min(min(p, k - p), 16)], 1);
         }
         __syncthreads();
         if (tid == 0) {
@@ -327,8 +353,8 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         }
         __syncthreads();
         for (int c = tid; c < nsub; c += blockDim.x) {
-            const int p = __popc(fmask[c]);
-            order[atomicAdd(&hist[16 - min(p, k - p)], 1)] = (unsigned short)c;
+            const int p = popc_m(fmask[c]);
+            order[atomicAdd(&hist[16 - min(min(p, k - p), 16)], 1)] = (unsigned short)c;
         }
         __syncthreads();
 
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         const bool sync_pass = sync_rounds && hist[17] * 4 > nsub;
         bool active = false, exhausted = false, have_u = false;
         int col = 0, state = 0, nxt = -1;
-        uint32_t F = 0u;
+        Mask F = 0;
         float tol = 0.f;
         // every lane keeps ONE column reserved ahead of the one it is solving, and prefetches that column's b (and u)
         // row -- exactly one 128-byte line each -- into L1 while it works: the refill then finds its operands on chip
@@ -408,9 +434,9 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
             if (sync_pass ? !__syncthreads_or(active) : !__any_sync(0xffffffffu, active)) break;
             int s = 0;
             bool dual = false;
-            uint32_t S = 0u;
+            Mask S = 0;
             if (active) {
-                const int p = __popc(F);
+                const int p = popc_m(F);
                 dual = (k - p) < p;
                 S = dual ? ((~F) & kmask) : F;
                 s = dual ? (k - p) : p;
@@ -436,17 +462,24 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                     have_u = true;
                 }
             }
+            // systems with more than 16 unknowns (possible only for k > 32) do not fit the register templates: the
+            // column is handed to k_nnls with its current passive set (flag bit in the warm-start mask)
+            if (KP > 32 && active && s > 16) {
+                masks[col] = (unsigned long long)F | DEFER_BIT;
+                active = false;
+                s = 0;
+            }
             const int smax = __reduce_max_sync(0xffffffffu, s);
             bool still = false;
             if (active) {
                 const float* Mat = dual ? Ps : Gs;
                 float4* xrow = reinterpret_cast<float4*>(xout + (size_t)col * RKP);
                 if (smax <= 8)
-                    still = round_reg<8>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                    still = round_reg<8, KP>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
                 else if (smax <= 12)
-                    still = round_reg<12>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                    still = round_reg<12, KP>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
                 else
-                    still = round_reg<16>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
+                    still = round_reg<16, KP>(k, kmask, dual, s, smax, S, Mat, bcol, ucol, zcol, F, state, tol, MAXIT, cnt, pivots_local, xrow);
                 if (!still) masks[col] = (unsigned long long)F;
             }
             active = still;
@@ -458,27 +491,32 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
 
 }  // namespace
 
-bool nnls_reg_supported(int k, int kp) { return kp == 32 && k <= 32; }
+bool nnls_reg_supported(int k, int kp) { return (kp == 32 && k <= 32) || (kp == 64 && k <= 62); }
 
-void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
-                     cudaStream_t st) {
+void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp, int num_sms, Counters* cnt,
+                     int flags, cudaStream_t st) {
     if (total_cols <= 0) return;
-    int nw = 8;
+    int nw = kp == 32 ? 8 : 4;   // per-warp staging tiles double in size at KP = 64
     if (const char* e = getenv("LGR_NNLS_REG_WARPS")) nw = atoi(e);
     if (nw < 1) nw = 1;
-    if (nw > 8) nw = 8;
+    if (nw > (kp == 32 ? 8 : 4)) nw = kp == 32 ? 8 : 4;
     while (nw > 1 && total_cols < (long long)num_sms * nw * 32) nw >>= 1;
     const int threads = nw * 32;
-    const size_t smem = reg_layout(nw).total;
+    const size_t smem = kp == 32 ? reg_layout<32>(nw).total : reg_layout<64>(nw).total;
     long long want = (total_cols + threads - 1) / threads;
     const int grid = (int)(want < num_sms ? want : num_sms);
     static const bool sync_rounds = getenv("LGR_NNLS_REG_NOSYNC") == nullptr;
-    k_nnls_reg<<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, flags | (sync_rounds ? 32 : 0));
+    const int fl = flags | (sync_rounds ? 32 : 0);
+    if (kp == 32)
+        k_nnls_reg<32><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, fl);
+    else
+        k_nnls_reg<64><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, fl);
     LGR_CUDA(cudaGetLastError());
 }
 
 void nnls_reg_init() {
-    LGR_CUDA(cudaFuncSetAttribute(k_nnls_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_layout(8).total));
+    LGR_CUDA(cudaFuncSetAttribute(k_nnls_reg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_layout<32>(8).total));
+    LGR_CUDA(cudaFuncSetAttribute(k_nnls_reg<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reg_layout<64>(4).total));
 }
 
 }  // namespace lgr
