@@ -72,8 +72,11 @@ typedef struct lgr_csc {
 #define LGR_FLAG_TRAJECTORY 0x1u  /* evaluate the objective after every iteration into out->obj_traj */
 #define LGR_FLAG_COLD_START 0x2u  /* disable NNLS warm starts (every solve starts from the empty passive set) */
 #define LGR_FLAG_PINNED_IO 0x4u   /* caller promises host buffers are page-locked (faster copies) */
-#define LGR_FLAG_TENSOR_U 0x10u   /* form u = CtC^-1 b of the H solve on the tensor cores (tcgen05, 3xTF32 split) instead
-                                     of fp32 FMAs inside the NNLS kernel; same results to ~1e-5, measured slower at k=30 */
+#define LGR_FLAG_TENSOR_U 0x10u   /* form u = CtC^-1 b of the H solve on the tensor cores (tcgen05, 3xTF32 split, TMEM
+                                     accumulators): as an epilogue of the B = L^T X sweep while the B tile is still in shared
+                                     memory, or as a separate pass when the tile geometry does not allow it.  Same results
+                                     to ~1e-5; at k = 30 it trades +0.11 ms in the sweep for -0.06 ms in the solver, so it is
+                                     off by default */
 #define LGR_FLAG_LEGACY_NNLS 0x20u /* verification only: run the H solves with the shared-memory-factor NNLS kernel
                                      (lgr_nnls.cu) instead of the register-resident one (lgr_nnls_reg.cu, k <= 32) */
 #define LGR_FLAG_LOCAL_SHARD 0x8u /* world > 1: E/P already hold only THIS rank's cells (one process per GPU, each

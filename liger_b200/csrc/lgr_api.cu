@@ -118,6 +118,7 @@ struct lgr_ctx {
     DBuf<NnlsGroup> grpT;      // tensor-core U = B P launch (tile offsets)
     long long tilesT = 0;
     bool use_tc = false;
+    bool fuse_u = false;       // U = B P in the tcgen05 epilogue of k_spmm_ltx_tiled (default on)
     DBuf<double> ctc_arena;   // per NNLS group: CtC and CtC^-1 (2 x KP x KP fp64), groups = H_0..H_d-1, V_0..V_d-1, W
     DBuf<int> ok_arena;
     DBuf<NnlsGroup> grpH, grpV, grpW;
@@ -333,12 +334,12 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         if (traj && it > 0) run_objective(c, c->objbuf.p + (it - 1));
         // ---- H phase ----
         {
-            Timed t(c, "k_spmm_ltx");
-            launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->st);
+            Timed t(c, "k_gram_inv");   // CtC and CtC^-1 of the H solves (the fused U = B P epilogue of K1 reads CtC^-1)
+            launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
         }
         {
-            Timed t(c, "k_gram_inv");
-            launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
+            Timed t(c, "k_spmm_ltx");
+            launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->fuse_u, c->st);
         }
         if (c->use_tc) {
             Timed t(c, "k_pb_tc");
@@ -595,7 +596,12 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->Bbuf.alloc(std::max<size_t>(b_total, 1));
     c->use_tc = (c->flags & LGR_FLAG_TENSOR_U) != 0;
     if (const char* e = getenv("LGR_TC_U")) c->use_tc = atoi(e) != 0;
-    if (c->use_tc) c->Ubuf.alloc(std::max<size_t>(b_total, 1));
+    // LGR_FLAG_TENSOR_U: prefer the tcgen05 epilogue fused into k_spmm_ltx_tiled; the stand-alone k_pb_tc otherwise
+    c->fuse_u = c->use_tc && (c->cb / 128) * c->kp == 128 && c->cb % 128 == 0 &&
+                spmm_ltx_smem(c->kp, c->cb, c->gt, true) <= (size_t)227 * 1024 - 1024;
+    if (const char* e = getenv("LGR_FUSE_U")) c->fuse_u = c->fuse_u && atoi(e) != 0;
+    if (c->fuse_u) c->use_tc = false;
+    if (c->use_tc || c->fuse_u) c->Ubuf.alloc(std::max<size_t>(b_total, 1));
     c->Rarena.alloc(r_total);
     c->Garena.alloc((size_t)c->d * kp * kp);
     c->gram_arena.alloc((size_t)2 * c->d * kp * kp);
@@ -656,6 +662,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.L = D.L.p;
         h.H = D.H.p;
         h.B = c->Bbuf.p + D.b_off;
+        h.U = c->fuse_u ? c->Ubuf.p + D.b_off : nullptr;
+        h.Pinv = ctc(i) + kk;
         h.hmask = D.hmask.p;
         h.V = D.V.p;
         h.CtBv = D.CtBv.p;
@@ -668,7 +676,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.sqnorm = sq[i];
         // H solve: CtC = LtL + lambda VtV, rhs = B (fp32), x = H
         sH[i] = GramSpec{h.LtL, h.VtV, 1.0, D.lambda, ctc(i), ctc(i) + kk, c->ok_arena.p + i};
-        const float* upre = c->use_tc ? c->Ubuf.p + D.b_off : nullptr;
+        const float* upre = (c->use_tc || c->fuse_u) ? c->Ubuf.p + D.b_off : nullptr;
         gH[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, upre, h.H, h.hmask, D.n, kp, bH};
         gT[i] = NnlsGroup{ctc(i), ctc(i) + kk, c->ok_arena.p + i, h.B, nullptr, c->use_tc ? (void*)(c->Ubuf.p + D.b_off) : nullptr,
                           nullptr, D.n, kp, tT};

@@ -114,6 +114,8 @@ struct DsDev {
     float* L;
     float* H;
     float* B;
+    float* U;            // u = CtC^-1 b of the H solve, written by the fused epilogue of k_spmm_ltx_tiled (else null)
+    const double* Pinv;  // CtC^-1 of the H solve (KP x KP fp64, k_gram_inv)
     unsigned long long* hmask;
     double* V;      // rows x KP
     double* CtBv;   // rows x KP   rhs of the V/U solve
@@ -176,8 +178,8 @@ NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
 
 void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st);
 void launch_spmm_ltx_gather(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st);
-void launch_spmm_ltx_tiled(const DsDev* ds, int nds, int total_blocks, int kp, int cb, int gt, cudaStream_t st);
-size_t spmm_ltx_smem(int kp, int cb, int gt);
+void launch_spmm_ltx_tiled(const DsDev* ds, int nds, int total_blocks, int kp, int cb, int gt, bool fuse_u, cudaStream_t st);
+size_t spmm_ltx_smem(int kp, int cb, int gt, bool fuse_u);
 void spmm_init();
 void launch_spmm_xh(const DsDev* ds, int nds, int total_tiles, int k, int kp, int tc, cudaStream_t st);
 void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStream_t st);

@@ -82,20 +82,62 @@ __device__ __forceinline__ void gather_range(const unsigned short* __restrict__ 
     if (any) flush(seg, acc, true);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 helpers for the fused epilogue  U = B P  (3 x TF32, see lgr_tc.cu for the stand-alone version)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start [0,14) >>4, LBO [16,30) >>4, SBO [32,46) >>4, version [46,48) = 1, no swizzle
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void split_tf32_4(const float4 v, float4& h, float4& l) {
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);   // sign, exponent, 10 leading mantissa bits
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);   // exact in fp32
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_spmm_ltx_tiled
 // ------------------------------------------------------------------------------------------------
 constexpr int LTX_THREADS = 1024;
 
-size_t spmm_ltx_smem(int kp, int cb, int gt) { return (size_t)(cb + gt) * kp * sizeof(float) + 64; }
+// [L~ tile | B tile | barriers]; with the fused U = B P epilogue the L~ region doubles as the two operand tiles
+// (hi / lo parts of B, 2 x CB rows) and the hi / lo parts of P follow the B tile
+size_t spmm_ltx_smem(int kp, int cb, int gt, bool fuse_u) {
+    const size_t lrows = fuse_u ? (size_t)std::max(gt, 2 * cb) : (size_t)gt;
+    return (lrows + cb) * kp * sizeof(float) + (fuse_u ? (size_t)2 * kp * kp * sizeof(float) : 0) + 64;
+}
 
-template <int KP>
+template <int KP, bool FUSE_U>
 __global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* __restrict__ ds, int nds, int CB, int GT) {
     constexpr int LPN = KP / 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* Ls = reinterpret_cast<float*>(smem_raw);             // GT x KP
-    float* Bp = Ls + (size_t)GT * KP;                            // CB x KP partial rows of B
-    uint64_t* bar = reinterpret_cast<uint64_t*>(Bp + (size_t)CB * KP);
+    const int LROWS = FUSE_U ? max(GT, 2 * CB) : GT;
+    float* Ls = reinterpret_cast<float*>(smem_raw);             // GT x KP (fused epilogue: 2 x CB x KP operand tiles)
+    float* Bp = Ls + (size_t)LROWS * KP;                         // CB x KP partial rows of B
+    float* Pt = Bp + (size_t)CB * KP;                            // fused epilogue: hi / lo parts of P, KP x KP each
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Pt + (FUSE_U ? 2 * KP * KP : 0));
+    __shared__ uint32_t tmem_base_s;
+    if (FUSE_U && threadIdx.x < 32) {   // 128 TMEM columns: one KP-column accumulator per 128-cell tile
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(128)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     const int i = find_ds(ds, nds, (int)blockIdx.x, &DsDev::ltx_blk_off);
     const DsDev& D = ds[i];
     const int n = D.n, rows = D.rows, ngt = D.ngt;
@@ -105,8 +147,11 @@ __global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* 
     const int q = lane / LPN, s = lane % LPN;
     const float4* Ls4 = reinterpret_cast<const float4*>(Ls);
     float4* Bp4 = reinterpret_cast<float4*>(Bp);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    for (int e = threadIdx.x; e < ncell * LPN; e += blockDim.x) Bp4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        if (FUSE_U) mbar_init(bar + 1, 1);
+    }
+    for (int e = threadIdx.x; e < (FUSE_U ? CB : ncell) * LPN; e += blockDim.x) Bp4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int nq = 32 / LPN, NQ = nwarps * nq, qid = warp * nq + q;
     for (int gt = 0; gt < ngt; ++gt) {
         __syncthreads();  // everyone is done reading the previous L~ tile (and sees the barrier init / the zeroed Bp)
@@ -145,15 +190,114 @@ __global__ void __launch_bounds__(LTX_THREADS, 1) k_spmm_ltx_tiled(const DsDev* 
     __syncthreads();
     float4* __restrict__ out = reinterpret_cast<float4*>(D.B) + (size_t)c0 * LPN;
     for (int e = threadIdx.x; e < ncell * LPN; e += blockDim.x) out[e] = Bp4[e];
+    if (!FUSE_U) return;
+
+    // ---- fused epilogue (LGR_FLAG_TENSOR_U): U = B P for this block's cells on the tensor cores (u = P b is what the
+    //      dual side of the NNLS needs for every column; P = CtC^-1 from k_gram_inv, which runs before this kernel).
+    //      3 x TF32: U = B_hi P_hi + B_lo P_hi + B_hi P_lo, fp32 accumulators in TMEM.  Operands in the canonical
+    //      K-major no-swizzle UMMA layout: 16-byte chunk (row r, k-chunk c) of a 128-row tile at (c * 128 + r) * 16. ----
+    constexpr int M = 128, CH = KP / 4;
+    const int ntile = CB / M;
+    float4* Ahi = reinterpret_cast<float4*>(Ls);
+    float4* Alo = Ahi + (size_t)CB * CH;
+    float4* Phi = reinterpret_cast<float4*>(Pt);
+    float4* Plo = Phi + KP * CH;
+    // B tile (row major) -> operand tiles.  Lanes walk a diagonal of an 8-row x 8-chunk block: the eight reads of a
+    // phase hit eight different chunk columns, the eight writes eight different rows (both conflict free).
+    for (int e = threadIdx.x; e < CB * CH; e += blockDim.x) {
+        const int blk = e >> 6, j = e & 7, dd = (e >> 3) & 7;
+        const int ro = blk / (CH / 8), co = blk % (CH / 8);
+        const int r = ro * 8 + j, c = co * 8 + ((dd + j) & 7);
+        float4 h, l;
+        split_tf32_4(Bp4[r * CH + c], h, l);
+        const int o = (r / M) * (M * CH) + c * M + (r % M);
+        Ahi[o] = h;
+        Alo[o] = l;
+    }
+    {   // P (symmetric: row n of the B operand is row n of P): chunk (n, c) at (c * KP + n) * 16
+        const double* __restrict__ Pinv = D.Pinv;
+        for (int e = threadIdx.x; e < KP * CH; e += blockDim.x) {
+            const int nn = e % KP, c = e / KP;
+            const float4 v = make_float4((float)Pinv[nn * KP + c * 4], (float)Pinv[nn * KP + c * 4 + 1],
+                                         (float)Pinv[nn * KP + c * 4 + 2], (float)Pinv[nn * KP + c * 4 + 3]);
+            float4 h, l;
+            split_tf32_4(v, h, l);
+            Phi[c * KP + nn] = h;
+            Plo[c * KP + nn] = l;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    if (threadIdx.x == 0) {
+        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = KP, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        constexpr uint32_t A_LBO = M * 16, P_LBO = KP * 16, SBO = 128, TILE_BYTES = M * KP * 4;
+        const uint32_t a_hi = smem_u32(Ahi), a_lo = smem_u32(Alo), p_hi = smem_u32(Phi), p_lo = smem_u32(Plo);
+        for (int t = 0; t < ntile; ++t) {
+            uint32_t accum = 0;
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+                const uint32_t a0 = ((term == 1) ? a_lo : a_hi) + (uint32_t)t * TILE_BYTES;
+                const uint32_t p0 = (term == 2) ? p_lo : p_hi;
+#pragma unroll
+                for (int ks = 0; ks < KP / 8; ++ks) {   // one MMA consumes K = 8 tf32 = two 16-byte chunks
+                    umma_tf32(tmem_d + (uint32_t)(t * KP), umma_desc_kmajor(a0 + ks * 2 * A_LBO, A_LBO, SBO),
+                              umma_desc_kmajor(p0 + ks * 2 * P_LBO, P_LBO, SBO), idesc, accum);
+                    accum = 1;
+                }
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"l"(
+                         (uint64_t)__cvta_generic_to_shared(bar + 1))
+                     : "memory");
+    }
+    mbar_wait(bar + 1, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {   // 32 warps = 4 lane quadrants x (CB / 128 tiles) x (KP / 16 column slices): each thread reads 16 floats of one row
+        const int qd = warp & 3, rest = warp >> 2;
+        const int t = rest % ntile, sl = rest / ntile;
+        if (sl < KP / 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(qd * 32) << 16) + (uint32_t)(t * KP + sl * 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int row = t * M + qd * 32 + lane;
+            if (row < ncell) {
+                float4* dst = reinterpret_cast<float4*>(D.U + (size_t)(c0 + row) * KP + sl * 16);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    dst[jj] = make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]), __uint_as_float(v[4 * jj + 2]),
+                                          __uint_as_float(v[4 * jj + 3]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(128) : "memory");
 }
 
-void launch_spmm_ltx_tiled(const DsDev* ds, int nds, int total_blocks, int kp, int cb, int gt, cudaStream_t st) {
+void launch_spmm_ltx_tiled(const DsDev* ds, int nds, int total_blocks, int kp, int cb, int gt, bool fuse_u, cudaStream_t st) {
     if (total_blocks <= 0) return;
-    const size_t smem = spmm_ltx_smem(kp, cb, gt);
-    if (kp == 32)
-        k_spmm_ltx_tiled<32><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
-    else
-        k_spmm_ltx_tiled<64><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
+    const size_t smem = spmm_ltx_smem(kp, cb, gt, fuse_u);
+    if (fuse_u) {
+        LGR_REQUIRE(cb % 128 == 0 && (cb / 128) * kp == 128, "fused U epilogue: cell block x KP must fill 128 TMEM columns");
+        if (kp == 32)
+            k_spmm_ltx_tiled<32, true><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
+        else
+            k_spmm_ltx_tiled<64, true><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
+    } else if (kp == 32) {
+        k_spmm_ltx_tiled<32, false><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
+    } else {
+        k_spmm_ltx_tiled<64, false><<<total_blocks, LTX_THREADS, smem, st>>>(ds, nds, cb, gt);
+    }
     LGR_CUDA(cudaGetLastError());
 }
 
@@ -288,8 +432,10 @@ void spmm_init() {
     const int maxs = 227 * 1024 - 1024;
     LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     LGR_CUDA(cudaFuncSetAttribute(k_spmm_xh<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    LGR_CUDA(cudaFuncSetAttribute(k_spmm_ltx_tiled<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
 }
 
 }  // namespace lgr

@@ -285,10 +285,13 @@ def test_context_api_and_properties():
     assert abs(traj[-1] - ref["objErr"]) < TOL_OBJ * ref["objErr"]
 
 
-def test_tensor_core_u_path(pbmc):
-    """LGR_FLAG_TENSOR_U: u = CtC^-1 b on tcgen05 tensor cores (3xTF32 split, TMEM accumulators) -- same factors."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_tensor_core_u_path(pbmc, fused, monkeypatch):
+    """LGR_FLAG_TENSOR_U: u = CtC^-1 b on tcgen05 tensor cores (3xTF32 split, TMEM accumulators) -- same factors.
+    fused: the epilogue of k_spmm_ltx_tiled (B tile still in shared memory); else the stand-alone k_pb_tc."""
     import liger_b200
     from liger_b200 import synthetic as syn
+    monkeypatch.setenv("LGR_FUSE_U", "1" if fused else "0")
     W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
     a = liger_b200.inmf(pbmc["Es"], k=20, niter=30, Winit=W0, Vinit=V0, tensor_u=True, trajectory=True)
     ref = orc.inmf(pbmc["Es"], 20, 5.0, 30, W0, V0, trajectory=True)
