@@ -476,9 +476,45 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         const int nt = (maxrows + gmax - 1) / gmax;
         c->gt = (maxrows + nt - 1) / nt;
     }
+    {   // Cell-block sizes of the two sweeps: one CTA per SM at a time, so the launch takes ceil(blocks / SMs) waves of a
+        // duration ~ block size.  Pick the size (multiple of 16, within what shared memory allows) that minimises
+        // waves x size over this rank's datasets: e.g. C3 (8 x 125 000 cells, 148 SMs) 1024 -> 1136 cells per K2 tile
+        // turns 6.65 waves (7 x 1024) into exactly 6 (x 1136).
+        const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
+        std::vector<long long> ns;
+        for (int i = 0; i < a->d; ++i) {
+            const long long nf = a->E[i].ncol;
+            ns.push_back(local ? nf : nf * (c->rank + 1) / c->world - nf * c->rank / c->world);
+        }
+        const size_t limit = (size_t)226 * 1024;
+        auto pick = [&](int lo, int hi, auto fits) {
+            int best = lo;
+            double best_cost = 1e300;
+            for (int v = lo; v <= hi; v += 16) {
+                if (!fits(v)) break;
+                long long blocks = 0;
+                for (long long n : ns) blocks += (n + v - 1) / v;
+                const long long waves = (blocks + c->num_sms - 1) / c->num_sms;
+                const double cost = (double)waves * (v + 24);   // + per-block fixed cost (tile staging, epilogue)
+                if (cost <= best_cost) {
+                    best_cost = cost;
+                    best = v;
+                }
+            }
+            return best;
+        };
+        const int base_tc = c->tc, base_cb = c->cb;
+        c->tc = pick(base_tc / 2, 2 * base_tc, [&](int v) { return spmm_xh_smem(c->kp, v) <= limit && (long long)v * (c->kp / 4) <= 65536; });
+        if (!(c->flags & LGR_FLAG_TENSOR_U))   // the fused tensor-core epilogue needs cb x KP = 128 TMEM columns' worth
+            c->cb = pick(base_cb / 2, 2 * base_cb, [&](int v) { return spmm_ltx_smem(c->kp, v, c->gt, false) <= limit; });
+    }
+    if (const char* e = getenv("LGR_CB")) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= 1024 && v % 16 == 0) c->cb = v;
+    }
     if (const char* e = getenv("LGR_TC")) {
         const int v = atoi(e);
-        if (v >= 32 && v <= 65536 && (size_t)v * c->kp * 4 <= 200 * 1024) c->tc = v;
+        if (v >= 32 && v <= 65536 && spmm_xh_smem(c->kp, v) <= (size_t)226 * 1024) c->tc = v;
     }
     if (const char* e = getenv("LGR_KERNEL_TIMING")) c->kt.on = atoi(e) != 0;
     if (c->world > 1) {
