@@ -314,6 +314,17 @@ void run_objective(lgr_ctx* c, double* slot) {
     launch_objective(c->ds_dev.p, c->d, c->k, c->kp, slot, c->st);
 }
 
+// FP64 solves (V_i / U_i, W): small batches go to the warp-per-column kernel, its singular groups to k_nnls
+void solve_f64(lgr_ctx* c, const NnlsGroup* grp, int ngroups, long long cols, int flags) {
+    static const bool no_warp = getenv("LGR_NNLS_NO_WARP") != nullptr;
+    if (!no_warp && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (flags & ~1) == 0 && nnls_warp_supported(c->k, c->kp, cols, c->num_sms)) {
+        launch_nnls_warp(grp, ngroups, cols, c->k, c->num_sms, c->counters.p, flags, c->st);
+        launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags | 16, c->st);
+    } else {
+        launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags, c->st);
+    }
+}
+
 void iterate(lgr_ctx* c, int niter, double* traj_host) {
     const bool traj = traj_host != nullptr;
     int cold = (c->flags & LGR_FLAG_COLD_START) ? 1 : 0;
@@ -370,7 +381,7 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         }
         {
             Timed t(c, "k_nnls_V");
-            launch_nnls(true, c->grpV.p, c->d, c->colsV, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
+            solve_f64(c, c->grpV.p, c->d, c->colsV, cold);
         }
         // ---- W: new V_i ----
         {
@@ -383,7 +394,7 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
         }
         {
             Timed t(c, "k_nnls_W");
-            launch_nnls(true, c->grpW.p, 1, (long long)c->m, c->k, c->kp, c->cfgD, c->counters.p, cold, c->st);
+            solve_f64(c, c->grpW.p, 1, (long long)c->m, cold);
         }
     }
     if (traj && niter > 0) {
@@ -1017,7 +1028,13 @@ int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* 
             launch_gram_inv(spec.p, 1, k, kp, st);
             NnlsGroup g{ctc.p, ctc.p + (size_t)kp * kp, ok.p, dB.p, nullptr, dX.p, mask.p, (int)ncols, k, 0};
             LGR_CUDA(cudaMemcpyAsync(grp.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
-            launch_nnls(true, grp.p, 1, (long long)ncols, k, kp, cfg, cnt.p, 1, st);
+            static const bool no_warp = getenv("LGR_NNLS_NO_WARP") != nullptr;
+            if (!no_warp && nnls_warp_supported(k, kp, ncols, prop.multiProcessorCount)) {
+                launch_nnls_warp(grp.p, 1, (long long)ncols, k, prop.multiProcessorCount, cnt.p, 1, st);
+                launch_nnls(true, grp.p, 1, (long long)ncols, k, kp, cfg, cnt.p, 1 | 16, st);
+            } else {
+                launch_nnls(true, grp.p, 1, (long long)ncols, k, kp, cfg, cnt.p, 1, st);
+            }
             LGR_CUDA(cudaMemcpyAsync(X, dX.p, (size_t)k * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
             LGR_CUDA(cudaStreamSynchronize(st));
         } catch (...) {

@@ -192,6 +192,10 @@ bool nnls_reg_supported(int k, int kp);
 void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int kp, int num_sms, Counters* cnt,
                      int flags, cudaStream_t st);
 void nnls_reg_init();
+// warp-per-column FP64 path for small batches (lgr_nnls_warp.cu): k <= 32; singular groups are skipped (flag 16 mop-up)
+bool nnls_warp_supported(int k, int kp, long long total_cols, int num_sms);
+void launch_nnls_warp(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
+                      cudaStream_t st);
 void launch_pb_tc(const NnlsGroup* groups, int ngroups, long long total_tiles, int kp, int num_sms, cudaStream_t st);
 void tc_init();
 void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st);
