@@ -362,7 +362,11 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             static const bool no_reg = getenv("LGR_NNLS_NO_REG") != nullptr;
             if (!no_reg && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
                 launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->kp, c->num_sms, c->counters.p, cold, c->st);
-                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold | 16 | (c->kp > 32 ? 64 : 0), c->st);
+                static const bool no_wbig = getenv("LGR_NNLS_NO_WBIG") != nullptr;
+                if (c->kp > 32 && !no_wbig)   // systems above 16 unknowns: warp-per-column continuation
+                    launch_nnls_wbig(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p,
+                            cold | 16 | ((c->kp > 32 && no_wbig) ? 64 : 0), c->st);
             } else {
                 launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
             }
