@@ -320,6 +320,10 @@ void solve_f64(lgr_ctx* c, const NnlsGroup* grp, int ngroups, long long cols, in
     if (!no_warp && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (flags & ~1) == 0 && nnls_warp_supported(c->k, c->kp, cols, c->num_sms)) {
         launch_nnls_warp(grp, ngroups, cols, c->k, c->num_sms, c->counters.p, flags, c->st);
         launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags | 16, c->st);
+    } else if (!no_warp && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (flags & ~1) == 0 &&
+               nnls_wbig64_supported(c->k, c->kp, cols, c->num_sms)) {
+        launch_nnls_wbig64(grp, ngroups, cols, c->k, c->num_sms, c->counters.p, flags, c->st);
+        launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags | 16, c->st);
     } else {
         launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags, c->st);
     }

@@ -195,6 +195,9 @@ void nnls_reg_init();
 // continues the columns k_nnls_reg<64> flagged as too big for its register templates (lgr_nnls_wbig.cu)
 void launch_nnls_wbig(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt,
                       cudaStream_t st);
+bool nnls_wbig64_supported(int k, int kp, long long total_cols, int num_sms);
+void launch_nnls_wbig64(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
+                        cudaStream_t st);
 // warp-per-column FP64 path for small batches (lgr_nnls_warp.cu): k <= 32; singular groups are skipped (flag 16 mop-up)
 bool nnls_warp_supported(int k, int kp, long long total_cols, int num_sms);
 void launch_nnls_warp(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,

@@ -15,12 +15,21 @@ namespace {
 
 constexpr int BKP = 64;
 constexpr int BMST = 65;
-constexpr float BEPS = 1.1920929e-7f;
 constexpr unsigned long long BDEFER = 1ull << 63;
+template <typename T> __device__ __forceinline__ T beps();
+template <> __device__ __forceinline__ float beps<float>() { return 1.1920929e-7f; }
+template <> __device__ __forceinline__ double beps<double>() { return 2.220446049250313e-16; }
+__device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float tabs(float a) { return fabsf(a); }
+__device__ __forceinline__ double tabs(double a) { return fabs(a); }
+__device__ __forceinline__ float tfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double tfma(double a, double b, double c) { return fma(a, b, c); }
 
-__device__ __forceinline__ float wmaxf(float v) {
+template <typename T>
+__device__ __forceinline__ T wmaxf(T v) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    for (int off = 16; off > 0; off >>= 1) v = tmax(v, __shfl_xor_sync(0xffffffffu, v, off));
     return v;
 }
 // index of the (t+1)-th set bit of a 64-bit mask (t < popcount)
@@ -30,58 +39,63 @@ __device__ __forceinline__ int nth_set64(unsigned long long S, int t) {
     return t < nlo ? (int)__fns(lo, 0, t + 1) : 32 + (int)__fns(hi, 0, t - nlo + 1);
 }
 // value of factor `idx` of a vector held as (v0: factors 0..31, v1: factors 32..63) across the warp
-__device__ __forceinline__ float pick(float v0, float v1, int idx) {
-    const float a = __shfl_sync(0xffffffffu, v0, idx & 31), b = __shfl_sync(0xffffffffu, v1, idx & 31);
+template <typename T>
+__device__ __forceinline__ T pick(T v0, T v1, int idx) {
+    const T a = __shfl_sync(0xffffffffu, v0, idx & 31), b = __shfl_sync(0xffffffffu, v1, idx & 31);
     return idx < 32 ? a : b;
 }
 
 // M_SS z = r_S, s <= W unknowns; lane t < s returns z_t (0 for pinned pivots)
-template <int W>
-__device__ __forceinline__ float solve_big(const float* __restrict__ M, const unsigned long long S, const int s, const float r0,
-                                           const float r1, const int lane, bool& ok) {
+template <int W, typename T>
+__device__ __forceinline__ T solve_big(const T* __restrict__ M, const unsigned long long S, const int s, const T r0, const T r1,
+                                       const int lane, bool& ok) {
     const int my = (lane < s) ? nth_set64(S, lane) : 0;
-    float a[W];
+    T a[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) a[j] = 0.f;
+    for (int j = 0; j < W; ++j) a[j] = (T)0;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         if (j >= s) break;   // warp-uniform
         const int gj = __shfl_sync(0xffffffffu, my, j);
         a[j] = M[my * BMST + gj];
     }
-    float r = pick(r0, r1, my);
-    float myinv = 0.f;
+    T r = pick(r0, r1, my);
+    T myinv = (T)0;
     ok = true;
     // Gauss-Jordan with a ROTATING register window: after step j the surviving columns shift down by one, so the pivot
     // column is always a[0] and the step body has static register indices inside a dynamic loop (a fully unrolled
     // 32 x 32 sweep is ~48 KB of code and starved the instruction cache: measured 2x slower)
     for (int j = 0; j < s; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, a[0], j);
-        const float orig = M[(int)__shfl_sync(0xffffffffu, my, j) * (BMST + 1)];
-        float inv = 0.f;
-        if (pj > orig * (BEPS * 4.f))
-            inv = 1.f / pj;
+        const T pj = __shfl_sync(0xffffffffu, a[0], j);
+        const T orig = M[(int)__shfl_sync(0xffffffffu, my, j) * (BMST + 1)];
+        T inv = (T)0;
+        if (pj > orig * (beps<T>() * (T)4))
+            inv = (T)1 / pj;
         else
             ok = false;
         if (lane == j) myinv = inv;
-        const float f = (lane == j) ? 0.f : a[0] * inv;   // multiplier of the pivot row for my row
+        const T f = (lane == j) ? (T)0 : a[0] * inv;   // multiplier of the pivot row for my row
 #pragma unroll
         for (int c = 1; c < W; ++c) {
-            const float rc = __shfl_sync(0xffffffffu, a[c], j);
-            a[c - 1] = fmaf(-f, rc, a[c]);
+            const T rc = __shfl_sync(0xffffffffu, a[c], j);
+            a[c - 1] = tfma(-f, rc, a[c]);
         }
-        a[W - 1] = 0.f;
-        const float rr = __shfl_sync(0xffffffffu, r, j);
-        r = fmaf(-f, rr, r);
+        a[W - 1] = (T)0;
+        const T rr = __shfl_sync(0xffffffffu, r, j);
+        r = tfma(-f, rr, r);
     }
-    return (lane < s) ? r * myinv : 0.f;
+    return (lane < s) ? r * myinv : (T)0;
 }
 
+// ALL = false: only the columns flagged by k_nnls_reg<64> (fp32 H solves).  ALL = true: every column of the launch, from
+// its warm-start set or cold (flags & 1) -- the FP64 V_i / U_i / W solves at k > 32.
+template <typename T, bool ALL>
 __global__ void __launch_bounds__(256) k_nnls_wbig(const NnlsGroup* __restrict__ groups, int ngroups, long long total_cols, int k,
-                                                   Counters* cnt) {
-    extern __shared__ __align__(16) float bsm[];
-    float* Gs = bsm;
-    float* Ps = bsm + BKP * BMST;
+                                                   Counters* cnt, int flags) {
+    extern __shared__ __align__(16) unsigned char bsm_raw[];
+    T* Gs = reinterpret_cast<T*>(bsm_raw);
+    T* Ps = Gs + BKP * BMST;
+    const bool cold_start = ALL && (flags & 1) != 0;
     __shared__ int next_col;
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned long long kmask = (1ull << k) - 1ull;   // k <= 62
@@ -89,7 +103,7 @@ __global__ void __launch_bounds__(256) k_nnls_wbig(const NnlsGroup* __restrict__
     const int MAXIT = 4 * k + 16;
 
     long long per = (total_cols + gridDim.x - 1) / gridDim.x;
-    per = (per + 31) & ~31LL;
+    if (!ALL) per = (per + 31) & ~31LL;
     long long pos = (long long)blockIdx.x * per;
     const long long stop = pos + per < total_cols ? pos + per : total_cols;
     unsigned long long pivots_local = 0;
@@ -105,30 +119,32 @@ __global__ void __launch_bounds__(256) k_nnls_wbig(const NnlsGroup* __restrict__
         __syncthreads();
         for (int e = tid; e < BKP * BKP; e += blockDim.x) {
             const int a = e / BKP, b = e % BKP;
-            Gs[a * BMST + b] = (float)grp.gram[e];
-            Ps[a * BMST + b] = (float)grp.ginv[e];
+            Gs[a * BMST + b] = (T)grp.gram[e];
+            Ps[a * BMST + b] = (T)grp.ginv[e];
         }
         if (tid == 0) next_col = 0;
         __syncthreads();
-        const float* __restrict__ rhs = reinterpret_cast<const float*>(grp.rhs) + (size_t)c0 * BKP;
-        float* __restrict__ xout = reinterpret_cast<float*>(grp.x) + (size_t)c0 * BKP;
+        const T* __restrict__ rhs = reinterpret_cast<const T*>(grp.rhs) + (size_t)c0 * BKP;
+        T* __restrict__ xout = reinterpret_cast<T*>(grp.x) + (size_t)c0 * BKP;
         unsigned long long* __restrict__ masks = grp.mask + c0;
         for (;;) {
             // a warp claims 32 columns at a time and looks for the flagged ones among them
+            // (ALL: one column per claim -- a small batch must spread over as many warps as possible)
+            constexpr int CLAIM = ALL ? 1 : 32;
             int base = 0;
-            if (lane == 0) base = atomicAdd(&next_col, 32);
+            if (lane == 0) base = atomicAdd(&next_col, CLAIM);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= ccols) break;
-            const unsigned long long mine = (base + lane < ccols) ? masks[base + lane] : 0ull;
-            unsigned todo = __ballot_sync(0xffffffffu, (mine & BDEFER) != 0ull);
+            const unsigned long long mine = (lane < CLAIM && base + lane < ccols) ? masks[base + lane] : 0ull;
+            unsigned todo = __ballot_sync(0xffffffffu, ALL ? (lane == 0) : ((mine & BDEFER) != 0ull));
             while (todo) {
                 const int src = __ffs((int)todo) - 1;
                 todo &= todo - 1;
                 const int c = base + src;
-                unsigned long long F = __shfl_sync(0xffffffffu, mine, src) & kmask;
-                const float b0 = rhs[(size_t)c * BKP + lane], b1 = rhs[(size_t)c * BKP + 32 + lane];
-                const float tol = wmaxf(fmaxf(fabsf(b0), fabsf(b1))) * (BEPS * 8.f);
-                float u0 = 0.f, u1 = 0.f, x0 = 0.f, x1 = 0.f;
+                unsigned long long F = cold_start ? 0ull : (__shfl_sync(0xffffffffu, mine, src) & kmask);
+                const T b0 = rhs[(size_t)c * BKP + lane], b1 = rhs[(size_t)c * BKP + 32 + lane];
+                const T tol = wmaxf(tmax(tabs(b0), tabs(b1))) * (beps<T>() * (T)8);
+                T u0 = (T)0, u1 = (T)0, x0 = (T)0, x1 = (T)0;
                 bool have_u = false;
                 int alpha = 3, beta = k + 1, iter = 0;
                 for (;;) {
@@ -137,38 +153,38 @@ __global__ void __launch_bounds__(256) k_nnls_wbig(const NnlsGroup* __restrict__
                     const unsigned long long S = dual ? ((~F) & kmask) : F;
                     const int s = dual ? (k - p) : p;
                     if (dual && !have_u) {   // u = P b
-                        float a0 = 0.f, a1 = 0.f;
+                        T a0 = (T)0, a1 = (T)0;
                         for (int t = 0; t < k; ++t) {
-                            const float bt = pick(b0, b1, t);
-                            a0 = fmaf(Ps[lane * BMST + t], bt, a0);
-                            a1 = fmaf(Ps[(lane + 32) * BMST + t], bt, a1);
+                            const T bt = pick(b0, b1, t);
+                            a0 = tfma(Ps[lane * BMST + t], bt, a0);
+                            a1 = tfma(Ps[(lane + 32) * BMST + t], bt, a1);
                         }
                         u0 = a0;
                         u1 = a1;
                         have_u = true;
                     }
-                    const float* M = dual ? Ps : Gs;
+                    const T* M = dual ? Ps : Gs;
                     bool ok = true;
-                    const float rr0 = dual ? u0 : b0, rr1 = dual ? u1 : b1;
-                    const float z = s <= 16   ? solve_big<16>(M, S, s, rr0, rr1, lane, ok)
-                                    : s <= 24 ? solve_big<24>(M, S, s, rr0, rr1, lane, ok)
-                                              : solve_big<32>(M, S, s, rr0, rr1, lane, ok);
+                    const T rr0 = dual ? u0 : b0, rr1 = dual ? u1 : b1;
+                    const T z = s <= 16   ? solve_big<16, T>(M, S, s, rr0, rr1, lane, ok)
+                                : s <= 24 ? solve_big<24, T>(M, S, s, rr0, rr1, lane, ok)
+                                          : solve_big<32, T>(M, S, s, rr0, rr1, lane, ok);
                     if (!ok && lane == 0) atomicAdd(&cnt->nnls_bad_pivot, 1ull);
                     const uint32_t Slo = (uint32_t)S, Shi = (uint32_t)(S >> 32);
                     const int nlo = __popc(Slo);
-                    const float zt0 = __shfl_sync(0xffffffffu, z, __popc(Slo & ((1u << lane) - 1u)));
-                    const float zt1 = __shfl_sync(0xffffffffu, z, (nlo + __popc(Shi & ((1u << lane) - 1u))) & 31);
-                    const float zf0 = (S & bit0) ? zt0 : 0.f, zf1 = (S & bit1) ? zt1 : 0.f;
-                    float a0 = 0.f, a1 = 0.f;
+                    const T zt0 = __shfl_sync(0xffffffffu, z, __popc(Slo & ((1u << lane) - 1u)));
+                    const T zt1 = __shfl_sync(0xffffffffu, z, (nlo + __popc(Shi & ((1u << lane) - 1u))) & 31);
+                    const T zf0 = (S & bit0) ? zt0 : (T)0, zf1 = (S & bit1) ? zt1 : (T)0;
+                    T a0 = (T)0, a1 = (T)0;
                     {
                         unsigned long long rem = S;
                         int t = 0;
                         while (rem) {   // warp-uniform
                             const int gi = __ffsll((long long)rem) - 1;
                             rem &= rem - 1;
-                            const float zt = __shfl_sync(0xffffffffu, z, t);
-                            a0 = fmaf(M[lane * BMST + gi], zt, a0);
-                            a1 = fmaf(M[(lane + 32) * BMST + gi], zt, a1);
+                            const T zt = __shfl_sync(0xffffffffu, z, t);
+                            a0 = tfma(M[lane * BMST + gi], zt, a0);
+                            a1 = tfma(M[(lane + 32) * BMST + gi], zt, a1);
                             ++t;
                         }
                     }
@@ -176,13 +192,13 @@ __global__ void __launch_bounds__(256) k_nnls_wbig(const NnlsGroup* __restrict__
                     if (dual) {
                         x0 = u0 - a0;
                         x1 = u1 - a1;
-                        const float tolx = wmaxf(fmaxf((F & bit0) ? fabsf(x0) : 0.f, (F & bit1) ? fabsf(x1) : 0.f)) * (BEPS * 8.f);
+                        const T tolx = wmaxf(tmax((F & bit0) ? tabs(x0) : (T)0, (F & bit1) ? tabs(x1) : (T)0)) * (beps<T>() * (T)8);
                         const uint32_t ilo = __ballot_sync(0xffffffffu, ((S & bit0) && zf0 > tol) || ((F & bit0) && x0 < -tolx));
                         const uint32_t ihi = __ballot_sync(0xffffffffu, ((S & bit1) && zf1 > tol) || ((F & bit1) && x1 < -tolx));
                         infeas = (unsigned long long)ilo | ((unsigned long long)ihi << 32);
                     } else {
-                        const float y0 = a0 - b0, y1 = a1 - b1;
-                        const float tolx = wmaxf(fmaxf(fabsf(zf0), fabsf(zf1))) * (BEPS * 8.f);
+                        const T y0 = a0 - b0, y1 = a1 - b1;
+                        const T tolx = wmaxf(tmax(tabs(zf0), tabs(zf1))) * (beps<T>() * (T)8);
                         const unsigned long long A = (~F) & kmask;
                         const uint32_t ilo = __ballot_sync(0xffffffffu, ((S & bit0) && zf0 < -tolx) || ((A & bit0) && y0 < -tol));
                         const uint32_t ihi = __ballot_sync(0xffffffffu, ((S & bit1) && zf1 < -tolx) || ((A & bit1) && y1 < -tol));
@@ -211,8 +227,8 @@ __global__ void __launch_bounds__(256) k_nnls_wbig(const NnlsGroup* __restrict__
                     if (infeas != 0ull && lane == 0) atomicAdd(&cnt->nnls_unconverged, 1ull);
                     break;
                 }
-                xout[(size_t)c * BKP + lane] = ((F & bit0) && x0 > 0.f) ? x0 : 0.f;
-                xout[(size_t)c * BKP + 32 + lane] = ((F & bit1) && x1 > 0.f) ? x1 : 0.f;
+                xout[(size_t)c * BKP + lane] = ((F & bit0) && x0 > (T)0) ? x0 : (T)0;
+                xout[(size_t)c * BKP + 32 + lane] = ((F & bit1) && x1 > (T)0) ? x1 : (T)0;
                 if (lane == 0) masks[c] = F;   // clears the flag
             }
         }
@@ -222,21 +238,37 @@ __global__ void __launch_bounds__(256) k_nnls_wbig(const NnlsGroup* __restrict__
 
 }  // namespace
 
-// continues the columns k_nnls_reg<64> flagged (bit 63 of their warm-start mask); all other columns are left alone
-void launch_nnls_wbig(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt,
-                      cudaStream_t st) {
+template <typename T, bool ALL>
+static void launch_wbig_t(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
+                          cudaStream_t st) {
     if (total_cols <= 0) return;
+    const size_t smem = (size_t)2 * BKP * BMST * sizeof(T);
     static bool init = false;
-    const size_t smem = (size_t)2 * BKP * BMST * sizeof(float);
     if (!init) {
-        LGR_CUDA(cudaFuncSetAttribute(k_nnls_wbig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LGR_CUDA(cudaFuncSetAttribute(k_nnls_wbig<T, ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         init = true;
     }
     long long want = (total_cols + 255) / 256;
-    const long long cap = (long long)num_sms * 4;
+    if (ALL) want = (total_cols + 7) / 8;           // small batches: one column per warp when there are that few
+    const long long cap = (long long)num_sms * (sizeof(T) == 4 ? 4 : 3);
     const int grid = (int)(want < cap ? want : cap);
-    k_nnls_wbig<<<grid, 256, smem, st>>>(groups, ngroups, total_cols, k, cnt);
+    k_nnls_wbig<T, ALL><<<grid, 256, smem, st>>>(groups, ngroups, total_cols, k, cnt, flags);
     LGR_CUDA(cudaGetLastError());
+}
+
+// continues the columns k_nnls_reg<64> flagged (bit 63 of their warm-start mask); all other columns are left alone
+void launch_nnls_wbig(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt,
+                      cudaStream_t st) {
+    launch_wbig_t<float, false>(groups, ngroups, total_cols, k, num_sms, cnt, 0, st);
+}
+
+// FP64, 32 < k <= 62, every column of a small batch (V_i / U_i / W solves); singular groups are skipped (flag 16 mop-up)
+bool nnls_wbig64_supported(int k, int kp, long long total_cols, int num_sms) {
+    return kp == 64 && k <= 62 && total_cols <= (long long)num_sms * 16 * 64;
+}
+void launch_nnls_wbig64(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
+                        cudaStream_t st) {
+    launch_wbig_t<double, true>(groups, ngroups, total_cols, k, num_sms, cnt, flags, st);
 }
 
 }  // namespace lgr
