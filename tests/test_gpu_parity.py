@@ -35,7 +35,8 @@ def _check(out, ref, tol=TOL_FACTOR, u=False):
 # ----------------------------------------------------------------------------------------------
 # bppnnls_prod  (RcppPlanc::bppnnls_prod; R/cINMF.R:481)
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("k,c", [(1, 5), (5, 1), (20, 127), (20, 129), (30, 1000), (33, 300), (50, 4097), (64, 65)])
+@pytest.mark.parametrize("k,c", [(1, 5), (5, 1), (20, 127), (20, 129), (30, 1000), (33, 300), (50, 4097), (64, 65),
+                                 (8, 160000)])   # the last one is beyond the warp-per-column kernel's batch limit
 def test_bppnnls_prod_matches_oracle(k, c):
     import liger_b200
     rng = np.random.default_rng(k * 1000 + c)
@@ -130,9 +131,11 @@ def test_inmf_bmmc_trajectory(bmmc):
     assert np.all(np.diff(out["traj"]) < 0)
 
 
-@pytest.mark.parametrize("k,ns,m", [(30, (333, 1000, 57), 300), (40, (200, 129), 150), (3, (40, 41, 42, 43), 64)])
+@pytest.mark.parametrize("k,ns,m", [(30, (333, 1000, 57), 300), (40, (200, 129), 150), (3, (40, 41, 42, 43), 64),
+                                    (63, (300, 170), 160), (50, (2500, 900), 200)])
 def test_inmf_synthetic_ragged(k, ns, m):
-    """ragged datasets, k > 32 (two-line factor rows), many datasets; vs the C oracle from identical inits."""
+    """ragged datasets, k > 32 (two-line factor rows; k = 50 exercises the flagged-column hand-over between the
+    register and the warp NNLS kernels, k = 63 is beyond both), many datasets; vs the C oracle from identical inits."""
     import liger_b200
     from liger_b200 import synthetic as syn
     Es = []
