@@ -65,8 +65,9 @@ typedef struct lgr_csc {
     const int32_t* rowidx; /* nnz, 0-based; need not be sorted within a column */
     const void* values;    /* nnz */
     int32_t value_dtype;   /* lgr_dtype */
-    int32_t reserved;
+    int32_t location;      /* 0: host pointers; LGR_CSC_DEVICE: device pointers (views returned by lgr_prep_scaled_view) */
 } lgr_csc;
+#define LGR_CSC_DEVICE 1
 
 /* flags for lgr_inmf_args.flags */
 #define LGR_FLAG_TRAJECTORY 0x1u  /* evaluate the objective after every iteration into out->obj_traj */
@@ -159,6 +160,20 @@ LGR_API int lgr_row_vars_sparse(int64_t nrow, int64_t ncol_x, const int32_t* col
    whose root mean square is 0; rms_out (nrow) may be NULL. */
 LGR_API int lgr_scale_not_center_by_row(int64_t nrow, int64_t ncol, const int32_t* colptr, const int32_t* rowidx,
                                         const double* values, double* out, double* rms_out, int32_t device);
+
+/* ---- device-resident preprocessing pipeline (second half) ----------------------------------
+   raw counts -> normalize -> per-gene statistics (to the host, which selects the variable genes) -> scaleNotCenter ->
+   scaleData that STAYS in HBM and feeds lgr_inmf / lgr_ctx_create through a device view: X is never copied back to the
+   host nor uploaded a second time. */
+typedef struct lgr_prep lgr_prep;
+LGR_API int lgr_prep_create(int32_t d, const lgr_csc* raw /* d matrices, genes_i x n_i, host */, int32_t device, lgr_prep** out);
+LGR_API int lgr_prep_normalize(lgr_prep* p);                      /* normalize.dgCMatrix, every dataset, in place */
+LGR_API int lgr_prep_gene_stats(lgr_prep* p, int32_t i, double* means /* genes_i */, double* vars /* genes_i */);
+/* scaleNotCenter of dataset i: rows feature_rows[0..m) (indices into its gene list, in feature order) */
+LGR_API int lgr_prep_scale(lgr_prep* p, int32_t i, int64_t m, const int32_t* feature_rows);
+LGR_API int lgr_prep_scaled_view(lgr_prep* p, int32_t i, lgr_csc* view);   /* m x n_i, f32 values, device pointers */
+LGR_API int lgr_prep_scaled_download(lgr_prep* p, int32_t i, int32_t* colptr, int32_t* rowidx, double* values);
+LGR_API void lgr_prep_destroy(lgr_prep* p);
 
 /* ---- resident-handle API (data stays in HBM between calls; used by bench + multi-GPU hosts) ---- */
 typedef struct lgr_ctx lgr_ctx;

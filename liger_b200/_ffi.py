@@ -19,7 +19,7 @@ c_uint64_p = C.POINTER(C.c_uint64)
 
 class lgr_csc(C.Structure):
     _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("colptr", c_int32_p), ("rowidx", c_int32_p),
-                ("values", C.c_void_p), ("value_dtype", C.c_int32), ("reserved", C.c_int32)]
+                ("values", C.c_void_p), ("value_dtype", C.c_int32), ("location", C.c_int32)]
 
 
 INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -61,6 +61,8 @@ EXPORTS = [
     "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
     "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id", "lgr_host_alloc",
     "lgr_host_free", "lgr_normalize_csc", "lgr_row_vars_sparse", "lgr_scale_not_center_by_row",
+    "lgr_prep_create", "lgr_prep_normalize", "lgr_prep_gene_stats", "lgr_prep_scale", "lgr_prep_scaled_view",
+    "lgr_prep_scaled_download", "lgr_prep_destroy",
 ]
 
 
@@ -103,6 +105,14 @@ def lib():
                                       c_double_p, c_double_p, C.c_int32]
     L.lgr_scale_not_center_by_row.argtypes = [C.c_int64, C.c_int64, c_int32_p, c_int32_p, c_double_p, c_double_p,
                                               c_double_p, C.c_int32]
+    L.lgr_prep_create.argtypes = [C.c_int32, C.POINTER(lgr_csc), C.c_int32, C.POINTER(C.c_void_p)]
+    L.lgr_prep_normalize.argtypes = [C.c_void_p]
+    L.lgr_prep_gene_stats.argtypes = [C.c_void_p, C.c_int32, c_double_p, c_double_p]
+    L.lgr_prep_scale.argtypes = [C.c_void_p, C.c_int32, C.c_int64, c_int32_p]
+    L.lgr_prep_scaled_view.argtypes = [C.c_void_p, C.c_int32, C.POINTER(lgr_csc)]
+    L.lgr_prep_scaled_download.argtypes = [C.c_void_p, C.c_int32, c_int32_p, c_int32_p, c_double_p]
+    L.lgr_prep_destroy.argtypes = [C.c_void_p]
+    L.lgr_prep_destroy.restype = None
     L.lgr_nccl_unique_id.argtypes = [C.c_void_p]
     L.lgr_host_alloc.argtypes = [C.c_size_t]
     L.lgr_host_alloc.restype = C.c_void_p

@@ -68,10 +68,25 @@ def pinned_empty(shape, dtype=np.float64):
     return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order="F")
 
 
+class DeviceCsc:
+    """A genes x cells CSC matrix that lives in HBM (a view handed out by lgr_prep_scaled_view).  It can be passed to
+    inmf / uinmf / Context in place of a scipy matrix; `owner` keeps the preprocessing handle alive."""
+
+    def __init__(self, struct, owner):
+        self.struct = struct
+        self.owner = owner
+        self.shape = (int(struct.nrow), int(struct.ncol))
+
+
 class _Csc:
     """Keeps the numpy buffers of one dgCMatrix-like input alive and exposes an lgr_csc view."""
 
     def __init__(self, mat, keep_f32=False):
+        if isinstance(mat, DeviceCsc):   # resident scaleData (preprocess.Pipeline): device pointers, nothing to copy
+            self.owner = mat
+            self.shape = mat.shape
+            self.struct = mat.struct
+            return
         if sp.issparse(mat):
             m = mat.tocsc()
             indptr, indices, data, shape = m.indptr, m.indices, m.data, m.shape

@@ -219,11 +219,20 @@ struct StagedCsc {
 };
 void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs) {
     const int n = c1 - c0;
-    const int base = M.colptr[c0];
-    for (int j = 1; j <= n; ++j)
-        LGR_REQUIRE(M.colptr[c0 + j] >= M.colptr[c0 + j - 1], "CSC column pointers must be non-decreasing");
+    const bool on_device = M.location == LGR_CSC_DEVICE;   // a view of resident data (lgr_prep_scaled_view)
+    int base = 0, last = 0;
+    if (on_device) {
+        LGR_CUDA(cudaMemcpy(&base, M.colptr + c0, sizeof(int), cudaMemcpyDeviceToHost));
+        LGR_CUDA(cudaMemcpy(&last, M.colptr + c0 + n, sizeof(int), cudaMemcpyDeviceToHost));
+        LGR_REQUIRE(last >= base, "CSC column pointers must be non-decreasing");
+    } else {
+        base = M.colptr[c0];
+        for (int j = 1; j <= n; ++j)
+            LGR_REQUIRE(M.colptr[c0 + j] >= M.colptr[c0 + j - 1], "CSC column pointers must be non-decreasing");
+        last = M.colptr[c0 + n];
+    }
     S.base = base;
-    S.nnz = (size_t)(M.colptr[c0 + n] - base);
+    S.nnz = (size_t)(last - base);
     S.colptr.alloc((size_t)n + 1);
     S.rowidx.alloc(S.nnz);
     S.val.alloc(S.nnz);
@@ -235,16 +244,17 @@ void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs) 
     LGR_CUDA(cudaEventRecord(alloc_done, alloc_stream()));
     LGR_CUDA(cudaStreamWaitEvent(cs, alloc_done, 0));
     LGR_CUDA(cudaEventDestroy(alloc_done));
-    // straight from the caller's array (no pageable staging vector: that would serialise the host with the copy stream)
-    LGR_CUDA(cudaMemcpyAsync(S.colptr.p, M.colptr + c0, ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, cs));
+    // straight from the caller's arrays (no pageable staging vector: that would serialise the host with the copy stream);
+    // cudaMemcpyDefault: host or device source
+    LGR_CUDA(cudaMemcpyAsync(S.colptr.p, M.colptr + c0, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, cs));
     if (S.nnz) {
-        LGR_CUDA(cudaMemcpyAsync(S.rowidx.p, M.rowidx + base, S.nnz * sizeof(int), cudaMemcpyHostToDevice, cs));
+        LGR_CUDA(cudaMemcpyAsync(S.rowidx.p, M.rowidx + base, S.nnz * sizeof(int), cudaMemcpyDefault, cs));
         if (M.value_dtype == LGR_F32)
             LGR_CUDA(cudaMemcpyAsync(S.val.p, static_cast<const float*>(M.values) + base, S.nnz * sizeof(float),
-                                     cudaMemcpyHostToDevice, cs));
+                                     cudaMemcpyDefault, cs));
         else
             LGR_CUDA(cudaMemcpyAsync(S.val64.p, static_cast<const double*>(M.values) + base, S.nnz * sizeof(double),
-                                     cudaMemcpyHostToDevice, cs));
+                                     cudaMemcpyDefault, cs));
     }
     LGR_CUDA(cudaEventRecord(S.done, cs));
 }
@@ -559,7 +569,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         const lgr_csc& E = a->E[i];
         LGR_REQUIRE(E.nrow == a->m, "every E[i] must have m rows");
         LGR_REQUIRE(E.ncol >= 1 && E.ncol < (int64_t)0x7fffffff, "E[i].ncol out of range");
-        LGR_REQUIRE(E.colptr && (E.colptr[E.ncol] == 0 || (E.rowidx && E.values)), "E[i] has null arrays");
+        LGR_REQUIRE(E.colptr && (E.location == LGR_CSC_DEVICE || E.colptr[E.ncol] == 0 || (E.rowidx && E.values)),
+                    "E[i] has null arrays");
         const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
         const int n_full = (int)E.ncol;
         const int s0 = local ? 0 : (int)((int64_t)n_full * c->rank / c->world);
@@ -582,7 +593,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         const lgr_csc& E = a->E[i];
         LGR_REQUIRE(E.nrow == a->m, "every E[i] must have m rows");
         LGR_REQUIRE(E.ncol >= 1 && E.ncol < (int64_t)0x7fffffff, "E[i].ncol out of range");
-        LGR_REQUIRE(E.colptr && (E.colptr[E.ncol] == 0 || (E.rowidx && E.values)), "E[i] has null arrays");
+        LGR_REQUIRE(E.colptr && (E.location == LGR_CSC_DEVICE || E.colptr[E.ncol] == 0 || (E.rowidx && E.values)),
+                    "E[i] has null arrays");
         D.n_full = (int)E.ncol;
         const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
         D.c0 = local ? 0 : (int)((int64_t)D.n_full * c->rank / c->world);
@@ -1182,6 +1194,172 @@ int lgr_scale_not_center_by_row(int64_t nrow, int64_t ncol, const int32_t* colpt
         if (rms_out) LGR_CUDA(cudaMemcpyAsync(rms_out, drms.p, (size_t)nrow * sizeof(double), cudaMemcpyDeviceToHost, ps.st));
         LGR_CUDA(cudaStreamSynchronize(ps.st));
     });
+}
+
+}  // extern "C"
+
+// ---- device-resident preprocessing pipeline -------------------------------------------------------------------------
+struct PrepDataset {
+    int nrow = 0, ncol = 0;
+    size_t nnz = 0;
+    DBuf<int> colptr, rowidx;
+    DBuf<double> val;                 // raw counts, then the normalised values (in place)
+    bool normalized = false;
+    // scaleData (features x cells)
+    int m = 0;
+    size_t snnz = 0;
+    DBuf<int> scolptr, srow;
+    DBuf<double> sval64;
+    DBuf<float> sval;
+    bool scaled = false;
+};
+struct lgr_prep {
+    StreamHolder stream_holder;
+    cudaStream_t st = nullptr;
+    int device = 0;
+    std::vector<PrepDataset> ds;
+};
+
+extern "C" {
+
+int lgr_prep_create(int32_t d, const lgr_csc* raw, int32_t device, lgr_prep** out) {
+    return guarded([&] {
+        LGR_REQUIRE(out && raw && d >= 1, "null argument");
+        *out = nullptr;
+        check_device();
+        if (device >= 0) LGR_CUDA(cudaSetDevice(device));
+        std::unique_ptr<lgr_prep> p(new lgr_prep);
+        LGR_CUDA(cudaGetDevice(&p->device));
+        LGR_CUDA(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+        p->stream_holder.s = p->st;
+        AllocStreamScope alloc_scope(p->st);
+        p->ds.resize(d);
+        for (int i = 0; i < d; ++i) {
+            const lgr_csc& M = raw[i];
+            LGR_REQUIRE(M.location == 0, "raw counts must be host matrices");
+            const size_t nnz = check_csc(M.nrow, M.ncol, M.colptr, M.rowidx, M.value_dtype == LGR_F64 ? static_cast<const double*>(M.values) : nullptr);
+            LGR_REQUIRE(M.value_dtype == LGR_F64, "raw counts must be double (dgCMatrix @x)");
+            LGR_REQUIRE(nnz == 0 || M.rowidx, "null row indices");
+            PrepDataset& D = p->ds[i];
+            D.nrow = (int)M.nrow;
+            D.ncol = (int)M.ncol;
+            D.nnz = nnz;
+            D.colptr.alloc((size_t)D.ncol + 1);
+            D.rowidx.alloc(std::max<size_t>(nnz, 1));
+            D.val.alloc(std::max<size_t>(nnz, 1));
+            LGR_CUDA(cudaMemcpyAsync(D.colptr.p, M.colptr, ((size_t)D.ncol + 1) * sizeof(int), cudaMemcpyHostToDevice, p->st));
+            if (nnz) {
+                LGR_CUDA(cudaMemcpyAsync(D.rowidx.p, M.rowidx, nnz * sizeof(int), cudaMemcpyHostToDevice, p->st));
+                LGR_CUDA(cudaMemcpyAsync(D.val.p, M.values, nnz * sizeof(double), cudaMemcpyHostToDevice, p->st));
+            }
+        }
+        LGR_CUDA(cudaStreamSynchronize(p->st));
+        *out = p.release();
+    });
+}
+
+int lgr_prep_normalize(lgr_prep* p) {
+    return guarded([&] {
+        LGR_REQUIRE(p, "null handle");
+        LGR_CUDA(cudaSetDevice(p->device));
+        for (auto& D : p->ds) {
+            if (D.normalized) continue;
+            prep_col_normalize(D.ncol, D.colptr.p, D.val.p, D.val.p, nullptr, p->st);
+            D.normalized = true;
+        }
+        LGR_CUDA(cudaStreamSynchronize(p->st));
+    });
+}
+
+int lgr_prep_gene_stats(lgr_prep* p, int32_t i, double* means, double* vars) {
+    return guarded([&] {
+        LGR_REQUIRE(p && i >= 0 && i < (int)p->ds.size(), "bad dataset index");
+        LGR_CUDA(cudaSetDevice(p->device));
+        AllocStreamScope alloc_scope(p->st);
+        PrepDataset& D = p->ds[i];
+        LGR_REQUIRE(D.normalized, "call lgr_prep_normalize first");
+        if (D.nrow == 0) return;
+        DBuf<double> dm((size_t)D.nrow), dv((size_t)D.nrow), dc((size_t)D.nrow);
+        prep_row_mean_var(D.nrow, D.ncol, D.nnz, D.rowidx.p, D.val.p, nullptr, (double)D.ncol, dm.p, dv.p, dc.p, p->st);
+        if (means) LGR_CUDA(cudaMemcpyAsync(means, dm.p, (size_t)D.nrow * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+        if (vars) LGR_CUDA(cudaMemcpyAsync(vars, dv.p, (size_t)D.nrow * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+        LGR_CUDA(cudaStreamSynchronize(p->st));
+    });
+}
+
+int lgr_prep_scale(lgr_prep* p, int32_t i, int64_t m, const int32_t* feature_rows) {
+    return guarded([&] {
+        LGR_REQUIRE(p && i >= 0 && i < (int)p->ds.size(), "bad dataset index");
+        LGR_REQUIRE(m >= 1 && m < (int64_t)0x7fffffff && feature_rows, "bad feature list");
+        LGR_CUDA(cudaSetDevice(p->device));
+        AllocStreamScope alloc_scope(p->st);
+        PrepDataset& D = p->ds[i];
+        LGR_REQUIRE(D.normalized, "call lgr_prep_normalize first");
+        std::vector<int> lut((size_t)std::max(D.nrow, 1), -1);
+        for (int64_t f = 0; f < m; ++f) {
+            LGR_REQUIRE(feature_rows[f] >= 0 && feature_rows[f] < D.nrow, "feature row out of range");
+            LGR_REQUIRE(lut[feature_rows[f]] < 0, "duplicate feature");
+            lut[feature_rows[f]] = (int)f;
+        }
+        DBuf<int> dlut(lut.size()), cnt((size_t)D.ncol + 1);
+        LGR_CUDA(cudaMemcpyAsync(dlut.p, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice, p->st));
+        cnt.zero(p->st);
+        prep_subset_count(D.ncol, D.colptr.p, D.rowidx.p, dlut.p, cnt.p, p->st);
+        D.scolptr.alloc((size_t)D.ncol + 1);
+        dev_exclusive_scan_int(cnt.p, D.scolptr.p, (size_t)D.ncol + 1, p->st);
+        int total = 0;
+        LGR_CUDA(cudaMemcpyAsync(&total, D.scolptr.p + D.ncol, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+        LGR_CUDA(cudaStreamSynchronize(p->st));   // also keeps `lut` alive until its copy has run
+        D.m = (int)m;
+        D.snnz = (size_t)total;
+        D.srow.alloc(std::max<size_t>(D.snnz, 1));
+        D.sval64.alloc(std::max<size_t>(D.snnz, 1));
+        D.sval.alloc(std::max<size_t>(D.snnz, 1));
+        DBuf<double> sub(std::max<size_t>(D.snnz, 1)), rms((size_t)m);
+        prep_subset_fill(D.ncol, D.colptr.p, D.rowidx.p, D.val.p, dlut.p, D.scolptr.p, D.srow.p, sub.p, p->st);
+        prep_scale_rows((int)m, D.ncol, D.snnz, D.srow.p, sub.p, D.sval64.p, rms.p, p->st);
+        prep_f64_to_f32(D.sval64.p, D.sval.p, D.snnz, p->st);
+        LGR_CUDA(cudaStreamSynchronize(p->st));
+        D.scaled = true;
+    });
+}
+
+int lgr_prep_scaled_view(lgr_prep* p, int32_t i, lgr_csc* view) {
+    return guarded([&] {
+        LGR_REQUIRE(p && view && i >= 0 && i < (int)p->ds.size(), "bad dataset index");
+        PrepDataset& D = p->ds[i];
+        LGR_REQUIRE(D.scaled, "call lgr_prep_scale first");
+        view->nrow = D.m;
+        view->ncol = D.ncol;
+        view->colptr = D.scolptr.p;
+        view->rowidx = D.srow.p;
+        view->values = D.sval.p;
+        view->value_dtype = LGR_F32;
+        view->location = LGR_CSC_DEVICE;
+    });
+}
+
+int lgr_prep_scaled_download(lgr_prep* p, int32_t i, int32_t* colptr, int32_t* rowidx, double* values) {
+    return guarded([&] {
+        LGR_REQUIRE(p && i >= 0 && i < (int)p->ds.size(), "bad dataset index");
+        LGR_CUDA(cudaSetDevice(p->device));
+        PrepDataset& D = p->ds[i];
+        LGR_REQUIRE(D.scaled, "call lgr_prep_scale first");
+        if (colptr) LGR_CUDA(cudaMemcpyAsync(colptr, D.scolptr.p, ((size_t)D.ncol + 1) * sizeof(int), cudaMemcpyDeviceToHost, p->st));
+        if (rowidx && D.snnz) LGR_CUDA(cudaMemcpyAsync(rowidx, D.srow.p, D.snnz * sizeof(int), cudaMemcpyDeviceToHost, p->st));
+        if (values && D.snnz) LGR_CUDA(cudaMemcpyAsync(values, D.sval64.p, D.snnz * sizeof(double), cudaMemcpyDeviceToHost, p->st));
+        LGR_CUDA(cudaStreamSynchronize(p->st));
+    });
+}
+
+void lgr_prep_destroy(lgr_prep* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    {
+        AllocStreamScope alloc_scope(p->st);
+        p->ds.clear();
+    }
+    delete p;
 }
 
 }  // extern "C"

@@ -233,5 +233,10 @@ void prep_row_mean_var(int nrow, int ncol_x, size_t nnz, const int* rowidx, cons
                        double ncol, double* means_out, double* vars_out, double* scratch_count, cudaStream_t st);
 void prep_scale_rows(int nrow, int ncol, size_t nnz, const int* rowidx, const double* x, double* out, double* rms,
                      cudaStream_t st);
+void prep_subset_count(int ncol, const int* colptr, const int* rowidx, const int* lut, int* count, cudaStream_t st);
+void prep_subset_fill(int ncol, const int* colptr, const int* rowidx, const double* x, const int* lut, const int* newptr,
+                      int* newrow, double* newx, cudaStream_t st);
+void prep_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
+void dev_exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t st);   // lgr_layout.cu (cub)
 
 }  // namespace lgr

@@ -187,6 +187,14 @@ void dev_build_padded(int mode, int n, int rows, int tile, int scale, int tagmod
     LGR_CUDA(cudaStreamSynchronize(st));
 }
 
+void dev_exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t st) {
+    if (!n) return;
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, st);
+    DBuf<unsigned char> tmp(bytes);
+    LGR_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, st));
+}
+
 // ---- factor layout conversion -------------------------------------------------------------------
 __global__ void k_colmajor_to_padded(const double* __restrict__ in, double* __restrict__ out, int rows, int k, int kp) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

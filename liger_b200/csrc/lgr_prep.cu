@@ -81,6 +81,42 @@ __global__ void __launch_bounds__(256) k_row_scale(size_t nnz, const int* __rest
     }
 }
 
+// ---- row subset of a CSC matrix (scaleNotCenter.dgCMatrix: object[features, ]) -------------------------------------
+// lut[row] = new row index (position in the feature list) or -1.  One warp per column.
+__global__ void __launch_bounds__(256) k_subset_count(int ncol, const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                                                      const int* __restrict__ lut, int* __restrict__ count) {
+    const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= ncol) return;
+    int c = 0;
+    for (int t = colptr[warp] + lane; t < colptr[warp + 1]; t += 32) c += lut[rowidx[t]] >= 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (lane == 0) count[warp] = c;
+}
+__global__ void __launch_bounds__(256) k_subset_fill(int ncol, const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                                                     const double* __restrict__ x, const int* __restrict__ lut,
+                                                     const int* __restrict__ newptr, int* __restrict__ newrow,
+                                                     double* __restrict__ newx) {
+    const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= ncol) return;
+    int o = newptr[warp];
+    const int b = colptr[warp], e = colptr[warp + 1];
+    for (int t0 = b; t0 < e; t0 += 32) {   // warp-uniform trip count; order inside the column is preserved
+        const int t = t0 + lane;
+        const int nr = (t < e) ? lut[rowidx[t]] : -1;
+        const unsigned keep = __ballot_sync(0xffffffffu, nr >= 0);
+        if (nr >= 0) {
+            const int dst = o + __popc(keep & ((1u << lane) - 1u));
+            newrow[dst] = nr;
+            newx[dst] = x[t];
+        }
+        o += __popc(keep);
+    }
+}
+__global__ void k_f64_to_f32_prep(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+
 static int stream_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16); }
 
 void prep_col_normalize(int ncol, const int* colptr, const double* x, double* out, double* colsum, cudaStream_t st) {
@@ -127,6 +163,24 @@ void prep_scale_rows(int nrow, int ncol, size_t nnz, const int* rowidx, const do
         k_row_scale<<<stream_grid(nnz), 256, 0, st>>>(nnz, rowidx, x, rms, out);
         LGR_CUDA(cudaGetLastError());
     }
+}
+
+
+void prep_subset_count(int ncol, const int* colptr, const int* rowidx, const int* lut, int* count, cudaStream_t st) {
+    if (ncol <= 0) return;
+    k_subset_count<<<(unsigned)(((size_t)ncol * 32 + 255) / 256), 256, 0, st>>>(ncol, colptr, rowidx, lut, count);
+    LGR_CUDA(cudaGetLastError());
+}
+void prep_subset_fill(int ncol, const int* colptr, const int* rowidx, const double* x, const int* lut, const int* newptr,
+                      int* newrow, double* newx, cudaStream_t st) {
+    if (ncol <= 0) return;
+    k_subset_fill<<<(unsigned)(((size_t)ncol * 32 + 255) / 256), 256, 0, st>>>(ncol, colptr, rowidx, x, lut, newptr, newrow, newx);
+    LGR_CUDA(cudaGetLastError());
+}
+void prep_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st) {
+    if (!n) return;
+    k_f64_to_f32_prep<<<stream_grid(n), 256, 0, st>>>(in, out, n);
+    LGR_CUDA(cudaGetLastError());
 }
 
 }  // namespace lgr

@@ -118,3 +118,116 @@ def scaleNotCenter(norm, genes, features, device=-1):
     res = sp.csc_matrix((out, sub.indices.copy(), sub.indptr.copy()), shape=sub.shape)
     res.eliminate_zeros()
     return res
+
+
+class Pipeline:
+    """normalize -> selectGenes -> scaleNotCenter with the matrices RESIDENT in HBM (lgr_prep_*): the raw counts are
+    uploaded once, only the per-gene statistics travel back to the host (the variable-gene rule and the set logic over
+    gene names are host code, as they are R code in the reference), and the resulting scaleData is handed to
+    inmf / uinmf / Context as device views -- X is never copied back nor uploaded a second time.
+
+        pipe = Pipeline(raws, genesList, nUMIs)
+        features = pipe.selectGenes()            # normalises first if needed
+        Es = pipe.scaleNotCenter(features)       # list of api.DeviceCsc
+        fit = liger_b200.run_inmf_list(Es, k=20, ...)
+    """
+
+    def __init__(self, raws, genesList, nUMIs, device=-1):
+        from . import api
+        self._api = api
+        self.genes = [list(g) for g in genesList]
+        self.nUMI = [np.asarray(u, dtype=np.float64) for u in nUMIs]
+        self._host = [api._Csc(_csc(r)) for r in raws]                     # keeps the upload buffers alive during the call
+        arr = (_ffi.lgr_csc * len(raws))(*[h.struct for h in self._host])
+        self.h = C.c_void_p()
+        _ffi.check(_ffi.lib().lgr_prep_create(len(raws), arr, device, C.byref(self.h)))
+        self.shapes = [h.shape for h in self._host]
+        self._host = None
+        self._normalized = False
+
+    def normalize(self):
+        if not self._normalized:
+            _ffi.check(_ffi.lib().lgr_prep_normalize(self.h))
+            self._normalized = True
+        return self
+
+    def geneStats(self, i):
+        self.normalize()
+        m = np.empty(self.shapes[i][0])
+        v = np.empty(self.shapes[i][0])
+        _ffi.check(_ffi.lib().lgr_prep_gene_stats(self.h, i, _dp(m), _dp(v)))
+        return m, v
+
+    def selectGenes(self, thresh=0.1, alpha=0.99, combine="union"):
+        """Same rule as selectGenes() above; returns (features, per-dataset selections)."""
+        shared = set(self.genes[0])
+        for g in self.genes[1:]:
+            shared &= set(g)
+        sel = []
+        for i, g in enumerate(self.genes):
+            means, vars_ = self.geneStats(i)
+            mask = np.array([x in shared for x in g], dtype=bool)
+            means, vars_ = means[mask], vars_[mask]
+            gs = [x for x, s_ in zip(g, mask) if s_]
+            ncol = self.shapes[i][1]
+            nolan = float(np.mean(1.0 / self.nUMI[i]))
+            a_corr = alpha / self.shapes[i][0]
+            upper = means + _norm.ppf(1.0 - a_corr / 2.0) * np.sqrt(means * nolan / ncol)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                keep = (vars_ / nolan > upper) & (np.log10(vars_) > np.log10(means * nolan) + thresh)
+            sel.append([x for x, s_ in zip(gs, keep) if s_])
+        if combine == "union":
+            feats, seen = [], set()
+            for s_ in sel:
+                for x in s_:
+                    if x not in seen:
+                        seen.add(x)
+                        feats.append(x)
+        elif combine == "intersection":
+            feats = [x for x in sel[0] if all(x in set(s_) for s_ in sel[1:])]
+        else:
+            raise ValueError("`combine` must be 'union' or 'intersection'")
+        return feats, sel
+
+    def scaleNotCenter(self, features):
+        """Builds scaleData of every dataset on the device; returns the list of device views."""
+        self.normalize()
+        views = []
+        for i, g in enumerate(self.genes):
+            pos = {x: j for j, x in enumerate(g)}
+            try:
+                rows = np.array([pos[f] for f in features], dtype=np.int32)
+            except KeyError as e:
+                raise ValueError(f"feature {e.args[0]!r} not found in dataset {i}") from None
+            _ffi.check(_ffi.lib().lgr_prep_scale(self.h, i, len(rows), _ip(rows)))
+            st = _ffi.lgr_csc()
+            _ffi.check(_ffi.lib().lgr_prep_scaled_view(self.h, i, C.byref(st)))
+            views.append(self._api.DeviceCsc(st, self))
+        self._views = views
+        return views
+
+    def scaledToHost(self, i):
+        """Host copy of scaleData_i (FP64 values) -- for checks; the factorisation does not need it."""
+        v = self._views[i].struct
+        n = int(v.ncol)
+        indptr = np.empty(n + 1, dtype=np.int32)
+        _ffi.check(_ffi.lib().lgr_prep_scaled_download(self.h, i, _ip(indptr), None, None))
+        nnz = int(indptr[-1])
+        indices = np.empty(max(nnz, 1), dtype=np.int32)
+        data = np.empty(max(nnz, 1), dtype=np.float64)
+        _ffi.check(_ffi.lib().lgr_prep_scaled_download(self.h, i, None, _ip(indices), _dp(data)))
+        out = sp.csc_matrix((data[:nnz], indices[:nnz], indptr), shape=(int(v.nrow), n))
+        out.eliminate_zeros()
+        out.sort_indices()
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            _ffi.lib().lgr_prep_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

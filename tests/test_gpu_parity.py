@@ -438,3 +438,27 @@ def test_preprocessing_edge_cases_on_gpu():
     assert s_gpu[2, :].nnz == 0                   # the empty gene (row 5 of x) stays all-zero
     with pytest.raises(ValueError):
         pp.scaleNotCenter(n_gpu, genes, ["nope"])
+
+
+def test_resident_pipeline_counts_to_factors(pbmc):
+    """raw counts -> normalize -> selectGenes -> scaleNotCenter -> runINMF with X resident in HBM from the first upload on
+    (lgr_prep_* + device views): same 173 genes, same scaleData as the oracle's, and the reference's golden factors."""
+    import liger_b200
+    from liger_b200 import preprocess as pp
+    pipe = pp.Pipeline(pbmc["raws"], pbmc["genes"], pbmc["nUMI"])
+    feats, sel = pipe.selectGenes(combine="union")
+    assert len(feats) == 173 and [len(x) for x in sel] == [168, 166]
+    assert len(pipe.selectGenes(combine="intersection")[0]) == 161
+    Es = pipe.scaleNotCenter(feats)
+    for i, e in enumerate(pbmc["Es"]):
+        host = pipe.scaledToHost(i)
+        assert host.shape == e.shape and rel(host.toarray(), e.toarray()) < 1e-13
+    assert abs(pipe.scaledToHost(0)[2, 4] - 0.4693316) < 1e-6 and abs(pipe.scaledToHost(1)[6, 8] - 2.360295) < 1e-6
+    g = pbmc["golden"]
+    out = liger_b200.run_inmf_list(Es, k=20, lambda_=5.0, nIteration=30, seed=1)
+    rows = g["golden_rows"]
+    assert rel(out["W"][rows], g["golden_W"]) < 5e-5
+    for i, n in enumerate(pbmc["names"]):
+        assert rel(out["H"][i], g[f"golden_H_{n}"]) < 5e-5
+        assert pattern_mismatches(out["H"][i], g[f"golden_H_{n}"]) == 0
+    pipe.close()
