@@ -1237,7 +1237,8 @@ int lgr_prep_create(int32_t d, const lgr_csc* raw, int32_t device, lgr_prep** ou
         for (int i = 0; i < d; ++i) {
             const lgr_csc& M = raw[i];
             LGR_REQUIRE(M.location == 0, "raw counts must be host matrices");
-            const size_t nnz = check_csc(M.nrow, M.ncol, M.colptr, M.rowidx, M.value_dtype == LGR_F64 ? static_cast<const double*>(M.values) : nullptr);
+            // (row indices are range-checked on the device below: a host scan of 1e8 entries costs more than the upload)
+            const size_t nnz = check_csc(M.nrow, M.ncol, M.colptr, nullptr, M.value_dtype == LGR_F64 ? static_cast<const double*>(M.values) : nullptr);
             LGR_REQUIRE(M.value_dtype == LGR_F64, "raw counts must be double (dgCMatrix @x)");
             LGR_REQUIRE(nnz == 0 || M.rowidx, "null row indices");
             PrepDataset& D = p->ds[i];
@@ -1253,7 +1254,13 @@ int lgr_prep_create(int32_t d, const lgr_csc* raw, int32_t device, lgr_prep** ou
                 LGR_CUDA(cudaMemcpyAsync(D.val.p, M.values, nnz * sizeof(double), cudaMemcpyHostToDevice, p->st));
             }
         }
+        DBuf<int> bad(1);
+        bad.zero(p->st);
+        for (auto& D : p->ds) prep_check_rows(D.nnz, D.rowidx.p, D.nrow, bad.p, p->st);
+        int hbad = 0;
+        LGR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
         LGR_CUDA(cudaStreamSynchronize(p->st));
+        LGR_REQUIRE(hbad == 0, "row index out of range");
         *out = p.release();
     });
 }

@@ -237,6 +237,7 @@ void prep_subset_count(int ncol, const int* colptr, const int* rowidx, const int
 void prep_subset_fill(int ncol, const int* colptr, const int* rowidx, const double* x, const int* lut, const int* newptr,
                       int* newrow, double* newx, cudaStream_t st);
 void prep_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
+void prep_check_rows(size_t nnz, const int* rowidx, int nrow, int* bad, cudaStream_t st);
 void dev_exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t st);   // lgr_layout.cu (cub)
 
 }  // namespace lgr

@@ -117,6 +117,11 @@ __global__ void k_f64_to_f32_prep(const double* __restrict__ in, float* __restri
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
 }
 
+__global__ void k_check_rows(size_t nnz, const int* __restrict__ rowidx, int nrow, int* __restrict__ bad) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (size_t)gridDim.x * blockDim.x)
+        if ((unsigned)rowidx[t] >= (unsigned)nrow) *bad = 1;
+}
+
 static int stream_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16); }
 
 void prep_col_normalize(int ncol, const int* colptr, const double* x, double* out, double* colsum, cudaStream_t st) {
@@ -175,6 +180,11 @@ void prep_subset_fill(int ncol, const int* colptr, const int* rowidx, const doub
                       int* newrow, double* newx, cudaStream_t st) {
     if (ncol <= 0) return;
     k_subset_fill<<<(unsigned)(((size_t)ncol * 32 + 255) / 256), 256, 0, st>>>(ncol, colptr, rowidx, x, lut, newptr, newrow, newx);
+    LGR_CUDA(cudaGetLastError());
+}
+void prep_check_rows(size_t nnz, const int* rowidx, int nrow, int* bad, cudaStream_t st) {
+    if (!nnz) return;
+    k_check_rows<<<stream_grid(nnz), 256, 0, st>>>(nnz, rowidx, nrow, bad);
     LGR_CUDA(cudaGetLastError());
 }
 void prep_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st) {

@@ -137,7 +137,8 @@ class Pipeline:
         self._api = api
         self.genes = [list(g) for g in genesList]
         self.nUMI = [np.asarray(u, dtype=np.float64) for u in nUMIs]
-        self._host = [api._Csc(_csc(r)) for r in raws]                     # keeps the upload buffers alive during the call
+        # scipy CSC matrices or (indptr, indices, data, shape) tuples (e.g. page-locked buffers): used in place, no copy
+        self._host = [api._Csc(r) for r in raws]
         arr = (_ffi.lgr_csc * len(raws))(*[h.struct for h in self._host])
         self.h = C.c_void_p()
         _ffi.check(_ffi.lib().lgr_prep_create(len(raws), arr, device, C.byref(self.h)))
