@@ -462,3 +462,30 @@ def test_resident_pipeline_counts_to_factors(pbmc):
         assert rel(out["H"][i], g[f"golden_H_{n}"]) < 5e-5
         assert pattern_mismatches(out["H"][i], g[f"golden_H_{n}"]) == 0
     pipe.close()
+
+
+def test_cinmf_block_solves_and_refinement(pbmc):
+    """inmf_solveH / solveV / solveW (R/cINMF.R:477-503) and runCINMF's fixed-W refinement loop (:392-407) on the GPU
+    NNLS, against the oracle's restatement of the same three solves."""
+    from liger_b200 import cinmf
+    Es = pbmc["Es"]
+    W, Vs, _, _ = orc.seeded_init(4, 173, 12, [300, 300])
+    H0 = cinmf.inmf_solveH(None, W, Vs[0], Es[0], 5.0)
+    assert rel(H0, orc.solve_H(W, Vs[0], Es[0], 5.0)) < 1e-9
+    V0 = cinmf.inmf_solveV(H0, W, None, Es[0], 5.0)
+    assert rel(V0, orc.solve_V(H0, W, Es[0], 5.0)) < 1e-8
+    Hs = [H0, cinmf.inmf_solveH(None, W, Vs[1], Es[1], 5.0)]
+    Wn = cinmf.inmf_solveW(Hs, W, [V0, Vs[1]], Es, 5.0)
+    assert rel(Wn, orc.solve_W(Hs, [V0, Vs[1]], Es)) < 1e-8
+    out = cinmf.refine_fixed_W(Es, W, Vs, lambda_=5.0, nIteration=2, seed=1)
+    Vr = [v.copy() for v in Vs]
+    Hr = [None, None]
+    for _ in range(4):
+        for i in range(2):
+            Hr[i] = orc.solve_H(W, Vr[i], Es[i], 5.0)
+        for i in range(2):
+            Vr[i] = orc.solve_V(Hr[i], W, Es[i], 5.0)
+    ref_obj = sum(orc.objerr_i(Hr[i].T, W, Vr[i], Es[i], 5.0) for i in range(2))
+    for i in range(2):
+        assert rel(out["H"][i], Hr[i]) < 1e-7 and rel(out["V"][i], Vr[i]) < 1e-7
+    assert abs(out["objErr"] - ref_obj) < 1e-6 * ref_obj
