@@ -163,7 +163,6 @@ struct Counters {
 // ---------------------------------------------------------------------------------------------
 // kernel launch wrappers (lgr_kernels.cu)
 // ---------------------------------------------------------------------------------------------
-constexpr int LTX_CELLS_PER_BLOCK = 64;
 inline int prep_rows_per_block(int kp) { return 2048 / kp; }  // keeps k_prep's static smem < 48 KB
 
 struct NnlsConfig {
@@ -177,7 +176,6 @@ struct NnlsConfig {
 NnlsConfig nnls_config(int k, int kp, bool is_double, int num_sms);
 
 void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st);
-void launch_spmm_ltx_gather(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st);
 void launch_spmm_ltx_tiled(const DsDev* ds, int nds, int total_blocks, int kp, int cb, int gt, bool fuse_u, cudaStream_t st);
 size_t spmm_ltx_smem(int kp, int cb, int gt, bool fuse_u);
 void spmm_init();

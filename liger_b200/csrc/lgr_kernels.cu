@@ -1,7 +1,6 @@
 // liger_b200 -- hot-path kernels of the iNMF / UINMF alternating-NNLS iteration (sm_100a).
 //
 //   k_prep        L~ = [W+V; U] (fp32 rows of KP), LtL = L~^T L~, VtV = V~^T V~          (R/cINMF.R:478-479)
-//   k_spmm_ltx    B = L~^T X     CSC gather of L rows, quarter-warp per non-zero            (R/cINMF.R:480)
 //   k_nnls<T>     batched block-principal-pivoting NNLS on a shared Gram                    (RcppPlanc::bppnnls_prod)
 //   k_spmm_xh     R = X H  (tiled CSR gather of H rows staged by TMA bulk copy) + G = H^T H (R/cINMF.R:486-488,497-499)
 //   k_vrhs/k_wrhs right-hand sides of the V_i/U_i and W solves                              (R/cINMF.R:488,499)
@@ -68,72 +67,6 @@ void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, in
     LGR_CUDA(cudaGetLastError());
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_spmm_ltx: B[c][:] = sum_{g in nz(c)} x_gc * L[g][:]      (CSC gather; warp per cell)
-//   KP/4 lanes cover one row of L with one 128-bit load each, so one warp instruction serves
-//   32/(KP/4) non-zeros; (row, value) pairs are loaded coalesced, one per lane, and broadcast by shuffle.
-// ------------------------------------------------------------------------------------------------
-template <int KP>
-__global__ void __launch_bounds__(256) k_spmm_ltx(const DsDev* __restrict__ ds, int nds) {
-    constexpr int LPN = KP / 4;    // lanes per non-zero
-    constexpr int NPI = 32 / LPN;  // non-zeros per warp instruction
-    const int i = find_ds(ds, nds, (int)blockIdx.x, &DsDev::ltx_blk_off);
-    const DsDev& D = ds[i];
-    const int n = D.n;
-    const int* __restrict__ colptr = D.colptr;
-    const int* __restrict__ rowidx = D.rowidx;
-    const float* __restrict__ val = D.val;
-    const float4* __restrict__ L4 = reinterpret_cast<const float4*>(D.L);
-    float4* __restrict__ B4 = reinterpret_cast<float4*>(D.B);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int q = lane / LPN, s = lane % LPN;
-    const int cell0 = ((int)blockIdx.x - D.ltx_blk_off) * LTX_CELLS_PER_BLOCK;
-    const int cell1 = min(cell0 + LTX_CELLS_PER_BLOCK, n);
-    for (int c = cell0 + warp; c < cell1; c += nwarps) {
-        const int beg = __ldg(colptr + c), end = __ldg(colptr + c + 1);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int base = beg; base < end; base += 32) {
-            const int e = base + lane;
-            int r = 0;
-            float v = 0.f;
-            if (e < end) {
-                r = ldg_stream(rowidx + e);
-                v = ldg_stream(val + e);
-            }
-            const int cnt = min(32, end - base);
-#pragma unroll
-            for (int stp = 0; stp < LPN; ++stp) {
-                const int t = stp * NPI + q;
-                const int rr = __shfl_sync(0xffffffffu, r, t);
-                const float vv = __shfl_sync(0xffffffffu, v, t);
-                if (stp * NPI < cnt) {  // warp-uniform
-                    const float4 l = ldg_nc4(L4 + (size_t)rr * LPN + s);
-                    acc.x = fmaf(vv, l.x, acc.x);
-                    acc.y = fmaf(vv, l.y, acc.y);
-                    acc.z = fmaf(vv, l.z, acc.z);
-                    acc.w = fmaf(vv, l.w, acc.w);
-                }
-            }
-        }
-#pragma unroll
-        for (int off = LPN; off < 32; off <<= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
-            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
-        }
-        if (q == 0) B4[(size_t)c * LPN + s] = acc;
-    }
-}
-
-void launch_spmm_ltx_gather(const DsDev* ds, int nds, int total_blocks, int kp, cudaStream_t st) {
-    if (total_blocks <= 0) return;
-    if (kp == 32)
-        k_spmm_ltx<32><<<total_blocks, 256, 0, st>>>(ds, nds);
-    else
-        k_spmm_ltx<64><<<total_blocks, 256, 0, st>>>(ds, nds);
-    LGR_CUDA(cudaGetLastError());
-}
 
 // ------------------------------------------------------------------------------------------------
 // right-hand sides of the V/U and W solves (fp64; tiny)

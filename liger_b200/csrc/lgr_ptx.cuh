@@ -1,4 +1,4 @@
-// liger_b200 -- small PTX helpers shared by the kernels (mbarrier + TMA bulk copy, streaming loads, vector RED).
+// liger_b200 -- small PTX helpers shared by the kernels (mbarrier + TMA bulk copy, vector RED).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,27 +33,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
             : "memory");
     } while (!done);
 }
-__device__ __forceinline__ float4 ldg_nc4(const float4* p) {
-    float4 r;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-// streaming loads for the sparse arrays: read once, do not pollute L1
-__device__ __forceinline__ int ldg_stream(const int* p) {
-    int r;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float ldg_stream(const float* p) {
-    float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ unsigned short ldg_stream(const unsigned short* p) {
-    unsigned short r;
-    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
-    return r;
-}
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
@@ -66,11 +45,5 @@ __device__ __forceinline__ int find_ds(const DS* ds, int nds, int blk, int DS::*
     return i;
 }
 
-
-__device__ __forceinline__ uint4 ldg_stream4(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
 
 }  // namespace lgr
