@@ -479,8 +479,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     LGR_CUDA(cudaGetDeviceProperties(&prop, c->device));
     LGR_REQUIRE(prop.major >= 10, "liger_b200 kernels are built for sm_100a (Blackwell B200) only");
     c->num_sms = prop.multiProcessorCount;
-    static std::once_flag once;
-    std::call_once(once, [] { kernels_init(); });
+    kernels_init();
     LGR_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     c->stream_holder.s = c->st;
     AllocStreamScope alloc_scope(c->st);
@@ -1019,8 +1018,7 @@ int lgr_bppnnls_prod(int32_t k, int64_t ncols, const double* CtC, const double* 
         LGR_REQUIRE(CtC && (ncols == 0 || (CtB && X)), "null argument");
         if (ncols == 0) return;
         if (device >= 0) LGR_CUDA(cudaSetDevice(device));
-        static std::once_flag once;
-        std::call_once(once, [] { kernels_init(); });
+        kernels_init();
         cudaDeviceProp prop;
         int dev = 0;
         LGR_CUDA(cudaGetDevice(&dev));

@@ -193,6 +193,7 @@ void nnls_reg_init();
 // continues the columns k_nnls_reg<64> flagged as too big for its register templates (lgr_nnls_wbig.cu)
 void launch_nnls_wbig(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt,
                       cudaStream_t st);
+void nnls_wbig_init();
 bool nnls_wbig64_supported(int k, int kp, long long total_cols, int num_sms);
 void launch_nnls_wbig64(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
                         cudaStream_t st);
@@ -206,7 +207,7 @@ void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int m
 void launch_wrhs(const DsDev* ds, int nds, int m, double* CtBw, double* Gsum, int k, int kp, cudaStream_t st);
 void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot, cudaStream_t st);
 size_t spmm_xh_smem(int kp, int tc);
-void kernels_init();  // opt-in shared memory attributes
+void kernels_init();  // opt-in shared memory attributes of every kernel, once per device (safe to call repeatedly)
 
 // layout / conversion kernels (lgr_layout.cu)
 void dev_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);

@@ -7,6 +7,8 @@
 //   k_objective   sum_i objErr_i from the sufficient statistics                             (src/objErr.cpp:19-29)
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "lgr_common.cuh"
 #include "lgr_ptx.cuh"
 
@@ -197,11 +199,19 @@ void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot,
 }
 
 void kernels_init() {
+    // cudaFuncSetAttribute is per device: remember which devices have been initialised
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    LGR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return;
     nnls_init();
     nnls_reg_init();
+    nnls_wbig_init();
     spmm_init();
     tc_init();
-    const int maxs = 227 * 1024 - 1024;  // static smem of the kernels counts against the 227 KB limit
+    if (dev >= 0 && dev < 64) done[dev] = true;
 }
 
 }  // namespace lgr

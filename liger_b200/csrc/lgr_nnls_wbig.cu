@@ -243,11 +243,6 @@ static void launch_wbig_t(const NnlsGroup* groups, int ngroups, long long total_
                           cudaStream_t st) {
     if (total_cols <= 0) return;
     const size_t smem = (size_t)2 * BKP * BMST * sizeof(T);
-    static bool init = false;
-    if (!init) {
-        LGR_CUDA(cudaFuncSetAttribute(k_nnls_wbig<T, ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        init = true;
-    }
     long long want = (total_cols + 255) / 256;
     if (ALL) want = (total_cols + 7) / 8;           // small batches: one column per warp when there are that few
     const long long cap = (long long)num_sms * (sizeof(T) == 4 ? 4 : 3);
@@ -269,6 +264,15 @@ bool nnls_wbig64_supported(int k, int kp, long long total_cols, int num_sms) {
 void launch_nnls_wbig64(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
                         cudaStream_t st) {
     launch_wbig_t<double, true>(groups, ngroups, total_cols, k, num_sms, cnt, flags, st);
+}
+
+
+// opt-in shared-memory sizes (per device; called from kernels_init)
+void nnls_wbig_init() {
+    LGR_CUDA(cudaFuncSetAttribute(k_nnls_wbig<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((size_t)2 * BKP * BMST * sizeof(float))));
+    LGR_CUDA(cudaFuncSetAttribute(k_nnls_wbig<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((size_t)2 * BKP * BMST * sizeof(double))));
 }
 
 }  // namespace lgr

@@ -41,3 +41,18 @@ def test_two_gpu_cell_sharding(tmp_path, pbmc, mode):
         else:
             H = np.vstack([r0[key], r1[key]])
         assert rel(H, ref["H"][i]) < 1e-3
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_one_process_two_devices(pbmc):
+    """The opt-in shared-memory attributes of the kernels are per device: a process that uses device 0 and then device 1
+    must get the same factors from both (k = 20 and k = 40 cover the register, warp and shared-memory NNLS kernels)."""
+    import liger_b200
+    for k in (20, 40):
+        W0, V0, _, _ = orc.seeded_init(1, 173, k, [300, 300])
+        a = liger_b200.inmf(pbmc["Es"], k=k, lambda_=5.0, niter=4, Winit=W0, Vinit=V0, device=0)
+        b = liger_b200.inmf(pbmc["Es"], k=k, lambda_=5.0, niter=4, Winit=W0, Vinit=V0, device=1)
+        assert rel(a["W"], b["W"]) < 1e-5 and rel(a["H"][0], b["H"][0]) < 1e-5
+    G = np.eye(40) + 0.1
+    B = np.random.default_rng(0).random((40, 500))
+    assert rel(liger_b200.bppnnls_prod(G, B, device=1), liger_b200.bppnnls_prod(G, B, device=0)) < 1e-12
