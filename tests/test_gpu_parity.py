@@ -228,15 +228,16 @@ def test_restarts_and_explicit_inits(pbmc):
 # ----------------------------------------------------------------------------------------------
 # uinmf  (RcppPlanc::uinmf; R/integration.R:1285-1287) -- parity unpinned in the reference; vs the oracle
 # ----------------------------------------------------------------------------------------------
-def test_uinmf_matches_oracle(pbmc):
+@pytest.mark.parametrize("k", [30, 44])     # 44: two-line factor rows, the k > 32 solver kernels on stacked [E; P] rows
+def test_uinmf_matches_oracle(pbmc, k):
     import liger_b200
     Es = [E[:150] for E in pbmc["Es"]]
     Ps = [pbmc["Es"][0][150:], None]
-    W0, V0, U0, _ = orc.seeded_init(3, 150, 30, [300, 300], [23, 0])
-    out = liger_b200.uinmf(Es, Ps, k=30, lambda_=[10.0, 1.0], niter=8, Winit=W0, Vinit=V0, Uinit=U0, trajectory=True)
-    ref = orc.uinmf(Es, Ps, 30, [10.0, 1.0], 8, W0, V0, U0, trajectory=True)
+    W0, V0, U0, _ = orc.seeded_init(3, 150, k, [300, 300], [23, 0])
+    out = liger_b200.uinmf(Es, Ps, k=k, lambda_=[10.0, 1.0], niter=8, Winit=W0, Vinit=V0, Uinit=U0, trajectory=True)
+    ref = orc.uinmf(Es, Ps, k, [10.0, 1.0], 8, W0, V0, U0, trajectory=True)
     _check(out, ref, u=True)
-    assert out["U"][0].shape == (23, 30) and out["U"][1] is None
+    assert out["U"][0].shape == (23, k) and out["U"][1] is None
     assert np.max(np.abs(out["traj"] - np.array(ref["traj"])) / np.array(ref["traj"])) < TOL_OBJ
     assert np.all(np.diff(out["traj"]) < 0)
 
