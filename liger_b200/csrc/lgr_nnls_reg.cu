@@ -49,6 +49,15 @@ __device__ __forceinline__ int top_m(unsigned long long x) { return 63 - __clzll
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 // word offset of element f of a lane's row in a [chunk][lane] staging tile (relative to the lane's chunk 0)
 __device__ __forceinline__ int bw(int f) { return (f >> 2) * 128 + (f & 3); }
+// packed fp32 x2 FMA (Blackwell): d.lo = a.lo * b.lo + c.lo, d.hi = a.hi * b.hi + c.hi in one instruction
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b) {
+    unsigned long long d, a, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct RegSmem {
@@ -180,10 +189,8 @@ __device__ __forceinline__ bool round_reg(const int k, const typename RT<KP>::Ma
 #pragma unroll
                 for (int c = 0; c < RKP / 4; ++c) {
                     const float4 mrow = row[c];
-                    acc[4 * c + 0] = fmaf(zt, mrow.x, acc[4 * c + 0]);
-                    acc[4 * c + 1] = fmaf(zt, mrow.y, acc[4 * c + 1]);
-                    acc[4 * c + 2] = fmaf(zt, mrow.z, acc[4 * c + 2]);
-                    acc[4 * c + 3] = fmaf(zt, mrow.w, acc[4 * c + 3]);
+                    ffma2(acc[4 * c + 0], acc[4 * c + 1], mrow.x, mrow.y, zt);
+                    ffma2(acc[4 * c + 2], acc[4 * c + 3], mrow.z, mrow.w, zt);
                 }
             }
         }
@@ -194,10 +201,8 @@ __device__ __forceinline__ bool round_reg(const int k, const typename RT<KP>::Ma
 #pragma unroll
             for (int c = 0; c < RKP / 4; ++c) {
                 const float4 mrow = row[c];
-                acc[4 * c + 0] = fmaf(zg, mrow.x, acc[4 * c + 0]);
-                acc[4 * c + 1] = fmaf(zg, mrow.y, acc[4 * c + 1]);
-                acc[4 * c + 2] = fmaf(zg, mrow.z, acc[4 * c + 2]);
-                acc[4 * c + 3] = fmaf(zg, mrow.w, acc[4 * c + 3]);
+                ffma2(acc[4 * c + 0], acc[4 * c + 1], mrow.x, mrow.y, zg);
+                ffma2(acc[4 * c + 2], acc[4 * c + 3], mrow.z, mrow.w, zg);
             }
         }
     }
@@ -450,10 +455,8 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
 #pragma unroll
                         for (int c = 0; c < RKP / 4; ++c) {
                             const float4 mrow = row[c];
-                            acc[4 * c + 0] = fmaf(bt, mrow.x, acc[4 * c + 0]);
-                            acc[4 * c + 1] = fmaf(bt, mrow.y, acc[4 * c + 1]);
-                            acc[4 * c + 2] = fmaf(bt, mrow.z, acc[4 * c + 2]);
-                            acc[4 * c + 3] = fmaf(bt, mrow.w, acc[4 * c + 3]);
+                            ffma2(acc[4 * c + 0], acc[4 * c + 1], mrow.x, mrow.y, bt);
+                            ffma2(acc[4 * c + 2], acc[4 * c + 3], mrow.z, mrow.w, bt);
                         }
                     }
 #pragma unroll
