@@ -36,6 +36,16 @@ __device__ __forceinline__ Group8 load_group(const unsigned short* __restrict__ 
     return r;
 }
 
+// packed fp32 x2 FMA (Blackwell FFMA2 with a scalar multiplier)
+__device__ __forceinline__ void ffma2_s(float& d0, float& d1, float a0, float a1, float b) {
+    unsigned long long d, a, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 // acc += sum_j val_j * tile[idx_j][4s..4s+3]; `tile4s` already points at this lane's 16-byte slot of row 0.
 __device__ __forceinline__ void gather8(float4& acc, const Group8& G, const float4* __restrict__ tile4s) {
     const unsigned c[8] = {G.i.x & 0xffffu, G.i.x >> 16, G.i.y & 0xffffu, G.i.y >> 16,
@@ -44,10 +54,8 @@ __device__ __forceinline__ void gather8(float4& acc, const Group8& G, const floa
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 h = tile4s[c[j]];
-        acc.x = fmaf(vv[j], h.x, acc.x);
-        acc.y = fmaf(vv[j], h.y, acc.y);
-        acc.z = fmaf(vv[j], h.z, acc.z);
-        acc.w = fmaf(vv[j], h.w, acc.w);
+        ffma2_s(acc.x, acc.y, h.x, h.y, vv[j]);
+        ffma2_s(acc.z, acc.w, h.z, h.w, vv[j]);
     }
 }
 
