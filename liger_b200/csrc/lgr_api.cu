@@ -330,10 +330,12 @@ void solve_f64(lgr_ctx* c, const NnlsGroup* grp, int ngroups, long long cols, in
     if (!no_warp && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (flags & ~1) == 0 && nnls_warp_supported(c->k, c->kp, cols, c->num_sms)) {
         launch_nnls_warp(grp, ngroups, cols, c->k, c->num_sms, c->counters.p, flags, c->st);
         launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags | 16, c->st);
+        c->tm.kernel_launches += 1;   // two kernels inside the caller's timed scope (which counts one)
     } else if (!no_warp && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (flags & ~1) == 0 &&
                nnls_wbig64_supported(c->k, c->kp, cols, c->num_sms)) {
         launch_nnls_wbig64(grp, ngroups, cols, c->k, c->num_sms, c->counters.p, flags, c->st);
         launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags | 16, c->st);
+        c->tm.kernel_launches += 1;
     } else {
         launch_nnls(true, grp, ngroups, cols, c->k, c->kp, c->cfgD, c->counters.p, flags, c->st);
     }
@@ -377,8 +379,11 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             if (!no_reg && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
                 launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->kp, c->num_sms, c->counters.p, cold, c->st);
                 static const bool no_wbig = getenv("LGR_NNLS_NO_WBIG") != nullptr;
-                if (c->kp > 32 && !no_wbig)   // systems above 16 unknowns: warp-per-column continuation
+                c->tm.kernel_launches += 1;   // register kernel + mop-up kernel (the timed scope counts one)
+                if (c->kp > 32 && !no_wbig) {   // systems above 16 unknowns: warp-per-column continuation
                     launch_nnls_wbig(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+                    c->tm.kernel_launches += 1;
+                }
                 launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p,
                             cold | 16 | ((c->kp > 32 && no_wbig) ? 64 : 0), c->st);
             } else {
