@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(1024) k_gram_inv(const GramSpec* __restrict__ 
     const GramSpec sp = specs[blockIdx.x];
     __shared__ double M[KP][KP + 1];
     __shared__ double colbuf[KP];
+    __shared__ double rowbuf[KP];
     __shared__ int ok_s;
     const int tid = threadIdx.x;
     constexpr int EPT = KP * KP / 1024 > 0 ? KP * KP / 1024 : 1;  // elements per thread (1 for KP=32, 4 for KP=64)
@@ -62,25 +63,30 @@ __global__ void __launch_bounds__(1024) k_gram_inv(const GramSpec* __restrict__ 
     __syncthreads();
     double maxdiag = 0.0;
     for (int a = 0; a < k; ++a) maxdiag = fmax(maxdiag, M[a][a]);
-    for (int c = 0; c < k; ++c) {  // in-place Gauss-Jordan, SPD => no pivoting
-        __syncthreads();
+    for (int c = 0; c < k; ++c) {  // in-place Gauss-Jordan, SPD => no pivoting; two barriers per step
+        __syncthreads();   // the previous step's update is complete
         const double piv = M[c][c];
-        if (tid < KP) colbuf[tid] = M[tid][c];
         if (!(piv > 1e-11 * maxdiag)) {
             if (tid == 0) ok_s = 0;
             break;   // uniform: every thread reads the same pivot
         }
-        __syncthreads();
         const double ip = 1.0 / piv;
-        if (tid < KP) M[c][tid] = (tid == c) ? ip : M[c][tid] * ip;
+        if (tid < KP) {
+            colbuf[tid] = M[tid][c];                              // column c before the step
+            rowbuf[tid] = (tid == c) ? ip : M[c][tid] * ip;       // row c after the step
+        }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             const int e = tid + j * 1024;
             const int r = e / KP, col = e % KP;
-            if (r != c && r < k && col < k) {
-                const double base = (col == c) ? 0.0 : M[r][col];
-                M[r][col] = base - colbuf[r] * M[c][col];
+            if (r < k && col < k) {
+                if (r == c) {
+                    M[r][col] = rowbuf[col];
+                } else {
+                    const double base = (col == c) ? 0.0 : M[r][col];
+                    M[r][col] = base - colbuf[r] * rowbuf[col];
+                }
             }
         }
     }
