@@ -72,7 +72,11 @@ typedef struct lgr_csc {
 /* flags for lgr_inmf_args.flags */
 #define LGR_FLAG_TRAJECTORY 0x1u  /* evaluate the objective after every iteration into out->obj_traj */
 #define LGR_FLAG_COLD_START 0x2u  /* disable NNLS warm starts (every solve starts from the empty passive set) */
-#define LGR_FLAG_PINNED_IO 0x4u   /* caller promises host buffers are page-locked (faster copies) */
+#define LGR_FLAG_PINNED_IO 0x4u   /* caller promises that every host buffer (inputs and outputs) is page-locked: the
+                                     library copies straight from / into them.  Without the flag each buffer is probed
+                                     (cudaPointerGetAttributes) and pageable ones -- R's heap, numpy arrays -- go through
+                                     a ring of page-locked bounce buffers filled by a few host threads, so that the DMA
+                                     engine still runs at PCIe speed */
 #define LGR_FLAG_TENSOR_U 0x10u   /* form u = CtC^-1 b of the H solve on the tensor cores (tcgen05, 3xTF32 split, TMEM
                                      accumulators): as an epilogue of the B = L^T X sweep while the B tile is still in shared
                                      memory, or as a separate pass when the tile geometry does not allow it.  Same results
@@ -94,8 +98,11 @@ typedef struct lgr_inmf_args {
     const lgr_csc* E;      /* d shared blocks, m x n_i */
     const lgr_csc* P;      /* NULL, or d unshared blocks u_i x n_i (nrow == 0 => none for that dataset) */
     const double* lambda;  /* d penalties (iNMF: the scalar repeated) */
-    const double* Winit;   /* m x k */
-    const double* const* Vinit; /* d pointers, each m x k */
+    const double* Winit;   /* m x k; NULL (together with Vinit / Uinit) = draw the initial factors inside the library,
+                              as RcppPlanc does when rliger passes Hinit = Vinit = Winit = NULL (R/suggestK.R:78-88):
+                              R's Mersenne-Twister stream seeded with init_seed, U(0, 2), column-major, in the order of
+                              .runINMF.list (R/integration.R:412-437): W, V_1..V_d, (U_1..U_d,) H_1..H_d */
+    const double* const* Vinit; /* d pointers, each m x k (NULL: drawn, see Winit) */
     const double* const* Uinit; /* NULL, or d pointers, each u_i x k (NULL where u_i == 0) */
     const double* const* Hinit; /* NULL, or d pointers, each n_i x k.  H is solved first, so Hinit only
                                    matters when niter == 0 (as in RcppPlanc). */
@@ -103,7 +110,7 @@ typedef struct lgr_inmf_args {
     int32_t device; /* CUDA ordinal; -1 = current device */
     int32_t rank;   /* cell-shard rank of this process, 0 when world == 1 */
     int32_t world;  /* number of processes sharing the factorisation (one GPU each) */
-    int32_t reserved;
+    int32_t init_seed; /* seed of the in-library initialisation when Winit / Vinit are NULL (0 is read as 1) */
     const void* nccl_unique_id; /* 128 bytes from lgr_nccl_unique_id() (same on all ranks); NULL if world == 1.
                                    Passing the SAME id again reuses the cached communicator (no ncclCommInitRank). */
     /* optional: polled between iterations; non-zero return aborts with LGR_ERR_INTERRUPT */
@@ -180,6 +187,9 @@ typedef struct lgr_ctx lgr_ctx;
 LGR_API int lgr_ctx_create(const lgr_inmf_args* args, lgr_ctx** ctx); /* uploads E/P, builds device layouts, sets inits */
 LGR_API int lgr_ctx_reset(lgr_ctx* ctx, const double* Winit, const double* const* Vinit, const double* const* Uinit);
 LGR_API int lgr_ctx_iterate(lgr_ctx* ctx, int32_t niter, double* obj_traj /* NULL or niter */);
+/* niter iterations followed by the final objective -- what lgr_inmf runs between its upload and its download -- inside
+   ONE CUDA-event bracket (lgr_timings.loop_ms then covers the loop and the objective pass). */
+LGR_API int lgr_ctx_run(lgr_ctx* ctx, int32_t niter, double* objErr);
 LGR_API int lgr_ctx_objective(lgr_ctx* ctx, double* obj);
 LGR_API int lgr_ctx_download(lgr_ctx* ctx, lgr_inmf_out* out);
 LGR_API int lgr_ctx_timings(lgr_ctx* ctx, lgr_timings* t);

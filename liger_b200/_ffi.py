@@ -30,7 +30,7 @@ class lgr_inmf_args(C.Structure):
                 ("m", C.c_int64), ("E", C.POINTER(lgr_csc)), ("P", C.POINTER(lgr_csc)),
                 ("lambda_", c_double_p), ("Winit", c_double_p), ("Vinit", C.POINTER(c_double_p)),
                 ("Uinit", C.POINTER(c_double_p)), ("Hinit", C.POINTER(c_double_p)),
-                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32),
+                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("init_seed", C.c_int32),
                 ("nccl_unique_id", C.c_void_p), ("interrupt", INTERRUPT_FN), ("interrupt_user", C.c_void_p)]
 
 
@@ -57,7 +57,7 @@ _lib = None
 # every symbol include/liger_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
     "lgr_inmf", "lgr_uinmf", "lgr_bppnnls_prod", "lgr_objerr_i", "lgr_ctx_create", "lgr_ctx_reset",
-    "lgr_ctx_iterate", "lgr_ctx_objective", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
+    "lgr_ctx_iterate", "lgr_ctx_run", "lgr_ctx_objective", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
     "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
     "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id", "lgr_host_alloc",
     "lgr_host_free", "lgr_normalize_csc", "lgr_row_vars_sparse", "lgr_scale_not_center_by_row",
@@ -84,6 +84,7 @@ def lib():
     L.lgr_ctx_create.argtypes = [C.POINTER(lgr_inmf_args), C.POINTER(C.c_void_p)]
     L.lgr_ctx_reset.argtypes = [C.c_void_p, c_double_p, C.POINTER(c_double_p), C.POINTER(c_double_p)]
     L.lgr_ctx_iterate.argtypes = [C.c_void_p, C.c_int32, c_double_p]
+    L.lgr_ctx_run.argtypes = [C.c_void_p, C.c_int32, c_double_p]
     L.lgr_ctx_objective.argtypes = [C.c_void_p, c_double_p]
     L.lgr_ctx_download.argtypes = [C.c_void_p, C.POINTER(lgr_inmf_out)]
     L.lgr_ctx_timings.argtypes = [C.c_void_p, C.POINTER(lgr_timings)]

@@ -111,7 +111,7 @@ class _Args:
     """Builds lgr_inmf_args and owns every buffer it points to."""
 
     def __init__(self, objectList, k, lambda_, niter, Winit, Vinit, Hinit=None, unsharedList=None, Uinit=None,
-                 flags=0, device=-1, rank=0, world=1, nccl_id=None, keep_f32=False):
+                 flags=0, device=-1, rank=0, world=1, nccl_id=None, keep_f32=False, init_seed=1):
         d = len(objectList)
         if d < 1:
             raise ValueError("objectList is empty")
@@ -136,16 +136,20 @@ class _Args:
             self.Parr = (lgr_csc * d)(*ps)
         lam = np.broadcast_to(np.asarray(lambda_, dtype=np.float64), (d,)).copy()
         self.lam = lam
-        self.W0 = _f64(Winit)
-        if self.W0.shape != (self.m, self.k):
-            raise ValueError(f"Winit must be {self.m} x {self.k}")
-        self.V0 = [_f64(v) for v in Vinit]
-        for v in self.V0:
-            if v.shape != (self.m, self.k):
-                raise ValueError(f"every Vinit must be {self.m} x {self.k}")
-        self.Varr = (c_double_p * d)(*[_dp(v) for v in self.V0])
+        if (Winit is None) != (Vinit is None):
+            raise ValueError("Winit and Vinit must both be given, or both be None (in-library seeded initialisation)")
+        self.W0 = self.V0 = self.Varr = None
+        if Winit is not None:
+            self.W0 = _f64(Winit)
+            if self.W0.shape != (self.m, self.k):
+                raise ValueError(f"Winit must be {self.m} x {self.k}")
+            self.V0 = [_f64(v) for v in Vinit]
+            for v in self.V0:
+                if v.shape != (self.m, self.k):
+                    raise ValueError(f"every Vinit must be {self.m} x {self.k}")
+            self.Varr = (c_double_p * d)(*[_dp(v) for v in self.V0])
         self.Uarr = None
-        if unsharedList is not None:
+        if unsharedList is not None and Winit is not None:
             self.U0 = [None if self.u[i] == 0 else _f64(Uinit[i]) for i in range(d)]
             self.Uarr = (c_double_p * d)(*[(_dp(x) if x is not None else None) for x in self.U0])
         self.Harr = None
@@ -161,8 +165,9 @@ class _Args:
         a.E = self.Earr
         a.P = self.Parr
         a.lambda_ = _dp(lam)
-        a.Winit = _dp(self.W0)
+        a.Winit = _dp(self.W0) if self.W0 is not None else None
         a.Vinit = self.Varr
+        a.init_seed = int(init_seed)
         a.Uinit = self.Uarr
         a.Hinit = self.Harr
         a.device, a.rank, a.world = int(device), int(rank), int(world)
@@ -178,7 +183,10 @@ class _Out:
         self.W = np.zeros((m, k), order="F")
         self.V = [np.zeros((m, k), order="F") for _ in range(d)]
         if pinned:
-            self.H = [pinned_empty((n, k)) for n in args.n]     # every entry is written by the library
+            self.H = [pinned_empty((n, k)) for n in args.n]
+            if args.struct.world > 1 and not (args.struct.flags & _ffi.FLAG_LOCAL_SHARD):
+                for h in self.H:      # slice mode: the library writes only this rank's rows
+                    h[...] = 0.0
         else:
             self.H = [np.zeros((n, k), order="F") for n in args.n]
         self.U = [np.zeros((u, k), order="F") if u > 0 else None for u in args.u]
@@ -208,7 +216,7 @@ class _Out:
 
 def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
          trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False, tensor_u=False,
-         rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False):
+         rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False, seed=1, pinned_io=False):
     """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
 
     Multi-GPU (one process per GPU): pass `rank`, `world`, the `nccl_id` created by rank 0 (nccl_unique_id()) and
@@ -220,14 +228,15 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
     Returns dict(H=[n_i x k], V=[m x k], W=m x k, objErr=float) exactly like RcppPlanc
     (H is cell x factor; the caller transposes, R/integration.R:453).
     """
-    if Winit is None or Vinit is None:
-        raise ValueError("liger_b200.inmf needs explicit Winit/Vinit (rliger's .runINMF.list always passes them; "
-                         "use liger_b200.integration.run_inmf_list for the seeded initialisation)")
+    if (Winit is None) != (Vinit is None):
+        raise ValueError("Winit and Vinit must both be given, or both be None")
+    # Winit = Vinit = None (R/suggestK.R:78-88 passes NULL for all three): the library draws W, V_i from R's
+    # Mersenne-Twister stream seeded with `seed`, in .runINMF.list's order
     flags = ((_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0) |
              (_ffi.FLAG_TENSOR_U if tensor_u else 0) | (0x8 if (local_shard and world > 1) else 0) |
-             (_ffi.FLAG_LEGACY_NNLS if legacy_nnls else 0))
+             (_ffi.FLAG_LEGACY_NNLS if legacy_nnls else 0) | (_ffi.FLAG_PINNED_IO if pinned_io else 0))
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device, rank=rank, world=world,
-              nccl_id=nccl_id)
+              nccl_id=nccl_id, init_seed=seed)
     o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs)
     _ffi.check(_ffi.lib().lgr_inmf(C.byref(a.struct), C.byref(o.struct)))
     res = {"H": o.H, "V": o.V, "W": o.W, "objErr": float(o.struct.objErr), "timings": o.timings()}
@@ -239,7 +248,7 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
 
 
 def uinmf(objectList, unsharedList, k=20, lambda_=5.0, niter=30, nCores=2, verbose=False, Winit=None, Vinit=None,
-          Uinit=None, trajectory=False, device=-1):
+          Uinit=None, trajectory=False, device=-1, seed=1):
     """Drop-in for RcppPlanc::uinmf (reference call site R/integration.R:1285-1287).
 
     unsharedList[i]: u_i x n_i CSC or None.  lambda_: scalar or per-dataset vector
@@ -247,11 +256,13 @@ def uinmf(objectList, unsharedList, k=20, lambda_=5.0, niter=30, nCores=2, verbo
     them internally -- parity unpinned); here explicit W/V/U inits are required at this level and
     liger_b200.integration.run_uinmf_list draws them from R's RNG stream.
     Returns dict(H, V, W, U, objErr)."""
-    if Winit is None or Vinit is None or Uinit is None:
-        raise ValueError("liger_b200.uinmf needs explicit Winit/Vinit/Uinit; use integration.run_uinmf_list")
+    given = [x is not None for x in (Winit, Vinit, Uinit)]
+    if any(given) and not all(given):
+        raise ValueError("liger_b200.uinmf: pass all of Winit/Vinit/Uinit, or none (the library then draws them from R's "
+                         "RNG stream seeded with `seed`, as RcppPlanc::uinmf draws its own)")
     flags = _ffi.FLAG_TRAJECTORY if trajectory else 0
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, None, unsharedList=unsharedList, Uinit=Uinit, flags=flags,
-              device=device)
+              device=device, init_seed=seed)
     o = _Out(a, traj=trajectory)
     _ffi.check(_ffi.lib().lgr_uinmf(C.byref(a.struct), C.byref(o.struct)))
     res = {"H": o.H, "V": o.V, "W": o.W, "U": o.U, "objErr": float(o.struct.objErr), "timings": o.timings()}
@@ -318,6 +329,13 @@ class Context:
     def objective(self):
         out = C.c_double(0.0)
         _ffi.check(_ffi.lib().lgr_ctx_objective(self.h, C.byref(out)))
+        return float(out.value)
+
+    def run(self, niter):
+        """niter iterations + the final objective inside one device-timed bracket (what lgr_inmf runs between its
+        upload and its download); returns the objective."""
+        out = C.c_double(0.0)
+        _ffi.check(_ffi.lib().lgr_ctx_run(self.h, int(niter), C.byref(out)))
         return float(out.value)
 
     def download(self, want_passive=False):

@@ -7,8 +7,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "lgr_common.cuh"
 #include "lgr_nccl.h"
@@ -108,6 +110,7 @@ struct lgr_ctx {
     StreamHolder stream_holder;
     int d = 0, k = 0, kp = 32, m = 0, device = 0, rank = 0, world = 1, tc = 1024, cb = 512, gt = 1024, num_sms = 148;
     uint32_t flags = 0;
+    int32_t init_seed = 0;
     cudaStream_t st = nullptr;
     std::vector<Dataset> ds;
     std::vector<DsDev> ds_host;
@@ -131,16 +134,15 @@ struct lgr_ctx {
     bool stats_valid = false;  // R / G arenas hold the statistics of the current H
     bool h_valid = false;
     lgr_timings tm{};
-    KernelTimer kt;
+    KernelTimer kt;   // per kernel
+    KernelTimer pt;   // per phase: "h_phase" (Gram, B = L^T X, H solves), "vw_phase" (statistics, V and W solves), "comm"
     int (*interrupt)(void*) = nullptr;
     void* interrupt_user = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~lgr_ctx() {
         if (comm) nccl_destroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (evA) cudaEventDestroy(evA);
-        if (evB) cudaEventDestroy(evB);
     }
 };
 
@@ -176,6 +178,27 @@ struct Timed {
         if (c->kt.on) {
             cudaEventRecord(b, c->st);
             c->kt.recs.push_back({id, a, b});
+        }
+    }
+};
+
+// CUDA events around a phase of the loop (only while kernel timing is on); resolved into lgr_timings after the loop
+struct Span {
+    lgr_ctx* c;
+    int id = -1;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Span(lgr_ctx* c_, const char* name) : c(c_) {
+        if (c->kt.on) {
+            id = c->pt.id_of(name);
+            a = c->pt.get();
+            b = c->pt.get();
+            cudaEventRecord(a, c->st);
+        }
+    }
+    ~Span() {
+        if (c->kt.on) {
+            cudaEventRecord(b, c->st);
+            c->pt.recs.push_back({id, a, b});
         }
     }
 };
@@ -217,7 +240,9 @@ struct StagedCsc {
         if (done) cudaEventDestroy(done);
     }
 };
-void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs) {
+// Runs on the staging thread (its allocation stream is the copy stream, so the buffers need no cross-stream hand-over
+// before the copies; the compute stream picks them up behind S.done).
+void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs, bool pinned_promise) {
     const int n = c1 - c0;
     const bool on_device = M.location == LGR_CSC_DEVICE;   // a view of resident data (lgr_prep_scaled_view)
     int base = 0, last = 0;
@@ -231,6 +256,7 @@ void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs) 
             LGR_REQUIRE(M.colptr[c0 + j] >= M.colptr[c0 + j - 1], "CSC column pointers must be non-decreasing");
         last = M.colptr[c0 + n];
     }
+    LGR_REQUIRE(base >= 0, "CSC column pointers must be non-negative");
     S.base = base;
     S.nnz = (size_t)(last - base);
     S.colptr.alloc((size_t)n + 1);
@@ -238,53 +264,93 @@ void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs) 
     S.val.alloc(S.nnz);
     if (S.nnz && M.value_dtype != LGR_F32) S.val64.alloc(S.nnz);
     LGR_CUDA(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
-    // the buffers were allocated in stream order on the allocation stream: the copy stream must not run ahead of it
-    cudaEvent_t alloc_done;
-    LGR_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
-    LGR_CUDA(cudaEventRecord(alloc_done, alloc_stream()));
-    LGR_CUDA(cudaStreamWaitEvent(cs, alloc_done, 0));
-    LGR_CUDA(cudaEventDestroy(alloc_done));
-    // straight from the caller's arrays (no pageable staging vector: that would serialise the host with the copy stream);
-    // cudaMemcpyDefault: host or device source
-    LGR_CUDA(cudaMemcpyAsync(S.colptr.p, M.colptr + c0, ((size_t)n + 1) * sizeof(int), cudaMemcpyDefault, cs));
+    const bool direct = pinned_promise || on_device;
+    // straight from the caller's arrays when they are page-locked (or device views); through the bounce ring otherwise
+    copy_in(S.colptr.p, M.colptr + c0, ((size_t)n + 1) * sizeof(int), cs, direct);
     if (S.nnz) {
-        LGR_CUDA(cudaMemcpyAsync(S.rowidx.p, M.rowidx + base, S.nnz * sizeof(int), cudaMemcpyDefault, cs));
+        copy_in(S.rowidx.p, M.rowidx + base, S.nnz * sizeof(int), cs, direct);
         if (M.value_dtype == LGR_F32)
-            LGR_CUDA(cudaMemcpyAsync(S.val.p, static_cast<const float*>(M.values) + base, S.nnz * sizeof(float),
-                                     cudaMemcpyDefault, cs));
+            copy_in(S.val.p, static_cast<const float*>(M.values) + base, S.nnz * sizeof(float), cs, direct);
         else
-            LGR_CUDA(cudaMemcpyAsync(S.val64.p, static_cast<const double*>(M.values) + base, S.nnz * sizeof(double),
-                                     cudaMemcpyDefault, cs));
+            copy_in(S.val64.p, static_cast<const double*>(M.values) + base, S.nnz * sizeof(double), cs, direct);
     }
     LGR_CUDA(cudaEventRecord(S.done, cs));
 }
-void finish_csc(StagedCsc& S, cudaStream_t st) {
+void finish_csc(StagedCsc& S, int nrow, int* bad, cudaStream_t st) {
     LGR_CUDA(cudaStreamWaitEvent(st, S.done, 0));
     if (S.base != 0) dev_add_int(S.colptr.p, S.colptr.n, -S.base, st);
     if (S.nnz && S.val64.p) dev_f64_to_f32(S.val64.p, S.val.p, S.nnz, st);
+    // the tiled layouts index device arrays with the caller's row indices: range-check them first (one streaming pass)
+    if (S.nnz) prep_check_rows(S.nnz, S.rowidx.p, nrow, bad, st);
+}
+
+// argument checks of one shared (E) or unshared (P) block; host pointers are only dereferenced for host matrices
+void check_block(const lgr_csc& M, int64_t nrow, int64_t ncol, const char* what) {
+    const std::string w(what);
+    LGR_REQUIRE(M.nrow == nrow, w + ": wrong number of rows");
+    LGR_REQUIRE(M.ncol == ncol, w + ": wrong number of cells");
+    LGR_REQUIRE(M.ncol >= 1 && M.ncol < (int64_t)0x7fffffff, w + ": ncol out of range");
+    LGR_REQUIRE(M.nrow >= 0 && M.nrow < (1 << 30), w + ": nrow out of range");
+    LGR_REQUIRE(M.colptr, w + ": null column pointers");
+    LGR_REQUIRE(M.value_dtype == LGR_F64 || M.value_dtype == LGR_F32, w + ": bad value_dtype");
+    if (M.location == LGR_CSC_DEVICE) {
+        LGR_REQUIRE(M.rowidx && M.values, w + ": null arrays");
+    } else {
+        LGR_REQUIRE(M.location == 0, w + ": bad location");
+        LGR_REQUIRE(M.colptr[M.ncol] == 0 || (M.rowidx && M.values), w + ": null arrays");
+    }
 }
 
 void upload_factor(const double* host, double* dev_padded, int rows, int k, int kp, cudaStream_t st) {
     if (rows == 0) return;
     DBuf<double> tmp((size_t)rows * k);
-    LGR_CUDA(cudaMemcpyAsync(tmp.p, host, (size_t)rows * k * sizeof(double), cudaMemcpyHostToDevice, st));
+    copy_in(tmp.p, host, (size_t)rows * k * sizeof(double), st, false);
     dev_colmajor_to_padded(tmp.p, dev_padded, rows, k, kp, st);
     LGR_CUDA(cudaStreamSynchronize(st));
 }
 
+// Rows x k draws of R's runif(., 0, 2) (column-major, like matrix(runif(rows * k, 0, 2), rows, k)) into a padded factor
+void draw_factor(lgr_rng* rng, double* dev_padded, int rows, int k, int kp, cudaStream_t st, std::vector<double>& tmp) {
+    if (rows == 0) return;
+    tmp.resize((size_t)rows * k);
+    lgr_r_runif(rng, (int64_t)rows * k, 0.0, 2.0, tmp.data());
+    upload_factor(tmp.data(), dev_padded, rows, k, kp, st);
+}
+
 void set_inits(lgr_ctx* c, const double* Winit, const double* const* Vinit, const double* const* Uinit) {
-    LGR_REQUIRE(Winit && Vinit, "Winit and Vinit are required");
-    upload_factor(Winit, c->W.p, c->m, c->k, c->kp, c->st);
+    // Winit == Vinit == NULL: RcppPlanc's internal random initialisation (R/suggestK.R:78-88 passes NULL for all three).
+    // Drawn here from R's Mersenne-Twister stream in .runINMF.list's order (R/integration.R:412-437): W, V_1..V_d,
+    // U_1..U_d; the H draws that follow in that order are only materialised when they are used (niter == 0).
+    const bool draw = !Winit && !Vinit;
+    LGR_REQUIRE(draw || (Winit && Vinit), "Winit and Vinit must both be given, or both be NULL (in-library seeded initialisation)");
+    std::unique_ptr<lgr_rng, void (*)(lgr_rng*)> rng(nullptr, lgr_r_free);
+    std::vector<double> tmp;
+    if (draw) {
+        rng.reset(lgr_r_set_seed(c->init_seed ? (uint32_t)c->init_seed : 1u));
+        draw_factor(rng.get(), c->W.p, c->m, c->k, c->kp, c->st, tmp);
+    } else {
+        upload_factor(Winit, c->W.p, c->m, c->k, c->kp, c->st);
+    }
     for (int i = 0; i < c->d; ++i) {
         Dataset& D = c->ds[i];
-        LGR_REQUIRE(Vinit[i], "Vinit[i] is NULL");
-        upload_factor(Vinit[i], D.V.p, c->m, c->k, c->kp, c->st);
-        if (D.u > 0) {
-            LGR_REQUIRE(Uinit && Uinit[i], "Uinit[i] is required for datasets with unshared features");
-            upload_factor(Uinit[i], D.V.p + (size_t)c->m * c->kp, D.u, c->k, c->kp, c->st);
+        if (draw) {
+            draw_factor(rng.get(), D.V.p, c->m, c->k, c->kp, c->st, tmp);
+        } else {
+            LGR_REQUIRE(Vinit[i], "Vinit[i] is NULL");
+            upload_factor(Vinit[i], D.V.p, c->m, c->k, c->kp, c->st);
         }
         D.hmask.zero(c->st);
         D.vmask.zero(c->st);
+    }
+    for (int i = 0; i < c->d; ++i) {
+        Dataset& D = c->ds[i];
+        if (D.u == 0) continue;
+        if (draw) {
+            draw_factor(rng.get(), D.V.p + (size_t)c->m * c->kp, D.u, c->k, c->kp, c->st, tmp);
+        } else {
+            LGR_REQUIRE(Uinit && Uinit[i], "Uinit[i] is required for datasets with unshared features");
+            upload_factor(Uinit[i], D.V.p + (size_t)c->m * c->kp, D.u, c->k, c->kp, c->st);
+        }
     }
     c->wmask.zero(c->st);
     c->counters.zero(c->st);
@@ -295,12 +361,11 @@ void set_inits(lgr_ctx* c, const double* Winit, const double* const* Vinit, cons
 
 void allreduce_stats(lgr_ctx* c) {
     if (c->world <= 1) return;
-    cudaEventRecord(c->evA, c->st);
+    Span sp(c, "comm");   // includes the wait for the slowest rank
     nccl_group_start();
     nccl_allreduce_sum_f32(c->comm, c->Rarena.p, c->Rarena.n, c->st);
     nccl_allreduce_sum_f64(c->comm, c->Garena.p, c->Garena.n, c->st);
     nccl_group_end();
-    cudaEventRecord(c->evB, c->st);
 }
 
 void run_prep(lgr_ctx* c) {
@@ -341,8 +406,14 @@ void solve_f64(lgr_ctx* c, const NnlsGroup* grp, int ngroups, long long cols, in
     }
 }
 
-void iterate(lgr_ctx* c, int niter, double* traj_host) {
+double objective(lgr_ctx* c);
+
+void iterate(lgr_ctx* c, int niter, double* traj_host, double* final_obj = nullptr) {
     const bool traj = traj_host != nullptr;
+    if (final_obj && niter == 0) {
+        *final_obj = objective(c);
+        return;
+    }
     int cold = (c->flags & LGR_FLAG_COLD_START) ? 1 : 0;
     const bool hist = getenv("LGR_NNLS_HIST") != nullptr;
     if (hist) {
@@ -353,10 +424,13 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
     if (getenv("LGR_NNLS_NO_DUAL")) cold |= 8;
     if (traj) c->objbuf.alloc((size_t)niter + 1);
     c->kt.begin_loop();
+    c->pt.begin_loop();
     c->tm.kernel_launches = 0;
+    c->tm.h_phase_ms = c->tm.vw_phase_ms = c->tm.comm_ms = 0.0;
     LGR_CUDA(cudaEventRecord(c->ev0, c->st));
     for (int it = 0; it < niter; ++it) {
         if (c->interrupt && c->interrupt(c->interrupt_user)) throw Error(LGR_ERR_INTERRUPT, "interrupted by caller");
+        std::unique_ptr<Span> phase(new Span(c, "h_phase"));
         run_prep(c);
         if (traj && it > 0) run_objective(c, c->objbuf.p + (it - 1));
         // ---- H phase ----
@@ -391,6 +465,8 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             }
         }
         c->h_valid = true;
+        phase.reset();
+        phase.reset(new Span(c, "vw_phase"));
         // ---- sufficient statistics of the V / W solves ----
         run_stats(c);
         // ---- V_i (and U_i): old W ----
@@ -419,17 +495,32 @@ void iterate(lgr_ctx* c, int niter, double* traj_host) {
             Timed t(c, "k_nnls_W");
             solve_f64(c, c->grpW.p, 1, (long long)c->m, cold);
         }
+        phase.reset();
     }
-    if (traj && niter > 0) {
+    DBuf<double> final_slot;
+    if ((traj && niter > 0) || final_obj) {
         run_prep(c);
-        run_objective(c, c->objbuf.p + (niter - 1));
+        if (traj && niter > 0) run_objective(c, c->objbuf.p + (niter - 1));
+        if (final_obj) {
+            final_slot.alloc(1);
+            run_objective(c, final_slot.p);
+        }
     }
     LGR_CUDA(cudaEventRecord(c->ev1, c->st));
     LGR_CUDA(cudaStreamSynchronize(c->st));
     float ms = 0.f;
     LGR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->tm.loop_ms = ms;
-    if (c->kt.on) c->kt.resolve();
+    if (final_obj) LGR_CUDA(cudaMemcpy(final_obj, final_slot.p, sizeof(double), cudaMemcpyDeviceToHost));
+    if (c->kt.on) {
+        c->kt.resolve();
+        c->pt.resolve();
+        for (size_t j = 0; j < c->pt.names.size(); ++j) {
+            if (c->pt.names[j] == "h_phase") c->tm.h_phase_ms = c->pt.ms[j];
+            if (c->pt.names[j] == "vw_phase") c->tm.vw_phase_ms = c->pt.ms[j];
+            if (c->pt.names[j] == "comm") c->tm.comm_ms = c->pt.ms[j];
+        }
+    }
     if (traj && niter > 0)
         LGR_CUDA(cudaMemcpy(traj_host, c->objbuf.p, (size_t)niter * sizeof(double), cudaMemcpyDeviceToHost));
     Counters cn;
@@ -474,6 +565,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->kp = a->k <= 32 ? 32 : 64;
     c->m = (int)a->m;
     c->flags = a->flags;
+    c->init_seed = a->init_seed;
     c->rank = a->rank;
     c->world = a->world;
     c->interrupt = a->interrupt;
@@ -497,8 +589,6 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     }
     LGR_CUDA(cudaEventCreate(&c->ev0));
     LGR_CUDA(cudaEventCreate(&c->ev1));
-    LGR_CUDA(cudaEventCreate(&c->evA));
-    LGR_CUDA(cudaEventCreate(&c->evB));
     c->tc = c->kp == 32 ? 1024 : 512;
     c->cb = c->kp == 32 ? 512 : 256;
     {   // gene tiles of at most 1024 (512) rows, balanced
@@ -566,66 +656,90 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     size_t b_total = 0, r_total = 0;
     int max_rows = 0;
     tr.mark("ctx setup");
-    // ---- pass 1: validate, then queue every H2D copy on the copy stream ----
-    std::vector<StagedCsc> stagedE(c->d), stagedP(c->d);
-    CopyStream cstream;
+    // ---- pass 1: validate everything, then a staging thread moves the blocks to the device on a copy stream (direct DMA
+    //      from page-locked buffers, through the bounce ring from pageable ones) while pass 2 builds the layouts ----
+    const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
+    const bool pinned_io = (c->flags & LGR_FLAG_PINNED_IO) != 0;
     for (int i = 0; i < c->d; ++i) {
-        const lgr_csc& E = a->E[i];
-        LGR_REQUIRE(E.nrow == a->m, "every E[i] must have m rows");
-        LGR_REQUIRE(E.ncol >= 1 && E.ncol < (int64_t)0x7fffffff, "E[i].ncol out of range");
-        LGR_REQUIRE(E.colptr && (E.location == LGR_CSC_DEVICE || E.colptr[E.ncol] == 0 || (E.rowidx && E.values)),
-                    "E[i] has null arrays");
-        const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
-        const int n_full = (int)E.ncol;
-        const int s0 = local ? 0 : (int)((int64_t)n_full * c->rank / c->world);
-        const int s1 = local ? n_full : (int)((int64_t)n_full * (c->rank + 1) / c->world);
-        tr.mark("validate");
-        stage_csc(E, s0, s1, stagedE[i], cstream.s);
-        tr.mark("stage_csc");
-        if (a->P && a->P[i].nrow > 0) {
-            LGR_REQUIRE(a->P[i].ncol == E.ncol, "P[i] must have the same cells as E[i]");
-            LGR_REQUIRE(a->P[i].nrow < (1 << 30), "P[i].nrow out of range");
-            LGR_REQUIRE(a->P[i].colptr && (a->P[i].colptr[a->P[i].ncol] == 0 || (a->P[i].rowidx && a->P[i].values)),
-                        "P[i] has null arrays");
-            stage_csc(a->P[i], s0, s1, stagedP[i], cstream.s);
-        }
+        check_block(a->E[i], a->m, a->E[i].ncol, "E[i]");
+        if (a->P && a->P[i].nrow > 0) check_block(a->P[i], a->P[i].nrow, a->E[i].ncol, "P[i]");
     }
-    tr.mark("stage H2D copies");
+    CopyStream cstream;   // declared before the staged buffers: they are allocated (and freed) in its stream order
+    std::vector<StagedCsc> stagedE(c->d), stagedP(c->d);
+    struct StageSync {
+        std::mutex mu;
+        std::condition_variable cv;
+        int staged = 0;   // datasets whose copies have been queued
+        std::exception_ptr err;
+    } sync;
+    const int device = c->device;
+    std::thread stager([&, device] {
+        try {
+            LGR_CUDA(cudaSetDevice(device));
+            AllocStreamScope scope(cstream.s);
+            for (int i = 0; i < c->d; ++i) {
+                const int n_full = (int)a->E[i].ncol;
+                const int s0 = local ? 0 : (int)((int64_t)n_full * c->rank / c->world);
+                const int s1 = local ? n_full : (int)((int64_t)n_full * (c->rank + 1) / c->world);
+                stage_csc(a->E[i], s0, s1, stagedE[i], cstream.s, pinned_io);
+                if (a->P && a->P[i].nrow > 0) stage_csc(a->P[i], s0, s1, stagedP[i], cstream.s, pinned_io);
+                {
+                    std::lock_guard<std::mutex> g(sync.mu);
+                    sync.staged = i + 1;
+                }
+                sync.cv.notify_all();
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> g(sync.mu);
+            sync.err = std::current_exception();
+            sync.cv.notify_all();
+        }
+    });
+    struct Joiner {
+        std::thread& t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } joiner{stager};
+    tr.mark("stage H2D copies (thread started)");
+    DBuf<int> bad_rows(1);
+    bad_rows.zero(c->st);
     // ---- pass 2: per dataset, wait for its copy and build the device layouts (the later copies keep streaming) ----
     for (int i = 0; i < c->d; ++i) {
+        {
+            std::unique_lock<std::mutex> g(sync.mu);
+            sync.cv.wait(g, [&] { return sync.staged > i || sync.err; });
+            if (sync.err) std::rethrow_exception(sync.err);
+        }
         Dataset& D = c->ds[i];
         const lgr_csc& E = a->E[i];
-        LGR_REQUIRE(E.nrow == a->m, "every E[i] must have m rows");
-        LGR_REQUIRE(E.ncol >= 1 && E.ncol < (int64_t)0x7fffffff, "E[i].ncol out of range");
-        LGR_REQUIRE(E.colptr && (E.location == LGR_CSC_DEVICE || E.colptr[E.ncol] == 0 || (E.rowidx && E.values)),
-                    "E[i] has null arrays");
         D.n_full = (int)E.ncol;
-        const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
         D.c0 = local ? 0 : (int)((int64_t)D.n_full * c->rank / c->world);
         const int c1 = local ? D.n_full : (int)((int64_t)D.n_full * (c->rank + 1) / c->world);
         D.n = c1 - D.c0;
         D.lambda = a->lambda[i];
         D.u = 0;
         const lgr_csc* P = (a->P && a->P[i].nrow > 0) ? &a->P[i] : nullptr;
-        if (P) {
-            LGR_REQUIRE(P->ncol == E.ncol, "P[i] must have the same cells as E[i]");
-            LGR_REQUIRE(P->nrow < (1 << 30), "P[i].nrow out of range");
-            D.u = (int)P->nrow;
-        }
+        if (P) D.u = (int)P->nrow;
         D.rows = m + D.u;
         max_rows = std::max(max_rows, D.rows);
         StagedCsc& SE = stagedE[i];
         StagedCsc& SP = stagedP[i];
+        finish_csc(SE, m, bad_rows.p, c->st);
+        if (P) finish_csc(SP, D.u, bad_rows.p, c->st);
+        {
+            int hbad = 0;
+            LGR_CUDA(cudaMemcpyAsync(&hbad, bad_rows.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+            LGR_REQUIRE(hbad == 0, "row index out of range in E[i] / P[i] (must be 0 <= i < nrow)");
+        }
         if (!P) {
-            finish_csc(SE, c->st);
             D.colptr = std::move(SE.colptr);
             D.rowidx = std::move(SE.rowidx);
             D.val = std::move(SE.val);
             D.nnz = SE.nnz;
             tr.mark("finish_csc");
         } else {
-            finish_csc(SE, c->st);
-            finish_csc(SP, c->st);
             D.nnz = SE.nnz + SP.nnz;
             D.colptr.alloc((size_t)D.n + 1);
             D.rowidx.alloc(D.nnz);
@@ -659,6 +773,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         D.r_off = r_total;
         r_total += (size_t)D.rows * kp;
     }
+    stager.join();
+    LGR_CUDA(cudaStreamSynchronize(c->st));   // the staged buffers go back to the pool in the copy stream's order
     LGR_CUDA(cudaStreamSynchronize(cstream.s));
     stagedE.clear();
     stagedP.clear();
@@ -819,38 +935,36 @@ void download(lgr_ctx* c, lgr_inmf_out* o) {
     LGR_CUDA(cudaEventCreate(&u1));
     LGR_CUDA(cudaEventRecord(u0, c->st));
     const int k = c->k, kp = c->kp, m = c->m;
-    if (o->W) {
-        DBuf<double> tmp((size_t)m * k);
-        dev_padded_to_colmajor(c->W.p, tmp.p, m, k, kp, c->st);
-        LGR_CUDA(cudaMemcpyAsync(o->W, tmp.p, (size_t)m * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    const bool pinned_io = (c->flags & LGR_FLAG_PINNED_IO) != 0;
+    // device layouts -> R layouts (column-major double) in scratch buffers, then one copy per output; pageable outputs are
+    // drained through the bounce ring (lgr_stage.cu)
+    auto factor_out = [&](const double* dev_padded, int rows, double* host) {
+        if (!host || rows == 0) return;
+        DBuf<double> tmp((size_t)rows * k);
+        dev_padded_to_colmajor(dev_padded, tmp.p, rows, k, kp, c->st);
+        copy_out(host, tmp.p, (size_t)rows * k * sizeof(double), c->st, pinned_io);
         LGR_CUDA(cudaStreamSynchronize(c->st));
-    }
+    };
+    factor_out(c->W.p, m, o->W);
     for (int i = 0; i < c->d; ++i) {
         Dataset& D = c->ds[i];
-        if (o->V && o->V[i]) {
-            DBuf<double> tmp((size_t)m * k);
-            dev_padded_to_colmajor(D.V.p, tmp.p, m, k, kp, c->st);
-            LGR_CUDA(cudaMemcpyAsync(o->V[i], tmp.p, (size_t)m * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            LGR_CUDA(cudaStreamSynchronize(c->st));
-        }
-        if (o->U && o->U[i] && D.u > 0) {
-            DBuf<double> tmp((size_t)D.u * k);
-            dev_padded_to_colmajor(D.V.p + (size_t)m * kp, tmp.p, D.u, k, kp, c->st);
-            LGR_CUDA(cudaMemcpyAsync(o->U[i], tmp.p, (size_t)D.u * k * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-            LGR_CUDA(cudaStreamSynchronize(c->st));
-        }
+        if (o->V) factor_out(D.V.p, m, o->V[i]);
+        if (o->U && D.u > 0) factor_out(D.V.p + (size_t)m * kp, D.u, o->U[i]);
         if (i == 0) tr.mark("download W,V");
         if (o->H && o->H[i] && D.n > 0) {
             DBuf<double> tmp((size_t)D.n * k);
             dev_hpad_to_colmajor(D.H.p, tmp.p, D.n, k, kp, c->st);
-            LGR_CUDA(cudaMemcpy2DAsync(o->H[i] + D.c0, (size_t)D.n_full * sizeof(double), tmp.p,
-                                       (size_t)D.n * sizeof(double), (size_t)D.n * sizeof(double), (size_t)k,
-                                       cudaMemcpyDeviceToHost, c->st));
+            if (D.n == D.n_full) {
+                copy_out(o->H[i], tmp.p, (size_t)D.n * k * sizeof(double), c->st, pinned_io);
+            } else {   // slice mode: this rank's rows [c0, c0 + n) of the caller's n_full x k matrix
+                LGR_CUDA(cudaMemcpy2DAsync(o->H[i] + D.c0, (size_t)D.n_full * sizeof(double), tmp.p,
+                                           (size_t)D.n * sizeof(double), (size_t)D.n * sizeof(double), (size_t)k,
+                                           cudaMemcpyDeviceToHost, c->st));
+            }
             LGR_CUDA(cudaStreamSynchronize(c->st));
         }
         if (o->H_passive && o->H_passive[i] && D.n > 0) {
-            LGR_CUDA(cudaMemcpyAsync(o->H_passive[i] + D.c0, D.hmask.p, (size_t)D.n * sizeof(unsigned long long),
-                                     cudaMemcpyDeviceToHost, c->st));
+            copy_out(o->H_passive[i] + D.c0, D.hmask.p, (size_t)D.n * sizeof(unsigned long long), c->st, pinned_io);
             LGR_CUDA(cudaStreamSynchronize(c->st));
         }
     }
@@ -898,8 +1012,7 @@ int run_oneshot(const lgr_inmf_args* args, lgr_inmf_out* out, bool need_unshared
         create(args, &raw);
         std::unique_ptr<lgr_ctx> c(raw);
         AllocStreamScope alloc_scope(c->st);
-        iterate(c.get(), args->niter, (args->flags & LGR_FLAG_TRAJECTORY) ? out->obj_traj : nullptr);
-        out->objErr = objective(c.get());
+        iterate(c.get(), args->niter, (args->flags & LGR_FLAG_TRAJECTORY) ? out->obj_traj : nullptr, &out->objErr);
         download(c.get(), out);
     });
 }
@@ -951,6 +1064,14 @@ int lgr_ctx_iterate(lgr_ctx* c, int32_t niter, double* obj_traj) {
         LGR_CUDA(cudaSetDevice(c->device));
         AllocStreamScope alloc_scope(c->st);
         iterate(c, niter, obj_traj);
+    });
+}
+int lgr_ctx_run(lgr_ctx* c, int32_t niter, double* objErr) {
+    return guarded([&] {
+        LGR_REQUIRE(c && niter >= 0 && objErr, "bad argument");
+        LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
+        iterate(c, niter, nullptr, objErr);
     });
 }
 int lgr_ctx_objective(lgr_ctx* c, double* obj) {

@@ -209,6 +209,11 @@ void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot,
 size_t spmm_xh_smem(int kp, int tc);
 void kernels_init();  // opt-in shared memory attributes of every kernel, once per device (safe to call repeatedly)
 
+// copies between caller host memory and the device (lgr_stage.cu): pageable buffers go through page-locked bounce buffers
+bool host_is_pinned(const void* p);
+void copy_in(void* dst, const void* src, size_t bytes, cudaStream_t cs, bool pinned_promise);
+void copy_out(void* dst, const void* src, size_t bytes, cudaStream_t st, bool pinned_promise);
+
 // layout / conversion kernels (lgr_layout.cu)
 void dev_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
 void dev_add_int(int* p, size_t n, int delta, cudaStream_t st);

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <memory>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -54,32 +55,61 @@ void check(ncclResult_t r, const char* what) {
 }
 }  // namespace
 
+// Communicators are cached per process, keyed by (unique id, rank, world, CUDA device): ncclCommInitRank costs ~0.3 s, so
+// a caller that passes the SAME unique id to successive lgr_inmf / lgr_uinmf / lgr_ctx_create calls (one per session, like
+// an R session would) pays for it once.  A new id makes a new communicator.  The cache holds one reference; contexts hold
+// the others (nccl_destroy drops one).  At most MAX_CACHED idle communicators are kept: the oldest idle one is destroyed
+// when a new id arrives, so a long-lived process that keeps creating ids does not accumulate them.
 struct NcclComm {
-    ncclComm_t comm;
+    ncclComm_t comm = nullptr;
+    int refs = 0;   // contexts using it
+    std::string key;
 };
+namespace {
+std::mutex g_mu;
+std::vector<NcclComm*> g_cache;
+constexpr size_t MAX_CACHED = 4;
+}  // namespace
 
 void nccl_unique_id(void* out128) {
     ncclUniqueId id;
     check(api().GetUniqueId(&id), "ncclGetUniqueId");
     memcpy(out128, &id, sizeof(id));
 }
-// Communicators are cached per process, keyed by (unique id, rank, world): ncclCommInitRank costs ~0.3 s, so a caller
-// that passes the SAME unique id to successive lgr_inmf / lgr_uinmf / lgr_ctx_create calls (one per session, like an R
-// session would) pays for it once.  A new id makes a new communicator.  Cached communicators live until process exit.
 NcclComm* nccl_init(const void* id128, int rank, int world) {
-    static std::mutex mu;
-    static std::vector<std::pair<std::string, NcclComm*>> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) throw Error(LGR_ERR_CUDA, "cudaGetDevice failed");
     std::string key(static_cast<const char*>(id128), sizeof(ncclUniqueId));
-    key += ":" + std::to_string(rank) + "/" + std::to_string(world);
-    std::lock_guard<std::mutex> lock(mu);
-    for (auto& kv : cache)
-        if (kv.first == key) return kv.second;
+    key += ":" + std::to_string(rank) + "/" + std::to_string(world) + "@" + std::to_string(dev);
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (NcclComm* c : g_cache)
+        if (c->key == key) {
+            c->refs += 1;
+            return c;
+        }
+    // evict idle communicators beyond the cap (oldest first)
+    for (size_t i = 0; i < g_cache.size() && g_cache.size() >= MAX_CACHED;) {
+        if (g_cache[i]->refs == 0) {
+            if (api().CommDestroy) api().CommDestroy(g_cache[i]->comm);
+            delete g_cache[i];
+            g_cache.erase(g_cache.begin() + i);
+        } else {
+            ++i;
+        }
+    }
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    NcclComm* c = new NcclComm;
+    std::unique_ptr<NcclComm> c(new NcclComm);   // not leaked when ncclCommInitRank fails
     check(api().CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
-    cache.emplace_back(key, c);
-    return c;
+    c->key = key;
+    c->refs = 1;
+    g_cache.push_back(c.get());
+    return c.release();
+}
+void nccl_destroy(NcclComm* c) {   // the context lets go; the cache keeps the communicator for the next call with this id
+    if (!c) return;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (c->refs > 0) c->refs -= 1;
 }
 void nccl_allreduce_sum_f32(NcclComm* c, float* buf, size_t n, cudaStream_t st) {
     check(api().AllReduce(buf, buf, n, ncclFloat32, ncclSum, c->comm, st), "ncclAllReduce(f32)");
@@ -89,5 +119,4 @@ void nccl_allreduce_sum_f64(NcclComm* c, double* buf, size_t n, cudaStream_t st)
 }
 void nccl_group_start() { check(api().GroupStart(), "ncclGroupStart"); }
 void nccl_group_end() { check(api().GroupEnd(), "ncclGroupEnd"); }
-void nccl_destroy(NcclComm*) {}   // cached communicators are released at process exit
 }  // namespace lgr

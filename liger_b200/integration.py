@@ -62,7 +62,14 @@ def run_uinmf_list(objectList, unsharedList, k=20, lambda_=5.0, nIteration=30, n
                    verbose=False, trajectory=False):
     mats = list(objectList.values()) if isinstance(objectList, dict) else list(objectList)
     names = list(objectList.keys()) if isinstance(objectList, dict) else None
-    uns = [unsharedList.get(nm) for nm in names] if isinstance(unsharedList, dict) else list(unsharedList)
+    if isinstance(unsharedList, dict):
+        if names is None:
+            raise ValueError("unsharedList is a dict but objectList is not: name the datasets in both, or pass two lists")
+        uns = [unsharedList.get(nm) for nm in names]
+    else:
+        uns = list(unsharedList)
+    if len(uns) != len(mats):
+        raise ValueError("unsharedList must have one entry (or None) per dataset")
     m = mats[0].shape[0]
     n_list = [x.shape[1] for x in mats]
     if min(n_list) < k:

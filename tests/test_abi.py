@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -77,3 +78,41 @@ def test_wrapper_validation_messages():
         liger_b200.runINMF({"a": E, "b": None}, k=5)
     with pytest.raises(ValueError, match="No scaled data for unshared feature"):
         liger_b200.run_uinmf_list([E, E], [None, None], k=5)
+
+
+def _build_cabi(tmp_path):
+    """gcc (plain C, -std=c99 -pedantic) against include/liger_b200.h, linked to the in-tree shared library."""
+    from liger_b200 import _ffi
+    exe = str(tmp_path / "test_cabi")
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "test_cabi.c"), "-o", exe, "-L", libdir, "-lliger_b200",
+                    f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    return exe
+
+
+def test_c_caller_without_gpu(tmp_path):
+    """The ABI from C (not ctypes): header compiles as C99, argument errors, R RNG known answer, no-device error."""
+    exe = _build_cabi(tmp_path)
+    r = subprocess.run([exe, "nogpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "cabi nogpu ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_caller_on_gpu(tmp_path):
+    """A C program runs a small iNMF (explicit and in-library inits), bppnnls_prod and objErr_i through the ABI and
+    sees malformed row indices rejected with LGR_ERR_INVALID."""
+    exe = _build_cabi(tmp_path)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "cabi gpu ok" in r.stdout
+
+
+def test_uinmf_list_pairing_is_validated():
+    import liger_b200
+    E = sp.random(30, 40, 0.3, format="csc", random_state=0)
+    with pytest.raises(ValueError, match="unsharedList is a dict"):
+        liger_b200.run_uinmf_list([E, E], {"a": E}, k=5)
+    with pytest.raises(ValueError, match="one entry"):
+        liger_b200.run_uinmf_list([E, E], [E], k=5)

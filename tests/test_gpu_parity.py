@@ -149,6 +149,83 @@ def test_inmf_synthetic_ragged(k, ns, m):
     assert np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"]) < TOL_OBJ
 
 
+@pytest.mark.parametrize("name,d,n,m,k,lam,niter", [
+    ("C3-mini", 8, 3000, 2000, 30, 5.0, 6),      # gt = 1000, ngt = 2, KP = 32: the geometry bench.py runs at C3
+    ("C4-mini", 4, 2000, 3000, 50, 5.0, 6),      # KP = 64, gt = 500, ngt = 6, register -> warp NNLS hand-over (k = 50)
+    ("C3-ragged", 3, 2777, 2000, 30, 2.0, 4),    # cell count not a multiple of any block size, other lambda
+])
+def test_inmf_multi_gene_tile_geometry(name, d, n, m, k, lam, niter):
+    """The code path the benchmark runs: m > 1024 (k <= 32) / m > 512 (k > 32) makes k_spmm_ltx_tiled walk several gene
+    tiles per cell block (mbarrier phase flips, partial B rows accumulated across tiles).  From identical inits against
+    the FP64 C oracle, with the north-star gates: factors <= 1e-3, trajectory <= 1e-4, zero patterns."""
+    import liger_b200
+    from liger_b200 import synthetic as syn
+    Es, _ = syn.make_numpy(d, n, m, k, block=1000, seed=31 + d)
+    W0, V0, _, _ = orc.seeded_init(1, m, k, [n] * d)
+    out = liger_b200.inmf(Es, k=k, lambda_=lam, niter=niter, Winit=W0, Vinit=V0, trajectory=True)
+    ref = c_oracle.inmf(Es, k, lam, niter, W0, V0, trajectory=True)
+    _check(out, ref)
+    assert np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"]) < TOL_OBJ
+    assert abs(out["objErr"] - ref["objErr"]) < TOL_OBJ * ref["objErr"]
+    assert out["timings"]["nnls_unconverged"] == 0
+
+
+def test_uinmf_c5_shape_in_miniature():
+    """C5 in miniature: 2 datasets, 2000 shared + 1000 unshared genes each, k = 30, per-dataset lambda -- stacked rows
+    (3000) walk three gene tiles; UINMF parity is unpinned in the reference, so: oracle from identical inits + the
+    documented objective (R/integration.R:1109-1113) decreasing monotonically."""
+    import liger_b200
+    from liger_b200 import synthetic as syn
+    d, n, m, u, k = 2, 2500, 2000, 1000, 30
+    Es, Ps = syn.make_numpy(d, n, m, k, u=u, block=1250, seed=77)
+    lam = [5.0, 2.0]
+    W0, V0, U0, _ = orc.seeded_init(1, m, k, [n] * d, [u] * d)
+    out = liger_b200.uinmf(Es, Ps, k=k, lambda_=lam, niter=6, Winit=W0, Vinit=V0, Uinit=U0, trajectory=True)
+    ref = c_oracle.inmf(Es, k, lam, 6, W0, V0, Ps=Ps, Uinit=U0, trajectory=True)
+    _check(out, ref, u=True)
+    assert np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"]) < TOL_OBJ
+    assert np.all(np.diff(out["traj"]) < 0)
+
+
+def test_inmf_null_inits_draw_the_seeded_stream(pbmc):
+    """RcppPlanc::inmf(..., Hinit = NULL, Vinit = NULL, Winit = NULL) (R/suggestK.R:78-88): the library draws W, V_i from R's
+    Mersenne-Twister stream in .runINMF.list's order, so seed = 1 lands on the reference's golden factors."""
+    import liger_b200
+    g = pbmc["golden"]
+    out = liger_b200.inmf(pbmc["Es"], k=20, lambda_=5.0, niter=30, Winit=None, Vinit=None, seed=1)
+    rows = g["golden_rows"]
+    assert rel(out["W"][rows], g["golden_W"]) < 5e-5
+    for i, n in enumerate(pbmc["names"]):
+        assert rel(out["H"][i].T, g[f"golden_H_{n}"]) < 5e-5
+    other = liger_b200.inmf(pbmc["Es"], k=20, lambda_=5.0, niter=30, Winit=None, Vinit=None, seed=2)
+    assert rel(other["W"], out["W"]) > 1e-3                      # another seed, another local optimum
+
+
+def test_pageable_and_pinned_host_buffers_agree():
+    """Inputs in pageable memory (what R hands over) go through the bounce ring of lgr_stage.cu in 4 MB chunks on four
+    threads (here: 24 MB of values = 6 chunks), outputs come back the same way; page-locked buffers are copied directly.
+    Same factors either way, and equal to the oracle's."""
+    import liger_b200
+    from liger_b200 import synthetic as syn
+    from liger_b200.api import pinned_empty
+    n, m, k = 30000, 2000, 30
+    Es, _ = syn.make_numpy(1, n, m, k, block=5000, seed=3)
+    E = Es[0]
+    assert E.data.nbytes > 5 * (4 << 20)
+    W0, V0, _, _ = orc.seeded_init(1, m, k, [n])
+    a = liger_b200.inmf([E], k=k, lambda_=5.0, niter=2, Winit=W0, Vinit=V0)                       # pageable in and out
+    pin = []
+    for arr in (E.indptr, E.indices, E.data):
+        h = pinned_empty(arr.shape, arr.dtype)
+        h[...] = arr
+        pin.append(h)
+    b = liger_b200.inmf([(pin[0], pin[1], pin[2], E.shape)], k=k, lambda_=5.0, niter=2, Winit=W0, Vinit=V0,
+                        pinned_outputs=True)
+    assert rel(a["W"], b["W"]) < 1e-5 and rel(a["H"][0], b["H"][0]) < 1e-5 and rel(a["V"][0], b["V"][0]) < 1e-5
+    ref = c_oracle.inmf([E], k, 5.0, 2, W0, V0)
+    _check(a, ref)
+
+
 def test_register_nnls_equals_shared_memory_nnls(pbmc):
     """The two H-solve kernels (register-resident, lgr_nnls_reg.cu; shared-memory factor, lgr_nnls.cu) solve the same
     strictly convex problems: same zero patterns away from degenerate coordinates, values to fp32 rounding."""
