@@ -66,6 +66,16 @@ typedef struct lgr_csc {
     const void* values;    /* nnz */
     int32_t value_dtype;   /* lgr_dtype */
     int32_t location;      /* 0: host pointers; LGR_CSC_DEVICE: device pointers (views returned by lgr_prep_scaled_view) */
+    /* Optional count structure (both NULL = none).  The caller asserts that every stored value is
+           values[t] = count * row_scale[row] * col_scale[col]      with an integer count in 1..256,
+       which is what rliger's scaleData is: normalize() divides a count by its cell's library size (col_scale = 1 / colSums,
+       R/preprocess.R:604) and scaleNotCenter() divides by the gene's root mean square (row_scale = 1 / rms,
+       src/data_processing.cpp:42-58).  The library verifies the assertion entry by entry (LGR_ERR_INVALID if it does not
+       hold) and then runs the two sweeps over X as dense-tile tensor-core contractions (csrc/lgr_dense.cu) instead of the
+       shared-memory gathers.  Same results to fp32 rounding.  Used for k <= 32 without unshared blocks; ignored otherwise.
+       row_scale: nrow doubles, col_scale: ncol doubles, host or device like the other arrays. */
+    const double* row_scale;
+    const double* col_scale;
 } lgr_csc;
 #define LGR_CSC_DEVICE 1
 
@@ -84,6 +94,7 @@ typedef struct lgr_csc {
                                      off by default */
 #define LGR_FLAG_LEGACY_NNLS 0x20u /* verification only: run the H solves with the shared-memory-factor NNLS kernel
                                      (lgr_nnls.cu) instead of the register-resident one (lgr_nnls_reg.cu, k <= 32) */
+#define LGR_FLAG_NO_DENSE 0x40u    /* ignore row_scale / col_scale: always run the gather sweeps */
 #define LGR_FLAG_LOCAL_SHARD 0x8u /* world > 1: E/P already hold only THIS rank's cells (one process per GPU, each
                                      with its own shard); without it every rank passes the full matrices and the
                                      library takes columns [n*rank/world, n*(rank+1)/world) */

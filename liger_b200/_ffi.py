@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libliger_b200.so")
 
 LGR_F64, LGR_F32 = 0, 1
 FLAG_TRAJECTORY, FLAG_COLD_START, FLAG_PINNED_IO, FLAG_LOCAL_SHARD, FLAG_TENSOR_U, FLAG_LEGACY_NNLS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+FLAG_NO_DENSE = 0x40
 STATUS = {0: "OK", 1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "NCCL", 5: "ALLOC", 6: "INTERRUPT"}
 
 c_double_p = C.POINTER(C.c_double)
@@ -19,7 +20,8 @@ c_uint64_p = C.POINTER(C.c_uint64)
 
 class lgr_csc(C.Structure):
     _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("colptr", c_int32_p), ("rowidx", c_int32_p),
-                ("values", C.c_void_p), ("value_dtype", C.c_int32), ("location", C.c_int32)]
+                ("values", C.c_void_p), ("value_dtype", C.c_int32), ("location", C.c_int32),
+                ("row_scale", c_double_p), ("col_scale", c_double_p)]
 
 
 INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)

@@ -78,6 +78,20 @@ class DeviceCsc:
         self.shape = (int(struct.nrow), int(struct.ncol))
 
 
+class CountScaled:
+    """scaleData together with its count structure  X[g, c] = count[g, c] * row_scale[g] * col_scale[c]  (integer counts
+    in 1..256; row_scale = 1 / row rms of scaleNotCenter, col_scale = 1 / library size of normalize).  The library verifies
+    the structure on upload and then runs the two sweeps over X on the tensor cores (csrc/lgr_dense.cu)."""
+
+    def __init__(self, mat, row_scale, col_scale):
+        self.mat = mat
+        self.row_scale = np.ascontiguousarray(row_scale, dtype=np.float64)
+        self.col_scale = np.ascontiguousarray(col_scale, dtype=np.float64)
+        self.shape = mat.shape if hasattr(mat, "shape") else tuple(mat[3])
+        if self.row_scale.shape != (self.shape[0],) or self.col_scale.shape != (self.shape[1],):
+            raise ValueError("row_scale / col_scale must have one entry per row / column")
+
+
 class _Csc:
     """Keeps the numpy buffers of one dgCMatrix-like input alive and exposes an lgr_csc view."""
 
@@ -87,6 +101,10 @@ class _Csc:
             self.shape = mat.shape
             self.struct = mat.struct
             return
+        scales = None
+        if isinstance(mat, CountScaled):
+            scales = mat
+            mat = mat.mat
         if sp.issparse(mat):
             m = mat.tocsc()
             indptr, indices, data, shape = m.indptr, m.indices, m.data, m.shape
@@ -105,6 +123,10 @@ class _Csc:
         self.shape = (int(shape[0]), int(shape[1]))
         self.struct = lgr_csc(self.shape[0], self.shape[1], self.indptr.ctypes.data_as(c_int32_p),
                               self.indices.ctypes.data_as(c_int32_p), self.data.ctypes.data_as(C.c_void_p), dt, 0)
+        if scales is not None:
+            self.scales = scales
+            self.struct.row_scale = _dp(scales.row_scale)
+            self.struct.col_scale = _dp(scales.col_scale)
 
 
 class _Args:
@@ -216,7 +238,7 @@ class _Out:
 
 def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
          trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False, tensor_u=False,
-         rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False, seed=1, pinned_io=False):
+         rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False, seed=1, pinned_io=False, no_dense=False):
     """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
 
     Multi-GPU (one process per GPU): pass `rank`, `world`, the `nccl_id` created by rank 0 (nccl_unique_id()) and
@@ -234,7 +256,8 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
     # Mersenne-Twister stream seeded with `seed`, in .runINMF.list's order
     flags = ((_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0) |
              (_ffi.FLAG_TENSOR_U if tensor_u else 0) | (0x8 if (local_shard and world > 1) else 0) |
-             (_ffi.FLAG_LEGACY_NNLS if legacy_nnls else 0) | (_ffi.FLAG_PINNED_IO if pinned_io else 0))
+             (_ffi.FLAG_LEGACY_NNLS if legacy_nnls else 0) | (_ffi.FLAG_PINNED_IO if pinned_io else 0) |
+             (_ffi.FLAG_NO_DENSE if no_dense else 0))
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device, rank=rank, world=world,
               nccl_id=nccl_id, init_seed=seed)
     o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs)

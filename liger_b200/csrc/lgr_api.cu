@@ -88,6 +88,7 @@ struct Dataset {
     DBuf<unsigned long long> hmask, vmask;
     DBuf<double> V, CtBv;
     size_t b_off = 0, r_off = 0;
+    DenseLayout dl;   // dense-tile path (count-structured X)
 };
 
 }  // namespace
@@ -120,6 +121,12 @@ struct lgr_ctx {
     DBuf<float> Bbuf, Ubuf, Rarena;
     DBuf<NnlsGroup> grpT;      // tensor-core U = B P launch (tile offsets)
     long long tilesT = 0;
+    bool dense = false;        // the two sweeps run as dense-tile tcgen05 contractions (lgr_dense.cu)
+    int dense_mask = 3;        // developer knob LGR_DENSE_MASK: bit 0 = B sweep dense, bit 1 = R sweep dense
+    std::vector<DenseDs> dds_host;
+    DBuf<DenseDs> dds_dev;
+    int k1_tiles = 0, gh_blocks = 0;
+    long long k2_flat = 0;
     bool use_tc = false;
     bool fuse_u = false;       // U = B P in the tcgen05 epilogue of k_spmm_ltx_tiled (default on)
     DBuf<double> ctc_arena;   // per NNLS group: CtC and CtC^-1 (2 x KP x KP fp64), groups = H_0..H_d-1, V_0..V_d-1, W
@@ -233,7 +240,7 @@ struct StagedCsc {
     int base = 0;             // first entry of the shard in the caller's arrays (column pointers are rebased on the device)
     DBuf<int> colptr, rowidx;
     DBuf<float> val;
-    DBuf<double> val64;
+    DBuf<double> val64, rs64, cs64;   // row / column scale of the count structure (dense path)
     size_t nnz = 0;
     cudaEvent_t done = nullptr;
     ~StagedCsc() {
@@ -242,7 +249,7 @@ struct StagedCsc {
 };
 // Runs on the staging thread (its allocation stream is the copy stream, so the buffers need no cross-stream hand-over
 // before the copies; the compute stream picks them up behind S.done).
-void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs, bool pinned_promise) {
+void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs, bool pinned_promise, bool want_scales) {
     const int n = c1 - c0;
     const bool on_device = M.location == LGR_CSC_DEVICE;   // a view of resident data (lgr_prep_scaled_view)
     int base = 0, last = 0;
@@ -273,6 +280,12 @@ void stage_csc(const lgr_csc& M, int c0, int c1, StagedCsc& S, cudaStream_t cs, 
             copy_in(S.val.p, static_cast<const float*>(M.values) + base, S.nnz * sizeof(float), cs, direct);
         else
             copy_in(S.val64.p, static_cast<const double*>(M.values) + base, S.nnz * sizeof(double), cs, direct);
+    }
+    if (want_scales) {
+        S.rs64.alloc((size_t)M.nrow);
+        S.cs64.alloc((size_t)n);
+        copy_in(S.rs64.p, M.row_scale, (size_t)M.nrow * sizeof(double), cs, direct);
+        copy_in(S.cs64.p, M.col_scale + c0, (size_t)n * sizeof(double), cs, direct);
     }
     LGR_CUDA(cudaEventRecord(S.done, cs));
 }
@@ -376,7 +389,14 @@ void run_prep(lgr_ctx* c) {
 void run_stats(lgr_ctx* c) {  // R = X H, G = H^T H (+ all-reduce)
     c->Rarena.zero(c->st);
     c->Garena.zero(c->st);
-    {
+    if (c->dense && (c->dense_mask & 2)) {
+        {
+            Timed t(c, "k_gram_h");
+            launch_gram_h(c->dds_dev.p, c->d, c->gh_blocks, c->k, c->st);
+        }
+        Timed t(c, "k_dense_xh");
+        launch_dense_xh(c->dds_dev.p, c->d, c->k2_flat, c->num_sms, c->st);
+    } else {
         Timed t(c, "k_spmm_xh");
         launch_spmm_xh(c->ds_dev.p, c->d, c->xh_tiles, c->k, c->kp, c->tc, c->st);
     }
@@ -438,7 +458,10 @@ void iterate(lgr_ctx* c, int niter, double* traj_host, double* final_obj = nullp
             Timed t(c, "k_gram_inv");   // CtC and CtC^-1 of the H solves (the fused U = B P epilogue of K1 reads CtC^-1)
             launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
         }
-        {
+        if (c->dense && (c->dense_mask & 1)) {
+            Timed t(c, "k_dense_ltx");
+            launch_dense_ltx(c->dds_dev.p, c->d, c->k1_tiles, c->num_sms, c->st);
+        } else {
             Timed t(c, "k_spmm_ltx");
             launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->fuse_u, c->st);
         }
@@ -664,6 +687,17 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         check_block(a->E[i], a->m, a->E[i].ncol, "E[i]");
         if (a->P && a->P[i].nrow > 0) check_block(a->P[i], a->P[i].nrow, a->E[i].ncol, "P[i]");
     }
+    {   // dense-tile sweeps: every block carries a verified-on-upload count structure, k <= 32, no unshared blocks
+        bool ok = c->kp == 32 && !(c->flags & (LGR_FLAG_NO_DENSE | LGR_FLAG_TENSOR_U | LGR_FLAG_LEGACY_NNLS)) && !getenv("LGR_NO_DENSE");
+        for (int i = 0; i < c->d && ok; ++i) {
+            ok = a->E[i].row_scale && a->E[i].col_scale;
+            if (a->P && a->P[i].nrow > 0) ok = false;
+        }
+        c->dense = ok;
+        if (const char* e = getenv("LGR_DENSE_MASK")) c->dense_mask = atoi(e) & 3;
+        if (c->dense_mask == 0) c->dense = false;
+    }
+    const bool dense = c->dense;
     CopyStream cstream;   // declared before the staged buffers: they are allocated (and freed) in its stream order
     std::vector<StagedCsc> stagedE(c->d), stagedP(c->d);
     struct StageSync {
@@ -681,8 +715,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
                 const int n_full = (int)a->E[i].ncol;
                 const int s0 = local ? 0 : (int)((int64_t)n_full * c->rank / c->world);
                 const int s1 = local ? n_full : (int)((int64_t)n_full * (c->rank + 1) / c->world);
-                stage_csc(a->E[i], s0, s1, stagedE[i], cstream.s, pinned_io);
-                if (a->P && a->P[i].nrow > 0) stage_csc(a->P[i], s0, s1, stagedP[i], cstream.s, pinned_io);
+                stage_csc(a->E[i], s0, s1, stagedE[i], cstream.s, pinned_io, dense);
+                if (a->P && a->P[i].nrow > 0) stage_csc(a->P[i], s0, s1, stagedP[i], cstream.s, pinned_io, false);
                 {
                     std::lock_guard<std::mutex> g(sync.mu);
                     sync.staged = i + 1;
@@ -747,14 +781,28 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
             dev_stack_csc(D.n, SE.colptr.p, SE.rowidx.p, SE.val.p, SP.colptr.p, SP.rowidx.p, SP.val.p, m, D.colptr.p, D.rowidx.p,
                           D.val.p, c->st);
         }
-        const int ntiles = (D.n + c->tc - 1) / c->tc;
-        (void)ntiles;
-        // the two padded tile formats of X (lgr_spmm.cu); the plain CSC upload is dropped afterwards
-        dev_build_padded(1, D.n, D.rows, c->tc, kp / 4, 0, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.ttag, D.tval, c->st);
-        tr.mark("build cell-tiled CSR");
-        D.ngt = (D.rows + c->gt - 1) / c->gt;
-        dev_build_padded(0, D.n, D.rows, c->gt, kp / 4, c->cb, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.ctag, D.cval, c->st);
-        tr.mark("build gene-tiled CSC");
+        if (dense) {
+            // count structure: X = N * rs * cs, verified entry by entry while the two entry streams are built
+            D.dl.rs.alloc((size_t)D.rows);
+            D.dl.cs.alloc((size_t)std::max(D.n, 1));
+            dev_f64_to_f32(SE.rs64.p, D.dl.rs.p, (size_t)D.rows, c->st);
+            dev_f64_to_f32(SE.cs64.p, D.dl.cs.p, (size_t)D.n, c->st);
+            dense_build(D.n, D.rows, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.dl.rs.p, D.dl.cs.p, D.dl, bad_rows.p, c->st);
+            int hbad = 0;
+            LGR_CUDA(cudaMemcpyAsync(&hbad, bad_rows.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+            LGR_REQUIRE(hbad == 0, "E[i]: row_scale / col_scale do not factor the values into integer counts in 1..256 "
+                                   "(pass NULL scales, or LGR_FLAG_NO_DENSE, for general matrices)");
+            tr.mark("build dense entry streams");
+        }
+        if (!dense || c->dense_mask != 3) {
+            // the two padded tile formats of X (lgr_spmm.cu); the plain CSC upload is dropped afterwards
+            dev_build_padded(1, D.n, D.rows, c->tc, kp / 4, 0, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.tptr8, D.tcell, D.ttag, D.tval, c->st);
+            tr.mark("build cell-tiled CSR");
+            D.ngt = (D.rows + c->gt - 1) / c->gt;
+            dev_build_padded(0, D.n, D.rows, c->gt, kp / 4, c->cb, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.cptr8, D.crow, D.ctag, D.cval, c->st);
+            tr.mark("build gene-tiled CSC");
+        }
         dev_sumsq(D.val.p, D.nnz, c->sq.p + i, c->st);
         LGR_CUDA(cudaStreamSynchronize(c->st));
         D.colptr.release();
@@ -861,6 +909,36 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.VtV = c->gram_arena.p + (size_t)(2 * i + 1) * kp * kp;
         h.lambda = D.lambda;
         h.sqnorm = sq[i];
+        h.Asplit = c->dense ? D.dl.Asplit.p : nullptr;
+        h.rs = c->dense ? D.dl.rs.p : nullptr;
+        if (c->dense) {
+            DenseDs q;
+            memset(&q, 0, sizeof(q));
+            q.n = D.n;
+            q.rows = D.rows;
+            q.ntile1 = D.dl.ntile1;
+            q.nstage1 = D.dl.nstage1;
+            q.k1_tile_off = c->k1_tiles;
+            q.ngb = D.dl.ngb;
+            q.ncstage = D.dl.ncstage;
+            q.gh_blk_off = c->gh_blocks;
+            q.k2_flat_off = c->k2_flat;
+            q.seg1 = D.dl.seg1.p;
+            q.ent1 = D.dl.ent1.p;
+            q.Asplit = D.dl.Asplit.p;
+            q.seg2 = D.dl.seg2.p;
+            q.ent2 = D.dl.ent2.p;
+            q.rs = D.dl.rs.p;
+            q.cs = D.dl.cs.p;
+            q.B = h.B;
+            q.H = h.H;
+            q.R = h.R;
+            q.G = h.G;
+            c->k1_tiles += D.dl.ntile1;
+            c->gh_blocks += (D.n + dense_gram_tile() - 1) / dense_gram_tile();
+            c->k2_flat += (long long)D.dl.ngb * D.dl.ncstage;
+            c->dds_host.push_back(q);
+        }
         // H solve: CtC = LtL + lambda VtV, rhs = B (fp32), x = H
         sH[i] = GramSpec{h.LtL, h.VtV, 1.0, D.lambda, ctc(i), ctc(i) + kk, c->ok_arena.p + i};
         const float* upre = (c->use_tc || c->fuse_u) ? c->Ubuf.p + D.b_off : nullptr;
@@ -881,6 +959,10 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->prep_blocks = prep;
     c->colsH = bH;
     c->colsV = bV;
+    if (c->dense) {
+        c->dds_dev.alloc((size_t)c->d);
+        LGR_CUDA(cudaMemcpyAsync(c->dds_dev.p, c->dds_host.data(), sizeof(DenseDs) * c->d, cudaMemcpyHostToDevice, c->st));
+    }
     c->ds_dev.alloc((size_t)c->d);
     c->grpH.alloc((size_t)c->d);
     c->grpV.alloc((size_t)c->d);
@@ -1336,6 +1418,10 @@ struct PrepDataset {
     DBuf<double> sval64;
     DBuf<float> sval;
     bool scaled = false;
+    // count structure of scaleData (values = count / library size / row rms): handed to lgr_inmf with the device view so
+    // that the sweeps can run on the tensor cores (lgr_dense.cu); only when every raw value is an integer in 1..256
+    bool counts_ok = false;
+    DBuf<double> inv_lib, inv_rms;
 };
 struct lgr_prep {
     StreamHolder stream_holder;
@@ -1385,6 +1471,13 @@ int lgr_prep_create(int32_t d, const lgr_csc* raw, int32_t device, lgr_prep** ou
         LGR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
         LGR_CUDA(cudaStreamSynchronize(p->st));
         LGR_REQUIRE(hbad == 0, "row index out of range");
+        for (auto& D : p->ds) {
+            bad.zero(p->st);
+            prep_check_counts(D.nnz, D.val.p, bad.p, p->st);
+            LGR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+            LGR_CUDA(cudaStreamSynchronize(p->st));
+            D.counts_ok = hbad == 0;
+        }
         *out = p.release();
     });
 }
@@ -1395,7 +1488,10 @@ int lgr_prep_normalize(lgr_prep* p) {
         LGR_CUDA(cudaSetDevice(p->device));
         for (auto& D : p->ds) {
             if (D.normalized) continue;
-            prep_col_normalize(D.ncol, D.colptr.p, D.val.p, D.val.p, nullptr, p->st);
+            AllocStreamScope alloc_scope(p->st);
+            D.inv_lib.alloc((size_t)std::max(D.ncol, 1));
+            prep_col_normalize(D.ncol, D.colptr.p, D.val.p, D.val.p, D.inv_lib.p, p->st);
+            prep_reciprocal((size_t)D.ncol, D.inv_lib.p, D.inv_lib.p, p->st);
             D.normalized = true;
         }
         LGR_CUDA(cudaStreamSynchronize(p->st));
@@ -1450,6 +1546,8 @@ int lgr_prep_scale(lgr_prep* p, int32_t i, int64_t m, const int32_t* feature_row
         prep_subset_fill(D.ncol, D.colptr.p, D.rowidx.p, D.val.p, dlut.p, D.scolptr.p, D.srow.p, sub.p, p->st);
         prep_scale_rows((int)m, D.ncol, D.snnz, D.srow.p, sub.p, D.sval64.p, rms.p, p->st);
         prep_f64_to_f32(D.sval64.p, D.sval.p, D.snnz, p->st);
+        D.inv_rms.alloc((size_t)m);
+        prep_reciprocal((size_t)m, rms.p, D.inv_rms.p, p->st);
         LGR_CUDA(cudaStreamSynchronize(p->st));
         D.scaled = true;
     });
@@ -1467,6 +1565,8 @@ int lgr_prep_scaled_view(lgr_prep* p, int32_t i, lgr_csc* view) {
         view->values = D.sval.p;
         view->value_dtype = LGR_F32;
         view->location = LGR_CSC_DEVICE;
+        view->row_scale = D.counts_ok ? D.inv_rms.p : nullptr;
+        view->col_scale = D.counts_ok ? D.inv_lib.p : nullptr;
     });
 }
 

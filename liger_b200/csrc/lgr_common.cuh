@@ -126,6 +126,33 @@ struct DsDev {
     double* VtV;    // KP x KP     V~^T V~
     double lambda;
     double sqnorm;  // ||[E;P]||_F^2 (global, after all-reduce)
+    // dense-tile path (lgr_dense.cu): k_prep also writes the bf16 3-term split of rs[g] * L~[g, :] in the operand-slab
+    // image k_dense_ltx copies into shared memory (null in the gather path)
+    unsigned short* Asplit;
+    const float* rs;   // rows: row scale of the count factorisation X = N * rs * cs
+};
+
+// device-side description of one dataset for the dense-tile sweeps (lgr_dense.cu)
+struct DenseDs {
+    int n, rows;
+    int ntile1;       // 256-cell tiles (k_dense_ltx)
+    int nstage1;      // 64-gene stages
+    int k1_tile_off;  // first flat tile of this dataset
+    int ngb;          // 512-gene blocks (k_dense_xh)
+    int ncstage;      // 32-cell stages
+    int gh_blk_off;   // first flat block in k_gram_h
+    long long k2_flat_off;   // first flat (gene block, cell stage) index of this dataset
+    const int* seg1;
+    const unsigned int* ent1;
+    const unsigned short* Asplit;
+    const int* seg2;
+    const unsigned int* ent2;
+    const float* rs;   // rows
+    const float* cs;   // n
+    float* B;
+    const float* H;
+    float* R;
+    double* G;
 };
 
 // One batch of NNLS columns sharing a Gram matrix (gram / ginv / ok are produced by k_gram_inv)
@@ -209,6 +236,22 @@ void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot,
 size_t spmm_xh_smem(int kp, int tc);
 void kernels_init();  // opt-in shared memory attributes of every kernel, once per device (safe to call repeatedly)
 
+// dense-tile tensor-core sweeps (lgr_dense.cu)
+struct DenseLayout {
+    int ntile1 = 0, nstage1 = 0, ngb = 0, ncstage = 0;
+    DBuf<int> seg1, seg2;
+    DBuf<unsigned int> ent1, ent2;
+    DBuf<unsigned short> Asplit;
+    DBuf<float> rs, cs;
+};
+void dense_build(int n, int rows, const int* colptr, const int* rowidx, const float* val, size_t nnz, const float* rs, const float* cs,
+                 DenseLayout& out, int* bad, cudaStream_t st);
+void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st);
+void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st);
+void launch_gram_h(const DenseDs* ds, int nds, int total_blocks, int k, cudaStream_t st);
+int dense_gram_tile();
+void dense_init();
+
 // copies between caller host memory and the device (lgr_stage.cu): pageable buffers go through page-locked bounce buffers
 bool host_is_pinned(const void* p);
 void copy_in(void* dst, const void* src, size_t bytes, cudaStream_t cs, bool pinned_promise);
@@ -242,6 +285,8 @@ void prep_subset_fill(int ncol, const int* colptr, const int* rowidx, const doub
                       int* newrow, double* newx, cudaStream_t st);
 void prep_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
 void prep_check_rows(size_t nnz, const int* rowidx, int nrow, int* bad, cudaStream_t st);
+void prep_check_counts(size_t nnz, const double* x, int* bad, cudaStream_t st);
+void prep_reciprocal(size_t n, const double* in, double* out, cudaStream_t st);
 void dev_exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t st);   // lgr_layout.cu (cub)
 
 }  // namespace lgr

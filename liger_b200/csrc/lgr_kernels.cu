@@ -36,6 +36,19 @@ __global__ void __launch_bounds__(256) k_prep(const DsDev* __restrict__ ds, int 
                 l = v + (gr < D.m ? W[(size_t)gr * KP + f] : 0.0);
             }
             D.L[(size_t)gr * KP + f] = (float)l;
+            if (KP == 32 && D.Asplit) {
+                // operand-slab image of k_dense_ltx: [64-gene stage][k-step of 16][chunk of 8 genes][row 4 f + t][gene % 8],
+                // t = hi / mid / lo bf16 term of rs[g] * L~[g, f] (the three terms sum to the fp32 value exactly)
+                const float x = (float)l * D.rs[gr];
+                const unsigned xb = __float_as_uint(x), hb = xb & 0xFFFF0000u;
+                const float r1 = x - __uint_as_float(hb);
+                const unsigned mb = __float_as_uint(r1) & 0xFFFF0000u;
+                const float r2 = r1 - __uint_as_float(mb);
+                unsigned short* img = D.Asplit + ((size_t)(gr >> 6) * 16384 + ((gr >> 4) & 3) * 4096 + ((gr >> 3) & 1) * 2048 + (gr & 7) * 2) / 2;
+                img[(4 * f + 0) * 8] = (unsigned short)(hb >> 16);
+                img[(4 * f + 1) * 8] = (unsigned short)(mb >> 16);
+                img[(4 * f + 2) * 8] = (unsigned short)(__float_as_uint(r2) >> 16);
+            }
         }
         Ls[r][f] = l;
         Vs[r][f] = v;
@@ -211,6 +224,7 @@ void kernels_init() {
     nnls_wbig_init();
     spmm_init();
     tc_init();
+    dense_init();
     if (dev >= 0 && dev < 64) done[dev] = true;
 }
 

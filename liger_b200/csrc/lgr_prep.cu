@@ -182,6 +182,30 @@ void prep_subset_fill(int ncol, const int* colptr, const int* rowidx, const doub
     k_subset_fill<<<(unsigned)(((size_t)ncol * 32 + 255) / 256), 256, 0, st>>>(ncol, colptr, rowidx, x, lut, newptr, newrow, newx);
     LGR_CUDA(cudaGetLastError());
 }
+// raw counts usable by the dense-tile sweeps: every stored value an integer in 1..256 (exact in bf16)
+__global__ void __launch_bounds__(256) k_check_counts(size_t nnz, const double* __restrict__ x, int* __restrict__ bad) {
+    int b = 0;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += (size_t)gridDim.x * blockDim.x) {
+        const double v = x[t];
+        b |= !(v >= 1.0 && v <= 256.0 && v == rint(v));
+    }
+    if (b) atomicOr(bad, 1);
+}
+void prep_check_counts(size_t nnz, const double* x, int* bad, cudaStream_t st) {
+    if (!nnz) return;
+    k_check_counts<<<(int)std::min<size_t>((nnz + 255) / 256, 148 * 16), 256, 0, st>>>(nnz, x, bad);
+    LGR_CUDA(cudaGetLastError());
+}
+__global__ void k_reciprocal(size_t n, const double* __restrict__ in, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] == 0.0 ? 0.0 : 1.0 / in[i];
+}
+void prep_reciprocal(size_t n, const double* in, double* out, cudaStream_t st) {
+    if (!n) return;
+    k_reciprocal<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in, out);
+    LGR_CUDA(cudaGetLastError());
+}
+
 void prep_check_rows(size_t nnz, const int* rowidx, int nrow, int* bad, cudaStream_t st) {
     if (!nnz) return;
     k_check_rows<<<stream_grid(nnz), 256, 0, st>>>(nnz, rowidx, nrow, bad);

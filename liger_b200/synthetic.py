@@ -28,14 +28,16 @@ def _bisect_scale(mean_fn, density):
     return float(np.sqrt(lo * hi))
 
 
-def make_numpy(d, n_per, m, r, density=0.05, u=0, block=5000, seed=SEED):
-    """Returns (Es, Ps): lists of scipy CSC float64 (m x n_i) and (u x n_i) or None."""
+def make_numpy(d, n_per, m, r, density=0.05, u=0, block=5000, seed=SEED, return_scales=False):
+    """Returns (Es, Ps): lists of scipy CSC float64 (m x n_i) and (u x n_i) or None.
+    return_scales: also returns [(row_scale, col_scale)] per dataset for the shared block: E = counts * row_scale[:, None] *
+    col_scale[None, :] (1 / row rms, 1 / library size) -- the count structure liger_b200.CountScaled carries."""
     A = np.random.default_rng([seed, 999]).gamma(0.5, 1.0, (m, r))
     Au = [np.random.default_rng([seed, 999, i]).gamma(0.5, 1.0, (u, r)) if u else None for i in range(d)]
     B0 = np.random.default_rng([seed, 0, 0]).gamma(0.5, 1.0, (r, min(block, n_per)))
     rate0 = A @ B0
     s = _bisect_scale(lambda x: float(np.mean(1.0 - np.exp(-x * rate0))), density)
-    Es, Ps = [], []
+    Es, Ps, scales = [], [], []
     for i in range(d):
         cols_e, cols_p = [], []
         for b, c0 in enumerate(range(0, n_per, block)):
@@ -53,16 +55,20 @@ def make_numpy(d, n_per, m, r, density=0.05, u=0, block=5000, seed=SEED):
                 cols_p.append(sp.csc_matrix(Cu))
         E = sp.hstack(cols_e, format="csc")
         lib = np.asarray(E.sum(axis=0)).ravel()
-        Es.append(_scale(E, lib))
+        Xs, rms = _scale(E, lib, True)
+        Es.append(Xs)
+        scales.append((1.0 / rms, 1.0 / lib))
         if u:
             P = sp.hstack(cols_p, format="csc")
             Ps.append(_scale(P, lib))
         else:
             Ps.append(None)
+    if return_scales:
+        return Es, Ps, scales
     return Es, Ps
 
 
-def _scale(X, lib):
+def _scale(X, lib, return_rms=False):
     X = sp.csc_matrix(X, dtype=np.float64)
     X.data = X.data / np.repeat(lib, np.diff(X.indptr))
     n = X.shape[1]
@@ -74,6 +80,8 @@ def _scale(X, lib):
     out = sp.csc_matrix(Xr)
     out.eliminate_zeros()
     out.sort_indices()
+    if return_rms:
+        return out, rms
     return out
 
 
@@ -143,18 +151,19 @@ def make_torch(d, n_per, m, r, density=0.05, u=0, block=25000, seed=SEED, device
         vals = vals / rms[rows.long()]
         indptr = torch.zeros(n_per + 1, dtype=torch.int64, device=dev)
         indptr[1:] = torch.cumsum(cnt, 0)
-        return indptr, rows, vals, libs
+        return indptr, rows, vals, libs, rms
 
-    Es, Ps = [], []
+    Es, Ps, scales = [], [], []
     nnz = 0
     for i in range(d):
         Bs = []
-        indptr, rows, vals, libs = one(A, m, i, Bs, None)
+        indptr, rows, vals, libs, rms = one(A, m, i, Bs, None)
         nnz += int(rows.numel())
+        scales.append(((1.0 / rms).cpu().numpy(), (1.0 / torch.cat(libs).to(torch.float64)).cpu().numpy()))
         Es.append((host(indptr, torch.int32).numpy(), host(rows, torch.int32).numpy(),
                    host(vals, torch.float64 if vdt is np.float64 else torch.float32).numpy(), (m, n_per)))
         if u:
-            indptr, rows, vals, _ = one(Au[i], u, i, Bs, libs)
+            indptr, rows, vals, _, _ = one(Au[i], u, i, Bs, libs)
             nnz += int(rows.numel())
             Ps.append((host(indptr, torch.int32).numpy(), host(rows, torch.int32).numpy(),
                        host(vals, torch.float64 if vdt is np.float64 else torch.float32).numpy(), (u, n_per)))
@@ -164,7 +173,7 @@ def make_torch(d, n_per, m, r, density=0.05, u=0, block=25000, seed=SEED, device
     if dev.type == "cuda":
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
-    return Es, Ps, {"scale": s, "nnz": nnz, "density": nnz / float(d * n_per * (m + u))}
+    return Es, Ps, {"scale": s, "nnz": nnz, "density": nnz / float(d * n_per * (m + u)), "scales": scales}
 
 
 def to_scipy(t):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from liger_b200 import _ffi
     # sizes computed by hand from include/liger_b200.h (LP64)
-    assert ctypes.sizeof(_ffi.lgr_csc) == 48
+    assert ctypes.sizeof(_ffi.lgr_csc) == 64
     assert ctypes.sizeof(_ffi.lgr_timings) == 72
     assert ctypes.sizeof(_ffi.lgr_inmf_args) == 120
     assert ctypes.sizeof(_ffi.lgr_inmf_out) == 56 + 72

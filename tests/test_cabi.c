@@ -79,6 +79,7 @@ static int run_gpu(void) {
     int32_t *p[D], *ri[D];
     double* x[D];
     lgr_csc E[D];
+    memset(E, 0, sizeof(E));   /* optional fields (row_scale / col_scale) = NULL */
     for (int i = 0; i < D; ++i) {
         toy_csc(M, n[i], 17u + (unsigned)i, &p[i], &ri[i], &x[i]);
         E[i].nrow = M;

@@ -226,6 +226,67 @@ def test_pageable_and_pinned_host_buffers_agree():
     _check(a, ref)
 
 
+# ----------------------------------------------------------------------------------------------
+# dense-tile tensor-core sweeps (csrc/lgr_dense.cu): count-structured X = counts * row_scale * col_scale
+# ----------------------------------------------------------------------------------------------
+def _count_scaled(d, n, m, r, seed, block=1000):
+    import liger_b200
+    from liger_b200 import synthetic as syn
+    Es, _, scales = syn.make_numpy(d, n, m, r, block=block, seed=seed, return_scales=True)
+    return Es, [liger_b200.CountScaled(E, rs, cs) for E, (rs, cs) in zip(Es, scales)]
+
+
+@pytest.mark.parametrize("name,d,n,m,k,niter", [
+    ("C3-mini", 4, 3000, 2000, 30, 6),       # 32 gene stages, 12 cell tiles per dataset, 4 gene blocks
+    ("ragged", 3, 1111, 333, 20, 5),         # n not a multiple of 256 / 32, m not a multiple of 64
+    ("tiny", 2, 40, 70, 8, 4),               # less than one tile in every dimension
+    ("wide", 1, 20000, 1100, 32, 3),         # more tiles than SMs x 1, k = 32 (full factor width), 3 gene blocks
+])
+def test_dense_tensor_core_sweeps_match_oracle_and_gather(name, d, n, m, k, niter):
+    """The tcgen05 sweeps (bf16 count tiles x 3-term bf16 split of the scaled factor, fp32 TMEM accumulators) against the
+    FP64 C oracle from identical inits (north-star gates), and against the fp32 gather sweeps on the same input."""
+    import liger_b200
+    Es, Cs = _count_scaled(d, n, m, min(k, 10), seed=100 + d)
+    W0, V0, _, _ = orc.seeded_init(1, m, k, [n] * d)
+    out = liger_b200.inmf(Cs, k=k, lambda_=5.0, niter=niter, Winit=W0, Vinit=V0, trajectory=True)
+    ref = c_oracle.inmf(Es, k, 5.0, niter, W0, V0, trajectory=True)
+    _check(out, ref)
+    assert np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"]) < TOL_OBJ
+    gat = liger_b200.inmf(Cs, k=k, lambda_=5.0, niter=niter, Winit=W0, Vinit=V0, no_dense=True)
+    assert rel(out["W"], gat["W"]) < 2e-5 and max(rel(a, b) for a, b in zip(out["H"], gat["H"])) < 2e-5
+    assert out["timings"]["nnls_unconverged"] == 0
+
+
+def test_dense_sweeps_large_counts_and_rejected_scales():
+    """Counts up to 256 are exact in bf16; a count of 257, a non-integer ratio or wrong scales must be rejected with
+    LGR_ERR_INVALID (the library verifies the structure entry by entry), never silently rounded."""
+    import liger_b200
+    from liger_b200._ffi import LigerB200Error
+    rng = np.random.default_rng(11)
+    m, n, k = 200, 900, 12
+    N = sp.random(m, n, 0.08, format="csc", random_state=4, data_rvs=lambda s: rng.integers(1, 257, s).astype(float))
+    N.data[:5] = 256.0
+    rs = 1.0 / (0.5 + rng.random(m))
+    cs = 1.0 / (100.0 + 50.0 * rng.random(n))
+    X = sp.csc_matrix(N.multiply(rs[:, None]).multiply(cs[None, :]))
+    W0, V0, _, _ = orc.seeded_init(2, m, k, [n])
+    out = liger_b200.inmf([liger_b200.CountScaled(X, rs, cs)], k=k, lambda_=5.0, niter=4, Winit=W0, Vinit=V0, trajectory=True)
+    ref = c_oracle.inmf([X], k, 5.0, 4, W0, V0, trajectory=True)
+    _check(out, ref)
+    assert np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"]) < TOL_OBJ
+    bad = N.copy()
+    bad.data[7] = 257.0
+    Xb = sp.csc_matrix(bad.multiply(rs[:, None]).multiply(cs[None, :]))
+    with pytest.raises(LigerB200Error) as e:
+        liger_b200.inmf([liger_b200.CountScaled(Xb, rs, cs)], k=k, niter=1, Winit=W0, Vinit=V0)
+    assert e.value.code == 1 and "integer counts" in str(e.value)
+    with pytest.raises(LigerB200Error):
+        liger_b200.inmf([liger_b200.CountScaled(X, rs * 1.37, cs)], k=k, niter=1, Winit=W0, Vinit=V0)
+    # the same matrix without the structure runs through the gather sweeps
+    out2 = liger_b200.inmf([Xb], k=k, lambda_=5.0, niter=2, Winit=W0, Vinit=V0)
+    assert np.isfinite(out2["W"]).all()
+
+
 def test_register_nnls_equals_shared_memory_nnls(pbmc):
     """The two H-solve kernels (register-resident, lgr_nnls_reg.cu; shared-memory factor, lgr_nnls.cu) solve the same
     strictly convex problems: same zero patterns away from degenerate coordinates, values to fp32 rounding."""
