@@ -40,6 +40,7 @@ CONFIGS = {
     "tiny": dict(d=2, n_per=3000, m=500, k=20, density=0.05),
 }
 LAMBDA = 5.0
+NO_DENSE = False
 
 
 def peaks():
@@ -142,7 +143,8 @@ def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
     of this same command (profiles/r*_traffic.json, written by scripts/make_profiles.py); None if not captured."""
     import glob
-    alias = {"k_nnls_H": "k_nnls_reg", "k_spmm_ltx": "k_spmm_ltx_tiled", "k_spmm_xh": "k_spmm_xh"}
+    alias = {"k_nnls_H": "k_nnls_reg", "k_spmm_ltx": "k_spmm_ltx_tiled", "k_spmm_xh": "k_spmm_xh",
+             "k_dense_ltx": "k_dense_ltx", "k_dense_xh": "k_dense_xh"}
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
     if not files or kernel not in alias:
         return None
@@ -262,7 +264,10 @@ class Job:
         rng = liger_b200.RRandom(1)       # R's set.seed(1) stream, the draw order of .runINMF.list
         self.W0 = np.abs(rng.runif(m * k, 0, 2)).reshape((m, k), order="F")
         self.V0 = [np.abs(rng.runif(m * k, 0, 2)).reshape((m, k), order="F") for _ in range(d)]
-        self.ctx = liger_b200.Context(self.Es, k, LAMBDA, self.W0, self.V0, device=local_rank, rank=rank, world=world,
+        # scaleData with its count structure (values = count * 1/rms[gene] * 1/library size[cell]): the library verifies it
+        # on upload and runs the two sweeps over X on the tensor cores; --no-dense runs the fp32 gather sweeps instead
+        self.mats = self.Es if NO_DENSE else [liger_b200.CountScaled(e, rs, cs) for e, (rs, cs) in zip(self.Es, self.info["scales"])]
+        self.ctx = liger_b200.Context(self.mats, k, LAMBDA, self.W0, self.V0, device=local_rank, rank=rank, world=world,
                                       nccl_id=nccl_id, flags=0x8 if world > 1 else 0)
 
     def close(self):
@@ -389,7 +394,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the weak-scaling / C4 extras at N > 1")
+    ap.add_argument("--no-dense", action="store_true", help="pass scaleData without its count structure: fp32 gather sweeps")
     args = ap.parse_args()
+    global NO_DENSE
+    NO_DENSE = args.no_dense
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
     cfg = dict(CONFIGS[args.config])
@@ -447,9 +455,11 @@ def main():
     #      median of 3 calls (the PCIe copy rate of a fresh box varies from call to call) ----
     e2e = None
     Es, W0, V0 = job.Es, job.W0, job.V0
+    scales = job.info["scales"]
+    wrap = (lambda mats: mats) if NO_DENSE else (lambda mats: [liger_b200.CountScaled(e, rs, cs) for e, (rs, cs) in zip(mats, scales)])
     if not args.no_e2e:
         def call(mats, pinned):
-            return liger_b200.inmf(mats, k=k, lambda_=LAMBDA, niter=args.steps, Winit=W0, Vinit=V0, pinned_outputs=pinned,
+            return liger_b200.inmf(wrap(mats), k=k, lambda_=LAMBDA, niter=args.steps, Winit=W0, Vinit=V0, pinned_outputs=pinned,
                                    pinned_io=pinned, device=local_rank, rank=rank, world=world, nccl_id=nccl_id,
                                    local_shard=True)   # same unique id => the library reuses its communicator
 
@@ -470,6 +480,8 @@ def main():
         runs = series(Es, True, 3)
         dt, tms, obj_e, d2h = runs[len(runs) // 2]
         h2d = sum(e[0].nbytes + e[1].nbytes + e[2].nbytes for e in Es) + W0.nbytes * (d + 1)
+        if not NO_DENSE:
+            h2d += sum(rs.nbytes + cs.nbytes for rs, cs in scales)
         e2e = {"value": job.n_total * args.steps / dt, "unit": "cell*iter/s", "h2d_bytes_per_step": h2d * world / args.steps,
                "d2h_bytes_per_step": d2h * world / args.steps, "seconds": dt, "seconds_all_calls": [r[0] for r in runs],
                "timings_ms": tms, "objErr": obj_e, "host_memory": "page-locked",

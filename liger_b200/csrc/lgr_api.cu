@@ -109,6 +109,7 @@ struct StreamHolder {
 
 struct lgr_ctx {
     StreamHolder stream_holder;
+    StreamHolder copy_holder;   // upload copy stream: buffers allocated in its order may live as long as the context
     int d = 0, k = 0, kp = 32, m = 0, device = 0, rank = 0, world = 1, tc = 1024, cb = 512, gt = 1024, num_sms = 148;
     uint32_t flags = 0;
     int32_t init_seed = 0;
@@ -698,7 +699,11 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         if (c->dense_mask == 0) c->dense = false;
     }
     const bool dense = c->dense;
-    CopyStream cstream;   // declared before the staged buffers: they are allocated (and freed) in its stream order
+    // the copy stream belongs to the context: staged buffers are allocated (and later freed) in its stream order, and on an
+    // error path they are released by the context's destructor
+    struct { cudaStream_t s; } cstream{nullptr};
+    LGR_CUDA(cudaStreamCreateWithFlags(&cstream.s, cudaStreamNonBlocking));
+    c->copy_holder.s = cstream.s;
     std::vector<StagedCsc> stagedE(c->d), stagedP(c->d);
     struct StageSync {
         std::mutex mu;

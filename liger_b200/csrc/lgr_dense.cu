@@ -177,7 +177,7 @@ __device__ __forceinline__ unsigned char* align1k(unsigned char* p) {
 // =====================================================================================================================
 // k_dense_ltx:  B = L~^T X
 // =====================================================================================================================
-__global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* __restrict__ ds, int nds, int total_tiles) {
+__global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* __restrict__ ds, int nds, int total_tiles, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
     SmemLayout sm = carve(align1k(smem_dyn), K1_ASTAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                     const uint32_t a0 = smem_u32(sm.A + slot * K1_ASTAGE_BYTES), x0 = smem_u32(sm.X + slot * XSTAGE_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < K1_KS; ++ks)
-                        umma_bf16(tacc, umma_desc(a0 + ks * ATILE_BYTES, 128 * 16, 128), umma_desc(x0 + ks * XTILE_BYTES, TILE_N * 16, 128),
+                        if (!(dbg & 2)) umma_bf16(tacc, umma_desc(a0 + ks * ATILE_BYTES, 128 * 16, 128), umma_desc(x0 + ks * XTILE_BYTES, TILE_N * 16, 128),
                                   IDESC_BF16, (s | ks) != 0);
                     umma_commit(sm.empty + slot);   // frees the slot (A slabs and X tiles) when these MMAs have read it
                 }
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
             const int* __restrict__ seg = D.seg1 + (size_t)(tile - D.k1_tile_off) * D.nstage1;
             for (int s = 0; s < D.nstage1; ++s, ++it) {
                 if ((int)(it % NST) != slot) continue;
-                const int e0 = __ldg(seg + s), e1 = __ldg(seg + s + 1);
+                const int e0 = __ldg(seg + s), e1 = (dbg & 1) ? e0 : __ldg(seg + s + 1);
                 scatter_stage(S, D.ent1, e0, e1, xbase, sm.empty + slot, ((it / NST) & 1u) ^ 1u, gt, 1 + slot);
                 fence_async_smem();
                 __syncwarp();
@@ -337,7 +337,7 @@ __device__ __forceinline__ K2Pos k2_item(const DenseDs* __restrict__ ds, int nds
     return r;
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds, int nds, long long total_flat) {
+__global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds, int nds, long long total_flat, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
     SmemLayout sm = carve(align1k(smem_dyn), K2_ASTAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __
                     for (int ks = 0; ks < K2_KS; ++ks) {
                         const uint64_t ad = umma_desc(a0 + ks * ATILE_BYTES, 128 * 16, 128);
                         const uint32_t accum = (cs != P.cs0 || ks != 0) ? 1u : 0u;
+                        if (dbg & 2) continue;
                         umma_bf16(tmem0, ad, umma_desc(x0 + (ks * 2 + 0) * XTILE_BYTES, TILE_N * 16, 128), IDESC_BF16, accum);
                         umma_bf16(tmem0 + TILE_N, ad, umma_desc(x0 + (ks * 2 + 1) * XTILE_BYTES, TILE_N * 16, 128), IDESC_BF16, accum);
                     }
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __
             const int* __restrict__ seg = D.seg2 + (size_t)P.gb * D.ncstage;
             for (int cs = P.cs0; cs < P.cs1; ++cs, ++it) {
                 if ((int)(it % NST) != slot) continue;
-                const int e0 = __ldg(seg + cs), e1 = __ldg(seg + cs + 1);
+                const int e0 = __ldg(seg + cs), e1 = (dbg & 1) ? e0 : __ldg(seg + cs + 1);
                 scatter_stage(S, D.ent2, e0, e1, xbase, sm.empty + slot, ((it / NST) & 1u) ^ 1u, gt, 1 + slot);
                 fence_async_smem();
                 __syncwarp();
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __
 #pragma unroll
                 for (int j = 0; j < K2_KS * KSTEP; ++j) {
                     const int c = c0 + j;
-                    h[j] = c < D.n ? __ldg(D.H + (size_t)c * 32 + lane) * __ldg(D.cs + c) : 0.f;
+                    h[j] = (c < D.n && !(dbg & 4)) ? __ldg(D.H + (size_t)c * 32 + lane) * __ldg(D.cs + c) : 0.f;
                 }
                 mbar_wait(sm.empty + slot, ((it / NST) & 1u) ^ 1u);
 #pragma unroll
@@ -564,13 +565,15 @@ __global__ void __launch_bounds__(GH_THREADS) k_gram_h(const DenseDs* __restrict
 void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st) {
     if (total_tiles <= 0) return;
     const int grid = std::min(total_tiles, num_sms);
-    k_dense_ltx<<<grid, K1_WARPS * 32, dense_smem(K1_ASTAGE_BYTES), st>>>(ds, nds, total_tiles);
+    static const int dbg = getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0;   // developer knob: 1 no scatter, 2 no MMA, 4 no H loads
+    k_dense_ltx<<<grid, K1_WARPS * 32, dense_smem(K1_ASTAGE_BYTES), st>>>(ds, nds, total_tiles, dbg);
     LGR_CUDA(cudaGetLastError());
 }
 void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st) {
     if (total_flat <= 0) return;
     const int grid = (int)std::min<long long>(total_flat, num_sms);
-    k_dense_xh<<<grid, K2_WARPS * 32, dense_smem(K2_ASTAGE_BYTES), st>>>(ds, nds, total_flat);
+    static const int dbg = getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0;
+    k_dense_xh<<<grid, K2_WARPS * 32, dense_smem(K2_ASTAGE_BYTES), st>>>(ds, nds, total_flat, dbg);
     LGR_CUDA(cudaGetLastError());
 }
 void launch_gram_h(const DenseDs* ds, int nds, int total_blocks, int k, cudaStream_t st) {
