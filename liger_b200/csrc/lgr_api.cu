@@ -147,7 +147,11 @@ struct lgr_ctx {
     int (*interrupt)(void*) = nullptr;
     void* interrupt_user = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;   // one captured ANLS iteration
+    int graph_cold = -1;
+    int64_t graph_launches = 0;
     ~lgr_ctx() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (comm) nccl_destroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -392,8 +396,8 @@ void run_stats(lgr_ctx* c) {  // R = X H, G = H^T H (+ all-reduce)
     c->Garena.zero(c->st);
     if (c->dense && (c->dense_mask & 2)) {
         {
-            Timed t(c, "k_gram_h");
-            launch_gram_h(c->dds_dev.p, c->d, c->gh_blocks, c->k, c->st);
+            Timed t(c, "k_gram_tc");
+            launch_gram_h(c->dds_dev.p, c->d, c->gh_blocks, c->k, c->num_sms, c->st);
         }
         Timed t(c, "k_dense_xh");
         launch_dense_xh(c->dds_dev.p, c->d, c->k2_flat, c->num_sms, c->st);
@@ -427,6 +431,80 @@ void solve_f64(lgr_ctx* c, const NnlsGroup* grp, int ngroups, long long cols, in
     }
 }
 
+// One ANLS iteration: H_i for all i -> V_i (U_i) with the old W -> W with the new V_i.  Everything is enqueued on c->st
+// with no host synchronisation, so the sequence can be captured into a CUDA graph.
+void enqueue_iteration(lgr_ctx* c, int cold, double* obj_slot) {
+    std::unique_ptr<Span> phase(new Span(c, "h_phase"));
+    run_prep(c);
+    if (obj_slot) run_objective(c, obj_slot);   // objective of the PREVIOUS iterate (uses the fresh L~ Grams)
+    // ---- H phase ----
+    {
+        Timed t(c, "k_gram_inv");   // CtC and CtC^-1 of the H solves (the fused U = B P epilogue of K1 reads CtC^-1)
+        launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
+    }
+    if (c->dense && (c->dense_mask & 1)) {
+        Timed t(c, "k_dense_ltx");
+        launch_dense_ltx(c->dds_dev.p, c->d, c->k1_tiles, c->num_sms, c->st);
+    } else {
+        Timed t(c, "k_spmm_ltx");
+        launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->fuse_u, c->st);
+    }
+    if (c->use_tc) {
+        Timed t(c, "k_pb_tc");
+        launch_pb_tc(c->grpT.p, c->d, c->tilesT, c->kp, c->num_sms, c->st);
+    }
+    {
+        Timed t(c, "k_nnls_H");
+        // fp32, k <= 32: register-resident solver; groups with a singular Gram fall through to k_nnls (flag 16)
+        static const bool no_reg = getenv("LGR_NNLS_NO_REG") != nullptr;
+        if (!no_reg && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
+            launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->kp, c->num_sms, c->counters.p, cold, c->st);
+            static const bool no_wbig = getenv("LGR_NNLS_NO_WBIG") != nullptr;
+            c->tm.kernel_launches += 1;   // register kernel + mop-up kernel (the timed scope counts one)
+            if (c->kp > 32 && !no_wbig) {   // systems above 16 unknowns: warp-per-column continuation
+                launch_nnls_wbig(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+                c->tm.kernel_launches += 1;
+            }
+            launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p,
+                        cold | 16 | ((c->kp > 32 && no_wbig) ? 64 : 0), c->st);
+        } else {
+            launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
+        }
+    }
+    c->h_valid = true;
+    phase.reset();
+    phase.reset(new Span(c, "vw_phase"));
+    // ---- sufficient statistics of the V / W solves ----
+    run_stats(c);
+    // ---- V_i (and U_i): old W ----
+    {
+        Timed t(c, "k_vrhs");
+        launch_vrhs(c->ds_dev.p, c->d, c->W.p, c->k, c->kp, c->max_rows, c->st);
+    }
+    {
+        Timed t(c, "k_gram_inv");
+        launch_gram_inv(c->specV.p, c->d, c->k, c->kp, c->st);
+    }
+    {
+        Timed t(c, "k_nnls_V");
+        solve_f64(c, c->grpV.p, c->d, c->colsV, cold);
+    }
+    // ---- W: new V_i ----
+    {
+        Timed t(c, "k_wrhs");
+        launch_wrhs(c->ds_dev.p, c->d, c->m, c->CtBw.p, c->Gsum.p, c->k, c->kp, c->st);
+    }
+    {
+        Timed t(c, "k_gram_inv");
+        launch_gram_inv(c->specW.p, 1, c->k, c->kp, c->st);
+    }
+    {
+        Timed t(c, "k_nnls_W");
+        solve_f64(c, c->grpW.p, 1, (long long)c->m, cold);
+    }
+    phase.reset();
+}
+
 double objective(lgr_ctx* c);
 
 void iterate(lgr_ctx* c, int niter, double* traj_host, double* final_obj = nullptr) {
@@ -449,77 +527,46 @@ void iterate(lgr_ctx* c, int niter, double* traj_host, double* final_obj = nullp
     c->tm.kernel_launches = 0;
     c->tm.h_phase_ms = c->tm.vw_phase_ms = c->tm.comm_ms = 0.0;
     LGR_CUDA(cudaEventRecord(c->ev0, c->st));
-    for (int it = 0; it < niter; ++it) {
-        if (c->interrupt && c->interrupt(c->interrupt_user)) throw Error(LGR_ERR_INTERRUPT, "interrupted by caller");
-        std::unique_ptr<Span> phase(new Span(c, "h_phase"));
-        run_prep(c);
-        if (traj && it > 0) run_objective(c, c->objbuf.p + (it - 1));
-        // ---- H phase ----
-        {
-            Timed t(c, "k_gram_inv");   // CtC and CtC^-1 of the H solves (the fused U = B P epilogue of K1 reads CtC^-1)
-            launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
-        }
-        if (c->dense && (c->dense_mask & 1)) {
-            Timed t(c, "k_dense_ltx");
-            launch_dense_ltx(c->dds_dev.p, c->d, c->k1_tiles, c->num_sms, c->st);
-        } else {
-            Timed t(c, "k_spmm_ltx");
-            launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->fuse_u, c->st);
-        }
-        if (c->use_tc) {
-            Timed t(c, "k_pb_tc");
-            launch_pb_tc(c->grpT.p, c->d, c->tilesT, c->kp, c->num_sms, c->st);
-        }
-        {
-            Timed t(c, "k_nnls_H");
-            // fp32, k <= 32: register-resident solver; groups with a singular Gram fall through to k_nnls (flag 16)
-            static const bool no_reg = getenv("LGR_NNLS_NO_REG") != nullptr;
-            if (!no_reg && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
-                launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->kp, c->num_sms, c->counters.p, cold, c->st);
-                static const bool no_wbig = getenv("LGR_NNLS_NO_WBIG") != nullptr;
-                c->tm.kernel_launches += 1;   // register kernel + mop-up kernel (the timed scope counts one)
-                if (c->kp > 32 && !no_wbig) {   // systems above 16 unknowns: warp-per-column continuation
-                    launch_nnls_wbig(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
-                    c->tm.kernel_launches += 1;
-                }
-                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p,
-                            cold | 16 | ((c->kp > 32 && no_wbig) ? 64 : 0), c->st);
-            } else {
-                launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
+    // One iteration is ~17 launches + memsets (+ the NCCL all-reduce): replayed from a CUDA graph unless something needs
+    // the host between kernels (per-kernel events, the trajectory's moving output slot, histograms).
+    static const bool no_graph = getenv("LGR_NO_GRAPH") != nullptr;
+    const bool use_graph = !no_graph && !c->kt.on && !traj && !hist && niter > 1;
+    if (use_graph) {
+        if (!c->graph_exec || c->graph_cold != cold) {
+            if (c->graph_exec) {
+                cudaGraphExecDestroy(c->graph_exec);
+                c->graph_exec = nullptr;
             }
+            const int64_t before = c->tm.kernel_launches;
+            cudaGraph_t g = nullptr;
+            LGR_CUDA(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueue_iteration(c, cold, nullptr);
+            } catch (...) {
+                cudaStreamEndCapture(c->st, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            LGR_CUDA(cudaStreamEndCapture(c->st, &g));
+            cudaError_t e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            LGR_CUDA(e);
+            c->graph_cold = cold;
+            c->graph_launches = c->tm.kernel_launches - before;
+            c->tm.kernel_launches = before;
         }
-        c->h_valid = true;
-        phase.reset();
-        phase.reset(new Span(c, "vw_phase"));
-        // ---- sufficient statistics of the V / W solves ----
-        run_stats(c);
-        // ---- V_i (and U_i): old W ----
-        {
-            Timed t(c, "k_vrhs");
-            launch_vrhs(c->ds_dev.p, c->d, c->W.p, c->k, c->kp, c->max_rows, c->st);
+        for (int it = 0; it < niter; ++it) {
+            if (c->interrupt && c->interrupt(c->interrupt_user)) throw Error(LGR_ERR_INTERRUPT, "interrupted by caller");
+            LGR_CUDA(cudaGraphLaunch(c->graph_exec, c->st));
+            c->tm.kernel_launches += c->graph_launches;
+            c->h_valid = true;
+            c->stats_valid = true;
         }
-        {
-            Timed t(c, "k_gram_inv");
-            launch_gram_inv(c->specV.p, c->d, c->k, c->kp, c->st);
+    } else {
+        for (int it = 0; it < niter; ++it) {
+            if (c->interrupt && c->interrupt(c->interrupt_user)) throw Error(LGR_ERR_INTERRUPT, "interrupted by caller");
+            enqueue_iteration(c, cold, (traj && it > 0) ? c->objbuf.p + (it - 1) : nullptr);
         }
-        {
-            Timed t(c, "k_nnls_V");
-            solve_f64(c, c->grpV.p, c->d, c->colsV, cold);
-        }
-        // ---- W: new V_i ----
-        {
-            Timed t(c, "k_wrhs");
-            launch_wrhs(c->ds_dev.p, c->d, c->m, c->CtBw.p, c->Gsum.p, c->k, c->kp, c->st);
-        }
-        {
-            Timed t(c, "k_gram_inv");
-            launch_gram_inv(c->specW.p, 1, c->k, c->kp, c->st);
-        }
-        {
-            Timed t(c, "k_nnls_W");
-            solve_f64(c, c->grpW.p, 1, (long long)c->m, cold);
-        }
-        phase.reset();
     }
     DBuf<double> final_slot;
     if ((traj && niter > 0) || final_obj) {

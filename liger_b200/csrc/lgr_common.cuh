@@ -248,7 +248,7 @@ void dense_build(int n, int rows, const int* colptr, const int* rowidx, const fl
                  DenseLayout& out, int* bad, cudaStream_t st);
 void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st);
 void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st);
-void launch_gram_h(const DenseDs* ds, int nds, int total_blocks, int k, cudaStream_t st);
+void launch_gram_h(const DenseDs* ds, int nds, int total_items, int k, int num_sms, cudaStream_t st);
 int dense_gram_tile();
 void dense_init();
 

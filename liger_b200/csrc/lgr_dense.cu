@@ -49,7 +49,6 @@ constexpr int K1_WARPS = 6 + SCAT_WARPS;          // A producer, MMA, 4 epilogue
 // ---- k_dense_xh geometry ----
 constexpr int K2_KS = 2;                          // k-steps per stage: 32 cells
 constexpr int K2_ASTAGE_BYTES = K2_KS * ATILE_BYTES;   // 8 KB
-constexpr int K2_WARPS = 6 + SCAT_WARPS + NST;    // (spare), MMA, 4 epilogue, scatter, converters
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -111,102 +110,254 @@ __device__ __forceinline__ void split3(float x, unsigned short& hi, unsigned sho
     lo = (unsigned short)(__float_as_uint(r2) >> 16);
 }
 
-// One slot's scatter group: clear the entries the slot held, then scatter the new stage's entries.
-struct ScatterState {
-    const uint32_t* old_ent = nullptr;
-    int old_e0 = 0, old_e1 = 0;
-};
-__device__ __forceinline__ void scatter_stage(ScatterState& S, const uint32_t* __restrict__ ent, int e0, int e1, uint32_t xbase,
-                                              uint64_t* empty_bar, uint32_t empty_parity, int gt, int bar_id) {
-    uint32_t nv[PRE], ov[PRE];
-#pragma unroll
-    for (int j = 0; j < PRE; ++j) {   // both loads are issued before the wait: their latency overlaps the slot's MMAs
-        const int en = e0 + gt + j * SCAT_GT, eo = S.old_e0 + gt + j * SCAT_GT;
-        nv[j] = en < e1 ? __ldg(ent + en) : 0xFFFFFFFFu;
-        ov[j] = eo < S.old_e1 ? __ldg(S.old_ent + eo) : 0xFFFFFFFFu;
-    }
-    mbar_wait(empty_bar, empty_parity);
-#pragma unroll
-    for (int j = 0; j < PRE; ++j)
-        if (ov[j] != 0xFFFFFFFFu) sts_u16(xbase + ((ov[j] & 0xFFFFu) << 1), 0u);
-    for (int e = S.old_e0 + gt + PRE * SCAT_GT; e < S.old_e1; e += SCAT_GT) sts_u16(xbase + ((__ldg(S.old_ent + e) & 0xFFFFu) << 1), 0u);
-    group_bar(bar_id);   // every clear of this slot precedes every new store (an address may change owner)
-#pragma unroll
-    for (int j = 0; j < PRE; ++j)
-        if (nv[j] != 0xFFFFFFFFu) sts_u16(xbase + ((nv[j] & 0xFFFFu) << 1), nv[j] >> 16);
-    for (int e = e0 + gt + PRE * SCAT_GT; e < e1; e += SCAT_GT) {
-        const uint32_t v = __ldg(ent + e);
-        sts_u16(xbase + ((v & 0xFFFFu) << 1), v >> 16);
-    }
-    S.old_ent = ent;
-    S.old_e0 = e0;
-    S.old_e1 = e1;
-}
+constexpr uint32_t NOENT = 0xFFFFFFFFu;
+__device__ unsigned long long g_dense_dbg[16];   // developer counters (LGR_DENSE_DBG & 16): cycles of CTA 0's MMA thread
 
-struct SmemLayout {
-    unsigned char* X;   // NST x 32 KB
-    unsigned char* A;   // NST x a_stage
-    uint64_t* fullX;    // NST
-    uint64_t* fullA;    // NST
-    uint64_t* empty;    // NST
-    uint64_t* accfull;  // 2
-    uint64_t* accempty; // 2
-    uint32_t* tmem;
+// ---- stage iterators: the sequence of pipeline stages of this CTA (global index `it`) with their entry segments ----
+// k_dense_ltx: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; every tile walks the gene stages of its dataset
+// The gene stages of a tile may be accumulated in any order: every CTA starts at its own rotation, so that the CTAs that
+// run side by side do not all ask the L2 for the same 16 KB slab of the factor image at the same time.
+__device__ __forceinline__ int k1_rot(int nstage) { return (int)((blockIdx.x * 5u) % (unsigned)nstage); }
+
+struct K1Stages {
+    const DenseDs* ds;
+    int nds, total_tiles;
+    int tile, s, nstage, rot;
+    uint32_t it;
+    const int* seg;
+    const uint32_t* ent;
+    __device__ __forceinline__ void init(const DenseDs* ds_, int nds_, int total_tiles_) {
+        ds = ds_;
+        nds = nds_;
+        total_tiles = total_tiles_;
+        tile = (int)blockIdx.x - (int)gridDim.x;
+        s = 0;
+        nstage = 0;
+        rot = 0;
+        it = 0xFFFFFFFFu;
+        seg = nullptr;
+        ent = nullptr;
+    }
+    __device__ __forceinline__ bool advance() {
+        ++s;
+        ++it;
+        if (s >= nstage) {
+            tile += (int)gridDim.x;
+            if (tile >= total_tiles) return false;
+            const int i = find_ds(ds, nds, tile, &DenseDs::k1_tile_off);
+            const DenseDs& D = ds[i];
+            s = 0;
+            nstage = D.nstage1;
+            rot = k1_rot(nstage);
+            seg = D.seg1 + (size_t)(tile - D.k1_tile_off) * D.nstage1;
+            ent = D.ent1;
+        }
+        return true;
+    }
+    __device__ __forceinline__ const int* segp() const {
+        int sr = s + rot;
+        if (sr >= nstage) sr -= nstage;
+        return seg + sr;
+    }
 };
-__device__ __forceinline__ SmemLayout carve(unsigned char* raw, int a_stage) {
-    SmemLayout s;
-    s.X = raw;
-    s.A = raw + NST * XSTAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s.A + NST * a_stage);
-    s.fullX = bars;
-    s.fullA = bars + NST;
-    s.empty = bars + 2 * NST;
-    s.accfull = bars + 3 * NST;
-    s.accempty = bars + 3 * NST + 2;
-    s.tmem = reinterpret_cast<uint32_t*>(bars + 3 * NST + 4);
-    return s;
+// k_dense_xh: flat positions [p0, p1) of (dataset, gene block, cell stage)
+struct K2Stages {
+    const DenseDs* ds;
+    int nds;
+    long long p, p1, item_end;
+    int i, cs;
+    uint32_t it;
+    const int* seg;
+    const uint32_t* ent;
+    __device__ __forceinline__ void init(const DenseDs* ds_, int nds_, long long p0_, long long p1_) {
+        ds = ds_;
+        nds = nds_;
+        p = p0_ - 1;
+        p1 = p1_;
+        item_end = p0_;
+        i = 0;
+        cs = 0;
+        it = 0xFFFFFFFFu;
+        seg = nullptr;
+        ent = nullptr;
+    }
+    __device__ __forceinline__ bool advance() {
+        ++p;
+        ++it;
+        ++cs;
+        if (p >= p1) return false;
+        if (p >= item_end) {
+            i = 0;
+            while (i + 1 < nds && p >= ds[i + 1].k2_flat_off) ++i;
+            const DenseDs& D = ds[i];
+            const long long local = p - D.k2_flat_off;
+            const int gb = (int)(local / D.ncstage);
+            cs = (int)(local % D.ncstage);
+            item_end = D.k2_flat_off + (long long)(gb + 1) * D.ncstage;
+            seg = D.seg2 + (size_t)gb * D.ncstage;
+            ent = D.ent2;
+        }
+        return true;
+    }
+    __device__ __forceinline__ const int* segp() const { return seg + cs; }
+};
+
+// One slot's scatter group (96 threads), software-pipelined over its rounds (= the stages with it % NST == slot):
+//   two rounds ahead  the segment bounds are loaded,
+//   one round ahead   the entries are loaded into registers,
+//   this round        wait for the slot, clear the entries of the slot's previous stage (still in registers), barrier,
+//                     scatter the new ones, publish.
+// Nothing between the slot wait and the publish depends on a global load issued in the same round.
+template <typename Stages>
+__device__ __forceinline__ void scatter_role(Stages I, int slot, int gt, int lane, uint32_t xbase, uint64_t* empty_bar, uint64_t* full_bar,
+                                             int dbg) {
+    struct Round {
+        const uint32_t* ent;
+        int e0, e1;
+        uint32_t it;
+        bool valid;
+    };
+    auto fetch_ptr = [&](Round& r) {
+        r.valid = false;
+        while (I.advance()) {
+            if ((int)(I.it % NST) == slot) {
+                r.valid = true;
+                break;
+            }
+        }
+        r.ent = I.ent;
+        r.it = I.it;
+        r.e0 = r.e1 = 0;
+        if (r.valid) {
+            const int* sp = I.segp();
+            r.e0 = __ldg(sp);
+            r.e1 = (dbg & 1) ? r.e0 : __ldg(sp + 1);
+        }
+    };
+    auto fetch_ent = [&](const Round& r, uint32_t(&v)[PRE]) {
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) {
+            const int e = r.e0 + gt + j * SCAT_GT;
+            v[j] = (r.valid && e < r.e1) ? __ldg(r.ent + e) : NOENT;
+        }
+    };
+    Round cur, nxt, ptr, old{nullptr, 0, 0, 0, false};
+    uint32_t cv[PRE], nv[PRE], ov[PRE];
+#pragma unroll
+    for (int j = 0; j < PRE; ++j) ov[j] = NOENT;
+    fetch_ptr(cur);
+    fetch_ent(cur, cv);
+    fetch_ptr(nxt);
+    fetch_ent(nxt, nv);
+    fetch_ptr(ptr);
+    while (cur.valid) {
+        mbar_wait(empty_bar, ((cur.it / NST) & 1u) ^ 1u);
+#pragma unroll
+        for (int j = 0; j < PRE; ++j)
+            if (ov[j] != NOENT) sts_u16(xbase + ((ov[j] & 0xFFFFu) << 1), 0u);
+        if (old.valid)
+            for (int e = old.e0 + gt + PRE * SCAT_GT; e < old.e1; e += SCAT_GT) sts_u16(xbase + ((__ldg(old.ent + e) & 0xFFFFu) << 1), 0u);
+        group_bar(1 + slot);   // every clear of this slot precedes every new store (an address may change owner)
+#pragma unroll
+        for (int j = 0; j < PRE; ++j)
+            if (cv[j] != NOENT) sts_u16(xbase + ((cv[j] & 0xFFFFu) << 1), cv[j] >> 16);
+        for (int e = cur.e0 + gt + PRE * SCAT_GT; e < cur.e1; e += SCAT_GT) {
+            const uint32_t v = __ldg(cur.ent + e);
+            sts_u16(xbase + ((v & 0xFFFFu) << 1), v >> 16);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar);
+        old = cur;
+        cur = nxt;
+        nxt = ptr;
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) {
+            ov[j] = cv[j];
+            cv[j] = nv[j];
+        }
+        fetch_ent(nxt, nv);
+        fetch_ptr(ptr);
+    }
 }
-size_t dense_smem(int a_stage) { return (size_t)NST * (XSTAGE_BYTES + a_stage) + (3 * NST + 4) * 8 + 16 + 1024; }
 
 __device__ __forceinline__ unsigned char* align1k(unsigned char* p) {
     return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+constexpr int MAX_SDS = 24;   // datasets whose descriptors are cached in shared memory (more: read from global memory)
+constexpr size_t K1_SMEM = (size_t)NST * (XSTAGE_BYTES + K1_ASTAGE_BYTES) + 32 * 8 + 1024;
+constexpr size_t K2_SMEM = (size_t)NST * (XSTAGE_BYTES + K2_ASTAGE_BYTES) + 32 * 8 + 1024;
+
+// non-blocking probe of an mbarrier phase (the MMA thread peeks at the next stage while the tensor core works)
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t phase) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return done;
+}
+
+// the dataset descriptors, cached in shared memory by the whole CTA (every role looks them up per tile / item)
+__device__ __forceinline__ const DenseDs* cache_ds(const DenseDs* __restrict__ ds, int nds, DenseDs* sds) {
+    if (nds > MAX_SDS) return ds;
+    const int words = nds * (int)(sizeof(DenseDs) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(ds);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sds);
+    for (int e = threadIdx.x; e < words; e += blockDim.x) dst[e] = __ldg(src + e);
+    return sds;
 }
 
 }  // namespace
 
 // =====================================================================================================================
 // k_dense_ltx:  B = L~^T X
+// Ring of NST slots, each = 16 KB of A slabs (bulk copy) + 32 KB of X tiles (scatter); one `full` barrier per slot collects
+// the producer's transaction bytes and the three scatter warps, one `empty` barrier is signalled by tcgen05.commit.
 // =====================================================================================================================
-__global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* __restrict__ ds, int nds, int total_tiles, int dbg) {
+__global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* __restrict__ ds_g, int nds, int total_tiles, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
-    SmemLayout sm = carve(align1k(smem_dyn), K1_ASTAGE_BYTES);
+    __shared__ DenseDs sds[MAX_SDS];
+    unsigned char* raw = align1k(smem_dyn);
+    unsigned char* smX = raw;
+    unsigned char* smA = raw + NST * XSTAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + NST * K1_ASTAGE_BYTES);
+    uint64_t* full = bars;              // NST
+    uint64_t* empty = bars + NST;       // NST
+    uint64_t* accfull = bars + 2 * NST; // 2
+    uint64_t* accempty = accfull + 2;   // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup: barriers, TMEM (all 512 columns: two 256-column accumulators), cleared X ring ----
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
-            mbar_init(sm.fullX + s, SCAT_WARPS / NST);
-            mbar_init(sm.fullA + s, 1);
-            mbar_init(sm.empty + s, 1);
+            mbar_init(full + s, SCAT_WARPS / NST + 1);
+            mbar_init(empty + s, 1);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(sm.accfull + a, 1);
-            mbar_init(sm.accempty + a, 4);
+            mbar_init(accfull + a, 1);
+            mbar_init(accempty + a, 4);
         }
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem)), "n"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
-        uint4* x4 = reinterpret_cast<uint4*>(sm.X);
+        uint4* x4 = reinterpret_cast<uint4*>(smX);
         for (int e = threadIdx.x; e < NST * XSTAGE_BYTES / 16; e += blockDim.x) x4[e] = make_uint4(0u, 0u, 0u, 0u);
     }
+    const DenseDs* ds = cache_ds(ds_g, nds, sds);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem0 = *sm.tmem;
+    const uint32_t tmem0 = *tmem_slot;
 
     if (warp == 0) {
         // ===== A producer: one bulk copy (16 KB = four [128 x 16] slabs of rs * L~, pre-split by k_prep) per stage =====
@@ -216,39 +367,70 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                 const int i = find_ds(ds, nds, tile, &DenseDs::k1_tile_off);
                 const DenseDs& D = ds[i];
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(D.Asplit);
-                for (int s = 0; s < D.nstage1; ++s, ++it) {
+                const int nstage = D.nstage1, rot = k1_rot(nstage);
+                for (int s = 0; s < nstage; ++s, ++it) {
                     const uint32_t slot = it % NST, ph = (it / NST) & 1u;
-                    mbar_wait(sm.empty + slot, ph ^ 1u);
-                    mbar_expect_tx(sm.fullA + slot, K1_ASTAGE_BYTES);
-                    bulk_g2s(sm.A + slot * K1_ASTAGE_BYTES, src + (size_t)s * K1_ASTAGE_BYTES, K1_ASTAGE_BYTES, sm.fullA + slot);
+                    int sr = s + rot;
+                    if (sr >= nstage) sr -= nstage;
+                    mbar_wait(empty + slot, ph ^ 1u);
+                    if (dbg & 8) {
+                        mbar_arrive(full + slot);
+                        continue;
+                    }
+                    mbar_expect_tx(full + slot, K1_ASTAGE_BYTES);
+                    bulk_g2s(smA + slot * K1_ASTAGE_BYTES, src + (size_t)sr * K1_ASTAGE_BYTES, K1_ASTAGE_BYTES, full + slot);
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer.  The tensor core queues only a few instructions, so whatever this thread does between two stages
+        //       must fit in the time the queued MMAs still run: one wait (peeked one stage ahead), one commit per stage =====
         if (lane == 0) {
             uint32_t it = 0, tcount = 0;
+            long long wAcc = 0, wFull = 0, wIssue = 0, tstart = 0, c0 = 0, c1 = 0;
+            const bool prof = (dbg & 16) != 0;
+            if (prof) tstart = clock64();
+            uint32_t ready = 0, slot = 0, ph = 0;
+            // descriptors of slot 0 / k-step 0; the address field (bits 0..13, in 16-byte units) is advanced by plain adds
+            const uint64_t adesc0 = umma_desc(smem_u32(smA), 128 * 16, 128), xdesc0 = umma_desc(smem_u32(smX), TILE_N * 16, 128);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const int i = find_ds(ds, nds, tile, &DenseDs::k1_tile_off);
                 const int nstage = ds[i].nstage1;
                 const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-                mbar_wait(sm.accempty + acc, accph ^ 1u);   // the epilogue has drained this accumulator
-                tc_fence_after();
+                if (prof) c0 = clock64();
+                mbar_wait(accempty + acc, accph ^ 1u);   // the epilogue has drained this accumulator
+                if (prof) wAcc += clock64() - c0;
                 const uint32_t tacc = tmem0 + acc * TILE_N;
                 for (int s = 0; s < nstage; ++s, ++it) {
-                    const uint32_t slot = it % NST, ph = (it / NST) & 1u;
-                    mbar_wait(sm.fullA + slot, ph);
-                    mbar_wait(sm.fullX + slot, ph);
+                    if (prof) c0 = clock64();
+                    if (!ready) mbar_wait(full + slot, ph);
+                    if (prof) c1 = clock64(), wFull += c1 - c0;
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sm.A + slot * K1_ASTAGE_BYTES), x0 = smem_u32(sm.X + slot * XSTAGE_BYTES);
+                    const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
+                    ready = mbar_test(full + ns, nph);   // peek: consumed at the next stage
+                    const uint64_t ad = adesc0 + (uint64_t)(slot * (K1_ASTAGE_BYTES >> 4)), xd = xdesc0 + (uint64_t)(slot * (XSTAGE_BYTES >> 4));
+                    if (!(dbg & 2)) {
 #pragma unroll
-                    for (int ks = 0; ks < K1_KS; ++ks)
-                        if (!(dbg & 2)) umma_bf16(tacc, umma_desc(a0 + ks * ATILE_BYTES, 128 * 16, 128), umma_desc(x0 + ks * XTILE_BYTES, TILE_N * 16, 128),
-                                  IDESC_BF16, (s | ks) != 0);
-                    umma_commit(sm.empty + slot);   // frees the slot (A slabs and X tiles) when these MMAs have read it
+                        for (int ks = 0; ks < K1_KS; ++ks)
+                            umma_bf16(tacc, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), xd + (uint64_t)(ks * (XTILE_BYTES >> 4)), IDESC_BF16,
+                                      (s | ks) != 0);
+                    }
+                    umma_commit(empty + slot);   // frees the slot (A slabs and X tiles) when these MMAs have read it
+                    if (prof) wIssue += clock64() - c1;
+                    slot = ns;
+                    ph = nph;
                 }
-                umma_commit(sm.accfull + acc);
+                umma_commit(accfull + acc);
+            }
+            if (prof && blockIdx.x == 0) {
+                g_dense_dbg[0] = (unsigned long long)(clock64() - tstart);
+                g_dense_dbg[1] = (unsigned long long)wAcc;
+                g_dense_dbg[2] = (unsigned long long)wFull;
+                g_dense_dbg[3] = 0;
+                g_dense_dbg[4] = (unsigned long long)wIssue;
+                g_dense_dbg[5] = 0;
+                g_dense_dbg[6] = it;
             }
         }
         __syncwarp();
@@ -262,12 +444,18 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
             const int c0 = (tile - D.k1_tile_off) * TILE_N;
             const int ncell = min(TILE_N, D.n - c0);
             const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-            mbar_wait(sm.accfull + acc, accph);
-            tc_fence_after();
             float* __restrict__ Bout = D.B + (size_t)c0 * 32 + q * 8 + fq;
             const float* __restrict__ cs = D.cs + c0;
+            mbar_wait(accfull + acc, accph);
+            tc_fence_after();
             for (int j = 0; j < TILE_N / 32; ++j) {
                 if (j * 32 >= ncell) break;
+                float csv[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const int c = j * 32 + 4 * g + t;
+                    csv[g] = c < ncell ? __ldg(cs + c) : 0.f;
+                }
                 uint32_t v[32];
                 tmem_ld32(tmem0 + ((uint32_t)(q * 32) << 16) + acc * TILE_N + j * 32, v);
 #pragma unroll
@@ -281,32 +469,19 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                 for (int g = 0; g < 8; ++g) {    // lane (fq, t) stores factor 8 q + fq of cell 4 g + t: 32-byte runs per cell
                     const uint32_t sel = t == 0 ? v[4 * g] : (t == 1 ? v[4 * g + 1] : (t == 2 ? v[4 * g + 2] : v[4 * g + 3]));
                     const int c = j * 32 + 4 * g + t;
-                    if (c < ncell) Bout[(size_t)c * 32] = __uint_as_float(sel) * __ldg(cs + c);
+                    if (c < ncell) Bout[(size_t)c * 32] = __uint_as_float(sel) * csv[g];
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(sm.accempty + acc);
+            if (lane == 0) mbar_arrive(accempty + acc);
         }
     } else {
         // ===== scatter warps: slot = (warp - 6) % NST, three warps per slot =====
         const int sw = warp - 6, slot = sw % NST, gt = (sw / NST) * 32 + lane;
-        const uint32_t xbase = smem_u32(sm.X + slot * XSTAGE_BYTES);
-        ScatterState S;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int i = find_ds(ds, nds, tile, &DenseDs::k1_tile_off);
-            const DenseDs& D = ds[i];
-            const int* __restrict__ seg = D.seg1 + (size_t)(tile - D.k1_tile_off) * D.nstage1;
-            for (int s = 0; s < D.nstage1; ++s, ++it) {
-                if ((int)(it % NST) != slot) continue;
-                const int e0 = __ldg(seg + s), e1 = (dbg & 1) ? e0 : __ldg(seg + s + 1);
-                scatter_stage(S, D.ent1, e0, e1, xbase, sm.empty + slot, ((it / NST) & 1u) ^ 1u, gt, 1 + slot);
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sm.fullX + slot);
-            }
-        }
+        K1Stages I;
+        I.init(ds, nds, total_tiles);
+        scatter_role(I, slot, gt, lane, smem_u32(smX + slot * XSTAGE_BYTES), empty + slot, full + slot, dbg);
     }
     tc_fence_before();
     __syncthreads();
@@ -337,65 +512,98 @@ __device__ __forceinline__ K2Pos k2_item(const DenseDs* __restrict__ ds, int nds
     return r;
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds, int nds, long long total_flat, int dbg) {
+constexpr int K2_CONV_WARPS = 2 * NST;   // two converter warps per slot: one k-step (16 cells) each
+constexpr int K2_WARPS_TOTAL = 5 + SCAT_WARPS + K2_CONV_WARPS;   // MMA, 4 epilogue, scatter, converters
+
+__global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds_g, int nds, long long total_flat, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
-    SmemLayout sm = carve(align1k(smem_dyn), K2_ASTAGE_BYTES);
+    __shared__ DenseDs sds[MAX_SDS];
+    unsigned char* raw = align1k(smem_dyn);
+    unsigned char* smX = raw;
+    unsigned char* smA = raw + NST * XSTAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + NST * K2_ASTAGE_BYTES);
+    uint64_t* full = bars;            // NST: three scatter warps + two converter warps
+    uint64_t* empty = bars + NST;     // NST
+    uint64_t* accfull = bars + 2 * NST;
+    uint64_t* accempty = accfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long p0 = total_flat * blockIdx.x / gridDim.x, p1 = total_flat * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
-            mbar_init(sm.fullX + s, SCAT_WARPS / NST);
-            mbar_init(sm.fullA + s, 1);
-            mbar_init(sm.empty + s, 1);
+            mbar_init(full + s, SCAT_WARPS / NST + K2_CONV_WARPS / NST);
+            mbar_init(empty + s, 1);
         }
-        mbar_init(sm.accfull, 1);
-        mbar_init(sm.accempty, 4);
+        mbar_init(accfull, 1);
+        mbar_init(accempty, 4);
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem)), "n"(512) : "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {   // X ring and A ring cleared once (rows 96..127 of every A slab stay zero for the whole kernel)
-        uint4* x4 = reinterpret_cast<uint4*>(sm.X);
+        uint4* x4 = reinterpret_cast<uint4*>(smX);
         for (int e = threadIdx.x; e < NST * (XSTAGE_BYTES + K2_ASTAGE_BYTES) / 16; e += blockDim.x) x4[e] = make_uint4(0u, 0u, 0u, 0u);
     }
+    const DenseDs* ds = cache_ds(ds_g, nds, sds);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem0 = *sm.tmem;
+    const uint32_t tmem0 = *tmem_slot;
 
-    if (warp == 1) {
+    if (warp == 0) {
         // ===== MMA issuer: per k-step of 16 cells two MMAs (genes 0..255 and 256..511 of the block) sharing the A slab =====
         if (lane == 0) {
             uint32_t it = 0, icount = 0;
+            long long wAcc = 0, wFull = 0, wIssue = 0, tstart = 0, c0 = 0, c1 = 0;
+            const bool prof = (dbg & 16) != 0;
+            if (prof) tstart = clock64();
+            uint32_t ready = 0, slot = 0, ph = 0;
+            const uint64_t adesc0 = umma_desc(smem_u32(smA), 128 * 16, 128), xdesc0 = umma_desc(smem_u32(smX), TILE_N * 16, 128);
             for (long long p = p0; p < p1; ++icount) {
                 const K2Pos P = k2_item(ds, nds, p, p1);
-                mbar_wait(sm.accempty, (icount & 1u) ^ 1u);
-                tc_fence_after();
+                if (prof) c0 = clock64();
+                mbar_wait(accempty, (icount & 1u) ^ 1u);
+                if (prof) wAcc += clock64() - c0;
                 for (int cs = P.cs0; cs < P.cs1; ++cs, ++it) {
-                    const uint32_t slot = it % NST, ph = (it / NST) & 1u;
-                    mbar_wait(sm.fullA + slot, ph);
-                    mbar_wait(sm.fullX + slot, ph);
+                    if (prof) c0 = clock64();
+                    if (!ready) mbar_wait(full + slot, ph);
+                    if (prof) c1 = clock64(), wFull += c1 - c0;
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sm.A + slot * K2_ASTAGE_BYTES), x0 = smem_u32(sm.X + slot * XSTAGE_BYTES);
+                    const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
+                    ready = mbar_test(full + ns, nph);
+                    const uint64_t ad = adesc0 + (uint64_t)(slot * (K2_ASTAGE_BYTES >> 4)), xd = xdesc0 + (uint64_t)(slot * (XSTAGE_BYTES >> 4));
+                    if (!(dbg & 2)) {
 #pragma unroll
-                    for (int ks = 0; ks < K2_KS; ++ks) {
-                        const uint64_t ad = umma_desc(a0 + ks * ATILE_BYTES, 128 * 16, 128);
-                        const uint32_t accum = (cs != P.cs0 || ks != 0) ? 1u : 0u;
-                        if (dbg & 2) continue;
-                        umma_bf16(tmem0, ad, umma_desc(x0 + (ks * 2 + 0) * XTILE_BYTES, TILE_N * 16, 128), IDESC_BF16, accum);
-                        umma_bf16(tmem0 + TILE_N, ad, umma_desc(x0 + (ks * 2 + 1) * XTILE_BYTES, TILE_N * 16, 128), IDESC_BF16, accum);
+                        for (int ks = 0; ks < K2_KS; ++ks) {
+                            const uint32_t accum = (cs != P.cs0 || ks != 0) ? 1u : 0u;
+                            umma_bf16(tmem0, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), xd + (uint64_t)((ks * 2 + 0) * (XTILE_BYTES >> 4)), IDESC_BF16,
+                                      accum);
+                            umma_bf16(tmem0 + TILE_N, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), xd + (uint64_t)((ks * 2 + 1) * (XTILE_BYTES >> 4)),
+                                      IDESC_BF16, accum);
+                        }
                     }
-                    umma_commit(sm.empty + slot);
+                    umma_commit(empty + slot);
+                    if (prof) wIssue += clock64() - c1;
+                    slot = ns;
+                    ph = nph;
                 }
-                umma_commit(sm.accfull);
+                umma_commit(accfull);
                 p += P.cs1 - P.cs0;
+            }
+            if (prof && blockIdx.x == 0) {
+                g_dense_dbg[8] = (unsigned long long)(clock64() - tstart);
+                g_dense_dbg[9] = (unsigned long long)wAcc;
+                g_dense_dbg[10] = (unsigned long long)wFull;
+                g_dense_dbg[11] = 0;
+                g_dense_dbg[12] = (unsigned long long)wIssue;
+                g_dense_dbg[14] = it;
             }
         }
         __syncwarp();
-    } else if (warp >= 2 && warp < 6) {
+    } else if (warp >= 1 && warp < 5) {
         // ===== epilogue: D rows are t * 32 + f, so quadrant q holds term q of all 32 factors; the three terms are summed by
         //       the reduction itself (red.global.add.f32 into R, which also sums over the CTAs that share a gene block) =====
         const int q = warp & 3;
@@ -403,7 +611,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __
         for (long long p = p0; p < p1; ++icount) {
             const K2Pos P = k2_item(ds, nds, p, p1);
             const DenseDs& D = ds[P.i];
-            mbar_wait(sm.accfull, icount & 1u);
+            mbar_wait(accfull, icount & 1u);
             tc_fence_after();
             if (q < 3) {
                 const int g0 = P.gb * 512;
@@ -424,139 +632,276 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k_dense_xh(const DenseDs* __
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(sm.accempty);
+            if (lane == 0) mbar_arrive(accempty);
             p += P.cs1 - P.cs0;
         }
-    } else if (warp >= 6 && warp < 6 + SCAT_WARPS) {
+    } else if (warp >= 5 && warp < 5 + SCAT_WARPS) {
         // ===== scatter warps =====
-        const int sw = warp - 6, slot = sw % NST, gt = (sw / NST) * 32 + lane;
-        const uint32_t xbase = smem_u32(sm.X + slot * XSTAGE_BYTES);
-        ScatterState S;
-        uint32_t it = 0;
-        for (long long p = p0; p < p1;) {
-            const K2Pos P = k2_item(ds, nds, p, p1);
-            const DenseDs& D = ds[P.i];
-            const int* __restrict__ seg = D.seg2 + (size_t)P.gb * D.ncstage;
-            for (int cs = P.cs0; cs < P.cs1; ++cs, ++it) {
-                if ((int)(it % NST) != slot) continue;
-                const int e0 = __ldg(seg + cs), e1 = (dbg & 1) ? e0 : __ldg(seg + cs + 1);
-                scatter_stage(S, D.ent2, e0, e1, xbase, sm.empty + slot, ((it / NST) & 1u) ^ 1u, gt, 1 + slot);
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sm.fullX + slot);
+        const int sw = warp - 5, slot = sw % NST, gt = (sw / NST) * 32 + lane;
+        K2Stages I;
+        I.init(ds, nds, p0, p1);
+        scatter_role(I, slot, gt, lane, smem_u32(smX + slot * XSTAGE_BYTES), empty + slot, full + slot, dbg);
+    } else if (warp >= 5 + SCAT_WARPS) {
+        // ===== converter warps (two per slot, one k-step of 16 cells each): A slab rows t * 32 + f = bf16 term t of
+        //       cs[c] * H[c, f].  Lane f reads H[c, f] of the 16 cells (coalesced 128-byte rows) one round ahead, splits them
+        //       BEFORE the slot wait, and then only stores one 16-byte chunk (8 cells) per term: consecutive lanes write
+        //       consecutive chunks, no bank conflicts =====
+        const int cw = warp - (5 + SCAT_WARPS), slot = cw % NST, ks = cw / NST;
+        uint4* abase = reinterpret_cast<uint4*>(smA + slot * K2_ASTAGE_BYTES + ks * ATILE_BYTES);
+        K2Stages I;
+        I.init(ds, nds, p0, p1);
+        float hn[KSTEP];   // raw H[c, lane] of the round being prefetched; csn: lane j < 16 holds cs of cell j
+        float csn = 0.f;
+        uint32_t cur_it = 0, nxt_it = 0;
+        bool cur_valid = false, nxt_valid = false;
+        auto fetch = [&](uint32_t& it_out, bool& valid) {   // loads only: nothing here may wait for a loaded value
+            valid = false;
+            while (I.advance()) {
+                if ((int)(I.it % NST) == slot) {
+                    valid = true;
+                    break;
+                }
             }
-            p += P.cs1 - P.cs0;
-        }
-    } else if (warp >= 6 + SCAT_WARPS) {
-        // ===== converter warps (one per slot): A slab rows t * 32 + f = bf16 term t of cs[c] * H[c, f], 16 cells per k-step.
-        //       Lane f reads H[c, f] for the stage's 32 cells (coalesced 128-byte rows) and writes one 16-byte chunk
-        //       (8 cells) per term: consecutive lanes write consecutive chunks, no bank conflicts =====
-        const int slot = warp - (6 + SCAT_WARPS);
-        unsigned char* abase = sm.A + slot * K2_ASTAGE_BYTES;
-        uint32_t it = 0;
-        for (long long p = p0; p < p1;) {
-            const K2Pos P = k2_item(ds, nds, p, p1);
-            const DenseDs& D = ds[P.i];
-            for (int cs = P.cs0; cs < P.cs1; ++cs, ++it) {
-                if ((int)(it % NST) != slot) continue;
-                const int c0 = cs * (K2_KS * KSTEP);
-                float h[K2_KS * KSTEP];
+            it_out = I.it;
+            if (valid) {
+                const DenseDs& D = ds[I.i];
+                const int c0 = I.cs * (K2_KS * KSTEP) + ks * KSTEP;
+                const bool live = !(dbg & 4);
+                csn = (lane < KSTEP && c0 + lane < D.n && live) ? __ldg(D.cs + c0 + lane) : 0.f;
 #pragma unroll
-                for (int j = 0; j < K2_KS * KSTEP; ++j) {
+                for (int j = 0; j < KSTEP; ++j) {
                     const int c = c0 + j;
-                    h[j] = (c < D.n && !(dbg & 4)) ? __ldg(D.H + (size_t)c * 32 + lane) * __ldg(D.cs + c) : 0.f;
+                    hn[j] = (c < D.n && live) ? __ldg(D.H + (size_t)c * 32 + lane) : 0.f;
                 }
-                mbar_wait(sm.empty + slot, ((it / NST) & 1u) ^ 1u);
-#pragma unroll
-                for (int oc = 0; oc < K2_KS * 2; ++oc) {   // (k-step, chunk of 8 cells)
-                    unsigned short hi[8], mid[8], lo[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) split3(h[oc * 8 + e], hi[e], mid[e], lo[e]);
-                    uint4* dst = reinterpret_cast<uint4*>(abase + oc * 2048);
-                    dst[lane] = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16,
-                                           hi[6] | (uint32_t)hi[7] << 16);
-                    dst[32 + lane] = make_uint4(mid[0] | (uint32_t)mid[1] << 16, mid[2] | (uint32_t)mid[3] << 16,
-                                                mid[4] | (uint32_t)mid[5] << 16, mid[6] | (uint32_t)mid[7] << 16);
-                    dst[64 + lane] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
-                                                lo[6] | (uint32_t)lo[7] << 16);
-                }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sm.fullA + slot);
             }
-            p += P.cs1 - P.cs0;
+        };
+        fetch(cur_it, cur_valid);
+        while (cur_valid) {
+            uint4 out[2][3];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {   // chunk of 8 cells
+                unsigned short hi[8], mid[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split3(hn[ch * 8 + e] * __shfl_sync(0xffffffffu, csn, ch * 8 + e), hi[e], mid[e], lo[e]);
+                out[ch][0] = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16,
+                                        hi[6] | (uint32_t)hi[7] << 16);
+                out[ch][1] = make_uint4(mid[0] | (uint32_t)mid[1] << 16, mid[2] | (uint32_t)mid[3] << 16, mid[4] | (uint32_t)mid[5] << 16,
+                                        mid[6] | (uint32_t)mid[7] << 16);
+                out[ch][2] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
+                                        lo[6] | (uint32_t)lo[7] << 16);
+            }
+            fetch(nxt_it, nxt_valid);   // the next round's H rows travel while this round waits for its slot
+            mbar_wait(empty + slot, ((cur_it / NST) & 1u) ^ 1u);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) abase[ch * 128 + t * 32 + lane] = out[ch][t];
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + slot);
+            cur_it = nxt_it;
+            cur_valid = nxt_valid;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(512) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(512) : "memory");
 }
 
 // =====================================================================================================================
-// G = H^T H  (k x k, fp64): one CTA per 1024-cell tile, 4 x 4 register patches of the upper triangle, fp64 atomics.
-// (In the gather path this is phase 2 of k_spmm_xh; the dense R sweep does not stage fp32 H rows.)
+// k_gram_tc:  G = H^T H (k x k, fp64 result) on the tensor cores -- the dense Gram of the V / W solves (R/cINMF.R:486,497).
+// H rows (fp32) are split into three bf16 terms; per 16 cells ONE operand tile [rows t * 32 + f] x [16 cells] serves as both
+// operands:  D[128 x 96] += T[128 x 16] * T[0..95, 16]^T, so D[t 32 + f, t' 32 + f'] = sum_c H_t[c, f] H_t'[c, f'] and
+// G[f, f'] is the sum of the nine (t, t') blocks (every bf16 x bf16 product is exact; fp32 accumulation in TMEM over at most
+// 512 cells, then fp64).  Work item = 512 cells of one dataset; two 96-column accumulators so that the epilogue of an item
+// overlaps the MMAs of the next.  In the gather path the same Gram is phase 2 of k_spmm_xh (fp32 register patches).
 // =====================================================================================================================
-constexpr int GH_TILE = 1024;
-constexpr int GH_THREADS = 288;     // 36 upper-triangular 4 x 4 patches (KP = 32) x 8 cell groups
-__global__ void __launch_bounds__(GH_THREADS) k_gram_h(const DenseDs* __restrict__ ds, int nds, int k) {
-    constexpr int KP = 32, NP = 8, NPATCH = 36, NCG = GH_THREADS / NPATCH;
-    __shared__ float4 Hs[128 * NP];   // 128 cells x 32 floats at a time (16 KB)
-    __shared__ float red[NCG * NPATCH * 16];
-    const int i = find_ds(ds, nds, (int)blockIdx.x, &DenseDs::gh_blk_off);
-    const DenseDs& D = ds[i];
-    const int c0 = ((int)blockIdx.x - D.gh_blk_off) * GH_TILE;
-    const int ncell = min(GH_TILE, D.n - c0);
-    const int t = threadIdx.x, cg = t / NPATCH, pt = t % NPATCH;
-    int pi = 0, pj = 0;
-    {
-        int rem = pt;
-        while (rem >= NP - pi) {
-            rem -= NP - pi;
-            ++pi;
+constexpr int GT_CELLS = 512;                 // cells per work item (accumulated in fp32)
+constexpr int GT_KS = 4;                      // k-steps per stage: 64 cells
+constexpr int GT_STAGE_BYTES = GT_KS * ATILE_BYTES;   // 16 KB
+constexpr int GT_CONV_WARPS = 4 * NST;        // four converter warps per slot, one k-step each
+constexpr int GT_WARPS = 5 + GT_CONV_WARPS;   // MMA, 4 epilogue, converters
+constexpr size_t GT_SMEM = (size_t)NST * GT_STAGE_BYTES + 32 * 8 + 1024;
+constexpr uint32_t IDESC_GRAM = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __restrict__ ds_g, int nds, int total_items, int k) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ DenseDs sds[MAX_SDS];
+    __shared__ double Gacc[32 * 32];
+    unsigned char* raw = align1k(smem_dyn);
+    unsigned char* smA = raw;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + NST * GT_STAGE_BYTES);
+    uint64_t* full = bars;              // NST: four converter warps
+    uint64_t* empty = bars + NST;       // NST
+    uint64_t* accfull = bars + 2 * NST; // 2
+    uint64_t* accempty = accfull + 2;   // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(full + s, GT_CONV_WARPS / NST);
+            mbar_init(empty + s, 1);
         }
-        pj = pi + rem;
-    }
-    float a[4][4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) a[x][y] = 0.f;
-    const float4* __restrict__ H4 = reinterpret_cast<const float4*>(D.H + (size_t)c0 * KP);
-    for (int b0 = 0; b0 < ncell; b0 += 128) {
-        const int nb = min(128, ncell - b0);
-        __syncthreads();
-        for (int e = t; e < nb * NP; e += GH_THREADS) Hs[e] = __ldg(H4 + (size_t)b0 * NP + e);
-        __syncthreads();
-        for (int c = cg; c < nb; c += NCG) {
-            const float4 u = Hs[c * NP + pi], v = Hs[c * NP + pj];
-            const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) a[x][y] = fmaf(uu[x], vv[y], a[x][y]);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(accfull + a, 1);
+            mbar_init(accempty + a, 4);
         }
     }
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) red[(cg * NPATCH + pt) * 16 + x * 4 + y] = a[x][y];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // rows 96..127 of every operand tile stay zero
+        uint4* x4 = reinterpret_cast<uint4*>(smA);
+        for (int e = threadIdx.x; e < NST * GT_STAGE_BYTES / 16; e += blockDim.x) x4[e] = make_uint4(0u, 0u, 0u, 0u);
+        for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) Gacc[e] = 0.0;
+    }
+    const DenseDs* ds = cache_ds(ds_g, nds, sds);
+    fence_async_smem();
+    tc_fence_before();
     __syncthreads();
-    for (int e = t; e < NPATCH * 16; e += GH_THREADS) {
-        const int p = e / 16, xy = e % 16, x = xy / 4, y = xy % 4;
-        double sum = 0.0;
-        for (int g = 0; g < NCG; ++g) sum += (double)red[(g * NPATCH + p) * 16 + xy];
-        int ppi = 0, rem = p;
-        while (rem >= NP - ppi) {
-            rem -= NP - ppi;
-            ++ppi;
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_slot;
+    // items blockIdx.x, + gridDim.x, ...: (dataset, 512-cell chunk) via gt_item_off; stages of an item: ceil(cells / 64)
+    auto item_info = [&](int item, int& i, int& c0, int& ncell) {
+        i = find_ds(ds, nds, item, &DenseDs::gh_blk_off);
+        c0 = (item - ds[i].gh_blk_off) * GT_CELLS;
+        ncell = min(GT_CELLS, ds[i].n - c0);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== MMA issuer =====
+            uint32_t slot = 0, ph = 0, icount = 0;
+            const uint64_t adesc0 = umma_desc(smem_u32(smA), 128 * 16, 128);
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++icount) {
+                int i, c0, ncell;
+                item_info(item, i, c0, ncell);
+                const int nst = (ncell + GT_KS * KSTEP - 1) / (GT_KS * KSTEP);
+                const uint32_t acc = icount & 1u, accph = (icount >> 1) & 1u;
+                mbar_wait(accempty + acc, accph ^ 1u);
+                for (int s = 0; s < nst; ++s) {
+                    mbar_wait(full + slot, ph);
+                    tc_fence_after();
+                    const uint64_t ad = adesc0 + (uint64_t)(slot * (GT_STAGE_BYTES >> 4));
+#pragma unroll
+                    for (int ks = 0; ks < GT_KS; ++ks)
+                        umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), IDESC_GRAM,
+                                  (s | ks) != 0);
+                    umma_commit(empty + slot);
+                    slot = slot + 1 == NST ? 0u : slot + 1;
+                    ph = slot == 0 ? ph ^ 1u : ph;
+                }
+                umma_commit(accfull + acc);
+            }
         }
-        const int ppj = ppi + rem;
-        const int fa = ppi * 4 + x, fb = ppj * 4 + y;
-        if (fa < k && fb < k) {
-            atomicAdd(&D.G[fa * KP + fb], sum);
-            if (ppi != ppj) atomicAdd(&D.G[fb * KP + fa], sum);
+        __syncwarp();
+    } else if (warp < 5) {
+        // ===== epilogue: quadrant q = term t of the rows; lane f sums the three column blocks (terms t') of its row and
+        //       adds the 32 partial entries G[f, :] into the CTA's fp64 accumulator =====
+        const int q = warp & 3;
+        uint32_t icount = 0;
+        int cur_ds = -1;
+        auto flush = [&]() {   // the four epilogue warps together: Gacc -> global G of dataset cur_ds (fp64 atomics)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (cur_ds >= 0) {
+                double* G = ds[cur_ds].G;
+                for (int e = (warp - 1) * 32 + lane; e < 32 * 32; e += 128) {
+                    const int fa = e >> 5, fb = e & 31;
+                    if (fa < k && fb < k) atomicAdd(&G[fa * 32 + fb], Gacc[e]);
+                    Gacc[e] = 0.0;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++icount) {
+            int i, c0, ncell;
+            item_info(item, i, c0, ncell);
+            if (i != cur_ds) {
+                flush();
+                cur_ds = i;
+            }
+            const uint32_t acc = icount & 1u, accph = (icount >> 1) & 1u;
+            mbar_wait(accfull + acc, accph);
+            tc_fence_after();
+            if (q < 3) {
+                float g[32];
+#pragma unroll
+                for (int f = 0; f < 32; ++f) g[f] = 0.f;
+#pragma unroll
+                for (int tb = 0; tb < 3; ++tb) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem0 + ((uint32_t)(q * 32) << 16) + acc * 96 + tb * 32, v);
+#pragma unroll
+                    for (int f = 0; f < 32; ++f) g[f] += __uint_as_float(v[f]);
+                }
+#pragma unroll
+                for (int f = 0; f < 32; ++f) atomicAdd(&Gacc[f * 32 + lane], (double)g[f]);   // G is symmetric: entry (f, lane) = (lane, f)
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accempty + acc);
+        }
+        flush();
+    } else {
+        // ===== converter warps: slot = cw % NST, k-step = cw / NST; lane f reads H[c, f] of 16 cells one round ahead =====
+        const int cw = warp - 5, slot = cw % NST, ks = cw / NST;
+        uint4* abase = reinterpret_cast<uint4*>(smA + slot * GT_STAGE_BYTES + ks * ATILE_BYTES);
+        float hn[KSTEP];
+        int item = (int)blockIdx.x - (int)gridDim.x, s = 0, nst = 0, i = 0, c0 = 0, ncell = 0;
+        uint32_t it = 0xFFFFFFFFu, cur_it = 0, nxt_it = 0;
+        bool cur_valid = false, nxt_valid = false;
+        auto fetch = [&](uint32_t& it_out, bool& valid) {   // loads only
+            valid = false;
+            for (;;) {
+                ++s;
+                ++it;
+                if (s >= nst) {
+                    item += (int)gridDim.x;
+                    if (item >= total_items) return;
+                    item_info(item, i, c0, ncell);
+                    nst = (ncell + GT_KS * KSTEP - 1) / (GT_KS * KSTEP);
+                    s = 0;
+                }
+                if ((int)(it % NST) == slot) break;
+            }
+            valid = true;
+            it_out = it;
+            const float* __restrict__ H = ds[i].H + (size_t)c0 * 32;
+            const int cc = s * (GT_KS * KSTEP) + ks * KSTEP;
+#pragma unroll
+            for (int j = 0; j < KSTEP; ++j) hn[j] = (cc + j < ncell) ? __ldg(H + (size_t)(cc + j) * 32 + lane) : 0.f;
+        };
+        fetch(cur_it, cur_valid);
+        while (cur_valid) {
+            uint4 out[2][3];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                unsigned short hi[8], mid[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split3(hn[ch * 8 + e], hi[e], mid[e], lo[e]);
+                out[ch][0] = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16,
+                                        hi[6] | (uint32_t)hi[7] << 16);
+                out[ch][1] = make_uint4(mid[0] | (uint32_t)mid[1] << 16, mid[2] | (uint32_t)mid[3] << 16, mid[4] | (uint32_t)mid[5] << 16,
+                                        mid[6] | (uint32_t)mid[7] << 16);
+                out[ch][2] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
+                                        lo[6] | (uint32_t)lo[7] << 16);
+            }
+            fetch(nxt_it, nxt_valid);
+            mbar_wait(empty + slot, ((cur_it / NST) & 1u) ^ 1u);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) abase[ch * 128 + t * 32 + lane] = out[ch][t];
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + slot);
+            cur_it = nxt_it;
+            cur_valid = nxt_valid;
         }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(256) : "memory");
 }
 
 // =====================================================================================================================
@@ -566,25 +911,41 @@ void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, 
     if (total_tiles <= 0) return;
     const int grid = std::min(total_tiles, num_sms);
     static const int dbg = getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0;   // developer knob: 1 no scatter, 2 no MMA, 4 no H loads
-    k_dense_ltx<<<grid, K1_WARPS * 32, dense_smem(K1_ASTAGE_BYTES), st>>>(ds, nds, total_tiles, dbg);
+    k_dense_ltx<<<grid, K1_WARPS * 32, K1_SMEM, st>>>(ds, nds, total_tiles, dbg);
     LGR_CUDA(cudaGetLastError());
+    if (dbg & 16) {
+        unsigned long long h[16];
+        LGR_CUDA(cudaStreamSynchronize(st));
+        LGR_CUDA(cudaMemcpyFromSymbol(h, g_dense_dbg, sizeof(h)));
+        fprintf(stderr, "[dense dbg] ltx CTA0 MMA thread: total %llu cyc, stages %llu | wait acc %llu, wait full %llu, issue %llu\n", h[0], h[6], h[1],
+                h[2], h[4]);
+    }
 }
 void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st) {
     if (total_flat <= 0) return;
     const int grid = (int)std::min<long long>(total_flat, num_sms);
     static const int dbg = getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0;
-    k_dense_xh<<<grid, K2_WARPS * 32, dense_smem(K2_ASTAGE_BYTES), st>>>(ds, nds, total_flat, dbg);
+    k_dense_xh<<<grid, K2_WARPS_TOTAL * 32, K2_SMEM, st>>>(ds, nds, total_flat, dbg);
+    LGR_CUDA(cudaGetLastError());
+    if (dbg & 16) {
+        unsigned long long h[16];
+        LGR_CUDA(cudaStreamSynchronize(st));
+        LGR_CUDA(cudaMemcpyFromSymbol(h, g_dense_dbg, sizeof(h)));
+        fprintf(stderr, "[dense dbg] xh  CTA0 MMA thread: total %llu cyc, stages %llu | wait acc %llu, wait full %llu, issue %llu\n", h[8], h[14], h[9],
+                h[10], h[12]);
+    }
+}
+void launch_gram_h(const DenseDs* ds, int nds, int total_items, int k, int num_sms, cudaStream_t st) {
+    if (total_items <= 0) return;
+    const int grid = std::min(total_items, num_sms);
+    k_gram_tc<<<grid, GT_WARPS * 32, GT_SMEM, st>>>(ds, nds, total_items, k);
     LGR_CUDA(cudaGetLastError());
 }
-void launch_gram_h(const DenseDs* ds, int nds, int total_blocks, int k, cudaStream_t st) {
-    if (total_blocks <= 0) return;
-    k_gram_h<<<total_blocks, GH_THREADS, 0, st>>>(ds, nds, k);
-    LGR_CUDA(cudaGetLastError());
-}
-int dense_gram_tile() { return GH_TILE; }
+int dense_gram_tile() { return GT_CELLS; }
 void dense_init() {
-    LGR_CUDA(cudaFuncSetAttribute(k_dense_ltx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem(K1_ASTAGE_BYTES)));
-    LGR_CUDA(cudaFuncSetAttribute(k_dense_xh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem(K2_ASTAGE_BYTES)));
+    LGR_CUDA(cudaFuncSetAttribute(k_dense_ltx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_dense_xh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
 }
 
 // =====================================================================================================================
@@ -593,10 +954,15 @@ void dense_init() {
 //   xh  stream: segments (512-gene block, 32-cell stage); entry offset addresses [k-step][half block][chunk of 8 cells][gene][cell % 8]
 // Every entry is verified to be an integer count in 1..256 (else *bad is raised: the scales do not factor X).
 // =====================================================================================================================
+// Order inside a segment: (rank of the entry among those of its shared-memory bank, bank).  A warp of a scatter group
+// stores 32 consecutive entries at a time, so consecutive entries must fall into different banks: with this order the
+// first rounds of a segment touch every bank once, and only the tail (the fullest banks) repeats banks.
+template <typename KeyT>
 __global__ void k_dense_keys(int n, int rows, const int* __restrict__ colptr, const int* __restrict__ rowidx, const float* __restrict__ val,
                              const float* __restrict__ rs, const float* __restrict__ cs, int nstage1, int ncstage,
-                             unsigned int* __restrict__ key1, unsigned int* __restrict__ ent1, int* __restrict__ cnt1,
-                             unsigned int* __restrict__ key2, unsigned int* __restrict__ ent2, int* __restrict__ cnt2, int* __restrict__ bad) {
+                             KeyT* __restrict__ key1, unsigned int* __restrict__ ent1, int* __restrict__ cnt1, int* __restrict__ bank1,
+                             KeyT* __restrict__ key2, unsigned int* __restrict__ ent2, int* __restrict__ cnt2, int* __restrict__ bank2,
+                             int* __restrict__ bad) {
     const int c = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (c >= n) return;
     const int b = colptr[c], e = colptr[c + 1];
@@ -611,7 +977,9 @@ __global__ void k_dense_keys(int n, int rows, const int* __restrict__ colptr, co
             const int nn = c % TILE_N, kk = g % (K1_KS * KSTEP);
             const unsigned int off = (unsigned)((kk / KSTEP) * XTILE_BYTES + ((kk % KSTEP) / 8) * (TILE_N * 16) + nn * 16 + (kk % 8) * 2) >> 1;
             const unsigned int key = (unsigned)(c / TILE_N) * (unsigned)nstage1 + (unsigned)(g / (K1_KS * KSTEP));
-            key1[t] = key;
+            const unsigned int bank = (off >> 1) & 31u;
+            const unsigned int rank = min((unsigned)atomicAdd(&bank1[(size_t)key * 32 + bank], 1), 1023u);
+            key1[t] = ((KeyT)key << 15) | (KeyT)((rank << 5) | bank);
             ent1[t] = off | (bf << 16);
             atomicAdd(&cnt1[key], 1);
         }
@@ -620,27 +988,53 @@ __global__ void k_dense_keys(int n, int rows, const int* __restrict__ colptr, co
             const unsigned int off =
                 (unsigned)(((kk / KSTEP) * 2 + sub) * XTILE_BYTES + ((kk % KSTEP) / 8) * (TILE_N * 16) + nn * 16 + (kk % 8) * 2) >> 1;
             const unsigned int key = (unsigned)(g / 512) * (unsigned)ncstage + (unsigned)(c / (K2_KS * KSTEP));
-            key2[t] = key;
+            const unsigned int bank = (off >> 1) & 31u;
+            const unsigned int rank = min((unsigned)atomicAdd(&bank2[(size_t)key * 32 + bank], 1), 1023u);
+            key2[t] = ((KeyT)key << 15) | (KeyT)((rank << 5) | bank);
             ent2[t] = off | (bf << 16);
             atomicAdd(&cnt2[key], 1);
         }
     }
 }
 
-static void sort_stream(DBuf<unsigned int>& key, DBuf<unsigned int>& ent, DBuf<int>& cnt, size_t nnz, size_t nseg, DBuf<int>& seg,
+template <typename KeyT>
+static void sort_stream(DBuf<KeyT>& key, DBuf<unsigned int>& ent, DBuf<int>& cnt, size_t nnz, size_t nseg, int key_bits, DBuf<int>& seg,
                         DBuf<unsigned int>& out, cudaStream_t st) {
-    DBuf<unsigned int> key2(nnz);
+    DBuf<KeyT> key2(std::max<size_t>(nnz, 1));
     out.alloc(std::max<size_t>(nnz, 1));
     seg.alloc(nseg + 1);
-    int bits = 1;
-    while (((size_t)1 << bits) < nseg) ++bits;
     size_t tmp_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, ent.p, out.p, (int)nnz, 0, bits, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, ent.p, out.p, (int)nnz, 0, key_bits, st);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt.p, seg.p, (int)(nseg + 1), st);
     DBuf<unsigned char> tmp(std::max(tmp_bytes, scan_bytes));
-    LGR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key2.p, ent.p, out.p, (int)nnz, 0, bits, st));
+    LGR_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key2.p, ent.p, out.p, (int)nnz, 0, key_bits, st));
     LGR_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, cnt.p, seg.p, (int)(nseg + 1), st));
     LGR_CUDA(cudaStreamSynchronize(st));   // the temporaries are released on return
+}
+
+template <typename KeyT>
+static void dense_build_t(int n, int rows, const int* colptr, const int* rowidx, const float* val, size_t nnz, const float* rs,
+                          const float* cs, DenseLayout& out, int* bad, size_t nseg1, size_t nseg2, int bits1, int bits2, cudaStream_t st) {
+    const size_t nz = std::max<size_t>(nnz, 1);
+    DBuf<KeyT> key1(nz), key2(nz);
+    DBuf<unsigned int> ent1(nz), ent2(nz);
+    DBuf<int> cnt1(nseg1 + 1), cnt2(nseg2 + 1), bank1(nseg1 * 32), bank2(nseg2 * 32);
+    cnt1.zero(st);
+    cnt2.zero(st);
+    bank1.zero(st);
+    bank2.zero(st);
+    if (nnz && n > 0) {
+        k_dense_keys<KeyT><<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(n, rows, colptr, rowidx, val, rs, cs, out.nstage1, out.ncstage,
+                                                                                       key1.p, ent1.p, cnt1.p, bank1.p, key2.p, ent2.p, cnt2.p,
+                                                                                       bank2.p, bad);
+        LGR_CUDA(cudaGetLastError());
+    }
+    bank1.release();
+    bank2.release();
+    sort_stream<KeyT>(key1, ent1, cnt1, nnz, nseg1, bits1, out.seg1, out.ent1, st);
+    key1.release();
+    ent1.release();
+    sort_stream<KeyT>(key2, ent2, cnt2, nnz, nseg2, bits2, out.seg2, out.ent2, st);
 }
 
 void dense_build(int n, int rows, const int* colptr, const int* rowidx, const float* val, size_t nnz, const float* rs, const float* cs,
@@ -650,20 +1044,17 @@ void dense_build(int n, int rows, const int* colptr, const int* rowidx, const fl
     out.ngb = (rows + 511) / 512;
     out.ncstage = (n + K2_KS * KSTEP - 1) / (K2_KS * KSTEP);
     const size_t nseg1 = (size_t)out.ntile1 * out.nstage1, nseg2 = (size_t)out.ngb * out.ncstage;
-    LGR_REQUIRE(nseg1 < (size_t)0x7fffffff && nseg2 < (size_t)0x7fffffff && nnz < (size_t)0x7fffffff, "dense layout: too many segments");
-    DBuf<unsigned int> key1(std::max<size_t>(nnz, 1)), ent1(std::max<size_t>(nnz, 1)), key2(std::max<size_t>(nnz, 1)), ent2(std::max<size_t>(nnz, 1));
-    DBuf<int> cnt1(nseg1 + 1), cnt2(nseg2 + 1);
-    cnt1.zero(st);
-    cnt2.zero(st);
-    if (nnz && n > 0) {
-        k_dense_keys<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(n, rows, colptr, rowidx, val, rs, cs, out.nstage1, out.ncstage,
-                                                                                 key1.p, ent1.p, cnt1.p, key2.p, ent2.p, cnt2.p, bad);
-        LGR_CUDA(cudaGetLastError());
-    }
-    sort_stream(key1, ent1, cnt1, nnz, nseg1, out.seg1, out.ent1, st);
-    key1.release();
-    ent1.release();
-    sort_stream(key2, ent2, cnt2, nnz, nseg2, out.seg2, out.ent2, st);
+    LGR_REQUIRE(nseg1 < (size_t)0x7fffffff / 32 && nseg2 < (size_t)0x7fffffff / 32 && nnz < (size_t)0x7fffffff, "dense layout: too many segments");
+    auto bits_of = [](size_t nseg) {
+        int b = 1;
+        while (((size_t)1 << b) < nseg) ++b;
+        return b + 15;   // segment | rank (10 bits) | bank (5 bits)
+    };
+    const int bits1 = bits_of(nseg1), bits2 = bits_of(nseg2);
+    if (bits1 <= 32 && bits2 <= 32)
+        dense_build_t<unsigned int>(n, rows, colptr, rowidx, val, nnz, rs, cs, out, bad, nseg1, nseg2, bits1, bits2, st);
+    else
+        dense_build_t<unsigned long long>(n, rows, colptr, rowidx, val, nnz, rs, cs, out, bad, nseg1, nseg2, bits1, bits2, st);
     // pre-split factor image of k_dense_ltx: nstage1 x 16 KB, zero (rows of term 3 and rows >= `rows` stay zero)
     out.Asplit.alloc((size_t)out.nstage1 * K1_ASTAGE_BYTES / 2);
     out.Asplit.zero(st);
