@@ -287,7 +287,20 @@ __device__ __forceinline__ unsigned char* align1k(unsigned char* p) {
 
 constexpr int MAX_SDS = 24;   // datasets whose descriptors are cached in shared memory (more: read from global memory)
 constexpr size_t K1_SMEM = (size_t)NST * (XSTAGE_BYTES + K1_ASTAGE_BYTES) + 32 * 8 + 1024;
-constexpr size_t K2_SMEM = (size_t)NST * (XSTAGE_BYTES + K2_ASTAGE_BYTES) + 32 * 8 + 1024;
+constexpr int K2_NSA = 8;   // A-slab ring of k_dense_xh: the converters run up to 8 stages ahead of the MMAs
+constexpr size_t K2_SMEM = (size_t)NST * XSTAGE_BYTES + (size_t)K2_NSA * K2_ASTAGE_BYTES + 40 * 8 + 1024;
+
+// one lane of a converged warp (the MMA warps run their loops warp-uniformly, so that descriptors and addresses stay in
+// uniform registers, and elect a lane only for the tcgen05 instructions themselves)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
 // non-blocking probe of an mbarrier phase (the MMA thread peeks at the next stage while the tensor core works)
 __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t phase) {
@@ -384,9 +397,11 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer.  The tensor core queues only a few instructions, so whatever this thread does between two stages
-        //       must fit in the time the queued MMAs still run: one wait (peeked one stage ahead), one commit per stage =====
-        if (lane == 0) {
+        // ===== MMA issuer.  The whole warp runs the loop (warp-uniform control flow keeps descriptors and barrier addresses in
+        //       uniform registers); one elected lane issues the tcgen05 instructions.  One wait (peeked one stage ahead) and
+        //       one commit per stage =====
+        {
+            const bool leader = elect_one();
             uint32_t it = 0, tcount = 0;
             long long wAcc = 0, wFull = 0, wIssue = 0, tstart = 0, c0 = 0, c1 = 0;
             const bool prof = (dbg & 16) != 0;
@@ -394,6 +409,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
             uint32_t ready = 0, slot = 0, ph = 0;
             // descriptors of slot 0 / k-step 0; the address field (bits 0..13, in 16-byte units) is advanced by plain adds
             const uint64_t adesc0 = umma_desc(smem_u32(smA), 128 * 16, 128), xdesc0 = umma_desc(smem_u32(smX), TILE_N * 16, 128);
+            // The tensor core queues only ~2 instructions: the issue of the 3rd MMA of a stage blocks until the 1st has
+            // finished.  The probe of the next stage's barrier and the address arithmetic therefore sit between the 2nd and the
+            // 3rd MMA, where they are hidden behind the queued work.
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const int i = find_ds(ds, nds, tile, &DenseDs::k1_tile_off);
                 const int nstage = ds[i].nstage1;
@@ -407,23 +425,27 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                     if (!ready) mbar_wait(full + slot, ph);
                     if (prof) c1 = clock64(), wFull += c1 - c0;
                     tc_fence_after();
-                    const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
-                    ready = mbar_test(full + ns, nph);   // peek: consumed at the next stage
                     const uint64_t ad = adesc0 + (uint64_t)(slot * (K1_ASTAGE_BYTES >> 4)), xd = xdesc0 + (uint64_t)(slot * (XSTAGE_BYTES >> 4));
-                    if (!(dbg & 2)) {
-#pragma unroll
-                        for (int ks = 0; ks < K1_KS; ++ks)
-                            umma_bf16(tacc, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), xd + (uint64_t)(ks * (XTILE_BYTES >> 4)), IDESC_BF16,
-                                      (s | ks) != 0);
+                    const bool mma = !(dbg & 2);
+                    if (mma && leader) {
+                        umma_bf16(tacc, ad, xd, IDESC_BF16, s != 0);
+                        umma_bf16(tacc, ad + (uint64_t)(ATILE_BYTES >> 4), xd + (uint64_t)(XTILE_BYTES >> 4), IDESC_BF16, 1u);
                     }
-                    umma_commit(empty + slot);   // frees the slot (A slabs and X tiles) when these MMAs have read it
+                    const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
+                    ready = __shfl_sync(0xffffffffu, mbar_test(full + ns, nph), 0);   // peek: consumed at the next stage
+                    if (mma && leader) {
+                        umma_bf16(tacc, ad + (uint64_t)(2 * (ATILE_BYTES >> 4)), xd + (uint64_t)(2 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
+                        umma_bf16(tacc, ad + (uint64_t)(3 * (ATILE_BYTES >> 4)), xd + (uint64_t)(3 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
+                    }
+                    if (leader) umma_commit(empty + slot);   // frees the slot (A slabs and X tiles) when these MMAs have read it
                     if (prof) wIssue += clock64() - c1;
                     slot = ns;
                     ph = nph;
                 }
-                umma_commit(accfull + acc);
+                if (leader) umma_commit(accfull + acc);   // the tile's accumulator is complete: the epilogue may start
+                __syncwarp();
             }
-            if (prof && blockIdx.x == 0) {
+            if (prof && blockIdx.x == 0 && leader) {
                 g_dense_dbg[0] = (unsigned long long)(clock64() - tstart);
                 g_dense_dbg[1] = (unsigned long long)wAcc;
                 g_dense_dbg[2] = (unsigned long long)wFull;
@@ -512,7 +534,7 @@ __device__ __forceinline__ K2Pos k2_item(const DenseDs* __restrict__ ds, int nds
     return r;
 }
 
-constexpr int K2_CONV_WARPS = 2 * NST;   // two converter warps per slot: one k-step (16 cells) each
+constexpr int K2_CONV_WARPS = NST;   // one converter warp per stage group (stages it % NST), both k-steps (32 cells)
 constexpr int K2_WARPS_TOTAL = 5 + SCAT_WARPS + K2_CONV_WARPS;   // MMA, 4 epilogue, scatter, converters
 
 __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds_g, int nds, long long total_flat, int dbg) {
@@ -521,10 +543,12 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
     unsigned char* raw = align1k(smem_dyn);
     unsigned char* smX = raw;
     unsigned char* smA = raw + NST * XSTAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + NST * K2_ASTAGE_BYTES);
-    uint64_t* full = bars;            // NST: three scatter warps + two converter warps
-    uint64_t* empty = bars + NST;     // NST
-    uint64_t* accfull = bars + 2 * NST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + K2_NSA * K2_ASTAGE_BYTES);
+    uint64_t* full = bars;              // NST: the three scatter warps of the X slot
+    uint64_t* empty = bars + NST;       // NST
+    uint64_t* fullA = bars + 2 * NST;   // K2_NSA: the converter warp of the A slot
+    uint64_t* emptyA = fullA + K2_NSA;  // K2_NSA
+    uint64_t* accfull = emptyA + K2_NSA;
     uint64_t* accempty = accfull + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -532,8 +556,12 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
-            mbar_init(full + s, SCAT_WARPS / NST + K2_CONV_WARPS / NST);
+            mbar_init(full + s, SCAT_WARPS / NST);
             mbar_init(empty + s, 1);
+        }
+        for (int s = 0; s < K2_NSA; ++s) {
+            mbar_init(fullA + s, 1);
+            mbar_init(emptyA + s, 1);
         }
         mbar_init(accfull, 1);
         mbar_init(accempty, 4);
@@ -544,7 +572,7 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
     }
     {   // X ring and A ring cleared once (rows 96..127 of every A slab stay zero for the whole kernel)
         uint4* x4 = reinterpret_cast<uint4*>(smX);
-        for (int e = threadIdx.x; e < NST * (XSTAGE_BYTES + K2_ASTAGE_BYTES) / 16; e += blockDim.x) x4[e] = make_uint4(0u, 0u, 0u, 0u);
+        for (int e = threadIdx.x; e < (NST * XSTAGE_BYTES + K2_NSA * K2_ASTAGE_BYTES) / 16; e += blockDim.x) x4[e] = make_uint4(0u, 0u, 0u, 0u);
     }
     const DenseDs* ds = cache_ds(ds_g, nds, sds);
     fence_async_smem();
@@ -554,13 +582,15 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
     const uint32_t tmem0 = *tmem_slot;
 
     if (warp == 0) {
-        // ===== MMA issuer: per k-step of 16 cells two MMAs (genes 0..255 and 256..511 of the block) sharing the A slab =====
-        if (lane == 0) {
+        // ===== MMA issuer (converged warp, elected lane): per k-step of 16 cells two MMAs (genes 0..255 and 256..511 of the block)
+        //       sharing the A slab =====
+        {
+            const bool leader = elect_one();
             uint32_t it = 0, icount = 0;
             long long wAcc = 0, wFull = 0, wIssue = 0, tstart = 0, c0 = 0, c1 = 0;
             const bool prof = (dbg & 16) != 0;
             if (prof) tstart = clock64();
-            uint32_t ready = 0, slot = 0, ph = 0;
+            uint32_t ready = 0, readyA = 0, slot = 0, ph = 0, sa = 0, pha = 0;
             const uint64_t adesc0 = umma_desc(smem_u32(smA), 128 * 16, 128), xdesc0 = umma_desc(smem_u32(smX), TILE_N * 16, 128);
             for (long long p = p0; p < p1; ++icount) {
                 const K2Pos P = k2_item(ds, nds, p, p1);
@@ -569,31 +599,40 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
                 if (prof) wAcc += clock64() - c0;
                 for (int cs = P.cs0; cs < P.cs1; ++cs, ++it) {
                     if (prof) c0 = clock64();
+                    if (!readyA) mbar_wait(fullA + sa, pha);
                     if (!ready) mbar_wait(full + slot, ph);
                     if (prof) c1 = clock64(), wFull += c1 - c0;
                     tc_fence_after();
-                    const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
-                    ready = mbar_test(full + ns, nph);
-                    const uint64_t ad = adesc0 + (uint64_t)(slot * (K2_ASTAGE_BYTES >> 4)), xd = xdesc0 + (uint64_t)(slot * (XSTAGE_BYTES >> 4));
-                    if (!(dbg & 2)) {
-#pragma unroll
-                        for (int ks = 0; ks < K2_KS; ++ks) {
-                            const uint32_t accum = (cs != P.cs0 || ks != 0) ? 1u : 0u;
-                            umma_bf16(tmem0, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), xd + (uint64_t)((ks * 2 + 0) * (XTILE_BYTES >> 4)), IDESC_BF16,
-                                      accum);
-                            umma_bf16(tmem0 + TILE_N, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), xd + (uint64_t)((ks * 2 + 1) * (XTILE_BYTES >> 4)),
-                                      IDESC_BF16, accum);
-                        }
+                    const uint64_t ad = adesc0 + (uint64_t)(sa * (K2_ASTAGE_BYTES >> 4)), xd = xdesc0 + (uint64_t)(slot * (XSTAGE_BYTES >> 4));
+                    const uint32_t accum = cs != P.cs0 ? 1u : 0u;
+                    const bool mma = !(dbg & 2);
+                    if (mma && leader) {   // k-step 0
+                        umma_bf16(tmem0, ad, xd, IDESC_BF16, accum);
+                        umma_bf16(tmem0 + TILE_N, ad, xd + (uint64_t)(XTILE_BYTES >> 4), IDESC_BF16, accum);
                     }
-                    umma_commit(empty + slot);
+                    const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
+                    const uint32_t nsa = sa + 1 == K2_NSA ? 0u : sa + 1, npha = nsa == 0 ? pha ^ 1u : pha;
+                    ready = __shfl_sync(0xffffffffu, mbar_test(full + ns, nph), 0);
+                    readyA = __shfl_sync(0xffffffffu, mbar_test(fullA + nsa, npha), 0);
+                    if (mma && leader) {   // k-step 1
+                        umma_bf16(tmem0, ad + (uint64_t)(ATILE_BYTES >> 4), xd + (uint64_t)(2 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
+                        umma_bf16(tmem0 + TILE_N, ad + (uint64_t)(ATILE_BYTES >> 4), xd + (uint64_t)(3 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
+                    }
+                    if (leader) {
+                        umma_commit(empty + slot);
+                        umma_commit(emptyA + sa);
+                    }
                     if (prof) wIssue += clock64() - c1;
                     slot = ns;
                     ph = nph;
+                    sa = nsa;
+                    pha = npha;
                 }
-                umma_commit(accfull);
+                if (leader) umma_commit(accfull);
+                __syncwarp();
                 p += P.cs1 - P.cs0;
             }
-            if (prof && blockIdx.x == 0) {
+            if (prof && blockIdx.x == 0 && leader) {
                 g_dense_dbg[8] = (unsigned long long)(clock64() - tstart);
                 g_dense_dbg[9] = (unsigned long long)wAcc;
                 g_dense_dbg[10] = (unsigned long long)wFull;
@@ -642,22 +681,22 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
         I.init(ds, nds, p0, p1);
         scatter_role(I, slot, gt, lane, smem_u32(smX + slot * XSTAGE_BYTES), empty + slot, full + slot, dbg);
     } else if (warp >= 5 + SCAT_WARPS) {
-        // ===== converter warps (two per slot, one k-step of 16 cells each): A slab rows t * 32 + f = bf16 term t of
-        //       cs[c] * H[c, f].  Lane f reads H[c, f] of the 16 cells (coalesced 128-byte rows) one round ahead, splits them
-        //       BEFORE the slot wait, and then only stores one 16-byte chunk (8 cells) per term: consecutive lanes write
-        //       consecutive chunks, no bank conflicts =====
-        const int cw = warp - (5 + SCAT_WARPS), slot = cw % NST, ks = cw / NST;
-        uint4* abase = reinterpret_cast<uint4*>(smA + slot * K2_ASTAGE_BYTES + ks * ATILE_BYTES);
+        // ===== converter warps: warp g serves the stages it with it % NST == g (A slots it % 8), both k-steps of a stage.
+        //       A slab rows t * 32 + f = bf16 term t of cs[c] * H[c, f].  Lane f reads H[c, f] of the stage's 32 cells (coalesced
+        //       128-byte rows) one round ahead -- issued AFTER the publish, so that the proxy fence of this round does not wait
+        //       for them -- splits them before the slot wait and then only stores one 16-byte chunk (8 cells) per term:
+        //       consecutive lanes write consecutive chunks, no bank conflicts =====
+        const int grp = warp - (5 + SCAT_WARPS);
         K2Stages I;
         I.init(ds, nds, p0, p1);
-        float hn[KSTEP];   // raw H[c, lane] of the round being prefetched; csn: lane j < 16 holds cs of cell j
+        float hn[K2_KS * KSTEP];   // raw H[c, lane] of the round being prefetched; csn: lane j holds cs of cell j
         float csn = 0.f;
         uint32_t cur_it = 0, nxt_it = 0;
         bool cur_valid = false, nxt_valid = false;
         auto fetch = [&](uint32_t& it_out, bool& valid) {   // loads only: nothing here may wait for a loaded value
             valid = false;
             while (I.advance()) {
-                if ((int)(I.it % NST) == slot) {
+                if ((int)(I.it % NST) == grp) {
                     valid = true;
                     break;
                 }
@@ -665,11 +704,11 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
             it_out = I.it;
             if (valid) {
                 const DenseDs& D = ds[I.i];
-                const int c0 = I.cs * (K2_KS * KSTEP) + ks * KSTEP;
+                const int c0 = I.cs * (K2_KS * KSTEP);
                 const bool live = !(dbg & 4);
-                csn = (lane < KSTEP && c0 + lane < D.n && live) ? __ldg(D.cs + c0 + lane) : 0.f;
+                csn = (c0 + lane < D.n && live) ? __ldg(D.cs + c0 + lane) : 0.f;
 #pragma unroll
-                for (int j = 0; j < KSTEP; ++j) {
+                for (int j = 0; j < K2_KS * KSTEP; ++j) {
                     const int c = c0 + j;
                     hn[j] = (c < D.n && live) ? __ldg(D.H + (size_t)c * 32 + lane) : 0.f;
                 }
@@ -677,28 +716,26 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
         };
         fetch(cur_it, cur_valid);
         while (cur_valid) {
-            uint4 out[2][3];
+            const uint32_t sa = cur_it % K2_NSA, pha = (cur_it / K2_NSA) & 1u;
+            uint4* abase = reinterpret_cast<uint4*>(smA + sa * K2_ASTAGE_BYTES);
+            mbar_wait(emptyA + sa, pha ^ 1u);   // 8-deep ring: the slot is normally free long before
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {   // chunk of 8 cells
+            for (int oc = 0; oc < K2_KS * 2; ++oc) {   // (k-step, chunk of 8 cells): 16-byte row chunks of the three terms
                 unsigned short hi[8], mid[8], lo[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split3(hn[ch * 8 + e] * __shfl_sync(0xffffffffu, csn, ch * 8 + e), hi[e], mid[e], lo[e]);
-                out[ch][0] = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16,
-                                        hi[6] | (uint32_t)hi[7] << 16);
-                out[ch][1] = make_uint4(mid[0] | (uint32_t)mid[1] << 16, mid[2] | (uint32_t)mid[3] << 16, mid[4] | (uint32_t)mid[5] << 16,
-                                        mid[6] | (uint32_t)mid[7] << 16);
-                out[ch][2] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
-                                        lo[6] | (uint32_t)lo[7] << 16);
+                for (int e = 0; e < 8; ++e) split3(hn[oc * 8 + e] * __shfl_sync(0xffffffffu, csn, oc * 8 + e), hi[e], mid[e], lo[e]);
+                uint4* dst = abase + oc * 128;
+                dst[lane] = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16,
+                                       hi[6] | (uint32_t)hi[7] << 16);
+                dst[32 + lane] = make_uint4(mid[0] | (uint32_t)mid[1] << 16, mid[2] | (uint32_t)mid[3] << 16, mid[4] | (uint32_t)mid[5] << 16,
+                                            mid[6] | (uint32_t)mid[7] << 16);
+                dst[64 + lane] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
+                                            lo[6] | (uint32_t)lo[7] << 16);
             }
-            fetch(nxt_it, nxt_valid);   // the next round's H rows travel while this round waits for its slot
-            mbar_wait(empty + slot, ((cur_it / NST) & 1u) ^ 1u);
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-                for (int t = 0; t < 3; ++t) abase[ch * 128 + t * 32 + lane] = out[ch][t];
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(full + slot);
+            if (lane == 0) mbar_arrive(fullA + sa);
+            fetch(nxt_it, nxt_valid);
             cur_it = nxt_it;
             cur_valid = nxt_valid;
         }
@@ -770,8 +807,9 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
     };
 
     if (warp == 0) {
-        if (lane == 0) {   // ===== MMA issuer =====
-            uint32_t slot = 0, ph = 0, icount = 0;
+        {   // ===== MMA issuer (converged warp, elected lane for the tcgen05 instructions) =====
+            const bool leader = elect_one();
+            uint32_t slot = 0, ph = 0, icount = 0, ready = 0;
             const uint64_t adesc0 = umma_desc(smem_u32(smA), 128 * 16, 128);
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++icount) {
                 int i, c0, ncell;
@@ -780,18 +818,25 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
                 const uint32_t acc = icount & 1u, accph = (icount >> 1) & 1u;
                 mbar_wait(accempty + acc, accph ^ 1u);
                 for (int s = 0; s < nst; ++s) {
-                    mbar_wait(full + slot, ph);
+                    if (!ready) mbar_wait(full + slot, ph);
                     tc_fence_after();
                     const uint64_t ad = adesc0 + (uint64_t)(slot * (GT_STAGE_BYTES >> 4));
-#pragma unroll
-                    for (int ks = 0; ks < GT_KS; ++ks)
-                        umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), ad + (uint64_t)(ks * (ATILE_BYTES >> 4)), IDESC_GRAM,
-                                  (s | ks) != 0);
-                    umma_commit(empty + slot);
-                    slot = slot + 1 == NST ? 0u : slot + 1;
-                    ph = slot == 0 ? ph ^ 1u : ph;
+                    if (leader) {
+                        umma_bf16(tmem0 + acc * 96, ad, ad, IDESC_GRAM, s != 0);
+                        umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(ATILE_BYTES >> 4), ad + (uint64_t)(ATILE_BYTES >> 4), IDESC_GRAM, 1u);
+                    }
+                    const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
+                    ready = __shfl_sync(0xffffffffu, mbar_test(full + ns, nph), 0);
+                    if (leader) {
+                        umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(2 * (ATILE_BYTES >> 4)), ad + (uint64_t)(2 * (ATILE_BYTES >> 4)), IDESC_GRAM, 1u);
+                        umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(3 * (ATILE_BYTES >> 4)), ad + (uint64_t)(3 * (ATILE_BYTES >> 4)), IDESC_GRAM, 1u);
+                        umma_commit(empty + slot);
+                    }
+                    slot = ns;
+                    ph = nph;
                 }
-                umma_commit(accfull + acc);
+                if (leader) umma_commit(accfull + acc);
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -886,7 +931,6 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
                 out[ch][2] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
                                         lo[6] | (uint32_t)lo[7] << 16);
             }
-            fetch(nxt_it, nxt_valid);
             mbar_wait(empty + slot, ((cur_it / NST) & 1u) ^ 1u);
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch)
@@ -895,6 +939,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + slot);
+            fetch(nxt_it, nxt_valid);   // after the publish: the fence must not wait for these loads
             cur_it = nxt_it;
             cur_valid = nxt_valid;
         }
@@ -978,8 +1023,8 @@ __global__ void k_dense_keys(int n, int rows, const int* __restrict__ colptr, co
             const unsigned int off = (unsigned)((kk / KSTEP) * XTILE_BYTES + ((kk % KSTEP) / 8) * (TILE_N * 16) + nn * 16 + (kk % 8) * 2) >> 1;
             const unsigned int key = (unsigned)(c / TILE_N) * (unsigned)nstage1 + (unsigned)(g / (K1_KS * KSTEP));
             const unsigned int bank = (off >> 1) & 31u;
-            const unsigned int rank = min((unsigned)atomicAdd(&bank1[(size_t)key * 32 + bank], 1), 1023u);
-            key1[t] = ((KeyT)key << 15) | (KeyT)((rank << 5) | bank);
+            const unsigned int rank = min((unsigned)atomicAdd(&bank1[(size_t)key * 32 + bank], 1), 31u);
+            key1[t] = ((KeyT)key << 10) | (KeyT)((rank << 5) | bank);
             ent1[t] = off | (bf << 16);
             atomicAdd(&cnt1[key], 1);
         }
@@ -989,8 +1034,8 @@ __global__ void k_dense_keys(int n, int rows, const int* __restrict__ colptr, co
                 (unsigned)(((kk / KSTEP) * 2 + sub) * XTILE_BYTES + ((kk % KSTEP) / 8) * (TILE_N * 16) + nn * 16 + (kk % 8) * 2) >> 1;
             const unsigned int key = (unsigned)(g / 512) * (unsigned)ncstage + (unsigned)(c / (K2_KS * KSTEP));
             const unsigned int bank = (off >> 1) & 31u;
-            const unsigned int rank = min((unsigned)atomicAdd(&bank2[(size_t)key * 32 + bank], 1), 1023u);
-            key2[t] = ((KeyT)key << 15) | (KeyT)((rank << 5) | bank);
+            const unsigned int rank = min((unsigned)atomicAdd(&bank2[(size_t)key * 32 + bank], 1), 31u);
+            key2[t] = ((KeyT)key << 10) | (KeyT)((rank << 5) | bank);
             ent2[t] = off | (bf << 16);
             atomicAdd(&cnt2[key], 1);
         }
@@ -1048,7 +1093,7 @@ void dense_build(int n, int rows, const int* colptr, const int* rowidx, const fl
     auto bits_of = [](size_t nseg) {
         int b = 1;
         while (((size_t)1 << b) < nseg) ++b;
-        return b + 15;   // segment | rank (10 bits) | bank (5 bits)
+        return b + 10;   // segment | rank (5 bits, clamped: the tail of an over-full bank may collide) | bank (5 bits)
     };
     const int bits1 = bits_of(nseg1), bits2 = bits_of(nseg2);
     if (bits1 <= 32 && bits2 <= 32)
