@@ -203,21 +203,25 @@ struct K2Stages {
 };
 
 // One slot's scatter group (96 threads), software-pipelined over its rounds (= the stages with it % NST == slot):
-//   two rounds ahead  the segment bounds are loaded,
-//   one round ahead   the entries are loaded into registers,
-//   this round        wait for the slot, clear the entries of the slot's previous stage (still in registers), barrier,
-//                     scatter the new ones, publish.
-// Nothing between the slot wait and the publish depends on a global load issued in the same round.
+//   end of round r    the entries of round r + 2 are loaded into registers (their bounds were loaded at the end of round
+//                     r - 1), the bounds of round r + 3 are loaded
+//   round r           wait for the slot, clear the entries of the slot's previous stage (round r - 1, still in registers),
+//                     group barrier, scatter the entries of round r, proxy fence, publish.
+// A prefetch distance of TWO rounds: when the scatter side is the slower one a round lasts only as long as its own stores,
+// which is less than a memory latency, and the proxy fence of a round waits for every load the thread has in flight.
+// Three register arrays rotate through the roles (being scattered / to be cleared, then reloaded / in flight); the loop is
+// unrolled three times so that no array is ever copied while its loads are in flight.
 template <typename Stages>
 __device__ __forceinline__ void scatter_role(Stages I, int slot, int gt, int lane, uint32_t xbase, uint64_t* empty_bar, uint64_t* full_bar,
                                              int dbg) {
     struct Round {
         const uint32_t* ent;
+        const int* sp;
         int e0, e1;
         uint32_t it;
         bool valid;
     };
-    auto fetch_ptr = [&](Round& r) {
+    auto locate = [&](Round& r) {            // next stage of this slot: index arithmetic on the shared-memory descriptors
         r.valid = false;
         while (I.advance()) {
             if ((int)(I.it % NST) == slot) {
@@ -227,30 +231,37 @@ __device__ __forceinline__ void scatter_role(Stages I, int slot, int gt, int lan
         }
         r.ent = I.ent;
         r.it = I.it;
+        r.sp = I.segp();
         r.e0 = r.e1 = 0;
+    };
+    auto load_bounds = [&](Round& r) {
         if (r.valid) {
-            const int* sp = I.segp();
-            r.e0 = __ldg(sp);
-            r.e1 = (dbg & 1) ? r.e0 : __ldg(sp + 1);
+            r.e0 = __ldg(r.sp);
+            r.e1 = (dbg & 1) ? r.e0 : __ldg(r.sp + 1);
         }
     };
-    auto fetch_ent = [&](const Round& r, uint32_t(&v)[PRE]) {
+    auto load_entries = [&](const Round& r, uint32_t(&v)[PRE]) {
 #pragma unroll
         for (int j = 0; j < PRE; ++j) {
             const int e = r.e0 + gt + j * SCAT_GT;
             v[j] = (r.valid && e < r.e1) ? __ldg(r.ent + e) : NOENT;
         }
     };
-    Round cur, nxt, ptr, old{nullptr, 0, 0, 0, false};
-    uint32_t cv[PRE], nv[PRE], ov[PRE];
+    Round cur, r1, r2, r3, old{nullptr, nullptr, 0, 0, 0, false};
+    uint32_t E0[PRE], E1[PRE], E2[PRE];
 #pragma unroll
-    for (int j = 0; j < PRE; ++j) ov[j] = NOENT;
-    fetch_ptr(cur);
-    fetch_ent(cur, cv);
-    fetch_ptr(nxt);
-    fetch_ent(nxt, nv);
-    fetch_ptr(ptr);
-    while (cur.valid) {
+    for (int j = 0; j < PRE; ++j) E2[j] = NOENT;
+    locate(cur);
+    load_bounds(cur);
+    load_entries(cur, E0);
+    locate(r1);
+    load_bounds(r1);
+    load_entries(r1, E1);
+    locate(r2);
+    load_bounds(r2);
+    locate(r3);
+    // one round: cv = entries of the current round, ov = entries of the previous round (cleared, then reloaded for round + 2)
+    auto one_round = [&](uint32_t(&cv)[PRE], uint32_t(&ov)[PRE]) {
         mbar_wait(empty_bar, ((cur.it / NST) & 1u) ^ 1u);
 #pragma unroll
         for (int j = 0; j < PRE; ++j)
@@ -268,16 +279,21 @@ __device__ __forceinline__ void scatter_role(Stages I, int slot, int gt, int lan
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar);
+        load_entries(r2, ov);   // round + 2 into the array that was just cleared from
+        load_bounds(r3);        // round + 3
         old = cur;
-        cur = nxt;
-        nxt = ptr;
-#pragma unroll
-        for (int j = 0; j < PRE; ++j) {
-            ov[j] = cv[j];
-            cv[j] = nv[j];
-        }
-        fetch_ent(nxt, nv);
-        fetch_ptr(ptr);
+        cur = r1;
+        r1 = r2;
+        r2 = r3;
+        locate(r3);
+    };
+    for (;;) {
+        if (!cur.valid) break;
+        one_round(E0, E2);
+        if (!cur.valid) break;
+        one_round(E1, E0);
+        if (!cur.valid) break;
+        one_round(E2, E1);
     }
 }
 
@@ -432,7 +448,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                         umma_bf16(tacc, ad + (uint64_t)(ATILE_BYTES >> 4), xd + (uint64_t)(XTILE_BYTES >> 4), IDESC_BF16, 1u);
                     }
                     const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
-                    ready = __shfl_sync(0xffffffffu, mbar_test(full + ns, nph), 0);   // peek: consumed at the next stage
+                    ready = mbar_test(full + ns, nph);   // peek: consumed at the next stage (test_wait has ~150 cycles of latency)
                     if (mma && leader) {
                         umma_bf16(tacc, ad + (uint64_t)(2 * (ATILE_BYTES >> 4)), xd + (uint64_t)(2 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
                         umma_bf16(tacc, ad + (uint64_t)(3 * (ATILE_BYTES >> 4)), xd + (uint64_t)(3 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
@@ -534,7 +550,7 @@ __device__ __forceinline__ K2Pos k2_item(const DenseDs* __restrict__ ds, int nds
     return r;
 }
 
-constexpr int K2_CONV_WARPS = NST;   // one converter warp per stage group (stages it % NST), both k-steps (32 cells)
+constexpr int K2_CONV_WARPS = 3;     // converter warp g serves the stages it with it % 3 == g (A slot it % 8), both k-steps (32 cells)
 constexpr int K2_WARPS_TOTAL = 5 + SCAT_WARPS + K2_CONV_WARPS;   // MMA, 4 epilogue, scatter, converters
 
 __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds_g, int nds, long long total_flat, int dbg) {
@@ -612,8 +628,8 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
                     }
                     const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
                     const uint32_t nsa = sa + 1 == K2_NSA ? 0u : sa + 1, npha = nsa == 0 ? pha ^ 1u : pha;
-                    ready = __shfl_sync(0xffffffffu, mbar_test(full + ns, nph), 0);
-                    readyA = __shfl_sync(0xffffffffu, mbar_test(fullA + nsa, npha), 0);
+                    ready = mbar_test(full + ns, nph);
+                    readyA = mbar_test(fullA + nsa, npha);
                     if (mma && leader) {   // k-step 1
                         umma_bf16(tmem0, ad + (uint64_t)(ATILE_BYTES >> 4), xd + (uint64_t)(2 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
                         umma_bf16(tmem0 + TILE_N, ad + (uint64_t)(ATILE_BYTES >> 4), xd + (uint64_t)(3 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
@@ -681,7 +697,7 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
         I.init(ds, nds, p0, p1);
         scatter_role(I, slot, gt, lane, smem_u32(smX + slot * XSTAGE_BYTES), empty + slot, full + slot, dbg);
     } else if (warp >= 5 + SCAT_WARPS) {
-        // ===== converter warps: warp g serves the stages it with it % NST == g (A slots it % 8), both k-steps of a stage.
+        // ===== converter warps: warp g serves the stages it with it % 3 == g (A slots it % 8), both k-steps of a stage.
         //       A slab rows t * 32 + f = bf16 term t of cs[c] * H[c, f].  Lane f reads H[c, f] of the stage's 32 cells (coalesced
         //       128-byte rows) one round ahead -- issued AFTER the publish, so that the proxy fence of this round does not wait
         //       for them -- splits them before the slot wait and then only stores one 16-byte chunk (8 cells) per term:
@@ -696,7 +712,7 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
         auto fetch = [&](uint32_t& it_out, bool& valid) {   // loads only: nothing here may wait for a loaded value
             valid = false;
             while (I.advance()) {
-                if ((int)(I.it % NST) == grp) {
+                if ((int)(I.it % K2_CONV_WARPS) == grp) {
                     valid = true;
                     break;
                 }
@@ -826,7 +842,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
                         umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(ATILE_BYTES >> 4), ad + (uint64_t)(ATILE_BYTES >> 4), IDESC_GRAM, 1u);
                     }
                     const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
-                    ready = __shfl_sync(0xffffffffu, mbar_test(full + ns, nph), 0);
+                    ready = mbar_test(full + ns, nph);
                     if (leader) {
                         umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(2 * (ATILE_BYTES >> 4)), ad + (uint64_t)(2 * (ATILE_BYTES >> 4)), IDESC_GRAM, 1u);
                         umma_bf16(tmem0 + acc * 96, ad + (uint64_t)(3 * (ATILE_BYTES >> 4)), ad + (uint64_t)(3 * (ATILE_BYTES >> 4)), IDESC_GRAM, 1u);
