@@ -986,6 +986,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
             q.H = h.H;
             q.R = h.R;
             q.G = h.G;
+            q.Hs = D.dl.Hs.p;
             c->k1_tiles += D.dl.ntile1;
             c->gh_blocks += (D.n + dense_gram_tile() - 1) / dense_gram_tile();
             c->k2_flat += (long long)D.dl.ngb * D.dl.ncstage;

@@ -153,6 +153,7 @@ struct DenseDs {
     const float* H;
     float* R;
     double* G;
+    unsigned short* Hs;   // bf16 split image of cs * H (A slabs of k_dense_xh), written by k_gram_tc: 6 KB per 32 cells
 };
 
 // One batch of NNLS columns sharing a Gram matrix (gram / ginv / ok are produced by k_gram_inv)
@@ -241,7 +242,7 @@ struct DenseLayout {
     int ntile1 = 0, nstage1 = 0, ngb = 0, ncstage = 0;
     DBuf<int> seg1, seg2;
     DBuf<unsigned int> ent1, ent2;
-    DBuf<unsigned short> Asplit;
+    DBuf<unsigned short> Asplit, Hs;
     DBuf<float> rs, cs;
 };
 void dense_build(int n, int rows, const int* colptr, const int* rowidx, const float* val, size_t nnz, const float* rs, const float* cs,

@@ -550,8 +550,8 @@ __device__ __forceinline__ K2Pos k2_item(const DenseDs* __restrict__ ds, int nds
     return r;
 }
 
-constexpr int K2_CONV_WARPS = 3;     // converter warp g serves the stages it with it % 3 == g (A slot it % 8), both k-steps (32 cells)
-constexpr int K2_WARPS_TOTAL = 5 + SCAT_WARPS + K2_CONV_WARPS;   // MMA, 4 epilogue, scatter, converters
+constexpr int K2_WARPS_TOTAL = 6 + SCAT_WARPS;   // A producer, MMA, 4 epilogue, scatter
+constexpr int K2_IMG_STAGE_BYTES = K2_KS * 2 * 96 * 16;   // 6 KB: the 96 used rows of the four [128 x 8] chunks of a stage
 
 __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds_g, int nds, long long total_flat, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
@@ -576,13 +576,13 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
             mbar_init(empty + s, 1);
         }
         for (int s = 0; s < K2_NSA; ++s) {
-            mbar_init(fullA + s, 1);
+            mbar_init(fullA + s, 1);   // the producer's arrive.expect_tx
             mbar_init(emptyA + s, 1);
         }
         mbar_init(accfull, 1);
         mbar_init(accempty, 4);
     }
-    if (warp == 0) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -598,6 +598,26 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
     const uint32_t tmem0 = *tmem_slot;
 
     if (warp == 0) {
+        // ===== A producer: the cs-scaled bf16 split of H is written by k_gram_tc as an image of the operand slabs (without
+        //       the 32 padding rows of each [128 x 8] chunk); four bulk copies of 1536 B per stage, 8 stages ahead =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long p = p0; p < p1;) {
+                const K2Pos P = k2_item(ds, nds, p, p1);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(ds[P.i].Hs);
+                for (int cs = P.cs0; cs < P.cs1; ++cs, ++it) {
+                    const uint32_t sa = it % K2_NSA, pha = (it / K2_NSA) & 1u;
+                    mbar_wait(emptyA + sa, pha ^ 1u);
+                    mbar_expect_tx(fullA + sa, K2_IMG_STAGE_BYTES);
+#pragma unroll
+                    for (int oc = 0; oc < K2_KS * 2; ++oc)
+                        bulk_g2s(smA + sa * K2_ASTAGE_BYTES + oc * 2048, src + (size_t)cs * K2_IMG_STAGE_BYTES + oc * 1536, 1536, fullA + sa);
+                }
+                p += P.cs1 - P.cs0;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
         // ===== MMA issuer (converged warp, elected lane): per k-step of 16 cells two MMAs (genes 0..255 and 256..511 of the block)
         //       sharing the A slab =====
         {
@@ -658,7 +678,7 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
             }
         }
         __syncwarp();
-    } else if (warp >= 1 && warp < 5) {
+    } else if (warp >= 2 && warp < 6) {
         // ===== epilogue: D rows are t * 32 + f, so quadrant q holds term q of all 32 factors; the three terms are summed by
         //       the reduction itself (red.global.add.f32 into R, which also sums over the CTAs that share a gene block) =====
         const int q = warp & 3;
@@ -690,75 +710,16 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
             if (lane == 0) mbar_arrive(accempty);
             p += P.cs1 - P.cs0;
         }
-    } else if (warp >= 5 && warp < 5 + SCAT_WARPS) {
+    } else {
         // ===== scatter warps =====
-        const int sw = warp - 5, slot = sw % NST, gt = (sw / NST) * 32 + lane;
+        const int sw = warp - 6, slot = sw % NST, gt = (sw / NST) * 32 + lane;
         K2Stages I;
         I.init(ds, nds, p0, p1);
         scatter_role(I, slot, gt, lane, smem_u32(smX + slot * XSTAGE_BYTES), empty + slot, full + slot, dbg);
-    } else if (warp >= 5 + SCAT_WARPS) {
-        // ===== converter warps: warp g serves the stages it with it % 3 == g (A slots it % 8), both k-steps of a stage.
-        //       A slab rows t * 32 + f = bf16 term t of cs[c] * H[c, f].  Lane f reads H[c, f] of the stage's 32 cells (coalesced
-        //       128-byte rows) one round ahead -- issued AFTER the publish, so that the proxy fence of this round does not wait
-        //       for them -- splits them before the slot wait and then only stores one 16-byte chunk (8 cells) per term:
-        //       consecutive lanes write consecutive chunks, no bank conflicts =====
-        const int grp = warp - (5 + SCAT_WARPS);
-        K2Stages I;
-        I.init(ds, nds, p0, p1);
-        float hn[K2_KS * KSTEP];   // raw H[c, lane] of the round being prefetched; csn: lane j holds cs of cell j
-        float csn = 0.f;
-        uint32_t cur_it = 0, nxt_it = 0;
-        bool cur_valid = false, nxt_valid = false;
-        auto fetch = [&](uint32_t& it_out, bool& valid) {   // loads only: nothing here may wait for a loaded value
-            valid = false;
-            while (I.advance()) {
-                if ((int)(I.it % K2_CONV_WARPS) == grp) {
-                    valid = true;
-                    break;
-                }
-            }
-            it_out = I.it;
-            if (valid) {
-                const DenseDs& D = ds[I.i];
-                const int c0 = I.cs * (K2_KS * KSTEP);
-                const bool live = !(dbg & 4);
-                csn = (c0 + lane < D.n && live) ? __ldg(D.cs + c0 + lane) : 0.f;
-#pragma unroll
-                for (int j = 0; j < K2_KS * KSTEP; ++j) {
-                    const int c = c0 + j;
-                    hn[j] = (c < D.n && live) ? __ldg(D.H + (size_t)c * 32 + lane) : 0.f;
-                }
-            }
-        };
-        fetch(cur_it, cur_valid);
-        while (cur_valid) {
-            const uint32_t sa = cur_it % K2_NSA, pha = (cur_it / K2_NSA) & 1u;
-            uint4* abase = reinterpret_cast<uint4*>(smA + sa * K2_ASTAGE_BYTES);
-            mbar_wait(emptyA + sa, pha ^ 1u);   // 8-deep ring: the slot is normally free long before
-#pragma unroll
-            for (int oc = 0; oc < K2_KS * 2; ++oc) {   // (k-step, chunk of 8 cells): 16-byte row chunks of the three terms
-                unsigned short hi[8], mid[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split3(hn[oc * 8 + e] * __shfl_sync(0xffffffffu, csn, oc * 8 + e), hi[e], mid[e], lo[e]);
-                uint4* dst = abase + oc * 128;
-                dst[lane] = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16,
-                                       hi[6] | (uint32_t)hi[7] << 16);
-                dst[32 + lane] = make_uint4(mid[0] | (uint32_t)mid[1] << 16, mid[2] | (uint32_t)mid[3] << 16, mid[4] | (uint32_t)mid[5] << 16,
-                                            mid[6] | (uint32_t)mid[7] << 16);
-                dst[64 + lane] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
-                                            lo[6] | (uint32_t)lo[7] << 16);
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(fullA + sa);
-            fetch(nxt_it, nxt_valid);
-            cur_it = nxt_it;
-            cur_valid = nxt_valid;
-        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(512) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(512) : "memory");
 }
 
 // =====================================================================================================================
@@ -907,7 +868,8 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
         // ===== converter warps: slot = cw % NST, k-step = cw / NST; lane f reads H[c, f] of 16 cells one round ahead =====
         const int cw = warp - 5, slot = cw % NST, ks = cw / NST;
         uint4* abase = reinterpret_cast<uint4*>(smA + slot * GT_STAGE_BYTES + ks * ATILE_BYTES);
-        float hn[KSTEP];
+        float hn[KSTEP], csn = 0.f;
+        uint4* img = nullptr;
         int item = (int)blockIdx.x - (int)gridDim.x, s = 0, nst = 0, i = 0, c0 = 0, ncell = 0;
         uint32_t it = 0xFFFFFFFFu, cur_it = 0, nxt_it = 0;
         bool cur_valid = false, nxt_valid = false;
@@ -929,6 +891,9 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
             it_out = it;
             const float* __restrict__ H = ds[i].H + (size_t)c0 * 32;
             const int cc = s * (GT_KS * KSTEP) + ks * KSTEP;
+            csn = (lane < KSTEP && cc + lane < ncell) ? __ldg(ds[i].cs + c0 + cc + lane) : 0.f;
+            // image of k_dense_xh's A slabs: [32-cell stage][k-step][chunk of 8 cells][row t * 32 + f][cell % 8], 6 KB per stage
+            img = reinterpret_cast<uint4*>(ds[i].Hs) + ((size_t)((c0 + cc) >> 5) * 6144 + (size_t)(((c0 + cc) >> 4) & 1) * 3072) / 16;
 #pragma unroll
             for (int j = 0; j < KSTEP; ++j) hn[j] = (cc + j < ncell) ? __ldg(H + (size_t)(cc + j) * 32 + lane) : 0.f;
         };
@@ -955,6 +920,20 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + slot);
+            // the same rows scaled by the cell scale, split again and written out: the A slabs of the R sweep (k_dense_xh)
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                unsigned short hi[8], mid[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split3(hn[ch * 8 + e] * __shfl_sync(0xffffffffu, csn, ch * 8 + e), hi[e], mid[e], lo[e]);
+                uint4* dst = img + ch * 96;
+                dst[lane] = make_uint4(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16, hi[4] | (uint32_t)hi[5] << 16,
+                                       hi[6] | (uint32_t)hi[7] << 16);
+                dst[32 + lane] = make_uint4(mid[0] | (uint32_t)mid[1] << 16, mid[2] | (uint32_t)mid[3] << 16, mid[4] | (uint32_t)mid[5] << 16,
+                                            mid[6] | (uint32_t)mid[7] << 16);
+                dst[64 + lane] = make_uint4(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16, lo[4] | (uint32_t)lo[5] << 16,
+                                            lo[6] | (uint32_t)lo[7] << 16);
+            }
             fetch(nxt_it, nxt_valid);   // after the publish: the fence must not wait for these loads
             cur_it = nxt_it;
             cur_valid = nxt_valid;
@@ -1119,6 +1098,10 @@ void dense_build(int n, int rows, const int* colptr, const int* rowidx, const fl
     // pre-split factor image of k_dense_ltx: nstage1 x 16 KB, zero (rows of term 3 and rows >= `rows` stay zero)
     out.Asplit.alloc((size_t)out.nstage1 * K1_ASTAGE_BYTES / 2);
     out.Asplit.zero(st);
+    // split image of cs * H for k_dense_xh (written by k_gram_tc every iteration): 6 KB per 32-cell stage; k_gram_tc covers
+    // whole 64-cell stages, so the last stage pair is allocated in full
+    out.Hs.alloc(((size_t)out.ncstage + 2) * 3072);
+    out.Hs.zero(st);
 }
 
 }  // namespace lgr
