@@ -302,7 +302,8 @@ __device__ __forceinline__ unsigned char* align1k(unsigned char* p) {
 }
 
 constexpr int MAX_SDS = 24;   // datasets whose descriptors are cached in shared memory (more: read from global memory)
-constexpr size_t K1_SMEM = (size_t)NST * (XSTAGE_BYTES + K1_ASTAGE_BYTES) + 32 * 8 + 1024;
+constexpr int K1_NSA = 5;   // A-slab ring of k_dense_ltx (decoupled from the X ring: the slabs are fetched further ahead)
+constexpr size_t K1_SMEM = (size_t)NST * XSTAGE_BYTES + (size_t)K1_NSA * K1_ASTAGE_BYTES + 40 * 8 + 1024;
 constexpr int K2_NSA = 8;   // A-slab ring of k_dense_xh: the converters run up to 8 stages ahead of the MMAs
 constexpr size_t K2_SMEM = (size_t)NST * XSTAGE_BYTES + (size_t)K2_NSA * K2_ASTAGE_BYTES + 40 * 8 + 1024;
 
@@ -354,10 +355,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
     unsigned char* raw = align1k(smem_dyn);
     unsigned char* smX = raw;
     unsigned char* smA = raw + NST * XSTAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + NST * K1_ASTAGE_BYTES);
-    uint64_t* full = bars;              // NST
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + K1_NSA * K1_ASTAGE_BYTES);
+    uint64_t* full = bars;              // NST: the three scatter warps of the X slot
     uint64_t* empty = bars + NST;       // NST
-    uint64_t* accfull = bars + 2 * NST; // 2
+    uint64_t* fullA = bars + 2 * NST;   // K1_NSA: the producer's transaction bytes
+    uint64_t* emptyA = fullA + K1_NSA;  // K1_NSA
+    uint64_t* accfull = emptyA + K1_NSA; // 2
     uint64_t* accempty = accfull + 2;   // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -365,8 +368,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
     // ---- one-time setup: barriers, TMEM (all 512 columns: two 256-column accumulators), cleared X ring ----
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
-            mbar_init(full + s, SCAT_WARPS / NST + 1);
+            mbar_init(full + s, SCAT_WARPS / NST);
             mbar_init(empty + s, 1);
+        }
+        for (int s = 0; s < K1_NSA; ++s) {
+            mbar_init(fullA + s, 1);
+            mbar_init(emptyA + s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(accfull + a, 1);
@@ -398,16 +405,16 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(D.Asplit);
                 const int nstage = D.nstage1, rot = k1_rot(nstage);
                 for (int s = 0; s < nstage; ++s, ++it) {
-                    const uint32_t slot = it % NST, ph = (it / NST) & 1u;
+                    const uint32_t slot = it % K1_NSA, ph = (it / K1_NSA) & 1u;
                     int sr = s + rot;
                     if (sr >= nstage) sr -= nstage;
-                    mbar_wait(empty + slot, ph ^ 1u);
+                    mbar_wait(emptyA + slot, ph ^ 1u);
                     if (dbg & 8) {
-                        mbar_arrive(full + slot);
+                        mbar_arrive(fullA + slot);
                         continue;
                     }
-                    mbar_expect_tx(full + slot, K1_ASTAGE_BYTES);
-                    bulk_g2s(smA + slot * K1_ASTAGE_BYTES, src + (size_t)sr * K1_ASTAGE_BYTES, K1_ASTAGE_BYTES, full + slot);
+                    mbar_expect_tx(fullA + slot, K1_ASTAGE_BYTES);
+                    bulk_g2s(smA + slot * K1_ASTAGE_BYTES, src + (size_t)sr * K1_ASTAGE_BYTES, K1_ASTAGE_BYTES, fullA + slot);
                 }
             }
         }
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
             long long wAcc = 0, wFull = 0, wIssue = 0, tstart = 0, c0 = 0, c1 = 0;
             const bool prof = (dbg & 16) != 0;
             if (prof) tstart = clock64();
-            uint32_t ready = 0, slot = 0, ph = 0;
+            uint32_t ready = 0, readyA = 0, slot = 0, ph = 0, sa = 0, pha = 0;
             // descriptors of slot 0 / k-step 0; the address field (bits 0..13, in 16-byte units) is advanced by plain adds
             const uint64_t adesc0 = umma_desc(smem_u32(smA), 128 * 16, 128), xdesc0 = umma_desc(smem_u32(smX), TILE_N * 16, 128);
             // The tensor core queues only ~2 instructions: the issue of the 3rd MMA of a stage blocks until the 1st has
@@ -438,25 +445,33 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                 const uint32_t tacc = tmem0 + acc * TILE_N;
                 for (int s = 0; s < nstage; ++s, ++it) {
                     if (prof) c0 = clock64();
+                    if (!readyA) mbar_wait(fullA + sa, pha);
                     if (!ready) mbar_wait(full + slot, ph);
                     if (prof) c1 = clock64(), wFull += c1 - c0;
                     tc_fence_after();
-                    const uint64_t ad = adesc0 + (uint64_t)(slot * (K1_ASTAGE_BYTES >> 4)), xd = xdesc0 + (uint64_t)(slot * (XSTAGE_BYTES >> 4));
+                    const uint64_t ad = adesc0 + (uint64_t)(sa * (K1_ASTAGE_BYTES >> 4)), xd = xdesc0 + (uint64_t)(slot * (XSTAGE_BYTES >> 4));
                     const bool mma = !(dbg & 2);
                     if (mma && leader) {
                         umma_bf16(tacc, ad, xd, IDESC_BF16, s != 0);
                         umma_bf16(tacc, ad + (uint64_t)(ATILE_BYTES >> 4), xd + (uint64_t)(XTILE_BYTES >> 4), IDESC_BF16, 1u);
                     }
                     const uint32_t ns = slot + 1 == NST ? 0u : slot + 1, nph = ns == 0 ? ph ^ 1u : ph;
+                    const uint32_t nsa = sa + 1 == K1_NSA ? 0u : sa + 1, npha = nsa == 0 ? pha ^ 1u : pha;
                     ready = mbar_test(full + ns, nph);   // peek: consumed at the next stage (test_wait has ~150 cycles of latency)
+                    readyA = mbar_test(fullA + nsa, npha);
                     if (mma && leader) {
                         umma_bf16(tacc, ad + (uint64_t)(2 * (ATILE_BYTES >> 4)), xd + (uint64_t)(2 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
                         umma_bf16(tacc, ad + (uint64_t)(3 * (ATILE_BYTES >> 4)), xd + (uint64_t)(3 * (XTILE_BYTES >> 4)), IDESC_BF16, 1u);
                     }
-                    if (leader) umma_commit(empty + slot);   // frees the slot (A slabs and X tiles) when these MMAs have read it
+                    if (leader) {   // frees the X slot and the A slot when these MMAs have read them
+                        umma_commit(empty + slot);
+                        umma_commit(emptyA + sa);
+                    }
                     if (prof) wIssue += clock64() - c1;
                     slot = ns;
                     ph = nph;
+                    sa = nsa;
+                    pha = npha;
                 }
                 if (leader) umma_commit(accfull + acc);   // the tile's accumulator is complete: the epilogue may start
                 __syncwarp();
