@@ -137,7 +137,7 @@ struct lgr_ctx {
     DBuf<Counters> counters;
     NnlsConfig cfgF{}, cfgD{};
     long long colsH = 0, colsV = 0; int ltx_blocks = 0, xh_tiles = 0, prep_blocks = 0, max_rows = 0;
-    size_t N_local = 0;
+    size_t N_local = 0, r_words = 0;
     NcclComm* comm = nullptr;
     bool stats_valid = false;  // R / G arenas hold the statistics of the current H
     bool h_valid = false;
@@ -380,10 +380,13 @@ void set_inits(lgr_ctx* c, const double* Winit, const double* const* Vinit, cons
 void allreduce_stats(lgr_ctx* c) {
     if (c->world <= 1) return;
     Span sp(c, "comm");   // includes the wait for the slowest rank
-    nccl_group_start();
+    // one collective: the fp64 Grams travel as (hi, lo) float pairs in the tail of the fp32 statistics arena
+    const int ng = (int)c->Garena.n;
+    float* tail = c->Rarena.p + c->r_words;
+    launch_pack_gram(c->Garena.p, tail, ng, c->st);
     nccl_allreduce_sum_f32(c->comm, c->Rarena.p, c->Rarena.n, c->st);
-    nccl_allreduce_sum_f64(c->comm, c->Garena.p, c->Garena.n, c->st);
-    nccl_group_end();
+    launch_unpack_gram(c->Garena.p, tail, ng, c->st);
+    c->tm.kernel_launches += 2;
 }
 
 void run_prep(lgr_ctx* c) {
@@ -889,7 +892,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     if (const char* e = getenv("LGR_FUSE_U")) c->fuse_u = c->fuse_u && atoi(e) != 0;
     if (c->fuse_u) c->use_tc = false;
     if (c->use_tc || c->fuse_u) c->Ubuf.alloc(std::max<size_t>(b_total, 1));
-    c->Rarena.alloc(r_total);
+    c->r_words = r_total;
+    c->Rarena.alloc(r_total + (c->world > 1 ? (size_t)2 * c->d * kp * kp : 0));   // tail: the Grams as float pairs (all-reduce)
     c->Garena.alloc((size_t)c->d * kp * kp);
     c->gram_arena.alloc((size_t)2 * c->d * kp * kp);
     c->W.alloc((size_t)m * kp);

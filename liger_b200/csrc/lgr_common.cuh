@@ -233,6 +233,8 @@ void launch_pb_tc(const NnlsGroup* groups, int ngroups, long long total_tiles, i
 void tc_init();
 void launch_vrhs(const DsDev* ds, int nds, const double* W, int k, int kp, int max_rows, cudaStream_t st);
 void launch_wrhs(const DsDev* ds, int nds, int m, double* CtBw, double* Gsum, int k, int kp, cudaStream_t st);
+void launch_pack_gram(const double* G, float* tail, int n, cudaStream_t st);
+void launch_unpack_gram(double* G, const float* tail, int n, cudaStream_t st);
 void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot, cudaStream_t st);
 size_t spmm_xh_smem(int kp, int tc);
 void kernels_init();  // opt-in shared memory attributes of every kernel, once per device (safe to call repeatedly)

@@ -211,6 +211,31 @@ void launch_objective(const DsDev* ds, int nds, int k, int kp, double* obj_slot,
     LGR_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------
+// One all-reduce per iteration instead of two: the fp64 Grams G_i ride in the tail of the fp32 statistics arena as (hi, lo)
+// float pairs (G = hi + lo to ~2^-48; the cross-rank sums of the two halves are fp32 sums of at most `world` terms).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_gram(const double* __restrict__ G, float* __restrict__ tail, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double g = G[e];
+    const float hi = (float)g;
+    tail[e] = hi;
+    tail[n + e] = (float)(g - (double)hi);
+}
+__global__ void k_unpack_gram(double* __restrict__ G, const float* __restrict__ tail, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) G[e] = (double)tail[e] + (double)tail[n + e];
+}
+void launch_pack_gram(const double* G, float* tail, int n, cudaStream_t st) {
+    k_pack_gram<<<(n + 255) / 256, 256, 0, st>>>(G, tail, n);
+    LGR_CUDA(cudaGetLastError());
+}
+void launch_unpack_gram(double* G, const float* tail, int n, cudaStream_t st) {
+    k_unpack_gram<<<(n + 255) / 256, 256, 0, st>>>(G, tail, n);
+    LGR_CUDA(cudaGetLastError());
+}
+
 void kernels_init() {
     // cudaFuncSetAttribute is per device: remember which devices have been initialised
     static std::mutex mu;
