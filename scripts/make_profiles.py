@@ -22,14 +22,16 @@ for r in rows[1:]:
 unit = rows[1][hdr.index("Metric Unit")]
 tot = sum(v[1] for v in agg.values())
 with open(f"{out}/{tag}_launches_summary.txt", "w") as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 12 --no-cpu --no-e2e (C3; -k filter = the library kernels, first 400 launches: layout build + 15 ANLS iterations from a cold start)\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 600, python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e (C3, count-structured input: dense-tile sweeps; the first 600 launches: generator kernels, layout build, ANLS iterations from a cold start)\n")
     f.write(f"# per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  unit: {unit}\n")
     f.write(f"{'kernel':60s} {'launches':>8s} {'total':>14s} {'share':>7s} {'avg':>12s}\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:60s} {n:8d} {t:14.1f} {t / tot * 100:6.1f}% {t / n:12.1f}\n")
 print(open(f"{out}/{tag}_launches_summary.txt").read())
 # ---- full capture -> raw metrics of the top kernels ----
-raw = subprocess.run(["ncu", "-i", f"gpurun_out/{tag}_top3.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+import glob
+rep = sorted(glob.glob(f"gpurun_out/{tag}_top*.ncu-rep"))[-1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -40,10 +42,12 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum",
         "sm__cycles_elapsed.max"]
 traffic = {}
 with open(f"{out}/{tag}_top_kernels_ncu.txt", "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on, python bench.py --steps 2 --warmup 12 --no-cpu --no-e2e (C3; launches 13-14 of the SpMM / NNLS kernels, i.e. warm-started iterations)\n")
+    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_dense_ltx|k_dense_xh|k_gram_tc|k_nnls_reg -s 16 -c 4, python scripts/dense_profile.py C3 125000 6 (C3; the four top kernels of the 5th ANLS iteration from a cold start)\n")
     for r in rows[2:]:
         for w in want:
             if w in hdr:
@@ -52,7 +56,7 @@ with open(f"{out}/{tag}_top_kernels_ncu.txt", "w") as f:
         def num(name):
             i = hdr.index(name); v = float(r[i].replace(",", "")); u = units[i]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-        kn = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
+        kn = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("unnamed>::", "")
         traffic[kn] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
         f.write(f"dram traffic per launch = {traffic[kn] / 1e6:.1f} MB\n---\n")
 json.dump(traffic, open(f"{out}/{tag}_traffic.json", "w"), indent=1)
