@@ -305,7 +305,8 @@ constexpr int MAX_SDS = 24;   // datasets whose descriptors are cached in shared
 constexpr int K1_NSA = 5;   // A-slab ring of k_dense_ltx (decoupled from the X ring: the slabs are fetched further ahead)
 constexpr size_t K1_SMEM = (size_t)NST * XSTAGE_BYTES + (size_t)K1_NSA * K1_ASTAGE_BYTES + 40 * 8 + 1024;
 constexpr int K2_NSA = 8;   // A-slab ring of k_dense_xh: the converters run up to 8 stages ahead of the MMAs
-constexpr size_t K2_SMEM = (size_t)NST * XSTAGE_BYTES + (size_t)K2_NSA * K2_ASTAGE_BYTES + 40 * 8 + 1024;
+constexpr int K2_EPI_WORDS = 2 * 3 * 32 * 33;   // epilogue staging: two buffers x three terms x [32 factors][33]
+constexpr size_t K2_SMEM = (size_t)NST * XSTAGE_BYTES + (size_t)K2_NSA * K2_ASTAGE_BYTES + (size_t)K2_EPI_WORDS * 4 + 40 * 8 + 1024;
 
 // one lane of a converged warp (the MMA warps run their loops warp-uniformly, so that descriptors and addresses stay in
 // uniform registers, and elect a lane only for the tcgen05 instructions themselves)
@@ -574,7 +575,8 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
     unsigned char* raw = align1k(smem_dyn);
     unsigned char* smX = raw;
     unsigned char* smA = raw + NST * XSTAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + K2_NSA * K2_ASTAGE_BYTES);
+    float* smEpi = reinterpret_cast<float*>(smA + K2_NSA * K2_ASTAGE_BYTES);   // epilogue staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smEpi + K2_EPI_WORDS);
     uint64_t* full = bars;              // NST: the three scatter warps of the X slot
     uint64_t* empty = bars + NST;       // NST
     uint64_t* fullA = bars + 2 * NST;   // K2_NSA: the converter warp of the A slot
@@ -694,29 +696,36 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
         }
         __syncwarp();
     } else if (warp >= 2 && warp < 6) {
-        // ===== epilogue: D rows are t * 32 + f, so quadrant q holds term q of all 32 factors; the three terms are summed by
-        //       the reduction itself (red.global.add.f32 into R, which also sums over the CTAs that share a gene block) =====
-        const int q = warp & 3;
+        // ===== epilogue: D rows are t * 32 + f, so quadrant q holds term q of all 32 factors.  Per 32 genes the three term
+        //       warps park their [factor][gene] blocks in shared memory, the four warps then sum the terms of 8 genes each and
+        //       add the row slices into R with one coalesced red.global.add.f32 per gene (R also sums over the CTAs that share
+        //       a gene block) =====
+        const int q = warp & 3, ew = warp - 2;
         uint32_t icount = 0;
         for (long long p = p0; p < p1; ++icount) {
             const K2Pos P = k2_item(ds, nds, p, p1);
             const DenseDs& D = ds[P.i];
             mbar_wait(accfull, icount & 1u);
             tc_fence_after();
-            if (q < 3) {
-                const int g0 = P.gb * 512;
-                const int ngene = min(512, D.rows - g0);
-                for (int j = 0; j < 512 / 32; ++j) {
-                    if (j * 32 >= ngene) break;
+            const int g0 = P.gb * 512;
+            const int ngene = min(512, D.rows - g0);
+            for (int j = 0; j < 512 / 32; ++j) {
+                if (j * 32 >= ngene) break;
+                float* buf = smEpi + (j & 1) * (3 * 32 * 33);
+                if (q < 3) {
                     uint32_t v[32];
                     tmem_ld32(tmem0 + ((uint32_t)(q * 32) << 16) + j * 32, v);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int g = g0 + j * 32 + c;
-                        if (j * 32 + c < ngene)
-                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(D.R + (size_t)g * 32 + lane),
-                                         "f"(__uint_as_float(v[c]) * __ldg(D.rs + g))
-                                         : "memory");
+                    for (int c = 0; c < 32; ++c) buf[(q * 32 + lane) * 33 + c] = __uint_as_float(v[c]);
+                }
+                asm volatile("bar.sync 5, 128;" ::: "memory");
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c = ew * 8 + cc;
+                    const int g = g0 + j * 32 + c;
+                    if (j * 32 + c < ngene) {
+                        const float sum = buf[lane * 33 + c] + buf[(32 + lane) * 33 + c] + buf[(64 + lane) * 33 + c];
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(D.R + (size_t)g * 32 + lane), "f"(sum * __ldg(D.rs + g)) : "memory");
                     }
                 }
             }

@@ -40,15 +40,15 @@ __device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
 // k_gram_inv: one CTA per group.  gram = cA*A + cB*B (fp64), ginv = gram^-1 by Gauss-Jordan (SPD: no
 // pivoting), ok = 0 when a pivot collapses (then the NNLS kernel uses primal solves only).
 // ------------------------------------------------------------------------------------------------
-template <int KP>
-__global__ void __launch_bounds__(1024) k_gram_inv(const GramSpec* __restrict__ specs, int k) {
+template <int KP, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_gram_inv(const GramSpec* __restrict__ specs, int k) {
     const GramSpec sp = specs[blockIdx.x];
     __shared__ double M[KP][KP + 1];
     __shared__ double colbuf[KP];
     __shared__ double rowbuf[KP];
     __shared__ int ok_s;
     const int tid = threadIdx.x;
-    constexpr int EPT = KP * KP / 1024 > 0 ? KP * KP / 1024 : 1;  // elements per thread (1 for KP=32, 4 for KP=64)
+    constexpr int EPT = KP * KP / THREADS;   // elements per thread (1 for KP = 32, 4 for KP = 64)
     for (int e = tid; e < KP * KP; e += blockDim.x) {
         const int a = e / KP, b = e % KP;
         double v = 0.0;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(1024) k_gram_inv(const GramSpec* __restrict__ 
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
-            const int e = tid + j * 1024;
+            const int e = tid + j * THREADS;
             const int r = e / KP, col = e % KP;
             if (r < k && col < k) {
                 if (r == c) {
@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(1024) k_gram_inv(const GramSpec* __restrict__ 
 void launch_gram_inv(const GramSpec* specs, int nspecs, int k, int kp, cudaStream_t st) {
     if (nspecs <= 0) return;
     if (kp == 32)
-        k_gram_inv<32><<<nspecs, 1024, 0, st>>>(specs, k);
+        k_gram_inv<32, 1024><<<nspecs, 1024, 0, st>>>(specs, k);
     else
-        k_gram_inv<64><<<nspecs, 1024, 0, st>>>(specs, k);
+        k_gram_inv<64, 1024><<<nspecs, 1024, 0, st>>>(specs, k);
     LGR_CUDA(cudaGetLastError());
 }
 

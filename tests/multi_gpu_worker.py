@@ -28,6 +28,18 @@ def main():
     dist.broadcast(idt, 0)
     nccl_id = bytes(idt.cpu().numpy().tobytes())
     mode = sys.argv[1]
+    if mode == "dense":      # count-structured synthetic data: the dense-tile tensor-core sweeps on cell shards
+        from liger_b200 import synthetic as syn
+        d, n, m, k = 3, 2100, 700, 24
+        Es, _, sc = syn.make_numpy(d, n, m, 8, block=700, seed=21, return_scales=True)
+        W0, V0, _, _ = orc.seeded_init(1, m, k, [n] * d)
+        Cs = [liger_b200.CountScaled(E, rs, cs) for E, (rs, cs) in zip(Es, sc)]
+        out = liger_b200.inmf(Cs, k=k, lambda_=5.0, niter=6, Winit=W0, Vinit=V0, device=local, rank=rank, world=world,
+                              nccl_id=nccl_id, trajectory=True)     # slice mode: the library takes this rank's columns
+        np.savez(os.path.join(sys.argv[2], f"{mode}_rank{rank}.npz"), W=out["W"], V0=out["V"][0], H0=out["H"][0], traj=out["traj"],
+                 obj=out["objErr"])
+        dist.destroy_process_group()
+        return
     if mode == "slice":      # every rank passes the FULL matrices; the library takes its column range
         ctx = liger_b200.Context(Es, 20, 5.0, W0, V0, device=local, rank=rank, world=world, nccl_id=nccl_id)
         lo = [0, 0]
