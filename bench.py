@@ -144,7 +144,7 @@ def ncu_traffic(kernel):
     of this same command (profiles/r*_traffic.json, written by scripts/make_profiles.py); None if not captured."""
     import glob
     alias = {"k_nnls_H": "k_nnls_reg", "k_spmm_ltx": "k_spmm_ltx_tiled", "k_spmm_xh": "k_spmm_xh",
-             "k_dense_ltx": "k_dense_ltx", "k_dense_xh": "k_dense_xh"}
+             "k_dense_ltx": "k_dense_ltx", "k_dense_xh": "k_dense_xh", "k_gram_tc": "k_gram_tc"}
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
     if not files or kernel not in alias:
         return None
@@ -311,6 +311,8 @@ def timed_runs(job, args, barrier, allmax, sampler=None):
 
 
 def roofline_of(job, res, args, hbm_peak, peak_src, with_traffic):
+    """`roofline` of the bench line: the kernel with the largest share of the step (by its CUDA-event time) against the HBM
+    roofline, with the same figure for every large kernel under `per_kernel` and the whole iteration under `iteration`."""
     ab = algorithmic_bytes(job.cfg, job.info["nnz"], job.n_local)
     kt = res["kt"]
     cands = {kn: v for kn, v in kt.items() if kernel_class(kn)}
@@ -321,16 +323,40 @@ def roofline_of(job, res, args, hbm_peak, peak_src, with_traffic):
     bytes_launch = ab[kernel_class(dom)]
     ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
     it_ms = res["loop_ms"] / args.steps
+    notes = {"nnls_H": "the H solve moves 2 x 4 n k + 16 n bytes but is bound by the SM's shared-memory data path and by latency "
+                       "(232 registers per thread, 8 warps per SM; ncu: l1tex 68 %, dram 4 %), not by HBM: see DESIGN.md section 5",
+             "ltx": "dense-tile tcgen05 sweep: bound by the tensor pipe / operand staging, see roofline.tensor",
+             "xh": "dense-tile tcgen05 sweep: bound by the tensor pipe / operand staging, see roofline.tensor"}
+    # tensor-pipe view of the two dense sweeps: algorithmic MMA flops (M = 128 rows incl. padding, N = cells or genes, K) over
+    # the measured dense bf16 peak of MEASURED_PEAKS.json
+    tensor = None
+    if any(kn.startswith("k_dense") for kn in kt):
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tf_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
+        except Exception:
+            tf_peak = 1400.0
+        cfg = job.cfg
+        gp = ((cfg["m"] + 63) // 64) * 64
+        flops = 2.0 * 128 * gp * job.n_local      # per sweep: every (cell, gene) pair meets the 128-row operand slab once
+        tensor = {"peak_tflops": tf_peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM, seconds-long loop)",
+                  "note": "flops of the issued tcgen05.mma tiles (128 x 256 x 16 bf16, 96 of the 128 rows carry data)"}
+        for kn in ("k_dense_ltx", "k_dense_xh"):
+            if kn in kt:
+                ms = kt[kn]["ms"] / max(kt[kn]["launches"], 1)
+                tensor[kn] = {"tflops": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / 1e12 / tf_peak}
     return {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
             "traffic": ncu_traffic(dom) if with_traffic else None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": per_launch_ms,
+            "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": per_launch_ms, "note": notes.get(kernel_class(dom)),
             "timing": "CUDA events on the library's launch stream around every launch, over the same K cold-start steps "
                       "run a second time (the `value` pass itself carries no per-kernel events)",
             "iteration": {"algorithmic_bytes": ab["iteration"], "achieved": ab["iteration"] / (it_ms * 1e-3) / 1e9,
                           "frac": ab["iteration"] / (it_ms * 1e-3) / 1e9 / hbm_peak},
             "per_kernel": {kn: {"ms_per_iter": v["ms"] / args.steps,
                                 "frac_of_hbm": (ab[kernel_class(kn)] / (v["ms"] / max(v["launches"], 1) * 1e-3) / 1e9 / hbm_peak)
-                                if kernel_class(kn) else None} for kn, v in kt.items()},
+                                if kernel_class(kn) else None,
+                                "traffic": ncu_traffic(kn) if with_traffic else None} for kn, v in kt.items()},
+            "tensor": tensor,
             "instrumented_ms_per_step": res["instrumented_loop_ms"] / args.steps,
             "phases_ms_per_iter": {"h_phase": res["h_phase_ms"] / args.steps, "vw_phase": res["vw_phase_ms"] / args.steps,
                                    "comm": res["comm_ms"] / args.steps}}

@@ -38,9 +38,13 @@ constexpr int KSTEP = 16;          // bf16 MMA K
 constexpr int XTILE_BYTES = TILE_N * KSTEP * 2;   // 8 KB: one [256 x 16] bf16 operand tile
 constexpr int ATILE_BYTES = 128 * KSTEP * 2;      // 4 KB: one [128 x 16] bf16 operand tile
 constexpr int XSTAGE_BYTES = 4 * XTILE_BYTES;     // 32 KB per ring slot (both kernels)
-constexpr int SCAT_WARPS = 3 * NST;               // three scatter warps per ring slot
-constexpr int SCAT_GT = 96;                       // threads of one slot's scatter group
-constexpr int PRE = 10;                           // entries per scatter thread held in registers across the slot wait
+#ifndef LGR_SCAT_PER_SLOT
+#define LGR_SCAT_PER_SLOT 3
+#endif
+constexpr int SCAT_PER_SLOT = LGR_SCAT_PER_SLOT;     // scatter warps per ring slot
+constexpr int SCAT_WARPS = SCAT_PER_SLOT * NST;
+constexpr int SCAT_GT = 32 * SCAT_PER_SLOT;       // threads of one slot's scatter group
+constexpr int PRE = SCAT_PER_SLOT == 3 ? 10 : 8;  // entries per scatter thread held in registers (capacity PRE x SCAT_GT per stage)
 
 // ---- k_dense_ltx geometry ----
 constexpr int K1_KS = 4;                          // k-steps per stage: 64 genes
