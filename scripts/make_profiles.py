@@ -22,7 +22,7 @@ for r in rows[1:]:
 unit = rows[1][hdr.index("Metric Unit")]
 tot = sum(v[1] for v in agg.values())
 with open(f"{out}/{tag}_launches_summary.txt", "w") as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 600, python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e (C3, count-structured input: dense-tile sweeps; the first 600 launches: generator kernels, layout build, ANLS iterations from a cold start)\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 600, python bench.py --steps 3 --warmup 3 --no-cpu --no-extra --no-e2e (C3, count-structured input: dense-tile sweeps; the library's first 600 launches: layout build (k_dense_keys, once per dataset), warm-up + timed + instrumented ANLS iterations from a cold start; the k_spmm_* / k_tile_* rows belong to the small pbmc parity run every bench line carries)\n")
     f.write(f"# per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  unit: {unit}\n")
     f.write(f"{'kernel':60s} {'launches':>8s} {'total':>14s} {'share':>7s} {'avg':>12s}\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
