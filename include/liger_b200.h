@@ -202,6 +202,25 @@ LGR_API int lgr_ctx_iterate(lgr_ctx* ctx, int32_t niter, double* obj_traj /* NUL
    ONE CUDA-event bracket (lgr_timings.loop_ms then covers the loop and the objective pass). */
 LGR_API int lgr_ctx_run(lgr_ctx* ctx, int32_t niter, double* objErr);
 LGR_API int lgr_ctx_objective(lgr_ctx* ctx, double* obj);
+/* The three block solves of the R-level ANLS (inmf_solveH / inmf_solveV / inmf_solveW, R/cINMF.R:477-503; their callers
+   R/cINMF.R:392-407, R/optimizeNewParam.R:97-134,288-291,327-329) on the RESIDENT data: X is uploaded once by
+   lgr_ctx_create, the right-hand sides are formed by the same sweeps as in lgr_inmf, nothing but the factors a caller asks
+   for crosses PCIe.  `blocks` is any OR of LGR_SOLVE_*; they run in the order H -> V -> W, each from the factors that are on
+   the device when it starts (H: CtC = (W+V)^T(W+V) + lambda V^T V, CtB = (W+V)^T E; V: CtC = (1+lambda) H^T H,
+   CtB = H^T E^T - H^T H W^T; W: CtC = sum H^T H, CtB = sum (H^T E^T - H^T H V^T)). */
+#define LGR_SOLVE_H 1u
+#define LGR_SOLVE_V 2u
+#define LGR_SOLVE_W 4u
+LGR_API int lgr_ctx_solve(lgr_ctx* ctx, uint32_t blocks);
+/* replace resident factors: W m x k, V[i] m x k, U[i] u_i x k, H[i] n_i x k, column-major; NULL (array or entry) = keep */
+LGR_API int lgr_ctx_set_factors(lgr_ctx* ctx, const double* W, const double* const* V, const double* const* U,
+                                const double* const* H);
+/* the two products over X for callers that assemble their own normal equations (residual right-hand sides of
+   optimizeNewK / optimizeNewData): which = 0: out[i] (n_i x k) = [E_i; P_i]^T ([W; 0] + [V_i; U_i]);
+   which = 1: out[i] ((m + u_i) x k) = [E_i; P_i] H_i.  Column-major; NULL entries are skipped. */
+LGR_API int lgr_ctx_products(lgr_ctx* ctx, int32_t which, double* const* out);
+/* objErr_i (src/objErr.cpp:13-31) of dataset i from the resident factors -- no upload, no layout build */
+LGR_API int lgr_ctx_objerr_i(lgr_ctx* ctx, int32_t i, double* obj);
 LGR_API int lgr_ctx_download(lgr_ctx* ctx, lgr_inmf_out* out);
 LGR_API int lgr_ctx_timings(lgr_ctx* ctx, lgr_timings* t);
 LGR_API void* lgr_ctx_stream(lgr_ctx* ctx); /* the cudaStream_t all kernels are launched on */

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libliger_b200.so")
 LGR_F64, LGR_F32 = 0, 1
 FLAG_TRAJECTORY, FLAG_COLD_START, FLAG_PINNED_IO, FLAG_LOCAL_SHARD, FLAG_TENSOR_U, FLAG_LEGACY_NNLS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FLAG_NO_DENSE = 0x40
+SOLVE_H, SOLVE_V, SOLVE_W = 1, 2, 4
 STATUS = {0: "OK", 1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "NCCL", 5: "ALLOC", 6: "INTERRUPT"}
 
 c_double_p = C.POINTER(C.c_double)
@@ -59,7 +60,8 @@ _lib = None
 # every symbol include/liger_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
     "lgr_inmf", "lgr_uinmf", "lgr_bppnnls_prod", "lgr_objerr_i", "lgr_ctx_create", "lgr_ctx_reset",
-    "lgr_ctx_iterate", "lgr_ctx_run", "lgr_ctx_objective", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
+    "lgr_ctx_iterate", "lgr_ctx_run", "lgr_ctx_objective", "lgr_ctx_solve", "lgr_ctx_set_factors", "lgr_ctx_products",
+    "lgr_ctx_objerr_i", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
     "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
     "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id", "lgr_host_alloc",
     "lgr_host_free", "lgr_normalize_csc", "lgr_row_vars_sparse", "lgr_scale_not_center_by_row",
@@ -88,6 +90,10 @@ def lib():
     L.lgr_ctx_iterate.argtypes = [C.c_void_p, C.c_int32, c_double_p]
     L.lgr_ctx_run.argtypes = [C.c_void_p, C.c_int32, c_double_p]
     L.lgr_ctx_objective.argtypes = [C.c_void_p, c_double_p]
+    L.lgr_ctx_solve.argtypes = [C.c_void_p, C.c_uint32]
+    L.lgr_ctx_set_factors.argtypes = [C.c_void_p, c_double_p, C.POINTER(c_double_p), C.POINTER(c_double_p), C.POINTER(c_double_p)]
+    L.lgr_ctx_products.argtypes = [C.c_void_p, C.c_int32, C.POINTER(c_double_p)]
+    L.lgr_ctx_objerr_i.argtypes = [C.c_void_p, C.c_int32, c_double_p]
     L.lgr_ctx_download.argtypes = [C.c_void_p, C.POINTER(lgr_inmf_out)]
     L.lgr_ctx_timings.argtypes = [C.c_void_p, C.POINTER(lgr_timings)]
     L.lgr_ctx_stream.argtypes = [C.c_void_p]

@@ -354,6 +354,48 @@ class Context:
         _ffi.check(_ffi.lib().lgr_ctx_objective(self.h, C.byref(out)))
         return float(out.value)
 
+    def solve(self, blocks):
+        """Block solves on the resident data (inmf_solveH / inmf_solveV / inmf_solveW, R/cINMF.R:477-503): `blocks` is a
+        string over "HVW" (run in the order H -> V -> W), each from the factors currently on the device."""
+        bits = 0
+        for ch in blocks.upper():
+            bits |= {"H": _ffi.SOLVE_H, "V": _ffi.SOLVE_V, "W": _ffi.SOLVE_W}[ch]
+        _ffi.check(_ffi.lib().lgr_ctx_solve(self.h, bits))
+
+    def set_factors(self, W=None, V=None, U=None, H=None):
+        """Replace resident factors (None keeps): W m x k, V[i] m x k, U[i] u_i x k, H[i] n_i x k (cell x factor)."""
+        d = self.args.d
+        keep = []
+
+        def arr(lst):
+            if lst is None:
+                return None
+            mats = [None if x is None else _f64(x) for x in lst]
+            keep.append(mats)
+            return (c_double_p * d)(*[(_dp(x) if x is not None else None) for x in mats])
+        Wm = None if W is None else _f64(W)
+        _ffi.check(_ffi.lib().lgr_ctx_set_factors(self.h, _dp(Wm) if Wm is not None else None, arr(V), arr(U), arr(H)))
+
+    def products(self, which):
+        """which = "ltx": [E_i; P_i]^T ([W; 0] + [V_i; U_i]) per dataset (n_i x k); which = "xh": [E_i; P_i] H_i
+        ((m + u_i) x k) -- the two sweeps over the resident X, for callers that assemble their own normal equations."""
+        d, k = self.args.d, self.args.k
+        if which == "ltx":
+            outs = [np.zeros((n, k), order="F") for n in self.args.n]
+        elif which == "xh":
+            outs = [np.zeros((self.args.m + u, k), order="F") for u in self.args.u]
+        else:
+            raise ValueError("which must be 'ltx' or 'xh'")
+        arr = (c_double_p * d)(*[_dp(o) for o in outs])
+        _ffi.check(_ffi.lib().lgr_ctx_products(self.h, 0 if which == "ltx" else 1, arr))
+        return outs
+
+    def objErr_i(self, i):
+        """objErr_i (src/objErr.cpp:13-31) of dataset i from the resident factors."""
+        out = C.c_double(0.0)
+        _ffi.check(_ffi.lib().lgr_ctx_objerr_i(self.h, int(i), C.byref(out)))
+        return float(out.value)
+
     def run(self, niter):
         """niter iterations + the final objective inside one device-timed bracket (what lgr_inmf runs between its
         upload and its download); returns the objective."""

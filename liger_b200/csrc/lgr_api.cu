@@ -434,13 +434,12 @@ void solve_f64(lgr_ctx* c, const NnlsGroup* grp, int ngroups, long long cols, in
     }
 }
 
-// One ANLS iteration: H_i for all i -> V_i (U_i) with the old W -> W with the new V_i.  Everything is enqueued on c->st
-// with no host synchronisation, so the sequence can be captured into a CUDA graph.
-void enqueue_iteration(lgr_ctx* c, int cold, double* obj_slot) {
-    std::unique_ptr<Span> phase(new Span(c, "h_phase"));
+// The three block solves (R/cINMF.R:477-503), each from the factors currently on the device.  Everything is enqueued on
+// c->st with no host synchronisation, so a sequence of them can be captured into a CUDA graph.
+// H_i for every dataset:  CtC = L~^T L~ + lambda V~^T V~,  CtB = L~^T X  (obj_slot: objective of the iterate BEFORE the solve)
+void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
     run_prep(c);
     if (obj_slot) run_objective(c, obj_slot);   // objective of the PREVIOUS iterate (uses the fresh L~ Grams)
-    // ---- H phase ----
     {
         Timed t(c, "k_gram_inv");   // CtC and CtC^-1 of the H solves (the fused U = B P epilogue of K1 reads CtC^-1)
         launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
@@ -475,11 +474,10 @@ void enqueue_iteration(lgr_ctx* c, int cold, double* obj_slot) {
         }
     }
     c->h_valid = true;
-    phase.reset();
-    phase.reset(new Span(c, "vw_phase"));
-    // ---- sufficient statistics of the V / W solves ----
-    run_stats(c);
-    // ---- V_i (and U_i): old W ----
+    c->stats_valid = false;
+}
+// V_i (and U_i):  CtC = (1 + lambda) H^T H,  CtB = H^T X^T - H^T H W^T   (needs the statistics of the current H)
+void enqueue_solve_v(lgr_ctx* c, int cold) {
     {
         Timed t(c, "k_vrhs");
         launch_vrhs(c->ds_dev.p, c->d, c->W.p, c->k, c->kp, c->max_rows, c->st);
@@ -492,7 +490,9 @@ void enqueue_iteration(lgr_ctx* c, int cold, double* obj_slot) {
         Timed t(c, "k_nnls_V");
         solve_f64(c, c->grpV.p, c->d, c->colsV, cold);
     }
-    // ---- W: new V_i ----
+}
+// W:  CtC = sum_i H_i^T H_i,  CtB = sum_i (H_i^T X_i^T - H_i^T H_i V_i^T)
+void enqueue_solve_w(lgr_ctx* c, int cold) {
     {
         Timed t(c, "k_wrhs");
         launch_wrhs(c->ds_dev.p, c->d, c->m, c->CtBw.p, c->Gsum.p, c->k, c->kp, c->st);
@@ -505,6 +505,17 @@ void enqueue_iteration(lgr_ctx* c, int cold, double* obj_slot) {
         Timed t(c, "k_nnls_W");
         solve_f64(c, c->grpW.p, 1, (long long)c->m, cold);
     }
+}
+
+// One ANLS iteration: H_i for all i -> V_i (U_i) with the old W -> W with the new V_i.
+void enqueue_iteration(lgr_ctx* c, int cold, double* obj_slot) {
+    std::unique_ptr<Span> phase(new Span(c, "h_phase"));
+    enqueue_solve_h(c, cold, obj_slot);
+    phase.reset();
+    phase.reset(new Span(c, "vw_phase"));
+    run_stats(c);   // sufficient statistics of the V / W solves
+    enqueue_solve_v(c, cold);
+    enqueue_solve_w(c, cold);
     phase.reset();
 }
 
@@ -617,6 +628,110 @@ double objective(lgr_ctx* c) {
     if (c->objbuf.n < 1) c->objbuf.alloc(1);
     DBuf<double> slot(1);
     run_objective(c, slot.p);
+    double v = 0.0;
+    LGR_CUDA(cudaMemcpyAsync(&v, slot.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+    return v;
+}
+
+// H_i (n_full x k column-major, R layout) -> this rank's rows [c0, c0 + n) of the padded fp32 H, passive sets from its signs
+void upload_h(lgr_ctx* c, int i, const double* host) {
+    Dataset& D = c->ds[i];
+    if (D.n == 0) return;
+    DBuf<double> tmp((size_t)D.n * c->k);
+    LGR_CUDA(cudaMemcpy2DAsync(tmp.p, (size_t)D.n * sizeof(double), host + D.c0, (size_t)D.n_full * sizeof(double),
+                               (size_t)D.n * sizeof(double), (size_t)c->k, cudaMemcpyHostToDevice, c->st));
+    dev_colmajor_to_hpad(tmp.p, D.H.p, D.n, c->k, c->kp, c->st);
+    dev_mask_from_positive(D.H.p, D.hmask.p, D.n, c->k, c->kp, c->st);
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+}
+
+// Replace any of the resident factors (NULL pointers / NULL entries keep what is on the device).
+void set_factors(lgr_ctx* c, const double* W, const double* const* V, const double* const* U, const double* const* H) {
+    if (W) upload_factor(W, c->W.p, c->m, c->k, c->kp, c->st);
+    int nh = 0;
+    for (int i = 0; i < c->d; ++i) {
+        Dataset& D = c->ds[i];
+        if (V && V[i]) upload_factor(V[i], D.V.p, c->m, c->k, c->kp, c->st);
+        if (U && U[i] && D.u > 0) upload_factor(U[i], D.V.p + (size_t)c->m * c->kp, D.u, c->k, c->kp, c->st);
+        if (H && H[i]) {
+            upload_h(c, i, H[i]);
+            ++nh;
+        }
+    }
+    if (nh) {
+        c->stats_valid = false;
+        if (nh == c->d) c->h_valid = true;
+    }
+}
+
+void read_counters(lgr_ctx* c) {
+    Counters cn;
+    LGR_CUDA(cudaMemcpy(&cn, c->counters.p, sizeof(cn), cudaMemcpyDeviceToHost));
+    c->tm.nnls_pivots = (int64_t)cn.nnls_pivots;
+    c->tm.nnls_unconverged = (int64_t)cn.nnls_unconverged;
+}
+
+// Block solves on the resident data, in the order H -> V -> W (the order of one ANLS iteration), each from the factors that
+// are on the device when it starts.  The passive sets of the previous solve of the same block are the starting guess.
+void solve_blocks(lgr_ctx* c, unsigned blocks) {
+    LGR_REQUIRE(blocks != 0 && (blocks & ~(unsigned)(LGR_SOLVE_H | LGR_SOLVE_V | LGR_SOLVE_W)) == 0, "lgr_ctx_solve: unknown block");
+    const int cold = (c->flags & LGR_FLAG_COLD_START) ? 1 : 0;
+    if (blocks & LGR_SOLVE_H) enqueue_solve_h(c, cold, nullptr);
+    if (blocks & (LGR_SOLVE_V | LGR_SOLVE_W)) {
+        LGR_REQUIRE(c->h_valid, "lgr_ctx_solve: the V / W solves need an H (solve H first, or set it)");
+        if (!c->stats_valid) run_stats(c);
+        if (blocks & LGR_SOLVE_V) enqueue_solve_v(c, cold);
+        if (blocks & LGR_SOLVE_W) enqueue_solve_w(c, cold);
+    }
+    LGR_CUDA(cudaStreamSynchronize(c->st));
+    read_counters(c);
+}
+
+// The two products over X of the block solves, for callers that build their own normal equations
+// (R/optimizeNewParam.R:97-134: residual right-hand sides):  which = 0:  out[i] = [X_i; P_i]^T ([W; 0] + [V_i; U_i])   n_i x k
+//                                                             which = 1:  out[i] = [X_i; P_i] H_i                    (m + u_i) x k
+void products(lgr_ctx* c, int which, double* const* out) {
+    LGR_REQUIRE(out, "lgr_ctx_products: out is NULL");
+    if (which == 0) {
+        run_prep(c);
+        if (c->dense && (c->dense_mask & 1))
+            launch_dense_ltx(c->dds_dev.p, c->d, c->k1_tiles, c->num_sms, c->st);
+        else
+            launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, false, c->st);
+    } else {
+        LGR_REQUIRE(c->h_valid, "lgr_ctx_products: X H needs an H (solve H first, or set it)");
+        if (!c->stats_valid) run_stats(c);
+    }
+    for (int i = 0; i < c->d; ++i) {
+        Dataset& D = c->ds[i];
+        if (!out[i]) continue;
+        const int rows = which == 0 ? D.n : D.rows;
+        if (rows == 0) continue;
+        const float* src = which == 0 ? c->Bbuf.p + D.b_off : c->Rarena.p + D.r_off;
+        DBuf<double> tmp((size_t)rows * c->k);
+        dev_hpad_to_colmajor(src, tmp.p, rows, c->k, c->kp, c->st);
+        if (which == 0 && D.n != D.n_full) {   // slice mode: this rank's rows of the caller's n_full x k matrix
+            LGR_CUDA(cudaMemcpy2DAsync(out[i] + D.c0, (size_t)D.n_full * sizeof(double), tmp.p, (size_t)D.n * sizeof(double),
+                                       (size_t)D.n * sizeof(double), (size_t)c->k, cudaMemcpyDeviceToHost, c->st));
+        } else {
+            copy_out(out[i], tmp.p, (size_t)rows * c->k * sizeof(double), c->st, false);
+        }
+        LGR_CUDA(cudaStreamSynchronize(c->st));
+    }
+}
+
+// objErr_i of ONE dataset from the resident factors (src/objErr.cpp:13-31); the sum over datasets is lgr_ctx_objective
+double objective_i(lgr_ctx* c, int i) {
+    LGR_REQUIRE(i >= 0 && i < c->d, "lgr_ctx_objerr_i: dataset index out of range");
+    if (!c->stats_valid) {
+        LGR_REQUIRE(c->h_valid, "objective requested before any H is available");
+        run_stats(c);
+    }
+    run_prep(c);
+    DBuf<double> slot(1);
+    LGR_CUDA(cudaMemsetAsync(slot.p, 0, sizeof(double), c->st));
+    launch_objective(c->ds_dev.p + i, 1, c->k, c->kp, slot.p, c->st);
     double v = 0.0;
     LGR_CUDA(cudaMemcpyAsync(&v, slot.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
     LGR_CUDA(cudaStreamSynchronize(c->st));
@@ -1043,18 +1158,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     set_inits(c.get(), a->Winit, a->Vinit, a->Uinit);
     tr.mark("set_inits");
     if (a->Hinit) {
-        for (int i = 0; i < c->d; ++i) {
-            Dataset& D = c->ds[i];
-            if (!a->Hinit[i] || D.n == 0) continue;
-            // local rows [c0, c0+n) of the n_full x k column-major matrix
-            DBuf<double> tmp((size_t)D.n * k);
-            LGR_CUDA(cudaMemcpy2DAsync(tmp.p, (size_t)D.n * sizeof(double), a->Hinit[i] + D.c0,
-                                       (size_t)D.n_full * sizeof(double), (size_t)D.n * sizeof(double), (size_t)k,
-                                       cudaMemcpyHostToDevice, c->st));
-            dev_colmajor_to_hpad(tmp.p, D.H.p, D.n, k, kp, c->st);
-            dev_mask_from_positive(D.H.p, D.hmask.p, D.n, k, kp, c->st);
-            LGR_CUDA(cudaStreamSynchronize(c->st));
-        }
+        for (int i = 0; i < c->d; ++i)
+            if (a->Hinit[i]) upload_h(c.get(), i, a->Hinit[i]);
         c->h_valid = true;
     }
     LGR_CUDA(cudaEventRecord(u1, c->st));
@@ -1219,6 +1324,38 @@ int lgr_ctx_objective(lgr_ctx* c, double* obj) {
         LGR_CUDA(cudaSetDevice(c->device));
         AllocStreamScope alloc_scope(c->st);
         *obj = objective(c);
+    });
+}
+int lgr_ctx_set_factors(lgr_ctx* c, const double* W, const double* const* V, const double* const* U, const double* const* H) {
+    return guarded([&] {
+        LGR_REQUIRE(c, "null ctx");
+        LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
+        set_factors(c, W, V, U, H);
+    });
+}
+int lgr_ctx_solve(lgr_ctx* c, uint32_t blocks) {
+    return guarded([&] {
+        LGR_REQUIRE(c, "null ctx");
+        LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
+        solve_blocks(c, blocks);
+    });
+}
+int lgr_ctx_products(lgr_ctx* c, int32_t which, double* const* out) {
+    return guarded([&] {
+        LGR_REQUIRE(c && (which == 0 || which == 1), "lgr_ctx_products: bad argument");
+        LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
+        products(c, which, out);
+    });
+}
+int lgr_ctx_objerr_i(lgr_ctx* c, int32_t i, double* obj) {
+    return guarded([&] {
+        LGR_REQUIRE(c && obj, "bad argument");
+        LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
+        *obj = objective_i(c, i);
     });
 }
 int lgr_ctx_download(lgr_ctx* c, lgr_inmf_out* out) {

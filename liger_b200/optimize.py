@@ -1,8 +1,8 @@
 """Mirror of the reference's "re-optimise from an existing factorisation" callers of the hot path
 (reference R/optimizeNewParam.R).  They are host-level algebra around the two native entry points this library
 replaces -- RcppPlanc::bppnnls_prod (-> lgr_bppnnls_prod) and RcppPlanc::inmf with explicit inits (-> lgr_inmf) --
-so every NNLS solve and every ANLS iteration below runs on the GPU; the small dense products stay on the host, as
-they do in R.
+so every NNLS solve and every ANLS iteration below runs on the GPU, and so do the products over the sparse data
+(lgr_ctx_products / lgr_ctx_solve on a resident copy of E); only the k x k corrections stay on the host, as they do in R.
 
     optimizeNewK       R/optimizeNewParam.R:41-163
     optimizeNewLambda  R/optimizeNewParam.R:353-385
@@ -15,7 +15,7 @@ uns = {factorization: {k, lambda}}); `scaleData` is the {name: genes x cells spa
 import numpy as np
 import scipy.sparse as sp
 
-from . import api
+from . import api, cinmf
 from .integration import runINMF
 
 
@@ -58,24 +58,33 @@ def optimizeNewK(scaleData, fit, kNew, lambda_=None, nIteration=30, seed=1, nCor
         # t(matrix(runif(g * kd, 0, 2), kd, g)): entry (gene, j) is draw gene * kd + j
         W_new = rng.runif(g * kd, 0.0, 2.0).reshape((g, kd))
         V_new = [rng.runif(g * kd, 0.0, 2.0).reshape((g, kd)) for _ in names]
-        H_new = []
-        for i in range(len(names)):
-            L_new = W_new + V_new[i]
-            L = W + V[i]
-            CtC = L_new.T @ L_new + lam * (V_new[i].T @ V_new[i])
-            CtB = -1.0 * ((L_new.T @ L) @ H[i] - _dense((E[i].T @ L_new).T))
-            H_new.append(api.bppnnls_prod(CtC, CtB, nCores=nCores))            # kd x n_i
+        # the two products over E (E^T L_new, E H_new^T) come from the library's sweeps over a resident copy of E (one
+        # upload, kd factors wide); the k x k / k x kd corrections stay host algebra, as in R
+        ctx = api.Context(E, kd, lam, W_new, V_new)
+        try:
+            EtL = ctx.products("ltx")                                              # n_i x kd each
+            H_new = []
+            for i in range(len(names)):
+                L_new = W_new + V_new[i]
+                L = W + V[i]
+                CtC = L_new.T @ L_new + lam * (V_new[i].T @ V_new[i])
+                CtB = -1.0 * ((L_new.T @ L) @ H[i] - EtL[i].T)
+                H_new.append(api.bppnnls_prod(CtC, CtB, nCores=nCores))            # kd x n_i
+            ctx.set_factors(H=[h.T for h in H_new])
+            EH = ctx.products("xh")                                                # g x kd each
+        finally:
+            ctx.close()
         for i in range(len(names)):
             Hn = H_new[i]
             CtC = (Hn @ Hn.T) * (1.0 + lam)
-            CtB = _dense((E[i] @ Hn.T).T) - (Hn @ H[i].T) @ (W + V[i]).T - (Hn @ Hn.T) @ W_new.T
+            CtB = EH[i].T - (Hn @ H[i].T) @ (W + V[i]).T - (Hn @ Hn.T) @ W_new.T
             V_new[i] = api.bppnnls_prod(CtC, CtB, nCores=nCores).T             # g x kd
         CtC = np.zeros((kd, kd))
         CtB = np.zeros((kd, g))
         for i in range(len(names)):
             Hn = H_new[i]
             CtC += Hn @ Hn.T
-            CtB += _dense((E[i] @ Hn.T).T) - (Hn @ H[i].T) @ (W + V[i]).T - (Hn @ Hn.T) @ V_new[i].T
+            CtB += EH[i].T - (Hn @ H[i].T) @ (W + V[i]).T - (Hn @ Hn.T) @ V_new[i].T
         W_new = api.bppnnls_prod(CtC, CtB, nCores=nCores).T
         HInit = [np.vstack([H[i], H_new[i]]).T for i in range(len(names))]     # n_i x kNew
         VInit = [np.hstack([V[i], V_new[i]]) for i in range(len(names))]
@@ -130,11 +139,8 @@ def optimizeNewData(scaleData, fit, scaleDataNew, useDatasets, merge=True, newCe
     Hs = {n: np.asarray(fit["H"][n], dtype=np.float64) for n in scaleData}
     Vs = {n: np.asarray(fit["V"][n], dtype=np.float64) for n in scaleData}
 
-    def h_for(E, V):
-        L = W + V
-        CtC = L.T @ L + lam * (V.T @ V)
-        CtB = _dense((E.T @ L).T)
-        return api.bppnnls_prod(CtC, CtB, nCores=nCores)
+    def h_for(E, V):                        # inmf_solveH on the new cells, k x n
+        return cinmf.inmf_solveH(None, W, V, E, lam, nCores).T
 
     if merge:
         if newCells is None:

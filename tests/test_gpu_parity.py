@@ -604,18 +604,19 @@ def test_resident_pipeline_counts_to_factors(pbmc):
 
 
 def test_cinmf_block_solves_and_refinement(pbmc):
-    """inmf_solveH / solveV / solveW (R/cINMF.R:477-503) and runCINMF's fixed-W refinement loop (:392-407) on the GPU
-    NNLS, against the oracle's restatement of the same three solves."""
+    """inmf_solveH / solveV / solveW (R/cINMF.R:477-503) and runCINMF's fixed-W refinement loop (:392-407) as block solves
+    on a resident context (the right-hand sides come from the library's fp32 sweeps over X, so the tolerance is the
+    factor tolerance of the path, not FP64 round-off), against the oracle's restatement of the same three solves."""
     from liger_b200 import cinmf
     Es = pbmc["Es"]
     W, Vs, _, _ = orc.seeded_init(4, 173, 12, [300, 300])
     H0 = cinmf.inmf_solveH(None, W, Vs[0], Es[0], 5.0)
-    assert rel(H0, orc.solve_H(W, Vs[0], Es[0], 5.0)) < 1e-9
+    assert rel(H0, orc.solve_H(W, Vs[0], Es[0], 5.0)) < 2e-5
     V0 = cinmf.inmf_solveV(H0, W, None, Es[0], 5.0)
-    assert rel(V0, orc.solve_V(H0, W, Es[0], 5.0)) < 1e-8
+    assert rel(V0, orc.solve_V(H0, W, Es[0], 5.0)) < 2e-5
     Hs = [H0, cinmf.inmf_solveH(None, W, Vs[1], Es[1], 5.0)]
     Wn = cinmf.inmf_solveW(Hs, W, [V0, Vs[1]], Es, 5.0)
-    assert rel(Wn, orc.solve_W(Hs, [V0, Vs[1]], Es)) < 1e-8
+    assert rel(Wn, orc.solve_W(Hs, [V0, Vs[1]], Es)) < 2e-5
     out = cinmf.refine_fixed_W(Es, W, Vs, lambda_=5.0, nIteration=2, seed=1)
     Vr = [v.copy() for v in Vs]
     Hr = [None, None]
@@ -626,5 +627,44 @@ def test_cinmf_block_solves_and_refinement(pbmc):
             Vr[i] = orc.solve_V(Hr[i], W, Es[i], 5.0)
     ref_obj = sum(orc.objerr_i(Hr[i].T, W, Vr[i], Es[i], 5.0) for i in range(2))
     for i in range(2):
-        assert rel(out["H"][i], Hr[i]) < 1e-7 and rel(out["V"][i], Vr[i]) < 1e-7
-    assert abs(out["objErr"] - ref_obj) < 1e-6 * ref_obj
+        assert rel(out["H"][i], Hr[i]) < 1e-4 and rel(out["V"][i], Vr[i]) < 1e-4
+    assert abs(out["objErr"] - ref_obj) < 1e-5 * ref_obj
+
+
+def test_resident_block_solver_products_and_objective(pbmc):
+    """lgr_ctx_solve / lgr_ctx_set_factors / lgr_ctx_products / lgr_ctx_objerr_i: one upload of X, then any sequence of
+    block solves, raw products and per-dataset objectives from the resident state; checked against the oracle's block
+    solves, scipy products and objerr_i."""
+    from liger_b200 import cinmf
+    Es = pbmc["Es"]
+    k = 12
+    W, Vs, _, _ = orc.seeded_init(7, 173, k, [300, 300])
+    s = cinmf.BlockSolver(Es, k, 5.0, W, Vs)
+    try:
+        with pytest.raises(Exception, match="need an H"):
+            s.ctx.solve("V")
+        ltx = s.ctx.products("ltx")
+        for i in range(2):
+            assert rel(ltx[i], np.asarray((Es[i].T @ (W + Vs[i])))) < 2e-6
+        Hs = s.solveH()
+        Hr = [orc.solve_H(W, Vs[i], Es[i], 5.0) for i in range(2)]
+        for i in range(2):
+            assert rel(Hs[i], Hr[i]) < 2e-5
+        xh = s.ctx.products("xh")
+        for i in range(2):
+            assert rel(xh[i], np.asarray(Es[i] @ Hs[i])) < 2e-6
+        for i in range(2):      # objErr_i per dataset, and their sum
+            assert abs(s.objErr(i) - orc.objerr_i(Hs[i].T, W, Vs[i], Es[i], 5.0)) < 1e-5 * s.objErr(i)
+        assert abs(s.objErr() - (s.objErr(0) + s.objErr(1))) < 1e-9 * s.objErr()
+        Vn = s.solveV()         # with the old W
+        for i in range(2):
+            assert rel(Vn[i], orc.solve_V(Hr[i], W, Es[i], 5.0)) < 5e-5
+        Wn = s.solveW()         # with the new V
+        assert rel(Wn, orc.solve_W(Hr, [orc.solve_V(Hr[i], W, Es[i], 5.0) for i in range(2)], Es)) < 5e-5
+        # replacing H from the host invalidates the statistics: the next product / solve uses the new H
+        H2 = [np.abs(h[::-1]).copy() for h in Hr]
+        s.set(Hs=H2)
+        xh2 = s.ctx.products("xh")
+        assert rel(xh2[0], np.asarray(Es[0] @ H2[0])) < 2e-6
+    finally:
+        s.close()
