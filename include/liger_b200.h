@@ -193,6 +193,35 @@ LGR_API int lgr_prep_scaled_view(lgr_prep* p, int32_t i, lgr_csc* view);   /* m 
 LGR_API int lgr_prep_scaled_download(lgr_prep* p, int32_t i, int32_t* colptr, int32_t* rowidx, double* values);
 LGR_API void lgr_prep_destroy(lgr_prep* p);
 
+/* ---- factor alignment: quantileNorm (R/integration.R:1621-1711 .quantileNorm.HList; src/quantile_norm.cpp:8-67
+   max_factor_rcpp / cluster_vote_rcpp; RANN::nn2 = ANN 1.1.2 kd-tree search; stats::quantile type 7; stats::approxfun
+   rule = 2; base::sample) -- the consumer of the H_i, run where they live.  Defaults of the reference in brackets. ---- */
+typedef struct lgr_qn_params {
+    int32_t quantiles;      /* [50]  number of quantile intervals: knots at seq(0, 1, by = 1 / quantiles) */
+    int32_t reference;      /* 0-based index of the reference dataset */
+    int32_t min_cells;      /* [20]  clusters smaller than this on either side are left untouched */
+    int32_t n_neighbors;    /* [20]  k of the kNN refinement */
+    int32_t center;         /* [0]   centre the columns before the arg-max */
+    int32_t max_sample;     /* [1000] cells sampled per cluster for the quantiles (2..4096) */
+    int32_t refine_knn;     /* [1]   majority vote over the approximate kNN graph */
+    uint32_t seed;          /* [1]   set.seed() of the sample() stream */
+    double eps;             /* [0.9] error bound of RANN::nn2 */
+    int32_t n_dims_use;     /* 0 = all factors */
+    int32_t pad0;
+    const int32_t* dims_use; /* 1-based factor ids (useDims), or NULL */
+} lgr_qn_params;
+typedef struct lgr_qn_info {
+    double cluster_ms, knn_ms, warp_ms;   /* device + host time of the three stages (CUDA events) */
+    int32_t vote_sweeps;                  /* sweeps the in-place vote needed to reach its fixed point (max over datasets) */
+    int32_t warped_clusters;              /* (dataset, cluster) pairs that were warped */
+    int32_t sampled;                      /* 1 if some cluster exceeded max_sample (R's sample() stream was replayed) */
+    int32_t pad0;
+} lgr_qn_info;
+/* H[i]: n_i x k column-major (cell x factor, i.e. t(H) of the liger object); Hnorm[i]: same shape (rbind them for H.norm);
+   clusters[i]: n_i labels = 1-based factor id, -1 where no factor is positive.  info may be NULL. */
+LGR_API int lgr_quantile_norm(int32_t d, int32_t k, const int64_t* n, const double* const* H, const lgr_qn_params* params,
+                              double* const* Hnorm, int32_t* const* clusters, lgr_qn_info* info, int32_t device);
+
 /* ---- resident-handle API (data stays in HBM between calls; used by bench + multi-GPU hosts) ---- */
 typedef struct lgr_ctx lgr_ctx;
 LGR_API int lgr_ctx_create(const lgr_inmf_args* args, lgr_ctx** ctx); /* uploads E/P, builds device layouts, sets inits */
@@ -222,6 +251,9 @@ LGR_API int lgr_ctx_products(lgr_ctx* ctx, int32_t which, double* const* out);
 /* objErr_i (src/objErr.cpp:13-31) of dataset i from the resident factors -- no upload, no layout build */
 LGR_API int lgr_ctx_objerr_i(lgr_ctx* ctx, int32_t i, double* obj);
 LGR_API int lgr_ctx_download(lgr_ctx* ctx, lgr_inmf_out* out);
+/* quantileNorm of the RESIDENT H_i (no upload of H; single-rank contexts only) */
+LGR_API int lgr_ctx_quantile_norm(lgr_ctx* ctx, const lgr_qn_params* params, double* const* Hnorm, int32_t* const* clusters,
+                                  lgr_qn_info* info);
 LGR_API int lgr_ctx_timings(lgr_ctx* ctx, lgr_timings* t);
 LGR_API void* lgr_ctx_stream(lgr_ctx* ctx); /* the cudaStream_t all kernels are launched on */
 /* per-kernel device time of the last lgr_ctx_iterate (CUDA events on the launch stream):

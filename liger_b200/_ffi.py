@@ -49,6 +49,17 @@ class lgr_inmf_out(C.Structure):
                 ("objErr", C.c_double), ("timings", lgr_timings)]
 
 
+class lgr_qn_params(C.Structure):
+    _fields_ = [("quantiles", C.c_int32), ("reference", C.c_int32), ("min_cells", C.c_int32), ("n_neighbors", C.c_int32),
+                ("center", C.c_int32), ("max_sample", C.c_int32), ("refine_knn", C.c_int32), ("seed", C.c_uint32),
+                ("eps", C.c_double), ("n_dims_use", C.c_int32), ("pad0", C.c_int32), ("dims_use", C.POINTER(C.c_int32))]
+
+
+class lgr_qn_info(C.Structure):
+    _fields_ = [("cluster_ms", C.c_double), ("knn_ms", C.c_double), ("warp_ms", C.c_double), ("vote_sweeps", C.c_int32),
+                ("warped_clusters", C.c_int32), ("sampled", C.c_int32), ("pad0", C.c_int32)]
+
+
 class LigerB200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"liger_b200 [{STATUS.get(code, code)}]: {msg}")
@@ -61,7 +72,7 @@ _lib = None
 EXPORTS = [
     "lgr_inmf", "lgr_uinmf", "lgr_bppnnls_prod", "lgr_objerr_i", "lgr_ctx_create", "lgr_ctx_reset",
     "lgr_ctx_iterate", "lgr_ctx_run", "lgr_ctx_objective", "lgr_ctx_solve", "lgr_ctx_set_factors", "lgr_ctx_products",
-    "lgr_ctx_objerr_i", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
+    "lgr_ctx_objerr_i", "lgr_quantile_norm", "lgr_ctx_quantile_norm", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
     "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
     "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id", "lgr_host_alloc",
     "lgr_host_free", "lgr_normalize_csc", "lgr_row_vars_sparse", "lgr_scale_not_center_by_row",
@@ -95,6 +106,10 @@ def lib():
     L.lgr_ctx_products.argtypes = [C.c_void_p, C.c_int32, C.POINTER(c_double_p)]
     L.lgr_ctx_objerr_i.argtypes = [C.c_void_p, C.c_int32, c_double_p]
     L.lgr_ctx_download.argtypes = [C.c_void_p, C.POINTER(lgr_inmf_out)]
+    L.lgr_quantile_norm.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(c_double_p), C.POINTER(lgr_qn_params),
+                                    C.POINTER(c_double_p), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(lgr_qn_info), C.c_int32]
+    L.lgr_ctx_quantile_norm.argtypes = [C.c_void_p, C.POINTER(lgr_qn_params), C.POINTER(c_double_p),
+                                        C.POINTER(C.POINTER(C.c_int32)), C.POINTER(lgr_qn_info)]
     L.lgr_ctx_timings.argtypes = [C.c_void_p, C.POINTER(lgr_timings)]
     L.lgr_ctx_stream.argtypes = [C.c_void_p]
     L.lgr_ctx_stream.restype = C.c_void_p

@@ -1358,6 +1358,77 @@ int lgr_ctx_objerr_i(lgr_ctx* c, int32_t i, double* obj) {
         *obj = objective_i(c, i);
     });
 }
+// quantileNorm of host matrices: upload H_i (FP64), align on the device, download H.norm and the cluster labels
+int lgr_quantile_norm(int32_t d, int32_t k, const int64_t* n, const double* const* H, const lgr_qn_params* params,
+                      double* const* Hnorm, int32_t* const* clusters, lgr_qn_info* info, int32_t device) {
+    return guarded([&] {
+        check_device();
+        LGR_REQUIRE(d >= 1 && n && H && params && Hnorm, "lgr_quantile_norm: bad argument");
+        int ndev = 0;
+        LGR_CUDA(cudaGetDeviceCount(&ndev));
+        const int dev = device < 0 ? 0 : device;
+        LGR_REQUIRE(dev < ndev, "device index out of range");
+        LGR_CUDA(cudaSetDevice(dev));
+        StreamHolder sh;
+        LGR_CUDA(cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking));
+        AllocStreamScope alloc_scope(sh.s);
+        std::vector<DBuf<double>> Hd(d);
+        std::vector<DBuf<int>> Ld(d);
+        std::vector<double*> hp(d);
+        std::vector<int*> lp(d);
+        std::vector<int> nn(d);
+        for (int i = 0; i < d; ++i) {
+            LGR_REQUIRE(n[i] >= 1 && n[i] < (1LL << 31) && H[i] && Hnorm[i], "lgr_quantile_norm: bad dataset");
+            nn[i] = (int)n[i];
+            Hd[i].alloc((size_t)n[i] * k);
+            Ld[i].alloc((size_t)n[i]);
+            copy_in(Hd[i].p, H[i], (size_t)n[i] * k * sizeof(double), sh.s, false);
+            hp[i] = Hd[i].p;
+            lp[i] = Ld[i].p;
+        }
+        LGR_CUDA(cudaStreamSynchronize(sh.s));
+        quantile_norm_core(d, k, nn.data(), hp.data(), *params, lp.data(), info, sh.s);
+        for (int i = 0; i < d; ++i) {
+            copy_out(Hnorm[i], Hd[i].p, (size_t)n[i] * k * sizeof(double), sh.s, false);
+            if (clusters && clusters[i])
+                LGR_CUDA(cudaMemcpyAsync(clusters[i], Ld[i].p, (size_t)n[i] * sizeof(int), cudaMemcpyDeviceToHost, sh.s));
+            LGR_CUDA(cudaStreamSynchronize(sh.s));
+        }
+    });
+}
+// quantileNorm of the resident H_i: the fp32 H of the context is widened on the device; nothing is uploaded
+int lgr_ctx_quantile_norm(lgr_ctx* c, const lgr_qn_params* params, double* const* Hnorm, int32_t* const* clusters,
+                          lgr_qn_info* info) {
+    return guarded([&] {
+        LGR_REQUIRE(c && params && Hnorm, "lgr_ctx_quantile_norm: bad argument");
+        LGR_REQUIRE(c->world == 1, "lgr_ctx_quantile_norm: the cells of a dataset must be on one GPU (single-rank contexts only)");
+        LGR_REQUIRE(c->h_valid, "lgr_ctx_quantile_norm: no H on the device yet");
+        LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
+        const int d = c->d, k = c->k;
+        std::vector<DBuf<double>> Hd(d);
+        std::vector<DBuf<int>> Ld(d);
+        std::vector<double*> hp(d);
+        std::vector<int*> lp(d);
+        std::vector<int> nn(d);
+        for (int i = 0; i < d; ++i) {
+            Dataset& D = c->ds[i];
+            nn[i] = D.n;
+            Hd[i].alloc((size_t)D.n * k);
+            Ld[i].alloc((size_t)D.n);
+            dev_hpad_to_colmajor(D.H.p, Hd[i].p, D.n, k, c->kp, c->st);
+            hp[i] = Hd[i].p;
+            lp[i] = Ld[i].p;
+        }
+        quantile_norm_core(d, k, nn.data(), hp.data(), *params, lp.data(), info, c->st);
+        for (int i = 0; i < d; ++i) {
+            if (Hnorm[i]) copy_out(Hnorm[i], Hd[i].p, (size_t)nn[i] * k * sizeof(double), c->st, false);
+            if (clusters && clusters[i])
+                LGR_CUDA(cudaMemcpyAsync(clusters[i], Ld[i].p, (size_t)nn[i] * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+    });
+}
 int lgr_ctx_download(lgr_ctx* c, lgr_inmf_out* out) {
     return guarded([&] {
         LGR_REQUIRE(c && out, "bad argument");

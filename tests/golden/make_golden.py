@@ -82,6 +82,10 @@ def main():
         assert Vdn[0] == Wdn[0]
         store[f"golden_H_{nm}"] = Hg
         store[f"golden_V_{nm}"] = Vg
+    # H.norm = quantileNorm(pbmcPlot) with the defaults stored in its command log (quantiles 50, reference "ctrl", minCells
+    # 20, nNeighbors 20, eps 0.9, refineKNN TRUE, maxSample 1000, seed 1; RANN 2.6.1): pins the alignment step (f3)
+    Hn, Hndn = rda.dense(pp["H.norm"])
+    store["golden_Hnorm"] = Hn
     fac = pp["uns"]["factorization"]
     store["golden_k"] = int(fac.value[0].value[0])
     store["golden_lambda"] = float(fac.value[1].value[0])

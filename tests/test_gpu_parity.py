@@ -668,3 +668,88 @@ def test_resident_block_solver_products_and_objective(pbmc):
         assert rel(xh2[0], np.asarray(Es[0] @ H2[0])) < 2e-6
     finally:
         s.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# quantileNorm on the device (f3; R/integration.R:1621-1711, src/quantile_norm.cpp)
+# ----------------------------------------------------------------------------------------------
+def test_quantile_norm_reproduces_reference_h_norm(pbmc):
+    """lgr_quantile_norm on the reference's golden H with the defaults of its command log: the H.norm stored in
+    data/pbmcPlot.rda to round-off (FP64 path, tolerance 1e-12), and the oracle's cluster labels exactly."""
+    from liger_b200 import align
+    from oracle import quantile_norm_oracle as qn
+    g = pbmc["golden"]
+    HList = {"ctrl": np.asarray(g["golden_H_ctrl"]), "stim": np.asarray(g["golden_H_stim"])}      # k x n
+    res = align.quantile_norm_hlist(HList, reference="ctrl", return_info=True)
+    gold = np.asarray(g["golden_Hnorm"])
+    assert res["H.norm"].shape == gold.shape
+    assert np.abs(res["H.norm"] - gold).max() < 1e-12
+    Hs = [HList["ctrl"].T.copy(), HList["stim"].T.copy()]
+    knn = [qn.knn_ann(h, 20, 0.9) for h in Hs]
+    _, clusters = qn.quantile_norm(Hs, reference=0, knn=knn)
+    assert (res["clusters"]["ctrl"] == clusters[0]).all() and (res["clusters"]["stim"] == clusters[1]).all()
+    assert res["info"]["vote_sweeps"] >= 2 and res["info"]["sampled"] == 0
+    # the front end: fit in, fit out; reference validation as in R
+    fit = {"H": HList, "W": np.zeros((3, 20)), "uns": {}}
+    out = align.quantileNorm(fit, reference="ctrl")
+    assert np.abs(out["H.norm"] - gold).max() < 1e-12 and out["uns"]["alignmentMethod"] == "quantileNorm"
+    with pytest.raises(ValueError, match="one existing dataset"):
+        align.quantileNorm(fit, reference="nope")
+    with pytest.raises(ValueError, match="one existing dataset"):
+        align.quantileNorm(fit, reference=[True, True])
+
+
+@pytest.mark.parametrize("case", ["sampled", "norefine_center_dims", "ref_last"])
+def test_quantile_norm_matches_oracle(case):
+    """Synthetic H with planted clusters: clusters above maxSample (R's sample() stream is replayed), refineKNN = FALSE with
+    centring and useDims, and a reference that is not the first dataset (earlier datasets see the unwarped reference)."""
+    from liger_b200 import align
+    from oracle import quantile_norm_oracle as qn
+    rng = np.random.default_rng(11)
+    k, sizes = 6, [700, 500, 600]
+    Hs = []
+    for n in sizes:
+        z = rng.integers(0, k, n)
+        h = rng.gamma(0.4, 0.3, (n, k)).astype(np.float32).astype(np.float64)
+        h[np.arange(n), z] += rng.gamma(3.0, 1.0, n)
+        h[rng.random((n, k)) < 0.15] = 0.0
+        h[5] = 0.0                                    # a cell with no positive loading: label -1
+        Hs.append(h)
+    kw = dict(quantiles=50, min_cells=20, n_neighbors=20, max_sample=1000, seed=1)
+    pkw = dict(quantiles=50, minCells=20, nNeighbors=20, maxSample=1000, seed=1)
+    ref = 0
+    if case == "sampled":
+        kw.update(max_sample=60, seed=7)
+        pkw.update(maxSample=60, seed=7)
+    elif case == "norefine_center_dims":
+        kw.update(refine_knn=False, center=True, dims_use=[1, 2, 4, 6])
+        pkw.update(refineKNN=False, center=True, useDims=[1, 2, 4, 6])
+    else:
+        ref = 2
+    knn = None if not kw.get("refine_knn", True) else [qn.knn_ann(h, 20, 0.9) for h in Hs]
+    out, clusters = qn.quantile_norm(Hs, reference=ref, knn=knn, **kw)
+    res = align.quantile_norm_hlist([h.T for h in Hs], reference=ref + 1, return_info=True, **pkw)
+    for i, name in enumerate(["1", "2", "3"]):
+        assert (res["clusters"][name] == clusters[i]).all()
+    assert np.abs(res["H.norm"] - np.vstack(out)).max() < 1e-11
+    assert res["info"]["sampled"] == (1 if case == "sampled" else 0)
+    assert res["info"]["warped_clusters"] > 0
+
+
+def test_quantile_norm_on_resident_h(pbmc):
+    """lgr_ctx_quantile_norm consumes the H that is still in HBM after the factorisation: same result as downloading H and
+    calling lgr_quantile_norm on it."""
+    import liger_b200
+    from liger_b200 import align
+    W, Vs, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    ctx = liger_b200.Context(pbmc["Es"], 20, 5.0, W, Vs)
+    try:
+        ctx.iterate(5)
+        H = ctx.download()["H"]
+        a = align.quantile_norm_resident(ctx, reference=0)
+        b = align.quantile_norm_hlist([h.T for h in H], reference=1)
+        assert np.abs(a["H.norm"] - b["H.norm"]).max() == 0.0
+        assert all((x == y).all() for x, y in zip(a["clusters"], b["clusters"].values()))
+        assert np.abs(a["H.norm"] - np.vstack(H)).max() > 1e-3        # something was warped
+    finally:
+        ctx.close()

@@ -143,3 +143,52 @@ def test_optimize_oracle_invariants(pbmc):
     assert np.allclose(sub["H"][1], fit["H"][1][:, idx[1]])
     lam2 = oo.optimize_new_lambda(Es, fit, 7.5, 2)
     assert lam2["lam"] == 7.5 and lam2["W"].shape == (173, 8)
+
+
+# ----------------------------------------------------------------------------------------------
+# quantileNorm (f3): the restatement against the H.norm the reference ships in data/pbmcPlot.rda
+# ----------------------------------------------------------------------------------------------
+def _golden_hlist(pbmc):
+    g = pbmc["golden"]
+    return [np.asarray(g["golden_H_ctrl"]).T.copy(), np.asarray(g["golden_H_stim"]).T.copy()]   # cell x factor
+
+
+def test_quantile_norm_oracle_reproduces_reference_h_norm(pbmc):
+    """quantileNorm(pbmcPlot) with the defaults of its command log: every row of the stored H.norm to round-off.  This
+    needs both reference quirks: ANN's approximate kd-tree search (RANN::nn2(eps = 0.9)) and the in-place cluster vote."""
+    from oracle import quantile_norm_oracle as qn
+    Hs = _golden_hlist(pbmc)
+    gold = np.asarray(pbmc["golden"]["golden_Hnorm"])
+    knn = [qn.knn_ann(h, 20, 0.9) for h in Hs]
+    out, clusters = qn.quantile_norm(Hs, reference=0, knn=knn)
+    assert np.abs(np.vstack(out) - gold).max() < 1e-12
+    # the reference dataset maps onto itself; 146 stim cells are warped
+    assert np.abs(out[0] - Hs[0]).max() < 1e-12
+    assert int((np.abs(out[1] - Hs[1]).max(axis=1) > 1e-12).sum()) == 146
+    # without the in-place update, or with exact neighbours, the warped rows differ: the quirks are load-bearing
+    out2, _ = qn.quantile_norm(Hs, reference=0, knn=knn, vote_in_place=False)
+    assert np.abs(np.vstack(out2) - gold).max() > 1e-3
+    out3, _ = qn.quantile_norm(Hs, reference=0)          # exact kNN
+    assert np.abs(np.vstack(out3) - gold).max() > 1e-3
+
+
+def test_quantile_norm_oracle_pieces():
+    from oracle import quantile_norm_oracle as qn
+    # stats::quantile type 7 known answers: quantile(c(1, 2, 4, 8, 16), c(0, .1, .5, .9, 1)) = 1.0 1.4 4.0 12.8 16.0
+    q = qn.quantile7(np.array([16.0, 1.0, 4.0, 2.0, 8.0]), np.array([0, 0.1, 0.5, 0.9, 1.0]))
+    assert np.allclose(q, [1.0, 1.4, 4.0, 12.8, 16.0], rtol=0, atol=1e-12)
+    # approxfun(c(0, 0, 1, 2), c(1, 3, 5, 9), rule = 2): ties collapse to the mean (0 -> 2); outside -> end values
+    v = qn.approx_rule2(np.array([0.0, 0.0, 1.0, 2.0]), np.array([1.0, 3.0, 5.0, 9.0]), np.array([-1.0, 0.0, 0.5, 1.5, 2.0, 7.0]))
+    assert np.allclose(v, [2.0, 2.0, 3.5, 7.0, 9.0, 9.0])
+    # set.seed(1); sample.int(10) under R >= 3.6 (sample.kind = "Rejection") = 9 4 7 1 2 5 3 10 6 8
+    idx = qn.r_sample_index(orc.RRandom(1), 10, 10) + 1
+    assert idx.tolist() == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]
+    # the ANN search with eps = 0 is the exact search
+    rng = np.random.default_rng(3)
+    X = rng.gamma(0.6, 1.0, (400, 6))
+    a = qn.knn_ann(X, 8, 0.0)
+    e = qn.knn_exact(X, 8)
+    assert (a == e).all()
+    # max_factor: first maximum of the scaled columns, -1 for an all-zero row
+    H = np.array([[1.0, 2.0], [3.0, 0.5], [0.0, 0.0], [2.0, 2.0]])
+    assert qn.max_factor(H).tolist() == [2, 1, -1, 2]
