@@ -212,6 +212,7 @@ typedef struct lgr_qn_params {
 } lgr_qn_params;
 typedef struct lgr_qn_info {
     double cluster_ms, knn_ms, warp_ms;   /* device + host time of the three stages (CUDA events) */
+    double tree_ms, search_ms;            /* inside knn_ms: host kd-tree builds (wall clock), device searches (CUDA events) */
     int32_t vote_sweeps;                  /* sweeps the in-place vote needed to reach its fixed point (max over datasets) */
     int32_t warped_clusters;              /* (dataset, cluster) pairs that were warped */
     int32_t sampled;                      /* 1 if some cluster exceeded max_sample (R's sample() stream was replayed) */

@@ -56,7 +56,8 @@ class lgr_qn_params(C.Structure):
 
 
 class lgr_qn_info(C.Structure):
-    _fields_ = [("cluster_ms", C.c_double), ("knn_ms", C.c_double), ("warp_ms", C.c_double), ("vote_sweeps", C.c_int32),
+    _fields_ = [("cluster_ms", C.c_double), ("knn_ms", C.c_double), ("warp_ms", C.c_double), ("tree_ms", C.c_double),
+                ("search_ms", C.c_double), ("vote_sweeps", C.c_int32),
                 ("warped_clusters", C.c_int32), ("sampled", C.c_int32), ("pad0", C.c_int32)]
 
 

@@ -22,6 +22,7 @@
 //   * base::sample() consumes R's RNG stream for every (dataset, cluster, factor) even when it only permutes; the host
 //     replays all calls (R >= 3.6 rejection sampling) when some cluster exceeds maxSample, and ships the drawn positions.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <string>
 #include <thread>
@@ -139,13 +140,17 @@ struct AnnBuilder {
     }
 };
 
-// one thread per query; qs: this block's query points as [dim][thread]
+// one thread per query; qs: this block's query points as [dim][thread].  The queries are taken in the tree's leaf order
+// (qorder = the builder's final point permutation): the threads of a warp then hold neighbouring points, walk nearly the
+// same path and touch the same nodes and points (coherent branches and loads); every query's result is unaffected.
 __global__ void __launch_bounds__(128) k_ann_search(const AnnNode* __restrict__ nodes, int root, const double* __restrict__ pts, int n,
                                                     int dim, const double* __restrict__ blo, const double* __restrict__ bhi, int kk,
-                                                    double max_err, int* __restrict__ nn_idx, int* __restrict__ overflow) {
+                                                    double max_err, const int* __restrict__ qorder, int* __restrict__ nn_idx,
+                                                    int* __restrict__ overflow) {
     extern __shared__ double qs[];
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = q < n;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = slot < n;
+    const int q = live ? qorder[slot] : 0;
     double* qp = qs + threadIdx.x;
     for (int d = 0; d < dim; ++d) qp[d * blockDim.x] = live ? pts[(size_t)q * dim + d] : 0.0;
     if (!live) return;
@@ -604,6 +609,7 @@ void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const l
             for (int c = 0; c < k; ++c)
                 for (int r = 0; r < n[i]; ++r) pts[i][(size_t)r * k + c] = colmajor[(size_t)c * n[i] + r];
         }
+        const auto t_build0 = std::chrono::steady_clock::now();
         std::vector<std::thread> th;
         for (int i = 0; i < d; ++i) {
             th.emplace_back([&, i] {
@@ -633,6 +639,10 @@ void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const l
             });
         }
         for (auto& t : th) t.join();
+        if (info) info->tree_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
+        cudaEvent_t s0, s1;
+        LGR_CUDA(cudaEventCreate(&s0));
+        LGR_CUDA(cudaEventCreate(&s1));
         const int kk_all = p.n_neighbors;
         for (int i = 0; i < d; ++i) {
             AnnBuilder& b = B[i];
@@ -640,7 +650,8 @@ void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const l
             const int kk = std::min(kk_all, n[i]);
             DBuf<AnnNode> nodes(b.nodes.size());
             DBuf<double> dpts(pts[i].size()), dlo(k), dhi(k);
-            DBuf<int> nn((size_t)n[i] * kk), overflow(1), changed(1), curA(n[i]), curB(n[i]);
+            DBuf<int> nn((size_t)n[i] * kk), overflow(1), changed(1), curA(n[i]), curB(n[i]), qorder(n[i]);
+            LGR_CUDA(cudaMemcpyAsync(qorder.p, b.pidx.data(), sizeof(int) * n[i], cudaMemcpyHostToDevice, st));
             overflow.zero(st);
             LGR_CUDA(cudaMemcpyAsync(nodes.p, b.nodes.data(), sizeof(AnnNode) * b.nodes.size(), cudaMemcpyHostToDevice, st));
             LGR_CUDA(cudaMemcpyAsync(dpts.p, pts[i].data(), sizeof(double) * pts[i].size(), cudaMemcpyHostToDevice, st));
@@ -649,13 +660,20 @@ void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const l
             const double max_err = (1.0 + p.eps) * (1.0 + p.eps);
             const size_t qsmem = (size_t)128 * k * sizeof(double);
             if (qsmem > 48 * 1024) LGR_CUDA(cudaFuncSetAttribute(k_ann_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
+            LGR_CUDA(cudaEventRecord(s0, st));
             k_ann_search<<<(n[i] + 127) / 128, 128, qsmem, st>>>(
-                nodes.p, (int)b.nodes.size() - 1, dpts.p, n[i], k, dlo.p, dhi.p, kk, max_err, nn.p, overflow.p);
+                nodes.p, (int)b.nodes.size() - 1, dpts.p, n[i], k, dlo.p, dhi.p, kk, max_err, qorder.p, nn.p, overflow.p);
             LGR_CUDA(cudaGetLastError());
+            LGR_CUDA(cudaEventRecord(s1, st));
             int ov = 0;
             LGR_CUDA(cudaMemcpyAsync(&ov, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             LGR_CUDA(cudaStreamSynchronize(st));
             LGR_REQUIRE(ov == 0, "quantileNorm: kd-tree search stack overflow");
+            if (info) {
+                float sms = 0.f;
+                cudaEventElapsedTime(&sms, s0, s1);
+                info->search_ms += sms;
+            }
             // in-place vote = fixed point of the sweeps
             LGR_CUDA(cudaMemcpyAsync(curA.p, rank[i].p, sizeof(int) * n[i], cudaMemcpyDeviceToDevice, st));
             int* cur = curA.p;
@@ -677,6 +695,8 @@ void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const l
             LGR_CUDA(cudaMemcpyAsync(rank[i].p, cur, sizeof(int) * n[i], cudaMemcpyDeviceToDevice, st));
             LGR_CUDA(cudaStreamSynchronize(st));
         }
+        cudaEventDestroy(s0);
+        cudaEventDestroy(s1);
     }
     LGR_CUDA(cudaEventRecord(e2, st));
 
