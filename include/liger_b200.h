@@ -223,6 +223,24 @@ typedef struct lgr_qn_info {
 LGR_API int lgr_quantile_norm(int32_t d, int32_t k, const int64_t* n, const double* const* H, const lgr_qn_params* params,
                               double* const* Hnorm, int32_t* const* clusters, lgr_qn_info* info, int32_t device);
 
+/* ---- factor alignment: centroidAlign (R/integration.R:2015-2084 .centroidAlign.Hraw; src/data_processing.cpp:10-20,61-85
+   normalize_byCol_dense_rcpp / safe_scale; src/centoidAlign.cpp:16-85 moe_correct_ridge_cpp).  Defaults in brackets. ---- */
+typedef struct lgr_ca_params {
+    const double* lambda;    /* [1 each] ridge penalty per dataset (d values) */
+    int32_t scale_emb;       /* [1] */
+    int32_t center_emb;      /* [1] */
+    int32_t scale_cluster;   /* [0] */
+    int32_t center_cluster;  /* [0] */
+    int32_t shift;           /* [0] subtract the global minimum of the memberships before normalising them */
+    int32_t n_dims_use;      /* 0 = all factors */
+    const int32_t* dims_use; /* 1-based factor ids (useDims), or NULL */
+} lgr_ca_params;
+/* H[i]: n_i x k column-major; aligned[i]: n_i x kd (kd = number of used dims; rbind them for H.norm); the three diagnostics
+   (diagnosis = TRUE: which.max of the raw row, of the aligned row, of the membership column; 1-based) may be NULL. */
+LGR_API int lgr_centroid_align(int32_t d, int32_t k, const int64_t* n, const double* const* H, const lgr_ca_params* params,
+                               double* const* aligned, int32_t* const* raw_which_max, int32_t* const* z_which_max,
+                               int32_t* const* r_which_max, int32_t device);
+
 /* ---- resident-handle API (data stays in HBM between calls; used by bench + multi-GPU hosts) ---- */
 typedef struct lgr_ctx lgr_ctx;
 LGR_API int lgr_ctx_create(const lgr_inmf_args* args, lgr_ctx** ctx); /* uploads E/P, builds device layouts, sets inits */
@@ -253,6 +271,8 @@ LGR_API int lgr_ctx_products(lgr_ctx* ctx, int32_t which, double* const* out);
 LGR_API int lgr_ctx_objerr_i(lgr_ctx* ctx, int32_t i, double* obj);
 LGR_API int lgr_ctx_download(lgr_ctx* ctx, lgr_inmf_out* out);
 /* quantileNorm of the RESIDENT H_i (no upload of H; single-rank contexts only) */
+/* centroidAlign of the RESIDENT H_i (single-rank contexts only) */
+LGR_API int lgr_ctx_centroid_align(lgr_ctx* ctx, const lgr_ca_params* params, double* const* aligned);
 LGR_API int lgr_ctx_quantile_norm(lgr_ctx* ctx, const lgr_qn_params* params, double* const* Hnorm, int32_t* const* clusters,
                                   lgr_qn_info* info);
 LGR_API int lgr_ctx_timings(lgr_ctx* ctx, lgr_timings* t);

@@ -115,3 +115,87 @@ def quantileNorm(obj, quantiles=50, reference=None, minCells=20, nNeighbors=20, 
     out["uns"] = dict(out.get("uns", {}))
     out["uns"]["alignmentMethod"] = "quantileNorm"
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# centroidAlign (R/integration.R:1880-2084)
+# ------------------------------------------------------------------------------------------------------------------
+def _ca_params(d, lambda_, useDims, scaleEmb, centerEmb, scaleCluster, centerCluster, shift):
+    lam = np.ascontiguousarray(np.full(d, float(lambda_)) if np.ndim(lambda_) == 0 else np.asarray(lambda_, dtype=np.float64))
+    if lam.shape[0] != d:      # .checkArgLen(lambda, length(object), repN = TRUE)
+        raise ValueError(f"`lambda` has to be a length 1 or {d} numeric vector.")
+    p = _ffi.lgr_ca_params()
+    p.lambda_ = lam.ctypes.data_as(c_double_p)
+    p.scale_emb, p.center_emb, p.scale_cluster, p.center_cluster = int(bool(scaleEmb)), int(bool(centerEmb)), int(bool(scaleCluster)), int(bool(centerCluster))
+    p.shift = int(bool(shift))
+    keep = [lam]
+    if useDims is not None:
+        dims = np.ascontiguousarray(useDims, dtype=np.int32)
+        p.n_dims_use = dims.shape[0]
+        p.dims_use = dims.ctypes.data_as(C.POINTER(C.c_int32))
+        keep.append(dims)
+    return p, keep
+
+
+def centroid_align_hlist(HList, lambda_=1.0, useDims=None, scaleEmb=True, centerEmb=True, scaleCluster=False,
+                         centerCluster=False, shift=False, diagnosis=False, device=-1):
+    """.centroidAlign.Hraw on {name: k x n_i} (datasets in order = the levels of datasetVar)."""
+    mats = list(HList.values()) if isinstance(HList, dict) else list(HList)
+    k = mats[0].shape[0]
+    Hs = [np.asfortranarray(np.asarray(h, dtype=np.float64).T) for h in mats]
+    d = len(Hs)
+    p, _keep = _ca_params(d, lambda_, useDims, scaleEmb, centerEmb, scaleCluster, centerCluster, shift)
+    kd = k if useDims is None else len(useDims)
+    outs = [np.zeros((h.shape[0], kd), order="F") for h in Hs]
+    n = (C.c_int64 * d)(*[h.shape[0] for h in Hs])
+    Harr = (c_double_p * d)(*[h.ctypes.data_as(c_double_p) for h in Hs])
+    Oarr = (c_double_p * d)(*[o.ctypes.data_as(c_double_p) for o in outs])
+    ip = C.POINTER(C.c_int32)
+    diag = [[np.zeros(h.shape[0], dtype=np.int32) for h in Hs] for _ in range(3)] if diagnosis else None
+    darr = [((ip * d)(*[x.ctypes.data_as(ip) for x in g]) if diagnosis else None) for g in (diag or [None] * 3)]
+    _ffi.check(_ffi.lib().lgr_centroid_align(d, k, n, Harr, C.byref(p), Oarr, darr[0], darr[1], darr[2], device))
+    res = {"aligned": np.vstack(outs)}
+    if diagnosis:
+        res["raw_which.max"], res["Z_which.max"], res["R_which.max"] = (np.concatenate(g) for g in diag)
+    return res
+
+
+def centroid_align_resident(ctx, lambda_=1.0, useDims=None, scaleEmb=True, centerEmb=True, scaleCluster=False,
+                            centerCluster=False, shift=False):
+    d, k = ctx.args.d, ctx.args.k
+    p, _keep = _ca_params(d, lambda_, useDims, scaleEmb, centerEmb, scaleCluster, centerCluster, shift)
+    kd = k if useDims is None else len(useDims)
+    outs = [np.zeros((n, kd), order="F") for n in ctx.args.n]
+    Oarr = (c_double_p * d)(*[o.ctypes.data_as(c_double_p) for o in outs])
+    _ffi.check(_ffi.lib().lgr_ctx_centroid_align(ctx.h, C.byref(p), Oarr))
+    return {"aligned": np.vstack(outs)}
+
+
+def centroidAlign(obj, lambda_=1.0, useDims=None, scaleEmb=True, centerEmb=True, scaleCluster=False, centerCluster=False,
+                  shift=False, diagnosis=False):
+    """centroidAlign.liger (R/integration.R:1898-1950) on a fit dict (H = {name: k x n_i}), or on an HList."""
+    is_fit = isinstance(obj, dict) and "H" in obj and "W" in obj
+    res = centroid_align_hlist(obj["H"] if is_fit else obj, lambda_=lambda_, useDims=useDims, scaleEmb=scaleEmb,
+                               centerEmb=centerEmb, scaleCluster=scaleCluster, centerCluster=centerCluster, shift=shift,
+                               diagnosis=diagnosis)
+    if not is_fit:
+        return res
+    out = dict(obj)
+    out["H.norm"] = res["aligned"]
+    out["uns"] = dict(out.get("uns", {}))
+    out["uns"]["alignmentMethod"] = "centroidAlign"
+    if diagnosis:
+        out["cellMeta"] = dict(out.get("cellMeta", {}))
+        for key in ("raw_which.max", "Z_which.max", "R_which.max"):
+            out["cellMeta"][key] = res[key]
+    return out
+
+
+def alignFactors(obj, method="quantileNorm", **kw):
+    """alignFactors (R/integration.R:1400-1426): dispatch on the method name."""
+    m = method.lower()
+    if m in ("quantilenorm", "quantile_norm", "quantile"):
+        return quantileNorm(obj, **kw)
+    if m in ("centroidalign", "centroid_align", "centroid"):
+        return centroidAlign(obj, **kw)
+    raise ValueError("`method` must be one of 'quantileNorm', 'quantile_norm', 'centroidAlign', 'centroid_align'")

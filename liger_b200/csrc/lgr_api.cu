@@ -1358,6 +1358,83 @@ int lgr_ctx_objerr_i(lgr_ctx* c, int32_t i, double* obj) {
         *obj = objective_i(c, i);
     });
 }
+// centroidAlign of host matrices
+int lgr_centroid_align(int32_t d, int32_t k, const int64_t* n, const double* const* H, const lgr_ca_params* params,
+                       double* const* aligned, int32_t* const* raw_which_max, int32_t* const* z_which_max,
+                       int32_t* const* r_which_max, int32_t device) {
+    return guarded([&] {
+        check_device();
+        LGR_REQUIRE(d >= 1 && n && H && params && aligned, "lgr_centroid_align: bad argument");
+        int ndev = 0;
+        LGR_CUDA(cudaGetDeviceCount(&ndev));
+        const int dev = device < 0 ? 0 : device;
+        LGR_REQUIRE(dev < ndev, "device index out of range");
+        LGR_CUDA(cudaSetDevice(dev));
+        StreamHolder sh;
+        LGR_CUDA(cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking));
+        AllocStreamScope alloc_scope(sh.s);
+        const int kd = params->n_dims_use > 0 ? params->n_dims_use : k;
+        std::vector<DBuf<double>> Hd(d), Od(d);
+        std::vector<DBuf<int>> Dg(3 * (size_t)d);
+        std::vector<const double*> hp(d);
+        std::vector<double*> op(d);
+        std::vector<int*> g0(d, nullptr), g1(d, nullptr), g2(d, nullptr);
+        std::vector<int> nn(d);
+        for (int i = 0; i < d; ++i) {
+            LGR_REQUIRE(n[i] >= 0 && n[i] < (1LL << 31) && (n[i] == 0 || (H[i] && aligned[i])), "lgr_centroid_align: bad dataset");
+            nn[i] = (int)n[i];
+            Hd[i].alloc(std::max<size_t>((size_t)n[i] * k, 1));
+            Od[i].alloc(std::max<size_t>((size_t)n[i] * kd, 1));
+            if (n[i]) copy_in(Hd[i].p, H[i], (size_t)n[i] * k * sizeof(double), sh.s, false);
+            hp[i] = Hd[i].p;
+            op[i] = Od[i].p;
+            if (raw_which_max && raw_which_max[i]) { Dg[3 * i].alloc(std::max<size_t>(n[i], 1)); g0[i] = Dg[3 * i].p; }
+            if (z_which_max && z_which_max[i]) { Dg[3 * i + 1].alloc(std::max<size_t>(n[i], 1)); g1[i] = Dg[3 * i + 1].p; }
+            if (r_which_max && r_which_max[i]) { Dg[3 * i + 2].alloc(std::max<size_t>(n[i], 1)); g2[i] = Dg[3 * i + 2].p; }
+        }
+        LGR_CUDA(cudaStreamSynchronize(sh.s));
+        centroid_align_core(d, k, nn.data(), hp.data(), *params, op.data(), g0.data(), g1.data(), g2.data(), sh.s);
+        for (int i = 0; i < d; ++i) {
+            if (!n[i]) continue;
+            copy_out(aligned[i], Od[i].p, (size_t)n[i] * kd * sizeof(double), sh.s, false);
+            if (g0[i]) LGR_CUDA(cudaMemcpyAsync(raw_which_max[i], g0[i], (size_t)n[i] * sizeof(int), cudaMemcpyDeviceToHost, sh.s));
+            if (g1[i]) LGR_CUDA(cudaMemcpyAsync(z_which_max[i], g1[i], (size_t)n[i] * sizeof(int), cudaMemcpyDeviceToHost, sh.s));
+            if (g2[i]) LGR_CUDA(cudaMemcpyAsync(r_which_max[i], g2[i], (size_t)n[i] * sizeof(int), cudaMemcpyDeviceToHost, sh.s));
+            LGR_CUDA(cudaStreamSynchronize(sh.s));
+        }
+    });
+}
+// centroidAlign of the resident H_i
+int lgr_ctx_centroid_align(lgr_ctx* c, const lgr_ca_params* params, double* const* aligned) {
+    return guarded([&] {
+        LGR_REQUIRE(c && params && aligned, "lgr_ctx_centroid_align: bad argument");
+        LGR_REQUIRE(c->world == 1, "lgr_ctx_centroid_align: the column statistics span all cells (single-rank contexts only)");
+        LGR_REQUIRE(c->h_valid, "lgr_ctx_centroid_align: no H on the device yet");
+        LGR_CUDA(cudaSetDevice(c->device));
+        AllocStreamScope alloc_scope(c->st);
+        const int d = c->d, k = c->k;
+        const int kd = params->n_dims_use > 0 ? params->n_dims_use : k;
+        std::vector<DBuf<double>> Hd(d), Od(d);
+        std::vector<const double*> hp(d);
+        std::vector<double*> op(d);
+        std::vector<int> nn(d);
+        for (int i = 0; i < d; ++i) {
+            Dataset& D = c->ds[i];
+            nn[i] = D.n;
+            Hd[i].alloc(std::max<size_t>((size_t)D.n * k, 1));
+            Od[i].alloc(std::max<size_t>((size_t)D.n * kd, 1));
+            if (D.n) dev_hpad_to_colmajor(D.H.p, Hd[i].p, D.n, k, c->kp, c->st);
+            hp[i] = Hd[i].p;
+            op[i] = Od[i].p;
+        }
+        centroid_align_core(d, k, nn.data(), hp.data(), *params, op.data(), nullptr, nullptr, nullptr, c->st);
+        for (int i = 0; i < d; ++i) {
+            if (!nn[i] || !aligned[i]) continue;
+            copy_out(aligned[i], Od[i].p, (size_t)nn[i] * kd * sizeof(double), c->st, false);
+            LGR_CUDA(cudaStreamSynchronize(c->st));
+        }
+    });
+}
 // quantileNorm of host matrices: upload H_i (FP64), align on the device, download H.norm and the cluster labels
 int lgr_quantile_norm(int32_t d, int32_t k, const int64_t* n, const double* const* H, const lgr_qn_params* params,
                       double* const* Hnorm, int32_t* const* clusters, lgr_qn_info* info, int32_t device) {

@@ -292,6 +292,9 @@ void prep_check_counts(size_t nnz, const double* x, int* bad, cudaStream_t st);
 void prep_reciprocal(size_t n, const double* in, double* out, cudaStream_t st);
 void dev_exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t st);   // lgr_layout.cu (cub)
 
+// lgr_centroid.cu: centroidAlign on device-resident FP64 H (column-major n_i x k, read only) -> out (n_i x kd)
+void centroid_align_core(int d, int k, const int* n, const double* const* Hdev, const lgr_ca_params& p, double* const* out_dev,
+                         int* const* raw_max, int* const* z_max, int* const* r_max, cudaStream_t st);
 // lgr_align.cu: quantileNorm on device-resident FP64 H (column-major n_i x k, replaced by H.norm)
 void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const lgr_qn_params& p, int* const* labels_dev,
                         lgr_qn_info* info, cudaStream_t st);

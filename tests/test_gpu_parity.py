@@ -753,3 +753,52 @@ def test_quantile_norm_on_resident_h(pbmc):
         assert np.abs(a["H.norm"] - np.vstack(H)).max() > 1e-3        # something was warped
     finally:
         ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# centroidAlign on the device (f3; R/integration.R:2015-2084, src/centoidAlign.cpp) -- parity unpinned in the reference
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["defaults", "cluster_scaled_shift", "dims_lambda"])
+def test_centroid_align_matches_oracle(pbmc, case):
+    from liger_b200 import align
+    from oracle import centroid_align_oracle as ca
+    g = pbmc["golden"]
+    HList = {"ctrl": np.asarray(g["golden_H_ctrl"]), "stim": np.asarray(g["golden_H_stim"])[:, :250]}
+    Hs = [h.T for h in HList.values()]
+    kw, okw = {}, {}
+    if case == "cluster_scaled_shift":
+        kw = dict(scaleCluster=True, centerCluster=True, shift=True)
+        okw = dict(scale_cluster=True, center_cluster=True, shift=True)
+    elif case == "dims_lambda":
+        kw = dict(useDims=[2, 3, 5, 7, 11, 13], lambda_=[0.5, 3.0], centerEmb=False)
+        okw = dict(dims_use=[2, 3, 5, 7, 11, 13], lam=[0.5, 3.0], center_emb=False)
+    ref = ca.centroid_align(Hs, diagnosis=True, **okw)
+    res = align.centroid_align_hlist(HList, diagnosis=True, **kw)
+    assert res["aligned"].shape == ref["aligned"].shape
+    assert rel(res["aligned"], ref["aligned"]) < 1e-11
+    for key in ("raw_which.max", "Z_which.max", "R_which.max"):
+        assert (res[key] == ref[key]).mean() > 0.999       # arg-max ties aside
+    fit = align.alignFactors({"H": HList, "W": np.zeros((3, 20)), "uns": {}}, method="centroid", **kw)
+    assert fit["uns"]["alignmentMethod"] == "centroidAlign" and rel(fit["H.norm"], ref["aligned"]) < 1e-11
+
+
+def test_centroid_align_errors_and_resident(pbmc):
+    import liger_b200
+    from liger_b200 import align
+    g = pbmc["golden"]
+    HList = {"ctrl": np.asarray(g["golden_H_ctrl"]), "stim": np.asarray(g["golden_H_stim"])}
+    # tests/testthat/test_factorization.R:221-222
+    with pytest.raises(Exception, match="Negative values found prior to normalizing"):
+        align.centroidAlign(HList, centerCluster=True, shift=False)
+    with pytest.raises(ValueError, match="length 1 or 2"):
+        align.centroidAlign(HList, lambda_=[1.0, 2.0, 3.0])
+    W, Vs, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    ctx = liger_b200.Context(pbmc["Es"], 20, 5.0, W, Vs)
+    try:
+        ctx.iterate(5)
+        H = ctx.download()["H"]
+        a = align.centroid_align_resident(ctx)
+        b = align.centroid_align_hlist([h.T for h in H])
+        assert rel(a["aligned"], b["aligned"]) < 1e-13
+    finally:
+        ctx.close()
