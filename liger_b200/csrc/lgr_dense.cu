@@ -351,8 +351,10 @@ __device__ __forceinline__ const DenseDs* cache_ds(const DenseDs* __restrict__ d
 
 // =====================================================================================================================
 // k_dense_ltx:  B = L~^T X
-// Ring of NST slots, each = 16 KB of A slabs (bulk copy) + 32 KB of X tiles (scatter); one `full` barrier per slot collects
-// the producer's transaction bytes and the three scatter warps, one `empty` barrier is signalled by tcgen05.commit.
+// X ring: NST slots of 32 KB (four [256 x 16] count tiles, written by the slot's three scatter warps; `full` = their three
+// arrivals, `empty` = tcgen05.commit).  A ring: K1_NSA slots of 16 KB (four pre-split factor slabs, one bulk copy each;
+// `fullA` = the copy's transaction bytes, `emptyA` = tcgen05.commit); it runs further ahead than the X ring.  The slabs are
+// contiguous images written by k_prep, so the copies are 1-D bulk copies (cp.async.bulk, UBLKCP), not tensor-map loads.
 // =====================================================================================================================
 __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* __restrict__ ds_g, int nds, int total_tiles, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
