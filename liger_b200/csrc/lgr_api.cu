@@ -110,6 +110,8 @@ struct StreamHolder {
 struct lgr_ctx {
     StreamHolder stream_holder;
     StreamHolder copy_holder;   // upload copy stream: buffers allocated in its order may live as long as the context
+    StreamHolder side_holder;   // side stream of the iteration: the Gram inverses run beside the sweeps that do not need them
+    cudaEvent_t ev_fork = nullptr, ev_join_h = nullptr, ev_join_v = nullptr;
     int d = 0, k = 0, kp = 32, m = 0, device = 0, rank = 0, world = 1, tc = 1024, cb = 512, gt = 1024, num_sms = 148;
     uint32_t flags = 0;
     int32_t init_seed = 0;
@@ -155,6 +157,9 @@ struct lgr_ctx {
         if (comm) nccl_destroy(comm);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join_h) cudaEventDestroy(ev_join_h);
+        if (ev_join_v) cudaEventDestroy(ev_join_v);
     }
 };
 
@@ -394,13 +399,31 @@ void run_prep(lgr_ctx* c) {
     Timed t(c, "k_prep");
     launch_prep(c->ds_dev.p, c->d, c->prep_blocks, c->W.p, c->k, c->kp, c->st);
 }
-void run_stats(lgr_ctx* c) {  // R = X H, G = H^T H (+ all-reduce)
+// the k x k Gram inverses are latency-bound single-CTA kernels: where the next big kernel does not read their result they
+// run on the side stream (fork / join by events; inside a graph capture these become plain dependencies)
+bool side_ok(lgr_ctx* c) { return c->side_holder.s != nullptr && !c->kt.on; }
+void fork_gram_inv(lgr_ctx* c, const GramSpec* specs, int n, cudaEvent_t join) {
+    LGR_CUDA(cudaEventRecord(c->ev_fork, c->st));
+    LGR_CUDA(cudaStreamWaitEvent(c->side_holder.s, c->ev_fork, 0));
+    launch_gram_inv(specs, n, c->k, c->kp, c->side_holder.s);
+    LGR_CUDA(cudaEventRecord(join, c->side_holder.s));
+    c->tm.kernel_launches += 1;
+}
+
+// R = X H, G = H^T H (+ all-reduce).  fork_ginv_v: also start the Gram inverses of the V solves as soon as G is final
+// (single rank, dense path: right after k_gram_tc, beside the R sweep); returns whether it did.
+bool run_stats(lgr_ctx* c, bool fork_ginv_v = false) {
+    bool forked = false;
     c->Rarena.zero(c->st);
     c->Garena.zero(c->st);
     if (c->dense && (c->dense_mask & 2)) {
         {
             Timed t(c, "k_gram_tc");
             launch_gram_h(c->dds_dev.p, c->d, c->gh_blocks, c->k, c->num_sms, c->st);
+        }
+        if (fork_ginv_v && c->world == 1 && side_ok(c)) {
+            fork_gram_inv(c, c->specV.p, c->d, c->ev_join_v);
+            forked = true;
         }
         Timed t(c, "k_dense_xh");
         launch_dense_xh(c->dds_dev.p, c->d, c->k2_flat, c->num_sms, c->st);
@@ -410,6 +433,7 @@ void run_stats(lgr_ctx* c) {  // R = X H, G = H^T H (+ all-reduce)
     }
     allreduce_stats(c);
     c->stats_valid = true;
+    return forked;
 }
 void run_objective(lgr_ctx* c, double* slot) {
     LGR_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), c->st));
@@ -440,8 +464,11 @@ void solve_f64(lgr_ctx* c, const NnlsGroup* grp, int ngroups, long long cols, in
 void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
     run_prep(c);
     if (obj_slot) run_objective(c, obj_slot);   // objective of the PREVIOUS iterate (uses the fresh L~ Grams)
-    {
-        Timed t(c, "k_gram_inv");   // CtC and CtC^-1 of the H solves (the fused U = B P epilogue of K1 reads CtC^-1)
+    const bool fork = side_ok(c) && !c->fuse_u && !c->use_tc;   // (the fused U = B P epilogue of the gather K1 reads CtC^-1)
+    if (fork) {
+        fork_gram_inv(c, c->specH.p, c->d, c->ev_join_h);
+    } else {
+        Timed t(c, "k_gram_inv");   // CtC and CtC^-1 of the H solves
         launch_gram_inv(c->specH.p, c->d, c->k, c->kp, c->st);
     }
     if (c->dense && (c->dense_mask & 1)) {
@@ -455,6 +482,7 @@ void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
         Timed t(c, "k_pb_tc");
         launch_pb_tc(c->grpT.p, c->d, c->tilesT, c->kp, c->num_sms, c->st);
     }
+    if (fork) LGR_CUDA(cudaStreamWaitEvent(c->st, c->ev_join_h, 0));
     {
         Timed t(c, "k_nnls_H");
         // fp32, k <= 32: register-resident solver; groups with a singular Gram fall through to k_nnls (flag 16)
@@ -477,12 +505,14 @@ void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
     c->stats_valid = false;
 }
 // V_i (and U_i):  CtC = (1 + lambda) H^T H,  CtB = H^T X^T - H^T H W^T   (needs the statistics of the current H)
-void enqueue_solve_v(lgr_ctx* c, int cold) {
+void enqueue_solve_v(lgr_ctx* c, int cold, bool ginv_forked = false) {
     {
         Timed t(c, "k_vrhs");
         launch_vrhs(c->ds_dev.p, c->d, c->W.p, c->k, c->kp, c->max_rows, c->st);
     }
-    {
+    if (ginv_forked) {
+        LGR_CUDA(cudaStreamWaitEvent(c->st, c->ev_join_v, 0));
+    } else {
         Timed t(c, "k_gram_inv");
         launch_gram_inv(c->specV.p, c->d, c->k, c->kp, c->st);
     }
@@ -513,8 +543,8 @@ void enqueue_iteration(lgr_ctx* c, int cold, double* obj_slot) {
     enqueue_solve_h(c, cold, obj_slot);
     phase.reset();
     phase.reset(new Span(c, "vw_phase"));
-    run_stats(c);   // sufficient statistics of the V / W solves
-    enqueue_solve_v(c, cold);
+    const bool ginv_forked = run_stats(c, true);   // sufficient statistics of the V / W solves
+    enqueue_solve_v(c, cold, ginv_forked);
     enqueue_solve_w(c, cold);
     phase.reset();
 }
@@ -778,6 +808,12 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     }
     LGR_CUDA(cudaEventCreate(&c->ev0));
     LGR_CUDA(cudaEventCreate(&c->ev1));
+    if (!getenv("LGR_NO_SIDE_STREAM")) {
+        LGR_CUDA(cudaStreamCreateWithFlags(&c->side_holder.s, cudaStreamNonBlocking));
+        LGR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        LGR_CUDA(cudaEventCreateWithFlags(&c->ev_join_h, cudaEventDisableTiming));
+        LGR_CUDA(cudaEventCreateWithFlags(&c->ev_join_v, cudaEventDisableTiming));
+    }
     c->tc = c->kp == 32 ? 1024 : 512;
     c->cb = c->kp == 32 ? 512 : 256;
     {   // gene tiles of at most 1024 (512) rows, balanced
