@@ -472,6 +472,19 @@ def main():
     job = Job(cfg, n_rank, rank, world, local_rank, nccl_id)
     sampler = ClockSampler(local_rank)
     res = timed_runs(job, args, barrier, allmax, sampler)
+    # the step after the path, on the H that is still in HBM (single GPU): quantileNorm with the reference's defaults
+    align_extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            from liger_b200 import align as _align
+            t0a = time.time()
+            qn = _align.quantile_norm_resident(job.ctx, reference=0)
+            align_extra = {"what": "quantileNorm (reference defaults: 50 quantiles, 20 approximate neighbours eps = 0.9, in-place vote) of "
+                                   "the resident H right after the timed iterations",
+                           "seconds": time.time() - t0a, **qn["info"]}
+            del qn
+        except Exception as e:      # never let the extra take the bench line down
+            align_extra = {"error": str(e)[:200]}
     value = job.n_total * args.steps / (res["loop_ms"] * 1e-3)
     roofline = roofline_of(job, res, args, hbm_peak, peak_src, args.config == "C3" and world == 1)
     job.close()
@@ -531,6 +544,8 @@ def main():
     extra = {"warm_ms_per_step": res["warm_ms"] / args.steps,
              "warm_value": job.n_total * args.steps / (res["warm_ms"] * 1e-3),
              "warm_note": "K further iterations from the converged state of the timed run (warm passive sets)"}
+    if align_extra is not None:
+        extra["quantile_norm"] = align_extra
     del Es
     job.Es = None
     if world > 1 and not args.no_extra:

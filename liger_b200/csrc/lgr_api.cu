@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include "lgr_common.cuh"
 #include "lgr_nccl.h"
@@ -220,6 +221,31 @@ struct Span {
     }
 };
 
+// Device views handed out by lgr_prep_scaled_view: a view is only as alive as the buffers behind it.  Re-scaling a dataset
+// (lgr_prep_scale) or destroying its pipeline frees them, so every view is registered by its column-pointer address and
+// shape, forgotten when its buffers go, and checked before a factorisation dereferences it.
+struct ViewInfo {
+    int64_t nrow, ncol;
+};
+std::mutex g_view_mu;
+std::unordered_map<const void*, ViewInfo> g_views;
+void view_register(const void* colptr, int64_t nrow, int64_t ncol) {
+    std::lock_guard<std::mutex> lk(g_view_mu);
+    g_views[colptr] = ViewInfo{nrow, ncol};
+}
+void view_forget(const void* colptr) {
+    if (!colptr) return;
+    std::lock_guard<std::mutex> lk(g_view_mu);
+    g_views.erase(colptr);
+}
+void view_require_live(const lgr_csc& M, const char* what) {
+    std::lock_guard<std::mutex> lk(g_view_mu);
+    auto it = g_views.find(M.colptr);
+    if (it == g_views.end() || it->second.nrow != M.nrow || it->second.ncol != M.ncol)
+        throw Error(LGR_ERR_INVALID, std::string(what) + ": stale or foreign device view (take it from lgr_prep_scaled_view AFTER the "
+                                     "last lgr_prep_scale of that dataset, and keep the pipeline alive until the call returns)");
+}
+
 void check_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -309,6 +335,7 @@ void finish_csc(StagedCsc& S, int nrow, int* bad, cudaStream_t st) {
 
 // argument checks of one shared (E) or unshared (P) block; host pointers are only dereferenced for host matrices
 void check_block(const lgr_csc& M, int64_t nrow, int64_t ncol, const char* what) {
+    if (M.location == LGR_CSC_DEVICE) view_require_live(M, what);
     const std::string w(what);
     LGR_REQUIRE(M.nrow == nrow, w + ": wrong number of rows");
     LGR_REQUIRE(M.ncol == ncol, w + ": wrong number of cells");
@@ -1910,6 +1937,8 @@ int lgr_prep_scale(lgr_prep* p, int32_t i, int64_t m, const int32_t* feature_row
         LGR_CUDA(cudaMemcpyAsync(dlut.p, lut.data(), lut.size() * sizeof(int), cudaMemcpyHostToDevice, p->st));
         cnt.zero(p->st);
         prep_subset_count(D.ncol, D.colptr.p, D.rowidx.p, dlut.p, cnt.p, p->st);
+        view_forget(D.scolptr.p);   // views of the previous scaling die with its buffers
+        D.scaled = false;
         D.scolptr.alloc((size_t)D.ncol + 1);
         dev_exclusive_scan_int(cnt.p, D.scolptr.p, (size_t)D.ncol + 1, p->st);
         int total = 0;
@@ -1945,6 +1974,7 @@ int lgr_prep_scaled_view(lgr_prep* p, int32_t i, lgr_csc* view) {
         view->location = LGR_CSC_DEVICE;
         view->row_scale = D.counts_ok ? D.inv_rms.p : nullptr;
         view->col_scale = D.counts_ok ? D.inv_lib.p : nullptr;
+        view_register(view->colptr, view->nrow, view->ncol);
     });
 }
 
@@ -1966,6 +1996,7 @@ void lgr_prep_destroy(lgr_prep* p) {
     cudaSetDevice(p->device);
     {
         AllocStreamScope alloc_scope(p->st);
+        for (auto& D : p->ds) view_forget(D.scolptr.p);
         p->ds.clear();
     }
     delete p;

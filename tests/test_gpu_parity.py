@@ -600,7 +600,17 @@ def test_resident_pipeline_counts_to_factors(pbmc):
     for i, n in enumerate(pbmc["names"]):
         assert rel(out["H"][i], g[f"golden_H_{n}"]) < 5e-5
         assert pattern_mismatches(out["H"][i], g[f"golden_H_{n}"]) == 0
+    # a view dies with the buffers behind it: re-scaling (here with fewer features) or closing the pipeline invalidates
+    # the views taken before, and the factorisation refuses them instead of reading freed memory
+    stale = Es
+    fresh = pipe.scaleNotCenter(feats[:150])
+    with pytest.raises(Exception, match="stale or foreign device view"):
+        liger_b200.run_inmf_list(stale, k=5, lambda_=5.0, nIteration=1, seed=1)
+    ok = liger_b200.run_inmf_list(fresh, k=5, lambda_=5.0, nIteration=1, seed=1)
+    assert ok["W"].shape == (150, 5)
     pipe.close()
+    with pytest.raises(Exception, match="stale or foreign device view"):
+        liger_b200.run_inmf_list(fresh, k=5, lambda_=5.0, nIteration=1, seed=1)
 
 
 def test_cinmf_block_solves_and_refinement(pbmc):
