@@ -193,6 +193,37 @@ LGR_API int lgr_prep_scaled_view(lgr_prep* p, int32_t i, lgr_csc* view);   /* m 
 LGR_API int lgr_prep_scaled_download(lgr_prep* p, int32_t i, int32_t* colptr, int32_t* rowidx, double* values);
 LGR_API void lgr_prep_destroy(lgr_prep* p);
 
+/* ---- online iNMF, scenario 1 (front end R/integration.R:722-933; the arithmetic is RcppPlanc::onlineINMF, R/integration.R:
+   902-910, which is not part of the reference tree: restated from the published algorithm -- Gao et al. 2021, Algorithm 1 --
+   with the bookkeeping documented in DESIGN.md section 8; PARITY UNPINNED).  k <= 32, d <= 16. ---- */
+typedef struct lgr_online_args {
+    int32_t d;               /* datasets */
+    int32_t k;
+    int64_t m;               /* shared genes */
+    const lgr_csc* E;        /* d host matrices, m x n_i (scaleData) */
+    double lambda;
+    int32_t max_epochs;      /* [5] */
+    int32_t minibatch_size;  /* [5000] cells per minibatch over all datasets; dataset i contributes round(n_i / N * size) */
+    int32_t hals_iter;       /* [1] HALS sweeps per minibatch */
+    uint32_t seed;           /* [1] set.seed(): W draw, the cells V_i starts from, the per-epoch permutations */
+    const double* Winit;     /* m x k or NULL */
+    const double* const* Vinit; /* d x (m x k) or NULL (both or neither) */
+    int32_t device;
+    uint32_t flags;          /* reserved, 0 */
+} lgr_online_args;
+typedef struct lgr_online_out {
+    double* W;               /* m x k */
+    double** V;              /* d x (m x k) */
+    double** H;              /* d x (n_i x k), cell x factor */
+    double** A;              /* d x (k x k) or NULL */
+    double** B;              /* d x (m x k) or NULL */
+    double objErr;
+    int32_t iterations;      /* minibatch iterations that were run */
+    int32_t pad0;
+    double loop_ms;          /* device time of the minibatch loop + final H solve (CUDA events) */
+} lgr_online_out;
+LGR_API int lgr_online_inmf(const lgr_online_args* args, lgr_online_out* out);
+
 /* ---- factor alignment: quantileNorm (R/integration.R:1621-1711 .quantileNorm.HList; src/quantile_norm.cpp:8-67
    max_factor_rcpp / cluster_vote_rcpp; RANN::nn2 = ANN 1.1.2 kd-tree search; stats::quantile type 7; stats::approxfun
    rule = 2; base::sample) -- the consumer of the H_i, run where they live.  Defaults of the reference in brackets. ---- */

@@ -294,6 +294,48 @@ def uinmf(objectList, unsharedList, k=20, lambda_=5.0, niter=30, nCores=2, verbo
     return res
 
 
+def online_inmf(objectList, k=20, lambda_=5.0, maxEpochs=5, minibatchSize=5000, HALSiter=1, Winit=None, Vinit=None, seed=1,
+                nCores=2, verbose=False, device=-1):
+    """Scenario 1 of RcppPlanc::onlineINMF (reference call site R/integration.R:902-910): online iNMF over `objectList`
+    from scratch.  PARITY UNPINNED against RcppPlanc (its source is not in the reference tree): the algorithm is the published
+    one, specified line by line in DESIGN.md section 8.  Returns dict(H=[n_i x k], V=[m x k], W, A=[k x k], B=[m x k],
+    objErr) like the R function (H is cell x factor; the caller transposes, R/integration.R:924)."""
+    if (Winit is None) != (Vinit is None):
+        raise ValueError("Winit and Vinit must both be given, or both be None")
+    cs = [_Csc(m) for m in objectList]
+    d = len(cs)
+    m = cs[0].shape[0]
+    ns = [c.shape[1] for c in cs]
+    if min(ns) < k:
+        raise ValueError(f"Number of factors (k={k}) should be less than the number of cells in the smallest dataset ({min(ns)}).")
+    if m < k:
+        raise ValueError(f"Number of factors (k={k}) should be less than the number of shared features ({m}).")
+    Earr = (lgr_csc * d)(*[c.struct for c in cs])
+    a = _ffi.lgr_online_args()
+    a.d, a.k, a.m, a.E, a.lambda_ = d, int(k), m, C.cast(Earr, C.c_void_p), float(lambda_)
+    a.max_epochs, a.minibatch_size, a.hals_iter, a.seed, a.device = int(maxEpochs), int(minibatchSize), int(HALSiter), int(seed), device
+    keep = []
+    if Winit is not None:
+        W0 = _f64(Winit)
+        V0 = [_f64(v) for v in Vinit]
+        keep = [W0, V0]
+        a.Winit = _dp(W0)
+        Varr0 = (c_double_p * d)(*[_dp(v) for v in V0])
+        keep.append(Varr0)
+        a.Vinit = Varr0
+    W = np.zeros((m, k), order="F")
+    V = [np.zeros((m, k), order="F") for _ in range(d)]
+    H = [np.zeros((n, k), order="F") for n in ns]
+    A = [np.zeros((k, k), order="F") for _ in range(d)]
+    B = [np.zeros((m, k), order="F") for _ in range(d)]
+    o = _ffi.lgr_online_out()
+    arrs = [(c_double_p * d)(*[_dp(x) for x in lst]) for lst in (V, H, A, B)]
+    o.W, o.V, o.H, o.A, o.B = _dp(W), arrs[0], arrs[1], arrs[2], arrs[3]
+    _ffi.check(_ffi.lib().lgr_online_inmf(C.byref(a), C.byref(o)))
+    return {"H": H, "V": V, "W": W, "A": A, "B": B, "objErr": float(o.objErr), "iterations": int(o.iterations),
+            "loop_ms": float(o.loop_ms)}
+
+
 def bppnnls_prod(CtC, CtB, nCores=2, device=-1):
     """Drop-in for RcppPlanc::bppnnls_prod(CtC, CtB, nCores) (R/cINMF.R:481): returns X (k x c) >= 0."""
     G = _f64(CtC)

@@ -497,47 +497,6 @@ __global__ void __launch_bounds__(256) k_quantile_warp(double* Hd, int nd, const
     }
 }
 
-// R >= 3.6 sample(): R_unif_index by rejection over ceil(log2(n)) bits assembled from 16-bit chunks of unif_rand()
-struct RSampler {
-    lgr_rng* rng;
-    double unif() {
-        double u;
-        lgr_r_runif(rng, 1, 0.0, 1.0, &u);
-        return u;
-    }
-    long long unif_index(long long dn) {
-        if (dn <= 0) return 0;
-        const int bits = (int)std::ceil(std::log2((double)dn));
-        for (;;) {
-            long long v = 0;
-            for (int n = 0; n <= bits; n += 16) {
-                const int v1 = (int)std::floor(unif() * 65536);
-                v = 65536 * v + v1;
-            }
-            if (bits < 64) v &= ((1LL << bits) - 1);
-            if (v < dn) return v;
-        }
-    }
-    // positions of sample.int(n, size) without replacement; `out` may be null (the stream is advanced all the same)
-    void sample(int n, int size, std::vector<int>& scratch, int* out) {
-        if (size < 2) {
-            for (int i = 0; i < size; ++i) {
-                const int j = (int)unif_index(n);
-                if (out) out[i] = j;
-            }
-            return;
-        }
-        scratch.resize(n);
-        for (int i = 0; i < n; ++i) scratch[i] = i;
-        int nn = n;
-        for (int i = 0; i < size; ++i) {
-            const int j = (int)unif_index(nn);
-            if (out) out[i] = scratch[j];
-            scratch[j] = scratch[--nn];
-        }
-    }
-};
-
 }  // namespace
 
 // Hdev[i]: n_i x k column-major FP64 on the device, replaced by H.norm; labels_dev[i]: n_i cluster labels (1-based factor id,

@@ -1421,6 +1421,286 @@ int lgr_ctx_objerr_i(lgr_ctx* c, int32_t i, double* obj) {
         *obj = objective_i(c, i);
     });
 }
+// ---------------------------------------------------------------------------------------------------------------------
+// online iNMF, scenario 1 (kernels: lgr_online.cu; specification: DESIGN.md section 8)
+// ---------------------------------------------------------------------------------------------------------------------
+int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
+    return guarded([&] {
+        check_device();
+        LGR_REQUIRE(a && o && a->E && o->W && o->V && o->H, "lgr_online_inmf: null argument");
+        LGR_REQUIRE(a->d >= 1 && a->d <= 16, "online iNMF: 1..16 datasets");
+        LGR_REQUIRE(a->k >= 1 && a->k <= 32, "online iNMF: k must be in 1..32");
+        LGR_REQUIRE(a->m >= 1 && a->m < (1 << 30), "m out of range");
+        LGR_REQUIRE(a->max_epochs >= 1 && a->minibatch_size >= 1 && a->hals_iter >= 1, "online iNMF: bad iteration parameters");
+        LGR_REQUIRE((a->Winit == nullptr) == (a->Vinit == nullptr), "Winit and Vinit must both be given, or both be NULL");
+        const int d = a->d, k = a->k, kp = 32, m = (int)a->m;
+        int ndev = 0;
+        LGR_CUDA(cudaGetDeviceCount(&ndev));
+        const int dev = a->device < 0 ? 0 : a->device;
+        LGR_REQUIRE(dev < ndev, "device index out of range");
+        LGR_CUDA(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        LGR_CUDA(cudaGetDeviceProperties(&prop, dev));
+        StreamHolder sh;
+        LGR_CUDA(cudaStreamCreateWithFlags(&sh.s, cudaStreamNonBlocking));
+        cudaStream_t st = sh.s;
+        AllocStreamScope alloc_scope(st);
+        kernels_init();
+
+        // ---- upload X_i (fp32 CSC), validate ----
+        std::vector<int> n(d);
+        long long N = 0;
+        std::vector<StagedCsc> S(d);
+        DBuf<int> bad(1);
+        bad.zero(st);
+        for (int i = 0; i < d; ++i) {
+            check_block(a->E[i], m, a->E[i].ncol, "E[i]");
+            LGR_REQUIRE(a->E[i].location == 0, "online iNMF takes host matrices");
+            n[i] = (int)a->E[i].ncol;
+            LGR_REQUIRE(n[i] >= k, "Number of factors (k) should be less than the number of cells in the smallest dataset.");
+            N += n[i];
+            stage_csc(a->E[i], 0, n[i], S[i], st, false, false);
+            finish_csc(S[i], m, bad.p, st);
+        }
+        LGR_REQUIRE(m >= k, "Number of factors (k) should be less than the number of shared features.");
+        int hbad = 0;
+        LGR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LGR_CUDA(cudaStreamSynchronize(st));
+        LGR_REQUIRE(hbad == 0, "E[i]: row index out of range");
+
+        // ---- initialisation (host): W ~ U(0, 2), V_i = k sampled cells of X_i, unit columns; then the minibatch schedule ----
+        std::unique_ptr<lgr_rng, void (*)(lgr_rng*)> rng(lgr_r_set_seed(a->seed ? a->seed : 1u), lgr_r_free);
+        RSampler rs{rng.get()};
+        std::vector<int> scratch;
+        std::vector<double> W0((size_t)m * k);
+        std::vector<std::vector<double>> V0(d, std::vector<double>((size_t)m * k, 0.0));
+        lgr_r_runif(rng.get(), (int64_t)m * k, 0.0, 2.0, W0.data());
+        std::vector<int> picks(k);
+        for (int i = 0; i < d; ++i) {
+            rs.sample(n[i], k, scratch, picks.data());
+            const lgr_csc& M = a->E[i];
+            for (int j = 0; j < k; ++j) {
+                const int c = picks[j];
+                for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p) {
+                    const double v = M.value_dtype == LGR_F32 ? (double)static_cast<const float*>(M.values)[p]
+                                                               : static_cast<const double*>(M.values)[p];
+                    V0[i][(size_t)j * m + M.rowidx[p]] += v;
+                }
+            }
+        }
+        auto unit_columns = [&](std::vector<double>& X) {
+            for (int j = 0; j < k; ++j) {
+                double ss = 0.0;
+                for (int g = 0; g < m; ++g) ss += X[(size_t)j * m + g] * X[(size_t)j * m + g];
+                const double nrm = ss > 0.0 ? std::sqrt(ss) : 1.0;
+                for (int g = 0; g < m; ++g) X[(size_t)j * m + g] /= nrm;
+            }
+        };
+        unit_columns(W0);
+        for (int i = 0; i < d; ++i) unit_columns(V0[i]);
+        // minibatch sizes and the walk of every dataset through its per-epoch permutations
+        std::vector<int> mb(d), pos(d, 0);
+        long long mb_total = 0;
+        for (int i = 0; i < d; ++i) {
+            mb[i] = std::max(1, (int)std::nearbyint((double)n[i] / (double)N * (double)a->minibatch_size));
+            mb[i] = std::min(mb[i], n[i]);
+            mb_total += mb[i];
+        }
+        const long long iters = (N * (long long)a->max_epochs) / a->minibatch_size;
+        LGR_REQUIRE(iters >= 1, "online iNMF: minibatchSize is larger than maxEpochs x the number of cells");
+        LGR_REQUIRE((double)iters * (double)mb_total < 2.0e9, "online iNMF: schedule too long");
+        std::vector<std::vector<int>> perm(d);
+        for (int i = 0; i < d; ++i) {
+            perm[i].resize(n[i]);
+            rs.sample(n[i], n[i], scratch, perm[i].data());
+        }
+        std::vector<int> sched((size_t)iters * mb_total);
+        std::vector<long long> ds_off(d + 1, 0);
+        for (int i = 0; i < d; ++i) ds_off[i + 1] = ds_off[i] + mb[i];
+        for (long long t = 0; t < iters; ++t) {
+            for (int i = 0; i < d; ++i) {
+                int* dst = sched.data() + (size_t)t * mb_total + ds_off[i];
+                int take = mb[i];
+                while (take > 0) {
+                    if (pos[i] == n[i]) {
+                        rs.sample(n[i], n[i], scratch, perm[i].data());
+                        pos[i] = 0;
+                    }
+                    const int c = std::min(take, n[i] - pos[i]);
+                    memcpy(dst, perm[i].data() + pos[i], sizeof(int) * c);
+                    dst += c;
+                    pos[i] += c;
+                    take -= c;
+                }
+            }
+        }
+        DBuf<int> d_sched(sched.size());
+        LGR_CUDA(cudaMemcpyAsync(d_sched.p, sched.data(), sizeof(int) * sched.size(), cudaMemcpyHostToDevice, st));
+
+        // ---- device state ----
+        DBuf<double> W((size_t)m * kp);
+        std::vector<DBuf<double>> V(d), A(d), Bs(d);
+        std::vector<DBuf<float>> Lt(d);
+        DBuf<double> grams((size_t)d * 4 * kp * kp);   // per dataset: LtL, VtV, CtC, CtC^-1
+        DBuf<int> ok(d);
+        DBuf<float> Bmb((size_t)mb_total * kp), Hmb((size_t)mb_total * kp);
+        DBuf<unsigned long long> masks((size_t)std::max<long long>(mb_total, 1));
+        DBuf<Counters> counters(1);
+        counters.zero(st);
+        upload_factor(a->Winit ? a->Winit : W0.data(), W.p, m, k, kp, st);
+        std::vector<const double*> hV(d);
+        std::vector<float*> hLt(d);
+        std::vector<double*> hLtL(d), hVtV(d);
+        std::vector<GramSpec> specs(d);
+        std::vector<NnlsGroup> grp(d);
+        std::vector<OnlineDs> ods(d);
+        std::vector<HalsDs> hds(d);
+        for (int i = 0; i < d; ++i) {
+            V[i].alloc((size_t)m * kp);
+            A[i].alloc((size_t)kp * kp);
+            Bs[i].alloc((size_t)m * kp);
+            Lt[i].alloc((size_t)m * kp);
+            A[i].zero(st);
+            Bs[i].zero(st);
+            upload_factor(a->Vinit ? a->Vinit[i] : V0[i].data(), V[i].p, m, k, kp, st);
+            hV[i] = V[i].p;
+            hLt[i] = Lt[i].p;
+            double* g4 = grams.p + (size_t)i * 4 * kp * kp;
+            hLtL[i] = g4;
+            hVtV[i] = g4 + kp * kp;
+            specs[i] = GramSpec{hLtL[i], hVtV[i], 1.0, a->lambda, g4 + 2 * kp * kp, g4 + 3 * kp * kp, ok.p + i};
+            grp[i] = NnlsGroup{g4 + 2 * kp * kp, g4 + 3 * kp * kp, ok.p + i, Bmb.p + (size_t)ds_off[i] * kp, nullptr,
+                               Hmb.p + (size_t)ds_off[i] * kp, masks.p + ds_off[i], mb[i], kp, ds_off[i]};
+            ods[i] = OnlineDs{Hmb.p + (size_t)ds_off[i] * kp, mb[i], A[i].p};
+            hds[i] = HalsDs{V[i].p, A[i].p, Bs[i].p};
+        }
+        DBuf<const double*> dV(d);
+        DBuf<float*> dLt(d);
+        DBuf<double*> dLtL(d), dVtV(d);
+        DBuf<GramSpec> dspecs(d);
+        DBuf<NnlsGroup> dgrp(d);
+        DBuf<OnlineDs> dods(d);
+        DBuf<HalsDs> dhds(d);
+        LGR_CUDA(cudaMemcpyAsync(dV.p, hV.data(), sizeof(void*) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(dLt.p, hLt.data(), sizeof(void*) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(dLtL.p, hLtL.data(), sizeof(void*) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(dVtV.p, hVtV.data(), sizeof(void*) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(dspecs.p, specs.data(), sizeof(GramSpec) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(dgrp.p, grp.data(), sizeof(NnlsGroup) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(dods.p, ods.data(), sizeof(OnlineDs) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(dhds.p, hds.data(), sizeof(HalsDs) * d, cudaMemcpyHostToDevice, st));
+        const NnlsConfig cfgF = nnls_config(k, kp, false, prop.multiProcessorCount);
+        auto solve_h = [&](const NnlsGroup* g, int ng, long long cols) {   // every solve starts from the empty passive set
+            launch_nnls_reg(g, ng, cols, k, kp, prop.multiProcessorCount, counters.p, 1, st);
+            launch_nnls(false, g, ng, cols, k, kp, cfgF, counters.p, 1 | 16, st);
+        };
+        auto grams_now = [&]() {
+            launch_online_gram(W.p, dV.p, d, m, k, dLt.p, dLtL.p, dVtV.p, st);
+            launch_gram_inv(dspecs.p, d, k, kp, st);
+        };
+        cudaEvent_t e0, e1;
+        LGR_CUDA(cudaEventCreate(&e0));
+        LGR_CUDA(cudaEventCreate(&e1));
+        LGR_CUDA(cudaEventRecord(e0, st));
+
+        // ---- the minibatch loop ----
+        for (long long t = 1; t <= iters; ++t) {
+            const double s = t == 1 ? 0.0 : (t == 2 ? 1.0 : (double)(t - 2) / (double)(t - 1));
+            const int* cells_t = d_sched.p + (size_t)(t - 1) * mb_total;
+            grams_now();
+            for (int i = 0; i < d; ++i)
+                launch_online_ltx(S[i].colptr.p, S[i].rowidx.p, S[i].val.p, cells_t + ds_off[i], mb[i], Lt[i].p,
+                                  Bmb.p + (size_t)ds_off[i] * kp, st);
+            solve_h(dgrp.p, d, mb_total);
+            launch_online_stats_a(dods.p, d, k, s, st);
+            for (int i = 0; i < d; ++i) {
+                launch_online_scale(Bs[i].p, (size_t)m * kp, s, st);
+                launch_online_stats_b(S[i].colptr.p, S[i].rowidx.p, S[i].val.p, cells_t + ds_off[i], mb[i],
+                                      Hmb.p + (size_t)ds_off[i] * kp, 1.0 / (double)mb[i], Bs[i].p, st);
+            }
+            launch_online_hals(W.p, dhds.p, d, m, k, a->lambda, a->hals_iter, st);
+        }
+
+        // ---- final H over all cells, objective ----
+        grams_now();
+        std::vector<DBuf<float>> Hall(d), Ball(d);
+        std::vector<DBuf<unsigned long long>> mall(d);
+        std::vector<NnlsGroup> gall(d);
+        long long off = 0;
+        for (int i = 0; i < d; ++i) {
+            Hall[i].alloc((size_t)n[i] * kp);
+            Ball[i].alloc((size_t)n[i] * kp);
+            mall[i].alloc((size_t)n[i]);
+            launch_online_ltx(S[i].colptr.p, S[i].rowidx.p, S[i].val.p, nullptr, n[i], Lt[i].p, Ball[i].p, st);
+            const double* g4 = grams.p + (size_t)i * 4 * kp * kp;
+            gall[i] = NnlsGroup{g4 + 2 * kp * kp, g4 + 3 * kp * kp, ok.p + i, Ball[i].p, nullptr, Hall[i].p, mall[i].p, n[i], kp, off};
+            off += n[i];
+        }
+        DBuf<NnlsGroup> dgall(d);
+        LGR_CUDA(cudaMemcpyAsync(dgall.p, gall.data(), sizeof(NnlsGroup) * d, cudaMemcpyHostToDevice, st));
+        solve_h(dgall.p, d, off);
+        // objErr = sum_i ||X_i||^2 - 2 <H_i, B_i> + tr(H_i^T H_i (L~^T L~ + lambda V^T V))
+        DBuf<double> acc((size_t)2 * d), G((size_t)d * kp * kp);
+        acc.zero(st);
+        G.zero(st);
+        std::vector<OnlineDs> gds(d);
+        for (int i = 0; i < d; ++i) {
+            launch_online_sumsq(S[i].val.p, S[i].nnz, acc.p + 2 * i, st);
+            launch_online_cross(Hall[i].p, Ball[i].p, (size_t)n[i] * kp, acc.p + 2 * i + 1, st);
+            gds[i] = OnlineDs{Hall[i].p, n[i], G.p + (size_t)i * kp * kp};
+        }
+        DBuf<OnlineDs> dgds(d);
+        LGR_CUDA(cudaMemcpyAsync(dgds.p, gds.data(), sizeof(OnlineDs) * d, cudaMemcpyHostToDevice, st));
+        launch_online_stats_a(dgds.p, d, k, 0.0, st);   // H^T H / n_i
+        LGR_CUDA(cudaEventRecord(e1, st));
+        std::vector<double> hacc((size_t)2 * d), hG((size_t)d * kp * kp), hgr((size_t)d * 4 * kp * kp);
+        LGR_CUDA(cudaMemcpyAsync(hacc.data(), acc.p, sizeof(double) * hacc.size(), cudaMemcpyDeviceToHost, st));
+        LGR_CUDA(cudaMemcpyAsync(hG.data(), G.p, sizeof(double) * hG.size(), cudaMemcpyDeviceToHost, st));
+        LGR_CUDA(cudaMemcpyAsync(hgr.data(), grams.p, sizeof(double) * hgr.size(), cudaMemcpyDeviceToHost, st));
+        LGR_CUDA(cudaStreamSynchronize(st));
+        double obj = 0.0;
+        for (int i = 0; i < d; ++i) {
+            double tr = 0.0;
+            const double* ctc = hgr.data() + (size_t)i * 4 * kp * kp + 2 * kp * kp;   // L~^T L~ + lambda V^T V
+            for (int x = 0; x < k; ++x)
+                for (int y = 0; y < k; ++y) {
+                    double gxy = hG[(size_t)i * kp * kp + x * kp + y];
+                    if (x == y && gxy == 1e-15) gxy = 0.0;   // (the lift of k_online_stats_a does not belong here)
+                    tr += gxy * (double)n[i] * ctc[x * kp + y];
+                }
+            obj += hacc[2 * i] - 2.0 * hacc[2 * i + 1] + tr;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        o->objErr = obj;
+        o->iterations = (int32_t)iters;
+        o->loop_ms = ms;
+
+        // ---- results ----
+        auto factor_out = [&](const double* dev_padded, int rows, double* host) {
+            if (!host) return;
+            DBuf<double> tmp((size_t)rows * k);
+            dev_padded_to_colmajor(dev_padded, tmp.p, rows, k, kp, st);
+            copy_out(host, tmp.p, (size_t)rows * k * sizeof(double), st, false);
+            LGR_CUDA(cudaStreamSynchronize(st));
+        };
+        factor_out(W.p, m, o->W);
+        for (int i = 0; i < d; ++i) {
+            factor_out(V[i].p, m, o->V[i]);
+            if (o->B && o->B[i]) factor_out(Bs[i].p, m, o->B[i]);
+            if (o->A && o->A[i]) factor_out(A[i].p, k, o->A[i]);
+            if (o->H[i]) {
+                DBuf<double> tmp((size_t)n[i] * k);
+                dev_hpad_to_colmajor(Hall[i].p, tmp.p, n[i], k, kp, st);
+                copy_out(o->H[i], tmp.p, (size_t)n[i] * k * sizeof(double), st, false);
+                LGR_CUDA(cudaStreamSynchronize(st));
+            }
+        }
+    });
+}
+
 // centroidAlign of host matrices
 int lgr_centroid_align(int32_t d, int32_t k, const int64_t* n, const double* const* H, const lgr_ca_params* params,
                        double* const* aligned, int32_t* const* raw_which_max, int32_t* const* z_which_max,

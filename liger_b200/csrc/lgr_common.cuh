@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <stdexcept>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -292,11 +293,75 @@ void prep_check_counts(size_t nnz, const double* x, int* bad, cudaStream_t st);
 void prep_reciprocal(size_t n, const double* in, double* out, cudaStream_t st);
 void dev_exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t st);   // lgr_layout.cu (cub)
 
+// lgr_online.cu: kernels of online iNMF (minibatch H solves, running statistics, HALS sweeps)
+struct OnlineDs {
+    const float* H;      // minibatch H rows (nb x 32)
+    int nb;              // minibatch size b_i
+    double* A;           // 32 x 32
+};
+struct HalsDs {
+    double* V;           // m x 32
+    const double* A;     // 32 x 32
+    const double* B;     // m x 32
+};
+void launch_online_gram(const double* W, const double* const* V, int d, int m, int k, float* const* Lt, double* const* LtL,
+                        double* const* VtV, cudaStream_t st);
+void launch_online_ltx(const int* colptr, const int* rowidx, const float* val, const int* cells, int nb, const float* Lt, float* B,
+                       cudaStream_t st);
+void launch_online_stats_a(const OnlineDs* ds, int d, int k, double s, cudaStream_t st);
+void launch_online_scale(double* x, size_t n, double s, cudaStream_t st);
+void launch_online_stats_b(const int* colptr, const int* rowidx, const float* val, const int* cells, int nb, const float* H, double inv_b,
+                           double* Bstat, cudaStream_t st);
+void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double lambda, int sweeps, cudaStream_t st);
+void launch_online_cross(const float* H, const float* B, size_t n, double* out, cudaStream_t st);
+void launch_online_sumsq(const float* x, size_t n, double* out, cudaStream_t st);
 // lgr_centroid.cu: centroidAlign on device-resident FP64 H (column-major n_i x k, read only) -> out (n_i x kd)
 void centroid_align_core(int d, int k, const int* n, const double* const* Hdev, const lgr_ca_params& p, double* const* out_dev,
                          int* const* raw_max, int* const* z_max, int* const* r_max, cudaStream_t st);
 // lgr_align.cu: quantileNorm on device-resident FP64 H (column-major n_i x k, replaced by H.norm)
 void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const lgr_qn_params& p, int* const* labels_dev,
                         lgr_qn_info* info, cudaStream_t st);
+
+// R >= 3.6 sample(): R_unif_index by rejection over ceil(log2(n)) bits assembled from 16-bit chunks of unif_rand()
+struct RSampler {
+    lgr_rng* rng;
+    double unif() {
+        double u;
+        lgr_r_runif(rng, 1, 0.0, 1.0, &u);
+        return u;
+    }
+    long long unif_index(long long dn) {
+        if (dn <= 0) return 0;
+        const int bits = (int)std::ceil(std::log2((double)dn));
+        for (;;) {
+            long long v = 0;
+            for (int n = 0; n <= bits; n += 16) {
+                const int v1 = (int)std::floor(unif() * 65536);
+                v = 65536 * v + v1;
+            }
+            if (bits < 64) v &= ((1LL << bits) - 1);
+            if (v < dn) return v;
+        }
+    }
+    // positions of sample.int(n, size) without replacement; `out` may be null (the stream is advanced all the same)
+    void sample(int n, int size, std::vector<int>& scratch, int* out) {
+        if (size < 2) {
+            for (int i = 0; i < size; ++i) {
+                const int j = (int)unif_index(n);
+                if (out) out[i] = j;
+            }
+            return;
+        }
+        scratch.resize(n);
+        for (int i = 0; i < n; ++i) scratch[i] = i;
+        int nn = n;
+        for (int i = 0; i < size; ++i) {
+            const int j = (int)unif_index(nn);
+            if (out) out[i] = scratch[j];
+            scratch[j] = scratch[--nn];
+        }
+    }
+};
+
 
 }  // namespace lgr

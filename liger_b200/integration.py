@@ -122,3 +122,26 @@ def runUINMF(scaleData, scaleUnsharedData, k=20, lambda_=5.0, nIteration=30, nRa
     out = run_uinmf_list(scaleData, scaleUnsharedData, k, lambda_, nIteration, nRandomStarts, seed, nCores, verbose)
     out["uns"] = {"factorization": {"k": k, "lambda": lambda_}}
     return out
+
+
+def runOnlineINMF(scaleData, k=20, lambda_=5.0, newDatasets=None, projection=False, maxEpochs=5, HALSiter=1,
+                  minibatchSize=5000, HInit=None, WInit=None, VInit=None, AInit=None, BInit=None, seed=1, nCores=2,
+                  verbose=False):
+    """runOnlineINMF.liger, scenario 1 (R/integration.R:722-933): online iNMF of {dataset: scaleData} from scratch.
+    Returns dict(W, H={name: k x n_i}, V, A, B, objErr, uns).  Scenarios 2 and 3 (`newDatasets`) are not built."""
+    if newDatasets is not None or projection:
+        raise NotImplementedError("liger_b200: scenarios 2 and 3 of runOnlineINMF (newDatasets / projection) are not built")
+    if any(x is not None for x in (HInit, AInit, BInit)):
+        raise NotImplementedError("liger_b200: HInit / AInit / BInit belong to scenarios 2 and 3, which are not built")
+    if any(v is None for v in scaleData.values()):
+        raise ValueError("Scaled data not available. Run `scaleNotCenter()` first.")
+    names = list(scaleData.keys())
+    res = api.online_inmf([scaleData[n] for n in names], k=k, lambda_=lambda_, maxEpochs=maxEpochs,
+                          minibatchSize=minibatchSize, HALSiter=HALSiter, Winit=WInit,
+                          Vinit=None if VInit is None else [VInit[n] if isinstance(VInit, dict) else v for n, v in zip(names, VInit)],
+                          seed=seed)
+    out = {"W": res["W"], "objErr": res["objErr"], "uns": {"factorization": {"k": k, "lambda": lambda_}}}
+    out["H"] = {n: h.T for n, h in zip(names, res["H"])}            # k x n_i, as the R wrapper stores them (:924)
+    for key in ("V", "A", "B"):
+        out[key] = dict(zip(names, res[key]))
+    return out

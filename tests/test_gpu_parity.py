@@ -812,3 +812,42 @@ def test_centroid_align_errors_and_resident(pbmc):
         assert rel(a["aligned"], b["aligned"]) < 1e-13
     finally:
         ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# online iNMF, scenario 1 (f4; R/integration.R:722-933 -> RcppPlanc::onlineINMF) -- parity unpinned in the reference
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,mbs,epochs,hals", [(10, 100, 3, 1), (20, 250, 2, 2)])
+def test_online_inmf_matches_oracle(pbmc, k, mbs, epochs, hals):
+    """lgr_online_inmf against the numpy restatement of the published algorithm from the same seed: identical minibatch
+    schedule and initialisation (R's RNG), factors within the path's tolerance, statistics A / B and objective too."""
+    import liger_b200
+    from oracle import online_oracle as oo
+    Es = pbmc["Es"]
+    ref = oo.online_inmf(Es, k, 5.0, max_epochs=epochs, minibatch_size=mbs, hals_iter=hals, seed=1)
+    out = liger_b200.online_inmf(Es, k=k, lambda_=5.0, maxEpochs=epochs, minibatchSize=mbs, HALSiter=hals, seed=1)
+    assert out["iterations"] == ref["iterations"] == 600 * epochs // mbs
+    assert rel(out["W"], ref["W"]) < TOL_FACTOR
+    for i in range(2):
+        assert rel(out["V"][i], ref["V"][i]) < TOL_FACTOR
+        assert rel(out["H"][i], ref["H"][i]) < TOL_FACTOR
+        assert rel(out["A"][i], ref["A"][i]) < TOL_FACTOR and rel(out["B"][i], ref["B"][i]) < TOL_FACTOR
+        assert out["H"][i].min() >= 0 and out["V"][i].min() > 0        # nonneg() floors W and V at 1e-16
+    assert abs(out["objErr"] - ref["objErr"]) < TOL_OBJ * ref["objErr"]
+
+
+def test_online_inmf_front_end_and_inits(pbmc):
+    import liger_b200
+    from liger_b200 import integration
+    from oracle import online_oracle as oo
+    Es = pbmc["Es"]
+    data = dict(zip(["ctrl", "stim"], Es))
+    W0, V0, _, _ = orc.seeded_init(3, 173, 8, [300, 300])
+    ref = oo.online_inmf(Es, 8, 5.0, max_epochs=2, minibatch_size=120, seed=5, Winit=W0, Vinit=V0)
+    fit = integration.runOnlineINMF(data, k=8, maxEpochs=2, minibatchSize=120, seed=5, WInit=W0, VInit=V0)
+    assert fit["H"]["ctrl"].shape == (8, 300) and fit["A"]["stim"].shape == (8, 8) and fit["B"]["ctrl"].shape == (173, 8)
+    assert rel(fit["W"], ref["W"]) < TOL_FACTOR and rel(fit["H"]["stim"].T, ref["H"][1]) < TOL_FACTOR
+    with pytest.raises(ValueError, match="should be less than the number of cells"):
+        liger_b200.online_inmf([Es[0][:, :5], Es[1]], k=8)
+    with pytest.raises(NotImplementedError):
+        integration.runOnlineINMF(data, k=8, newDatasets={"x": Es[0]})
