@@ -851,3 +851,13 @@ def test_online_inmf_front_end_and_inits(pbmc):
         liger_b200.online_inmf([Es[0][:, :5], Es[1]], k=8)
     with pytest.raises(NotImplementedError):
         integration.runOnlineINMF(data, k=8, newDatasets={"x": Es[0]})
+
+
+def test_alignment_and_online_fuzz():
+    """Random small shapes and parameters (ragged sizes, k = 2.., quantiles = 1.., maxSample = 2.., eps = 0..2, single-dataset
+    and non-first-reference cases) of quantileNorm / centroidAlign / online iNMF against their oracles (scripts/align_fuzz.py)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "align_fuzz.py"), "2", "8"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
