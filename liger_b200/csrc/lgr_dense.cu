@@ -215,6 +215,10 @@ struct K2Stages {
 // which is less than a memory latency, and the proxy fence of a round waits for every load the thread has in flight.
 // Three register arrays rotate through the roles (being scattered / to be cleared, then reloaded / in flight); the loop is
 // unrolled three times so that no array is ever copied while its loads are in flight.
+#ifndef LGR_PF_AHEAD
+#define LGR_PF_AHEAD 13120
+#endif
+constexpr int PF_AHEAD = LGR_PF_AHEAD;   // entries (16 stages of ~820)
 template <typename Stages>
 __device__ __forceinline__ void scatter_role(Stages I, int slot, int gt, int lane, uint32_t xbase, uint64_t* empty_bar, uint64_t* full_bar,
                                              int dbg) {
@@ -283,6 +287,10 @@ __device__ __forceinline__ void scatter_role(Stages I, int slot, int gt, int lan
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar);
+        // L2 prefetch of the entry stream PF_AHEAD entries further on (the stages of a tile / of a CTA's range are contiguous
+        // in memory): the proxy fence of the NEXT round waits for the demand loads issued just below, so what a round costs is
+        // their latency -- an L2 hit instead of a DRAM access.  A hint only: the entry arrays carry PF_AHEAD + 4 KB of slack.
+        if ((dbg >> 8) > 0 && gt < 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(cur.ent + cur.e0 + ((dbg >> 8) << 8) + gt * 32));
         load_entries(r2, ov);   // round + 2 into the array that was just cleared from
         load_bounds(r3);        // round + 3
         old = cur;
@@ -980,7 +988,8 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
 void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st) {
     if (total_tiles <= 0) return;
     const int grid = std::min(total_tiles, num_sms);
-    static const int dbg = getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0;   // developer knob: 1 no scatter, 2 no MMA, 4 no H loads
+    static const int dbg = (getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0) |
+                           ((getenv("LGR_PF_AHEAD") ? atoi(getenv("LGR_PF_AHEAD")) / 256 : PF_AHEAD / 256) << 8);   // developer knob: 1 no scatter, 2 no MMA, 4 no H loads
     k_dense_ltx<<<grid, K1_WARPS * 32, K1_SMEM, st>>>(ds, nds, total_tiles, dbg);
     LGR_CUDA(cudaGetLastError());
     if (dbg & 16) {
@@ -994,7 +1003,8 @@ void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, 
 void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st) {
     if (total_flat <= 0) return;
     const int grid = (int)std::min<long long>(total_flat, num_sms);
-    static const int dbg = getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0;
+    static const int dbg = (getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0) |
+                           ((getenv("LGR_PF_AHEAD") ? atoi(getenv("LGR_PF_AHEAD")) / 256 : PF_AHEAD / 256) << 8);
     k_dense_xh<<<grid, K2_WARPS_TOTAL * 32, K2_SMEM, st>>>(ds, nds, total_flat, dbg);
     LGR_CUDA(cudaGetLastError());
     if (dbg & 16) {
@@ -1071,7 +1081,7 @@ template <typename KeyT>
 static void sort_stream(DBuf<KeyT>& key, DBuf<unsigned int>& ent, DBuf<int>& cnt, size_t nnz, size_t nseg, int key_bits, DBuf<int>& seg,
                         DBuf<unsigned int>& out, cudaStream_t st) {
     DBuf<KeyT> key2(std::max<size_t>(nnz, 1));
-    out.alloc(std::max<size_t>(nnz, 1));
+    out.alloc(std::max<size_t>(nnz, 1) + (size_t)65536 + 1024);   // slack: the scatter warps prefetch past the end
     seg.alloc(nseg + 1);
     size_t tmp_bytes = 0, scan_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, ent.p, out.p, (int)nnz, 0, key_bits, st);
