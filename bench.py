@@ -472,22 +472,10 @@ def main():
     job = Job(cfg, n_rank, rank, world, local_rank, nccl_id)
     sampler = ClockSampler(local_rank)
     res = timed_runs(job, args, barrier, allmax, sampler)
-    # the step after the path, on the H that is still in HBM (single GPU): quantileNorm with the reference's defaults
-    align_extra = None
-    if world == 1 and not args.no_extra:
-        try:
-            from liger_b200 import align as _align
-            t0a = time.time()
-            qn = _align.quantile_norm_resident(job.ctx, reference=0)
-            align_extra = {"what": "quantileNorm (reference defaults: 50 quantiles, 20 approximate neighbours eps = 0.9, in-place vote) of "
-                                   "the resident H right after the timed iterations",
-                           "seconds": time.time() - t0a, **qn["info"]}
-            del qn
-        except Exception as e:      # never let the extra take the bench line down
-            align_extra = {"error": str(e)[:200]}
     value = job.n_total * args.steps / (res["loop_ms"] * 1e-3)
     roofline = roofline_of(job, res, args, hbm_peak, peak_src, args.config == "C3" and world == 1)
-    job.close()
+    if world > 1 or args.no_extra:
+        job.close()      # (at N = 1 the context lives on for the quantileNorm extra, which runs after the e2e measurements)
 
     # ---- e2e: lgr_inmf with HOST buffers (upload + K iterations from a cold start + objective + download), through the
     #      public API at N GPUs: every rank passes its own host shard; timed barrier-to-barrier, max over ranks;
@@ -497,8 +485,15 @@ def main():
     scales = job.info["scales"]
     wrap = (lambda mats: mats) if NO_DENSE else (lambda mats: [liger_b200.CountScaled(e, rs, cs) for e, (rs, cs) in zip(mats, scales)])
     if not args.no_e2e:
+        from liger_b200.api import pinned_empty
+        n_loc = [int(e[3][1]) for e in Es]
+        # result buffers of the page-locked series: allocated once, like the inputs (a host that keeps pinned buffers)
+        pinned_out = {"W": pinned_empty((m, k)), "V": [pinned_empty((m, k)) for _ in range(d)],
+                      "H": [pinned_empty((n, k)) for n in n_loc]}
+
         def call(mats, pinned):
-            return liger_b200.inmf(wrap(mats), k=k, lambda_=LAMBDA, niter=args.steps, Winit=W0, Vinit=V0, pinned_outputs=pinned,
+            return liger_b200.inmf(wrap(mats), k=k, lambda_=LAMBDA, niter=args.steps, Winit=W0, Vinit=V0,
+                                   outputs=pinned_out if pinned else None,
                                    pinned_io=pinned, device=local_rank, rank=rank, world=world, nccl_id=nccl_id,
                                    local_shard=True)   # same unique id => the library reuses its communicator
 
@@ -544,8 +539,23 @@ def main():
     extra = {"warm_ms_per_step": res["warm_ms"] / args.steps,
              "warm_value": job.n_total * args.steps / (res["warm_ms"] * 1e-3),
              "warm_note": "K further iterations from the converged state of the timed run (warm passive sets)"}
+    # the step after the path, on the H that is still in HBM (single GPU): quantileNorm with the reference's defaults
+    align_extra = None
+    if world == 1 and not args.no_extra:
+        try:
+            from liger_b200 import align as _align
+            t0a = time.time()
+            qn = _align.quantile_norm_resident(job.ctx, reference=0)
+            align_extra = {"what": "quantileNorm (reference defaults: 50 quantiles, 20 approximate neighbours eps = 0.9, in-place vote) of "
+                                   "the resident H of the timed run (measured after everything else: its host threads and allocations must not disturb the e2e calls)",
+                           "seconds": time.time() - t0a, **qn["info"]}
+            del qn
+        except Exception as e:      # never let the extra take the bench line down
+            align_extra = {"error": str(e)[:200]}
     if align_extra is not None:
         extra["quantile_norm"] = align_extra
+    if world == 1 and not args.no_extra:
+        job.close()
     del Es
     job.Es = None
     if world > 1 and not args.no_extra:

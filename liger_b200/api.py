@@ -200,11 +200,21 @@ class _Args:
 
 
 class _Out:
-    def __init__(self, args, want_passive=False, traj=False, pinned=False):
+    def __init__(self, args, want_passive=False, traj=False, pinned=False, reuse=None):
         d, k, m = args.d, args.k, args.m
-        self.W = np.zeros((m, k), order="F")
-        self.V = [np.zeros((m, k), order="F") for _ in range(d)]
-        if pinned:
+        if reuse is not None:      # caller-owned result buffers (a host that keeps page-locked buffers between calls)
+            self.W, self.V, self.H = reuse["W"], list(reuse["V"]), list(reuse["H"])
+            ok = (self.W.shape == (m, k) and len(self.V) == d and len(self.H) == d and
+                  all(v.shape == (m, k) for v in self.V) and all(h.shape == (n, k) for h, n in zip(self.H, args.n)) and
+                  all(x.dtype == np.float64 and x.flags.f_contiguous for x in [self.W] + self.V + self.H))
+            if not ok:
+                raise ValueError("outputs: W (m x k), V (d x m x k), H (d x n_i x k) as Fortran-ordered float64 arrays")
+        else:
+            self.W = np.zeros((m, k), order="F")
+            self.V = [np.zeros((m, k), order="F") for _ in range(d)]
+        if reuse is not None:
+            pass
+        elif pinned:
             self.H = [pinned_empty((n, k)) for n in args.n]
             if args.struct.world > 1 and not (args.struct.flags & _ffi.FLAG_LOCAL_SHARD):
                 for h in self.H:      # slice mode: the library writes only this rank's rows
@@ -238,8 +248,12 @@ class _Out:
 
 def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
          trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False, tensor_u=False,
-         rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False, seed=1, pinned_io=False, no_dense=False):
+         rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False, seed=1, pinned_io=False, no_dense=False,
+         outputs=None):
     """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
+
+    outputs: optional dict(W, V, H) of caller-owned Fortran-ordered float64 result buffers (e.g. page-locked, kept between
+    calls); the returned dict then holds those same arrays.
 
     Multi-GPU (one process per GPU): pass `rank`, `world`, the `nccl_id` created by rank 0 (nccl_unique_id()) and
     `local_shard=True` when objectList already holds only this rank's cells; H is then this rank's rows.
@@ -260,7 +274,7 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
              (_ffi.FLAG_NO_DENSE if no_dense else 0))
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device, rank=rank, world=world,
               nccl_id=nccl_id, init_seed=seed)
-    o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs)
+    o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs, reuse=outputs)
     _ffi.check(_ffi.lib().lgr_inmf(C.byref(a.struct), C.byref(o.struct)))
     res = {"H": o.H, "V": o.V, "W": o.W, "objErr": float(o.struct.objErr), "timings": o.timings()}
     if trajectory:
