@@ -1603,22 +1603,49 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         LGR_CUDA(cudaEventCreate(&e1));
         LGR_CUDA(cudaEventRecord(e0, st));
 
-        // ---- the minibatch loop ----
-        for (long long t = 1; t <= iters; ++t) {
-            const double s = t == 1 ? 0.0 : (t == 2 ? 1.0 : (double)(t - 2) / (double)(t - 1));
-            const int* cells_t = d_sched.p + (size_t)(t - 1) * mb_total;
+        // ---- the minibatch loop: one iteration = ten launches driven by a device-side iteration counter, captured into a
+        //      CUDA graph once and replayed (LGR_NO_GRAPH: launched one by one) ----
+        std::vector<OnlineX> oxs(d);
+        for (int i = 0; i < d; ++i)
+            oxs[i] = OnlineX{S[i].colptr.p, S[i].rowidx.p, S[i].val.p, Lt[i].p, Bs[i].p, 1.0 / (double)mb[i], (int)ds_off[i], 0};
+        DBuf<OnlineX> doxs(d);
+        DBuf<int> t_dev(1);
+        const int one = 1;
+        LGR_CUDA(cudaMemcpyAsync(doxs.p, oxs.data(), sizeof(OnlineX) * d, cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaMemcpyAsync(t_dev.p, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        LGR_CUDA(cudaStreamSynchronize(st));
+        auto one_iteration = [&]() {
             grams_now();
-            for (int i = 0; i < d; ++i)
-                launch_online_ltx(S[i].colptr.p, S[i].rowidx.p, S[i].val.p, cells_t + ds_off[i], mb[i], Lt[i].p,
-                                  Bmb.p + (size_t)ds_off[i] * kp, st);
+            launch_online_ltx_all(doxs.p, d, d_sched.p, (int)mb_total, t_dev.p, Bmb.p, st);
             solve_h(dgrp.p, d, mb_total);
-            launch_online_stats_a(dods.p, d, k, s, st);
-            for (int i = 0; i < d; ++i) {
-                launch_online_scale(Bs[i].p, (size_t)m * kp, s, st);
-                launch_online_stats_b(S[i].colptr.p, S[i].rowidx.p, S[i].val.p, cells_t + ds_off[i], mb[i],
-                                      Hmb.p + (size_t)ds_off[i] * kp, 1.0 / (double)mb[i], Bs[i].p, st);
-            }
+            launch_online_stats_all(dods.p, doxs.p, d, m, k, d_sched.p, (int)mb_total, t_dev.p, Hmb.p, st);
             launch_online_hals(W.p, dhds.p, d, m, k, a->lambda, a->hals_iter, st);
+            launch_online_next(t_dev.p, st);
+        };
+        if (getenv("LGR_NO_GRAPH") || iters < 3) {
+            for (long long t = 1; t <= iters; ++t) one_iteration();
+        } else {
+            one_iteration();   // un-captured first pass: lazy per-kernel initialisation (function attributes) happens here
+            cudaGraph_t g = nullptr;
+            cudaGraphExec_t ge = nullptr;
+            LGR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try {
+                one_iteration();
+            } catch (...) {
+                cudaStreamEndCapture(st, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            LGR_CUDA(cudaStreamEndCapture(st, &g));
+            cudaError_t ce = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            LGR_CUDA(ce);
+            for (long long t = 2; t <= iters; ++t) {
+                ce = cudaGraphLaunch(ge, st);
+                if (ce != cudaSuccess) break;
+            }
+            cudaGraphExecDestroy(ge);
+            LGR_CUDA(ce);
         }
 
         // ---- final H over all cells, objective ----

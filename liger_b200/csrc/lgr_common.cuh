@@ -304,14 +304,25 @@ struct HalsDs {
     const double* A;     // 32 x 32
     const double* B;     // m x 32
 };
+struct OnlineX {          // one dataset's resident fp32 CSC and its per-minibatch constants
+    const int* colptr;
+    const int* rowidx;
+    const float* val;
+    const float* Lt;      // L~_i, m x 32
+    double* Bstat;        // B_i, m x 32
+    double inv_b;         // 1 / b_i
+    int off;              // first minibatch cell of this dataset in the flat [0, mb_total) range
+    int pad0;
+};
+void launch_online_ltx_all(const OnlineX* xs, int d, const int* sched, int mb_total, const int* t_dev, float* B, cudaStream_t st);
+void launch_online_stats_all(const OnlineDs* ds, const OnlineX* xs, int d, int m, int k, const int* sched, int mb_total, int* t_dev,
+                             const float* H, cudaStream_t st);
+void launch_online_next(int* t_dev, cudaStream_t st);
 void launch_online_gram(const double* W, const double* const* V, int d, int m, int k, float* const* Lt, double* const* LtL,
                         double* const* VtV, cudaStream_t st);
 void launch_online_ltx(const int* colptr, const int* rowidx, const float* val, const int* cells, int nb, const float* Lt, float* B,
                        cudaStream_t st);
 void launch_online_stats_a(const OnlineDs* ds, int d, int k, double s, cudaStream_t st);
-void launch_online_scale(double* x, size_t n, double s, cudaStream_t st);
-void launch_online_stats_b(const int* colptr, const int* rowidx, const float* val, const int* cells, int nb, const float* H, double inv_b,
-                           double* Bstat, cudaStream_t st);
 void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double lambda, int sweeps, cudaStream_t st);
 void launch_online_cross(const float* H, const float* B, size_t n, double* out, cudaStream_t st);
 void launch_online_sumsq(const float* x, size_t n, double* out, cudaStream_t st);

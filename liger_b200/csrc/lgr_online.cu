@@ -7,7 +7,7 @@
 //   k_online_ltx       B[c, :] = sum_g X[g, cell_c] L~[g, :] for the minibatch's cells (warp per cell, lane = factor)
 //   k_nnls_reg         the H solve of the minibatch (lgr_nnls_reg.cu, unchanged)
 //   k_online_stats_a   A_i <- s A_i + H_b^T H_b / b_i            (k x k, fp64)
-//   k_online_scale_b / k_online_stats_b   B_i <- s B_i + X_b H_b / b_i      (m x k, fp64 atomics)
+//   k_online_scale_all / k_online_stats_b_all   B_i <- s B_i + X_b H_b / b_i      (m x k, fp64 atomics)
 //   k_online_hals      one HALS sweep over the columns of W, then of every V_i (warp per gene row, lane = factor: the
 //                      column updates of a row depend only on that row, so rows are independent and the sweep over
 //                      columns is sequential inside a warp)
@@ -77,23 +77,6 @@ __global__ void __launch_bounds__(1024) k_online_stats_a(const OnlineDs* __restr
     if (a == b && a < k && v == 0.0) v = 1e-15;
     D.A[a * OKP + b] = (a < k && b < k) ? v : 0.0;
 }
-__global__ void k_online_scale(double* __restrict__ x, size_t n, double s) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] *= s;
-}
-// warp per minibatch cell: Bstat[g, :] += X[g, cell] * H[c, :] / b
-__global__ void __launch_bounds__(256) k_online_stats_b(const int* __restrict__ colptr, const int* __restrict__ rowidx,
-                                                        const float* __restrict__ val, const int* __restrict__ cells, int nb,
-                                                        const float* __restrict__ H, double inv_b, double* __restrict__ Bstat) {
-    const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (w >= nb) return;
-    const int c = cells[w];
-    const double h = (double)H[(size_t)w * OKP + lane] * inv_b;
-    if (h == 0.0) return;   // this lane's factor does not load on the cell (H is sparse: most lanes leave here)
-    const int p0 = colptr[c], p1 = colptr[c + 1];
-    for (int p = p0; p < p1; ++p) atomicAdd(Bstat + (size_t)rowidx[p] * OKP + lane, (double)val[p] * h);
-}
-
 // HALS: warp per gene row, lane l = factor l.  A_i are staged in shared memory with stride 33.
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -154,6 +137,67 @@ __global__ void __launch_bounds__(256) k_online_hals(double* __restrict__ W, con
     }
 }
 
+// ---- the minibatch iteration as ONE replayable launch sequence: the iteration number lives on the device (*t_dev, 1-based;
+//      k_online_next increments it), every kernel derives the minibatch's cells (sched + (t - 1) * mb_total) and the running-
+//      average weight s_t from it, and one launch covers all datasets -- so the ten launches of an iteration are captured
+//      into a CUDA graph once and replayed ----
+__device__ __forceinline__ double online_weight(int t) { return t == 1 ? 0.0 : (t == 2 ? 1.0 : (double)(t - 2) / (double)(t - 1)); }
+__device__ __forceinline__ int online_find_ds(const OnlineX* __restrict__ xs, int d, int w) {
+    int i = 0;
+    while (i + 1 < d && w >= xs[i + 1].off) ++i;
+    return i;
+}
+__global__ void __launch_bounds__(256) k_online_ltx_all(const OnlineX* __restrict__ xs, int d, const int* __restrict__ sched, int mb_total,
+                                                        const int* __restrict__ t_dev, float* __restrict__ B) {
+    const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= mb_total) return;
+    const OnlineX X = xs[online_find_ds(xs, d, w)];
+    const int c = sched[(size_t)(*t_dev - 1) * mb_total + w];
+    const int p0 = X.colptr[c], p1 = X.colptr[c + 1];
+    float acc = 0.f;
+    for (int p = p0; p < p1; p += 32) {
+        const int q = p + lane;
+        const int r = q < p1 ? X.rowidx[q] : 0;
+        const float v = q < p1 ? X.val[q] : 0.f;
+        const int cnt = min(32, p1 - p);
+        for (int t = 0; t < cnt; ++t) {
+            const int rr = __shfl_sync(0xffffffffu, r, t);
+            const float vv = __shfl_sync(0xffffffffu, v, t);
+            acc = fmaf(vv, X.Lt[(size_t)rr * OKP + lane], acc);
+        }
+    }
+    B[(size_t)w * OKP + lane] = acc;
+}
+__global__ void __launch_bounds__(1024) k_online_stats_a_t(const OnlineDs* __restrict__ ds, int k, const int* __restrict__ t_dev) {
+    const OnlineDs D = ds[blockIdx.x];
+    const double s = online_weight(*t_dev);
+    const int a = threadIdx.x >> 5, b = threadIdx.x & 31;
+    double acc = 0.0;
+    if (a < k && b < k)
+        for (int c = 0; c < D.nb; ++c) acc = fma((double)D.H[(size_t)c * OKP + a], (double)D.H[(size_t)c * OKP + b], acc);
+    double v = s * D.A[a * OKP + b] + acc / (double)D.nb;
+    if (a == b && a < k && v == 0.0) v = 1e-15;
+    D.A[a * OKP + b] = (a < k && b < k) ? v : 0.0;
+}
+__global__ void k_online_scale_all(const OnlineX* __restrict__ xs, int m, const int* __restrict__ t_dev) {
+    const double s = online_weight(*t_dev);
+    double* x = xs[blockIdx.y].Bstat;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)m * OKP) x[i] *= s;
+}
+__global__ void __launch_bounds__(256) k_online_stats_b_all(const OnlineX* __restrict__ xs, int d, const int* __restrict__ sched, int mb_total,
+                                                            const int* __restrict__ t_dev, const float* __restrict__ H) {
+    const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= mb_total) return;
+    const OnlineX X = xs[online_find_ds(xs, d, w)];
+    const int c = sched[(size_t)(*t_dev - 1) * mb_total + w];
+    const double h = (double)H[(size_t)w * OKP + lane] * X.inv_b;
+    if (h == 0.0) return;
+    const int p0 = X.colptr[c], p1 = X.colptr[c + 1];
+    for (int p = p0; p < p1; ++p) atomicAdd(X.Bstat + (size_t)X.rowidx[p] * OKP + lane, (double)X.val[p] * h);
+}
+__global__ void k_online_next(int* t_dev) { *t_dev += 1; }
+
 // objective pieces over all cells of one dataset: cross = sum_c H[c, :] . B[c, :]   (B = L~^T X)
 __global__ void k_online_cross(const float* __restrict__ H, const float* __restrict__ B, size_t n, double* __restrict__ out) {
     double s = 0.0;
@@ -185,17 +229,6 @@ void launch_online_stats_a(const OnlineDs* ds, int d, int k, double s, cudaStrea
     k_online_stats_a<<<d, 1024, 0, st>>>(ds, k, s);
     LGR_CUDA(cudaGetLastError());
 }
-void launch_online_scale(double* x, size_t n, double s, cudaStream_t st) {
-    if (!n) return;
-    k_online_scale<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, s);
-    LGR_CUDA(cudaGetLastError());
-}
-void launch_online_stats_b(const int* colptr, const int* rowidx, const float* val, const int* cells, int nb, const float* H, double inv_b,
-                           double* Bstat, cudaStream_t st) {
-    if (nb <= 0) return;
-    k_online_stats_b<<<(unsigned)(((size_t)nb * 32 + 255) / 256), 256, 0, st>>>(colptr, rowidx, val, cells, nb, H, inv_b, Bstat);
-    LGR_CUDA(cudaGetLastError());
-}
 void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double lambda, int sweeps, cudaStream_t st) {
     LGR_REQUIRE(d <= HALS_MAX_D, "online iNMF: at most 16 datasets");
     const size_t smem = (size_t)d * OKP * 33 * sizeof(double);
@@ -205,6 +238,22 @@ void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double
         attr = true;
     }
     k_online_hals<<<(unsigned)(((size_t)m * 32 + 255) / 256), 256, smem, st>>>(W, ds, d, m, k, lambda, sweeps);
+    LGR_CUDA(cudaGetLastError());
+}
+void launch_online_ltx_all(const OnlineX* xs, int d, const int* sched, int mb_total, const int* t_dev, float* B, cudaStream_t st) {
+    k_online_ltx_all<<<(unsigned)(((size_t)mb_total * 32 + 255) / 256), 256, 0, st>>>(xs, d, sched, mb_total, t_dev, B);
+    LGR_CUDA(cudaGetLastError());
+}
+void launch_online_stats_all(const OnlineDs* ds, const OnlineX* xs, int d, int m, int k, const int* sched, int mb_total, int* t_dev,
+                             const float* H, cudaStream_t st) {
+    k_online_stats_a_t<<<d, 1024, 0, st>>>(ds, k, t_dev);
+    dim3 g((unsigned)(((size_t)m * OKP + 255) / 256), (unsigned)d);
+    k_online_scale_all<<<g, 256, 0, st>>>(xs, m, t_dev);
+    k_online_stats_b_all<<<(unsigned)(((size_t)mb_total * 32 + 255) / 256), 256, 0, st>>>(xs, d, sched, mb_total, t_dev, H);
+    LGR_CUDA(cudaGetLastError());
+}
+void launch_online_next(int* t_dev, cudaStream_t st) {
+    k_online_next<<<1, 1, 0, st>>>(t_dev);
     LGR_CUDA(cudaGetLastError());
 }
 void launch_online_cross(const float* H, const float* B, size_t n, double* out, cudaStream_t st) {
