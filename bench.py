@@ -214,7 +214,9 @@ def run_reference(args, cfg, rank):
     line = {"impl": "reference", "metric": "iNMF cell*iterations/s", "value": val, "unit": "cell*iter/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(cfg, args, max(args.gpus, 1), "strong", n_s * cfg["d"]),
+            "config": workload_config(cfg, args, max(args.gpus, 1), "strong", n_s * cfg["d"],
+                                      "datasets" if (args.gpus > 1 and args.placement != "cells" and cfg["d"] % args.gpus == 0 and
+                                                     args.scaling == "strong") else "cells"),
             "cpu_baseline": {"value": val, "unit": "cell*iter/s", "cores": nth, "kind": "port", "sample": sample,
                              "note": "CPU restatement of RcppPlanc inmf (oracle/inmf_oracle.c); the reference's R/RcppPlanc stack cannot be built here"},
             "e2e": {"value": val, "unit": "cell*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -237,13 +239,16 @@ def make_inputs(cfg, n_per, device=None, value_dtype="float64", shard=0, pin=Tru
     return Es, info
 
 
-def workload_config(cfg, args, world, scaling, total_cells):
-    per = "in total, split by cells over the GPUs" if scaling == "strong" else "per GPU"
+def workload_config(cfg, args, world, scaling, total_cells, placement="cells"):
+    per = ("in total, whole datasets placed on the GPUs" if placement == "datasets" and world > 1 else
+           "in total, split by cells over the GPUs") if scaling == "strong" else "per GPU"
     return {"workload": f"{args.config}: synthetic planted-Poisson iNMF, {cfg['d']} datasets x {cfg['n_per']} cells x "
                         f"{cfg['m']} genes {per}, {int(cfg['density'] * 100)}% density, k={cfg['k']}, lambda={LAMBDA}, "
                         f"{args.steps} ANLS iterations from the seeded cold start + final objective",
             "datasets": cfg["d"], "cells_per_dataset": cfg["n_per"], "genes": cfg["m"], "k": cfg["k"],
-            "density": cfg["density"], "total_cells": int(total_cells), "parallelism": f"cell-shard x{world}",
+            "density": cfg["density"], "total_cells": int(total_cells),
+            "parallelism": (f"dataset-shard x{world} ({cfg['d'] // world} whole dataset(s) per GPU)" if placement == "datasets" and world > 1
+                            else f"cell-shard x{world}"),
             "scaling": scaling,
             "l2_policy": "inputs larger than L2 at N <= 4 (X is >= 0.35 GB per GPU in two layouts); every iteration also "
                          "rewrites B, H and the statistics, so no sweep finds its input in L2 from the previous one"}
@@ -252,23 +257,31 @@ def workload_config(cfg, args, world, scaling, total_cells):
 class Job:
     """One resident workload on this rank: inputs, inits, context."""
 
-    def __init__(self, cfg, n_per_rank, rank, world, local_rank, nccl_id, pin=True):
+    def __init__(self, cfg, n_per_rank, rank, world, local_rank, nccl_id, pin=True, placement="cells"):
         import liger_b200
-        self.cfg, self.rank, self.world = cfg, rank, world
+        self.rank, self.world, self.placement = rank, world, placement
+        d_all, m, k = cfg["d"], cfg["m"], cfg["k"]
+        if placement == "datasets":   # whole-dataset placement: this rank holds d / world datasets with ALL their cells
+            d = d_all // world
+            cfg = dict(cfg, d=d)
+            first = rank * d
+        else:                         # cell sharding: this rank holds n_per_rank cells of every dataset
+            d, first = d_all, 0
+        self.cfg = cfg                # the rank-local view (algorithmic bytes, tensor flops)
         t = time.time()
         self.Es, self.info = make_inputs(cfg, n_per_rank, value_dtype="float64", shard=rank, pin=pin)
         self.gen_seconds = time.time() - t
-        d, m, k = cfg["d"], cfg["m"], cfg["k"]
         self.n_local = d * n_per_rank
         self.n_total = self.n_local * world
         rng = liger_b200.RRandom(1)       # R's set.seed(1) stream, the draw order of .runINMF.list
         self.W0 = np.abs(rng.runif(m * k, 0, 2)).reshape((m, k), order="F")
-        self.V0 = [np.abs(rng.runif(m * k, 0, 2)).reshape((m, k), order="F") for _ in range(d)]
+        V_all = [np.abs(rng.runif(m * k, 0, 2)).reshape((m, k), order="F") for _ in range(d_all)]
+        self.V0 = V_all[first:first + d]
         # scaleData with its count structure (values = count * 1/rms[gene] * 1/library size[cell]): the library verifies it
         # on upload and runs the two sweeps over X on the tensor cores; --no-dense runs the fp32 gather sweeps instead
         self.mats = self.Es if NO_DENSE else [liger_b200.CountScaled(e, rs, cs) for e, (rs, cs) in zip(self.Es, self.info["scales"])]
         self.ctx = liger_b200.Context(self.mats, k, LAMBDA, self.W0, self.V0, device=local_rank, rank=rank, world=world,
-                                      nccl_id=nccl_id, flags=0x8 if world > 1 else 0)
+                                      nccl_id=nccl_id, flags=(0x80 if placement == "datasets" else 0x8) if world > 1 else 0)
 
     def close(self):
         self.ctx.close()
@@ -420,6 +433,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the weak-scaling / C4 extras at N > 1")
+    ap.add_argument("--placement", choices=["auto", "cells", "datasets"], default="auto",
+                    help="multi-GPU placement of the strong-scaling job: whole datasets per rank when the dataset count divides "
+                         "(auto), or cell shards of every dataset")
     ap.add_argument("--no-dense", action="store_true", help="pass scaleData without its count structure: fp32 gather sweeps")
     args = ap.parse_args()
     global NO_DENSE
@@ -467,9 +483,17 @@ def main():
         return float(t.item())
 
     # ---- the workload: strong scaling splits the configuration's cells over the ranks; every rank generates ITS shard ----
-    d, m, k = cfg["d"], cfg["m"], cfg["k"]
-    n_rank = cfg["n_per"] // world if args.scaling == "strong" else cfg["n_per"]
-    job = Job(cfg, n_rank, rank, world, local_rank, nccl_id)
+    m, k = cfg["m"], cfg["k"]
+    # strong scaling with d divisible by N: whole-dataset placement (V_i / U_i solves local, one small all-reduce for W);
+    # otherwise cell sharding (every rank holds a slice of every dataset, statistics all-reduced)
+    placement = "cells"
+    if world > 1 and args.scaling == "strong" and args.placement != "cells" and cfg["d"] % world == 0:
+        placement = "datasets"
+    if args.placement == "datasets" and placement != "datasets":
+        raise SystemExit("--placement datasets needs --scaling strong and a dataset count divisible by the number of GPUs")
+    n_rank = cfg["n_per"] if placement == "datasets" else (cfg["n_per"] // world if args.scaling == "strong" else cfg["n_per"])
+    job = Job(cfg, n_rank, rank, world, local_rank, nccl_id, placement=placement)
+    d = job.cfg["d"]      # datasets on this rank
     sampler = ClockSampler(local_rank)
     res = timed_runs(job, args, barrier, allmax, sampler)
     value = job.n_total * args.steps / (res["loop_ms"] * 1e-3)
@@ -495,7 +519,8 @@ def main():
             return liger_b200.inmf(wrap(mats), k=k, lambda_=LAMBDA, niter=args.steps, Winit=W0, Vinit=V0,
                                    outputs=pinned_out if pinned else None,
                                    pinned_io=pinned, device=local_rank, rank=rank, world=world, nccl_id=nccl_id,
-                                   local_shard=True)   # same unique id => the library reuses its communicator
+                                   local_shard=placement == "cells", dataset_shard=placement == "datasets")
+            # (same unique id => the library reuses its communicator)
 
         def series(mats, pinned, reps):
             runs = []
@@ -618,7 +643,7 @@ def main():
         line = {"metric": "iNMF cell*iterations/s", "value": value, "unit": "cell*iter/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["loop_ms"] / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (fp64 Gram / V,W solves / objective)",
-                "data": "synthetic", "config": workload_config(cfg, args, world, args.scaling, job.n_total),
+                "data": "synthetic", "config": workload_config(cfg, args, world, args.scaling, job.n_total, placement),
                 "clocks": res["clocks"], "e2e": e2e, "gpu_launches": res["launches"], "roofline": roofline,
                 "cpu_baseline": cpu, "parity": parity, "extra": extra,
                 "objErr": res["obj"], "nnz_per_gpu": job.info["nnz"], "gen_seconds": job.gen_seconds,

@@ -99,6 +99,14 @@ typedef struct lgr_csc {
                                      with its own shard); without it every rank passes the full matrices and the
                                      library takes columns [n*rank/world, n*(rank+1)/world) */
 
+#define LGR_FLAG_DATASET_SHARD 0x80u /* world > 1: WHOLE-DATASET placement (the degenerate case of cell sharding when the
+                                     datasets divide over the ranks): E/P/lambda/Vinit describe only THIS rank's datasets, with all
+                                     their cells; V_i / U_i / H_i are solved and returned locally, and the only collective per
+                                     iteration is the all-reduce of the W solve's normal equations (sum_i (R_i - G_i V_i^T) and
+                                     sum_i G_i: (m + k) x k doubles) instead of every R_i and G_i.  W and objErr come back identical
+                                     on every rank.  Explicit Winit / Vinit required (the seeded draw is defined on the global
+                                     dataset order). */
+
 /* Arguments of one iNMF / UINMF factorisation.  iNMF: P == NULL, Uinit == NULL. */
 typedef struct lgr_inmf_args {
     int32_t d;     /* number of datasets */

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libliger_b200.so")
 LGR_F64, LGR_F32 = 0, 1
 FLAG_TRAJECTORY, FLAG_COLD_START, FLAG_PINNED_IO, FLAG_LOCAL_SHARD, FLAG_TENSOR_U, FLAG_LEGACY_NNLS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FLAG_NO_DENSE = 0x40
+FLAG_DATASET_SHARD = 0x80
 SOLVE_H, SOLVE_V, SOLVE_W = 1, 2, 4
 STATUS = {0: "OK", 1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "NCCL", 5: "ALLOC", 6: "INTERRUPT"}
 

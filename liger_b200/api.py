@@ -249,14 +249,15 @@ class _Out:
 def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=None, nCores=2, verbose=False,
          trajectory=False, device=-1, return_passive=False, cold_start=False, pinned_outputs=False, tensor_u=False,
          rank=0, world=1, nccl_id=None, local_shard=False, legacy_nnls=False, seed=1, pinned_io=False, no_dense=False,
-         outputs=None):
+         outputs=None, dataset_shard=False):
     """Drop-in for RcppPlanc::inmf (reference call site R/integration.R:438-441).
 
     outputs: optional dict(W, V, H) of caller-owned Fortran-ordered float64 result buffers (e.g. page-locked, kept between
     calls); the returned dict then holds those same arrays.
 
     Multi-GPU (one process per GPU): pass `rank`, `world`, the `nccl_id` created by rank 0 (nccl_unique_id()) and
-    `local_shard=True` when objectList already holds only this rank's cells; H is then this rank's rows.
+    `local_shard=True` when objectList already holds only this rank's cells; H is then this rank's rows.  `dataset_shard=True`:
+    whole-dataset placement -- objectList / Vinit hold only this rank's datasets (LGR_FLAG_DATASET_SHARD).
 
     objectList: list of scipy CSC matrices (genes x cells; the `scaleData` of each dataset).
     Hinit: list of n_i x k, Vinit: list of m x k, Winit: m x k.  `nCores`/`verbose` are accepted for
@@ -271,7 +272,7 @@ def inmf(objectList, k=20, lambda_=5.0, niter=30, Hinit=None, Vinit=None, Winit=
     flags = ((_ffi.FLAG_TRAJECTORY if trajectory else 0) | (_ffi.FLAG_COLD_START if cold_start else 0) |
              (_ffi.FLAG_TENSOR_U if tensor_u else 0) | (0x8 if (local_shard and world > 1) else 0) |
              (_ffi.FLAG_LEGACY_NNLS if legacy_nnls else 0) | (_ffi.FLAG_PINNED_IO if pinned_io else 0) |
-             (_ffi.FLAG_NO_DENSE if no_dense else 0))
+             (_ffi.FLAG_NO_DENSE if no_dense else 0) | (_ffi.FLAG_DATASET_SHARD if (dataset_shard and world > 1) else 0))
     a = _Args(objectList, k, lambda_, niter, Winit, Vinit, Hinit, flags=flags, device=device, rank=rank, world=world,
               nccl_id=nccl_id, init_seed=seed)
     o = _Out(a, want_passive=return_passive, traj=trajectory, pinned=pinned_outputs, reuse=outputs)

@@ -131,6 +131,7 @@ struct lgr_ctx {
     DBuf<DenseDs> dds_dev;
     int k1_tiles = 0, gh_blocks = 0;
     long long k2_flat = 0;
+    bool dshard = false;       // LGR_FLAG_DATASET_SHARD: this rank holds whole datasets; only the W solve's equations are all-reduced
     bool use_tc = false;
     bool fuse_u = false;       // U = B P in the tcgen05 epilogue of k_spmm_ltx_tiled (default on)
     DBuf<double> ctc_arena;   // per NNLS group: CtC and CtC^-1 (2 x KP x KP fp64), groups = H_0..H_d-1, V_0..V_d-1, W
@@ -410,7 +411,7 @@ void set_inits(lgr_ctx* c, const double* Winit, const double* const* Vinit, cons
 }
 
 void allreduce_stats(lgr_ctx* c) {
-    if (c->world <= 1) return;
+    if (c->world <= 1 || c->dshard) return;   // (dataset placement: the statistics of a dataset are complete on its rank)
     Span sp(c, "comm");   // includes the wait for the slowest rank
     // one collective: the fp64 Grams travel as (hi, lo) float pairs in the tail of the fp32 statistics arena
     const int ng = (int)c->Garena.n;
@@ -448,7 +449,7 @@ bool run_stats(lgr_ctx* c, bool fork_ginv_v = false) {
             Timed t(c, "k_gram_tc");
             launch_gram_h(c->dds_dev.p, c->d, c->gh_blocks, c->k, c->num_sms, c->st);
         }
-        if (fork_ginv_v && c->world == 1 && side_ok(c)) {
+        if (fork_ginv_v && (c->world == 1 || c->dshard) && side_ok(c)) {
             fork_gram_inv(c, c->specV.p, c->d, c->ev_join_v);
             forked = true;
         }
@@ -554,6 +555,13 @@ void enqueue_solve_w(lgr_ctx* c, int cold) {
         Timed t(c, "k_wrhs");
         launch_wrhs(c->ds_dev.p, c->d, c->m, c->CtBw.p, c->Gsum.p, c->k, c->kp, c->st);
     }
+    if (c->dshard) {   // the W solve's normal equations are sums over ALL datasets: the one collective of this placement
+        Span sp(c, "comm");
+        nccl_group_start();
+        nccl_allreduce_sum_f64(c->comm, c->CtBw.p, c->CtBw.n, c->st);
+        nccl_allreduce_sum_f64(c->comm, c->Gsum.p, c->Gsum.n, c->st);
+        nccl_group_end();
+    }
     {
         Timed t(c, "k_gram_inv");
         launch_gram_inv(c->specW.p, 1, c->k, c->kp, c->st);
@@ -648,6 +656,10 @@ void iterate(lgr_ctx* c, int niter, double* traj_host, double* final_obj = nullp
             run_objective(c, final_slot.p);
         }
     }
+    if (c->dshard) {   // every rank summed objErr_i over its own datasets
+        if (traj && niter > 0) nccl_allreduce_sum_f64(c->comm, c->objbuf.p, (size_t)niter, c->st);
+        if (final_obj) nccl_allreduce_sum_f64(c->comm, final_slot.p, 1, c->st);
+    }
     LGR_CUDA(cudaEventRecord(c->ev1, c->st));
     LGR_CUDA(cudaStreamSynchronize(c->st));
     float ms = 0.f;
@@ -685,6 +697,7 @@ double objective(lgr_ctx* c) {
     if (c->objbuf.n < 1) c->objbuf.alloc(1);
     DBuf<double> slot(1);
     run_objective(c, slot.p);
+    if (c->dshard) nccl_allreduce_sum_f64(c->comm, slot.p, 1, c->st);
     double v = 0.0;
     LGR_CUDA(cudaMemcpyAsync(&v, slot.p, sizeof(double), cudaMemcpyDeviceToHost, c->st));
     LGR_CUDA(cudaStreamSynchronize(c->st));
@@ -814,6 +827,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->init_seed = a->init_seed;
     c->rank = a->rank;
     c->world = a->world;
+    c->dshard = a->world > 1 && (a->flags & LGR_FLAG_DATASET_SHARD) != 0;
+    if (c->dshard) LGR_REQUIRE(a->Winit && a->Vinit, "LGR_FLAG_DATASET_SHARD needs explicit Winit / Vinit (the seeded draw follows the global dataset order)");
     c->interrupt = a->interrupt;
     c->interrupt_user = a->interrupt_user;
     if (a->device >= 0) LGR_CUDA(cudaSetDevice(a->device));
@@ -855,7 +870,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         // duration ~ block size.  Pick the size (multiple of 16, within what shared memory allows) that minimises
         // waves x size over this rank's datasets: e.g. C3 (8 x 125 000 cells, 148 SMs) 1024 -> 1136 cells per K2 tile
         // turns 6.65 waves (7 x 1024) into exactly 6 (x 1136).
-        const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
+        const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0 || c->dshard;
         std::vector<long long> ns;
         for (int i = 0; i < a->d; ++i) {
             const long long nf = a->E[i].ncol;
@@ -910,7 +925,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     tr.mark("ctx setup");
     // ---- pass 1: validate everything, then a staging thread moves the blocks to the device on a copy stream (direct DMA
     //      from page-locked buffers, through the bounce ring from pageable ones) while pass 2 builds the layouts ----
-    const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0;
+    const bool local = (c->flags & LGR_FLAG_LOCAL_SHARD) != 0 || c->dshard;
     const bool pinned_io = (c->flags & LGR_FLAG_PINNED_IO) != 0;
     for (int i = 0; i < c->d; ++i) {
         check_block(a->E[i], a->m, a->E[i].ncol, "E[i]");
@@ -1079,7 +1094,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->Gsum.alloc((size_t)kp * kp);
     c->wmask.alloc((size_t)m);
     c->counters.alloc(1);
-    if (c->world > 1) nccl_allreduce_sum_f64(c->comm, c->sq.p, (size_t)c->d, c->st);
+    if (c->world > 1 && !c->dshard) nccl_allreduce_sum_f64(c->comm, c->sq.p, (size_t)c->d, c->st);
     std::vector<double> sq((size_t)c->d);
     LGR_CUDA(cudaMemcpyAsync(sq.data(), c->sq.p, sq.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     LGR_CUDA(cudaStreamSynchronize(c->st));

@@ -40,6 +40,27 @@ def main():
                  obj=out["objErr"])
         dist.destroy_process_group()
         return
+    if mode == "datasets":   # whole-dataset placement (LGR_FLAG_DATASET_SHARD): rank r holds dataset r with all its cells
+        assert world == 2
+        ctx = liger_b200.Context([Es[rank]], 20, 5.0, W0, [V0[rank]], device=local, rank=rank, world=world, nccl_id=nccl_id,
+                                 flags=0x80)
+        traj = ctx.iterate(10, trajectory=True)
+        res = ctx.download()
+        obj = ctx.objective()
+        ctx.close()
+        # also the one-shot entry point, dense-tile sweeps on count-structured data, two datasets per rank
+        from liger_b200 import synthetic as syn
+        d, n, m, k = 4, 1500, 600, 16
+        Xs, _, sc = syn.make_numpy(d, n, m, 8, block=500, seed=33, return_scales=True)
+        Wd, Vd, _, _ = orc.seeded_init(1, m, k, [n] * d)
+        mine = [2 * rank, 2 * rank + 1]
+        Cs = [liger_b200.CountScaled(Xs[i], *sc[i]) for i in mine]
+        out = liger_b200.inmf(Cs, k=k, lambda_=5.0, niter=5, Winit=Wd, Vinit=[Vd[i] for i in mine], device=local, rank=rank,
+                              world=world, nccl_id=nccl_id, dataset_shard=True)
+        np.savez(os.path.join(sys.argv[2], f"{mode}_rank{rank}.npz"), W=res["W"], V=res["V"][0], H=res["H"][0], traj=traj, obj=obj,
+                 dW=out["W"], dV=out["V"][0], dH=out["H"][1], dobj=out["objErr"])
+        dist.destroy_process_group()
+        return
     if mode == "slice":      # every rank passes the FULL matrices; the library takes its column range
         ctx = liger_b200.Context(Es, 20, 5.0, W0, V0, device=local, rank=rank, world=world, nccl_id=nccl_id)
         lo = [0, 0]

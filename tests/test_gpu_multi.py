@@ -64,6 +64,34 @@ def test_two_gpu_dense_sweeps(tmp_path):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_two_gpu_dataset_placement(tmp_path, pbmc):
+    """LGR_FLAG_DATASET_SHARD: rank r holds dataset r entirely; the only collective is the all-reduce of the W solve's
+    normal equations.  W / objective identical on both ranks and equal to the oracle's; V_r, H_r local."""
+    from liger_b200 import synthetic as syn
+    from oracle import c_oracle
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), "datasets", str(tmp_path)]
+    subprocess.run(cmd, check=True, timeout=600, cwd=ROOT)
+    W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    ref = orc.inmf(pbmc["Es"], 20, 5.0, 10, W0, V0, trajectory=True)
+    r = [np.load(tmp_path / f"datasets_rank{i}.npz") for i in range(2)]
+    assert np.array_equal(r[0]["W"], r[1]["W"]) and float(r[0]["obj"]) == float(r[1]["obj"])
+    assert np.array_equal(r[0]["traj"], r[1]["traj"])
+    assert rel(r[0]["W"], ref["W"]) < 1e-3
+    assert np.max(np.abs(r[0]["traj"] - np.array(ref["traj"])) / np.array(ref["traj"])) < 1e-4
+    assert abs(float(r[0]["obj"]) - ref["objErr"]) < 1e-4 * ref["objErr"]
+    for i in range(2):
+        assert rel(r[i]["V"], ref["V"][i]) < 1e-3 and rel(r[i]["H"], ref["H"][i]) < 1e-3
+    d, n, m, k = 4, 1500, 600, 16
+    Xs, _ = syn.make_numpy(d, n, m, 8, block=500, seed=33)
+    Wd, Vd, _, _ = orc.seeded_init(1, m, k, [n] * d)
+    refd = c_oracle.inmf(Xs, k, 5.0, 5, Wd, Vd)
+    assert np.array_equal(r[0]["dW"], r[1]["dW"]) and rel(r[0]["dW"], refd["W"]) < 1e-3
+    assert abs(float(r[0]["dobj"]) - refd["objErr"]) < 1e-4 * refd["objErr"] and float(r[0]["dobj"]) == float(r[1]["dobj"])
+    for i in range(2):
+        assert rel(r[i]["dV"], refd["V"][2 * i]) < 1e-3 and rel(r[i]["dH"], refd["H"][2 * i + 1]) < 1e-3
+
+
 def test_one_process_two_devices(pbmc):
     """The opt-in shared-memory attributes of the kernels are per device: a process that uses device 0 and then device 1
     must get the same factors from both (k = 20 and k = 40 cover the register, warp and shared-memory NNLS kernels)."""
