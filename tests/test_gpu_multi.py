@@ -92,6 +92,7 @@ def test_two_gpu_dataset_placement(tmp_path, pbmc):
         assert rel(r[i]["dV"], refd["V"][2 * i]) < 1e-3 and rel(r[i]["dH"], refd["H"][2 * i + 1]) < 1e-3
 
 
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 def test_one_process_two_devices(pbmc):
     """The opt-in shared-memory attributes of the kernels are per device: a process that uses device 0 and then device 1
     must get the same factors from both (k = 20 and k = 40 cover the register, warp and shared-memory NNLS kernels)."""
