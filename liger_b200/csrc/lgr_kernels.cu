@@ -18,28 +18,47 @@ namespace lgr {
 // k_prep: L~ rows + partial Grams.  One CTA = PREP_ROWS_PER_BLOCK rows of one dataset.
 // ------------------------------------------------------------------------------------------------
 template <int KP>
-__global__ void __launch_bounds__(256) k_prep(const DsDev* __restrict__ ds, int nds, const double* __restrict__ W, int k) {
+__global__ void __launch_bounds__(512) k_prep(const DsDev* __restrict__ ds, int nds, const double* __restrict__ W, int k) {
     constexpr int RB = 2048 / KP;
+    constexpr int PER = RB * KP / 512;   // entries per thread (4)
     __shared__ double Ls[RB][KP + 1];
     __shared__ double Vs[RB][KP + 1];
     const int i = find_ds(ds, nds, (int)blockIdx.x, &DsDev::prep_blk_off);
     const DsDev D = ds[i];
     const int r0 = ((int)blockIdx.x - D.prep_blk_off) * RB;
     const int nr = min(RB, D.rows - r0);
-    for (int e = threadIdx.x; e < RB * KP; e += blockDim.x) {
-        const int r = e / KP, f = e % KP;
+    // all global loads of the thread first (they are independent: one memory latency instead of PER), then the arithmetic
+    double lv[PER], vv[PER];
+    float rsv[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int e = threadIdx.x + q * 512;
+        const int r = e / KP, f = e % KP, gr = r0 + r;
         double l = 0.0, v = 0.0;
+        float rs = 0.f;
         if (r < nr) {
-            const int gr = r0 + r;
             if (f < k) {
                 v = D.V[(size_t)gr * KP + f];
-                l = v + (gr < D.m ? W[(size_t)gr * KP + f] : 0.0);
+                l = gr < D.m ? W[(size_t)gr * KP + f] : 0.0;
             }
+            if (KP == 32 && D.Asplit) rs = D.rs[gr];
+        }
+        lv[q] = l;
+        vv[q] = v;
+        rsv[q] = rs;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int e = threadIdx.x + q * 512;
+        const int r = e / KP, f = e % KP;
+        const double v = vv[q], l = v + lv[q];
+        if (r < nr) {
+            const int gr = r0 + r;
             D.L[(size_t)gr * KP + f] = (float)l;
             if (KP == 32 && D.Asplit) {
                 // operand-slab image of k_dense_ltx: [64-gene stage][k-step of 16][chunk of 8 genes][row 4 f + t][gene % 8],
                 // t = hi / mid / lo bf16 term of rs[g] * L~[g, f] (the three terms sum to the fp32 value exactly)
-                const float x = (float)l * D.rs[gr];
+                const float x = (float)l * rsv[q];
                 const unsigned xb = __float_as_uint(x), hb = xb & 0xFFFF0000u;
                 const float r1 = x - __uint_as_float(hb);
                 const unsigned mb = __float_as_uint(r1) & 0xFFFF0000u;
@@ -76,9 +95,9 @@ __global__ void __launch_bounds__(256) k_prep(const DsDev* __restrict__ ds, int 
 
 void launch_prep(const DsDev* ds, int nds, int total_blocks, const double* W, int k, int kp, cudaStream_t st) {
     if (kp == 32)
-        k_prep<32><<<total_blocks, 256, 0, st>>>(ds, nds, W, k);
+        k_prep<32><<<total_blocks, 512, 0, st>>>(ds, nds, W, k);
     else
-        k_prep<64><<<total_blocks, 256, 0, st>>>(ds, nds, W, k);
+        k_prep<64><<<total_blocks, 512, 0, st>>>(ds, nds, W, k);
     LGR_CUDA(cudaGetLastError());
 }
 
