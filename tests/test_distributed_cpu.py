@@ -83,3 +83,48 @@ def test_cell_sharded_anls_world2_gloo(tmp_path, pbmc):
     for i, key in enumerate(("H0", "H1")):
         H = np.vstack([r0[key], r1[key]])
         assert H.shape == ref["H"][i].shape and rel(H, ref["H"][i]) < 1e-10
+
+
+def _worker_datasets(rank, world, port, niter, outdir):
+    """Whole-dataset placement (LGR_FLAG_DATASET_SHARD): rank r owns dataset r with all its cells; H_r and V_r are solved
+    locally and the ONLY collective of an iteration is the sum of the W solve's normal equations."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import inmf_oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(os.path.join(GOLDEN, "pbmc_golden.npz"))
+    Es = [sp.csc_matrix((g[f"scale_{n}_data"], g[f"scale_{n}_indices"], g[f"scale_{n}_indptr"]),
+                        shape=tuple(g[f"scale_{n}_shape"])) for n in ("ctrl", "stim")]
+    m, k, lam = 173, 20, 5.0
+    W, Vs, _, _ = orc.seeded_init(1, m, k, [E.shape[1] for E in Es])
+    X, V = Es[rank], Vs[rank]                                      # this rank's dataset, whole
+    obj = 0.0
+    for _ in range(niter):
+        H = orc.solve_H(W, V, X, lam)
+        G = H.T @ H
+        R = np.asarray(X @ H)
+        V = orc.bppnnls_prod((1 + lam) * G, R.T - G @ W.T).T        # local V solve (old W): no communication
+        eq = torch.from_numpy(np.concatenate([G.ravel(), (R.T - G @ V.T).ravel()]))
+        dist.all_reduce(eq, op=dist.ReduceOp.SUM)                   # sum_i G_i and sum_i (R_i - G_i V_i^T)^T: (k + m) x k doubles
+        eq = eq.numpy()
+        W = orc.bppnnls_prod(eq[:k * k].reshape(k, k), eq[k * k:].reshape(k, m)).T
+    o = torch.tensor([orc.objerr_i(orc.solve_H(W, V, X, lam).T, W, V, X, lam)], dtype=torch.float64)
+    dist.all_reduce(o, op=dist.ReduceOp.SUM)                        # objective: one scalar at the end
+    np.savez(os.path.join(outdir, f"ds_rank{rank}.npz"), W=W, V=V, H=H, obj=float(o[0]))
+    dist.destroy_process_group()
+
+
+def test_dataset_placement_anls_world2_gloo(tmp_path, pbmc):
+    from oracle import inmf_oracle as orc
+    niter = 6
+    port = _free_port()
+    mp.spawn(_worker_datasets, args=(2, port, niter, str(tmp_path)), nprocs=2, join=True)
+    W0, V0, _, _ = orc.seeded_init(1, 173, 20, [300, 300])
+    ref = orc.inmf(pbmc["Es"], 20, 5.0, niter, W0, V0)
+    r = [np.load(tmp_path / f"ds_rank{i}.npz") for i in range(2)]
+    assert np.array_equal(r[0]["W"], r[1]["W"]) and r[0]["obj"] == r[1]["obj"]
+    assert rel(r[0]["W"], ref["W"]) < 1e-10
+    for i in range(2):
+        assert rel(r[i]["V"], ref["V"][i]) < 1e-10 and rel(r[i]["H"], ref["H"][i]) < 1e-10
