@@ -72,7 +72,8 @@ typedef struct lgr_csc {
        R/preprocess.R:604) and scaleNotCenter() divides by the gene's root mean square (row_scale = 1 / rms,
        src/data_processing.cpp:42-58).  The library verifies the assertion entry by entry (LGR_ERR_INVALID if it does not
        hold) and then runs the two sweeps over X as dense-tile tensor-core contractions (csrc/lgr_dense.cu) instead of the
-       shared-memory gathers.  Same results to fp32 rounding.  Used for k <= 32 without unshared blocks; ignored otherwise.
+       shared-memory gathers.  Same results to fp32 rounding.  Used for k <= 32 (UINMF: when the unshared blocks carry their
+       structure too, with the same col_scale as their shared block); ignored otherwise.
        row_scale: nrow doubles, col_scale: ncol doubles, host or device like the other arrays. */
     const double* row_scale;
     const double* col_scale;

@@ -931,11 +931,11 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         check_block(a->E[i], a->m, a->E[i].ncol, "E[i]");
         if (a->P && a->P[i].nrow > 0) check_block(a->P[i], a->P[i].nrow, a->E[i].ncol, "P[i]");
     }
-    {   // dense-tile sweeps: every block carries a verified-on-upload count structure, k <= 32, no unshared blocks
+    {   // dense-tile sweeps: every block (shared and unshared) carries a verified-on-upload count structure, k <= 32
         bool ok = c->kp == 32 && !(c->flags & (LGR_FLAG_NO_DENSE | LGR_FLAG_TENSOR_U | LGR_FLAG_LEGACY_NNLS)) && !getenv("LGR_NO_DENSE");
         for (int i = 0; i < c->d && ok; ++i) {
             ok = a->E[i].row_scale && a->E[i].col_scale;
-            if (a->P && a->P[i].nrow > 0) ok = false;
+            if (ok && a->P && a->P[i].nrow > 0) ok = a->P[i].row_scale && a->P[i].col_scale;
         }
         c->dense = ok;
         if (const char* e = getenv("LGR_DENSE_MASK")) c->dense_mask = atoi(e) & 3;
@@ -964,7 +964,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
                 const int s0 = local ? 0 : (int)((int64_t)n_full * c->rank / c->world);
                 const int s1 = local ? n_full : (int)((int64_t)n_full * (c->rank + 1) / c->world);
                 stage_csc(a->E[i], s0, s1, stagedE[i], cstream.s, pinned_io, dense);
-                if (a->P && a->P[i].nrow > 0) stage_csc(a->P[i], s0, s1, stagedP[i], cstream.s, pinned_io, false);
+                if (a->P && a->P[i].nrow > 0) stage_csc(a->P[i], s0, s1, stagedP[i], cstream.s, pinned_io, dense);
                 {
                     std::lock_guard<std::mutex> g(sync.mu);
                     sync.staged = i + 1;
@@ -1033,14 +1033,19 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
             // count structure: X = N * rs * cs, verified entry by entry while the two entry streams are built
             D.dl.rs.alloc((size_t)D.rows);
             D.dl.cs.alloc((size_t)std::max(D.n, 1));
-            dev_f64_to_f32(SE.rs64.p, D.dl.rs.p, (size_t)D.rows, c->st);
+            dev_f64_to_f32(SE.rs64.p, D.dl.rs.p, (size_t)m, c->st);
+            if (P) {   // stacked [E; P]: the unshared rows bring their own row scale, the cells' scale is shared
+                dev_f64_to_f32(SP.rs64.p, D.dl.rs.p + m, (size_t)D.u, c->st);
+                prep_check_same((size_t)D.n, SE.cs64.p, SP.cs64.p, bad_rows.p, c->st);
+            }
             dev_f64_to_f32(SE.cs64.p, D.dl.cs.p, (size_t)D.n, c->st);
             dense_build(D.n, D.rows, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.dl.rs.p, D.dl.cs.p, D.dl, bad_rows.p, c->st);
             int hbad = 0;
             LGR_CUDA(cudaMemcpyAsync(&hbad, bad_rows.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
             LGR_CUDA(cudaStreamSynchronize(c->st));
-            LGR_REQUIRE(hbad == 0, "E[i]: row_scale / col_scale do not factor the values into integer counts in 1..256 "
-                                   "(pass NULL scales, or LGR_FLAG_NO_DENSE, for general matrices)");
+            LGR_REQUIRE(hbad == 0, "E[i] / P[i]: row_scale / col_scale do not factor the values into integer counts in 1..256, or "
+                                   "the unshared block's col_scale differs from the shared block's (pass NULL scales, or "
+                                   "LGR_FLAG_NO_DENSE, for general matrices)");
             tr.mark("build dense entry streams");
         }
         if (!dense || c->dense_mask != 3) {

@@ -291,6 +291,7 @@ void prep_f64_to_f32(const double* in, float* out, size_t n, cudaStream_t st);
 void prep_check_rows(size_t nnz, const int* rowidx, int nrow, int* bad, cudaStream_t st);
 void prep_check_counts(size_t nnz, const double* x, int* bad, cudaStream_t st);
 void prep_reciprocal(size_t n, const double* in, double* out, cudaStream_t st);
+void prep_check_same(size_t n, const double* a, const double* b, int* bad, cudaStream_t st);   // bad |= 1 when a != b anywhere
 void dev_exclusive_scan_int(const int* in, int* out, size_t n, cudaStream_t st);   // lgr_layout.cu (cub)
 
 // lgr_online.cu: kernels of online iNMF (minibatch H solves, running statistics, HALS sweeps)

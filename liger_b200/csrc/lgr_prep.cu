@@ -200,6 +200,15 @@ __global__ void k_reciprocal(size_t n, const double* __restrict__ in, double* __
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] == 0.0 ? 0.0 : 1.0 / in[i];
 }
+__global__ void k_check_same(size_t n, const double* __restrict__ a, const double* __restrict__ b, int* __restrict__ bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) atomicOr(bad, 1);
+}
+void prep_check_same(size_t n, const double* a, const double* b, int* bad, cudaStream_t st) {
+    if (!n) return;
+    k_check_same<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a, b, bad);
+    LGR_CUDA(cudaGetLastError());
+}
 void prep_reciprocal(size_t n, const double* in, double* out, cudaStream_t st) {
     if (!n) return;
     k_reciprocal<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in, out);

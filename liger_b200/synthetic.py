@@ -28,16 +28,17 @@ def _bisect_scale(mean_fn, density):
     return float(np.sqrt(lo * hi))
 
 
-def make_numpy(d, n_per, m, r, density=0.05, u=0, block=5000, seed=SEED, return_scales=False):
+def make_numpy(d, n_per, m, r, density=0.05, u=0, block=5000, seed=SEED, return_scales=False, return_unshared_scales=False):
     """Returns (Es, Ps): lists of scipy CSC float64 (m x n_i) and (u x n_i) or None.
     return_scales: also returns [(row_scale, col_scale)] per dataset for the shared block: E = counts * row_scale[:, None] *
-    col_scale[None, :] (1 / row rms, 1 / library size) -- the count structure liger_b200.CountScaled carries."""
+    col_scale[None, :] (1 / row rms, 1 / library size) -- the count structure liger_b200.CountScaled carries.
+    return_unshared_scales: a fourth list with the same pair for the unshared blocks (own row rms, the SAME library sizes)."""
     A = np.random.default_rng([seed, 999]).gamma(0.5, 1.0, (m, r))
     Au = [np.random.default_rng([seed, 999, i]).gamma(0.5, 1.0, (u, r)) if u else None for i in range(d)]
     B0 = np.random.default_rng([seed, 0, 0]).gamma(0.5, 1.0, (r, min(block, n_per)))
     rate0 = A @ B0
     s = _bisect_scale(lambda x: float(np.mean(1.0 - np.exp(-x * rate0))), density)
-    Es, Ps, scales = [], [], []
+    Es, Ps, scales, pscales = [], [], [], []
     for i in range(d):
         cols_e, cols_p = [], []
         for b, c0 in enumerate(range(0, n_per, block)):
@@ -60,9 +61,14 @@ def make_numpy(d, n_per, m, r, density=0.05, u=0, block=5000, seed=SEED, return_
         scales.append((1.0 / rms, 1.0 / lib))
         if u:
             P = sp.hstack(cols_p, format="csc")
-            Ps.append(_scale(P, lib))
+            Pscaled, prms = _scale(P, lib, True)
+            Ps.append(Pscaled)
+            pscales.append((1.0 / prms, 1.0 / lib))
         else:
             Ps.append(None)
+            pscales.append(None)
+    if return_unshared_scales:
+        return Es, Ps, scales, pscales
     if return_scales:
         return Es, Ps, scales
     return Es, Ps
@@ -153,7 +159,7 @@ def make_torch(d, n_per, m, r, density=0.05, u=0, block=25000, seed=SEED, device
         indptr[1:] = torch.cumsum(cnt, 0)
         return indptr, rows, vals, libs, rms
 
-    Es, Ps, scales = [], [], []
+    Es, Ps, scales, pscales = [], [], [], []
     nnz = 0
     for i in range(d):
         Bs = []
@@ -163,17 +169,20 @@ def make_torch(d, n_per, m, r, density=0.05, u=0, block=25000, seed=SEED, device
         Es.append((host(indptr, torch.int32).numpy(), host(rows, torch.int32).numpy(),
                    host(vals, torch.float64 if vdt is np.float64 else torch.float32).numpy(), (m, n_per)))
         if u:
-            indptr, rows, vals, _, _ = one(Au[i], u, i, Bs, libs)
+            indptr, rows, vals, _, prms = one(Au[i], u, i, Bs, libs)
             nnz += int(rows.numel())
+            pscales.append(((1.0 / prms).cpu().numpy(), scales[-1][1]))     # own row rms, the shared block's library sizes
             Ps.append((host(indptr, torch.int32).numpy(), host(rows, torch.int32).numpy(),
                        host(vals, torch.float64 if vdt is np.float64 else torch.float32).numpy(), (u, n_per)))
         else:
             Ps.append(None)
+            pscales.append(None)
         del Bs
     if dev.type == "cuda":
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
-    return Es, Ps, {"scale": s, "nnz": nnz, "density": nnz / float(d * n_per * (m + u)), "scales": scales}
+    return Es, Ps, {"scale": s, "nnz": nnz, "density": nnz / float(d * n_per * (m + u)), "scales": scales,
+                    "unshared_scales": pscales}
 
 
 def to_scipy(t):

@@ -187,6 +187,37 @@ def test_uinmf_c5_shape_in_miniature():
     assert np.all(np.diff(out["traj"]) < 0)
 
 
+def test_uinmf_dense_tensor_core_sweeps():
+    """UINMF with count-structured shared AND unshared blocks: the stacked [E_i; P_i] sweeps run as dense-tile tcgen05
+    contractions (rows = 1400 + 700: six gene blocks, 33 gene stages), checked against the FP64 oracle from identical
+    inits; a different col_scale on an unshared block is refused."""
+    import liger_b200
+    from liger_b200 import synthetic as syn
+    d, n, m, u, k = 2, 2300, 1400, 700, 24
+    Es, Ps, sc, psc = syn.make_numpy(d, n, m, 10, u=u, block=1150, seed=91, return_unshared_scales=True)
+    lam = [5.0, 3.0]
+    W0, V0, U0, _ = orc.seeded_init(1, m, k, [n] * d, [u] * d)
+    Ec = [liger_b200.CountScaled(E, *s) for E, s in zip(Es, sc)]
+    Pc = [liger_b200.CountScaled(P, *s) for P, s in zip(Ps, psc)]
+    ctx = liger_b200.Context(Ec, k, lam, W0, V0, unsharedList=Pc, Uinit=U0)
+    try:
+        ctx.set_kernel_timing(True)
+        ctx.iterate(2)
+        names = set(ctx.kernel_times().keys())
+        assert "k_dense_ltx" in names and "k_dense_xh" in names and "k_spmm_ltx" not in names
+    finally:
+        ctx.close()
+    out = liger_b200.uinmf(Ec, Pc, k=k, lambda_=lam, niter=6, Winit=W0, Vinit=V0, Uinit=U0, trajectory=True)
+    ref = c_oracle.inmf(Es, k, lam, 6, W0, V0, Ps=Ps, Uinit=U0, trajectory=True)
+    _check(out, ref, u=True)
+    assert np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"]) < TOL_OBJ
+    gather = liger_b200.uinmf(Es, Ps, k=k, lambda_=lam, niter=6, Winit=W0, Vinit=V0, Uinit=U0)
+    assert rel(out["W"], gather["W"]) < 1e-4 and rel(out["U"][1], gather["U"][1]) < 1e-4
+    bad = [Pc[0], liger_b200.CountScaled(Ps[1], psc[1][0], psc[1][1] * 1.5)]
+    with pytest.raises(Exception, match="col_scale differs|do not factor"):
+        liger_b200.uinmf(Ec, bad, k=k, lambda_=lam, niter=1, Winit=W0, Vinit=V0, Uinit=U0)
+
+
 def test_inmf_null_inits_draw_the_seeded_stream(pbmc):
     """RcppPlanc::inmf(..., Hinit = NULL, Vinit = NULL, Winit = NULL) (R/suggestK.R:78-88): the library draws W, V_i from R's
     Mersenne-Twister stream in .runINMF.list's order, so seed = 1 lands on the reference's golden factors."""
