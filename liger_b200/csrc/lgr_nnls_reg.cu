@@ -445,7 +445,11 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 dual = (k - p) < p;
                 S = dual ? ((~F) & kmask) : F;
                 s = dual ? (k - p) : p;
-                if (dual && !have_u) {   // u = P b, once per column, broadcast reads of P
+                // u = P b, once per column, broadcast reads of P.  A fresh column without a passive set (first iteration, cold start)
+                // every fresh column takes it first and starts from F = {u > 0}, the support of the clipped unconstrained
+                // solution, instead of from the empty set (which reaches the same point two rounds later)
+                const bool seed = state == (3 | ((k + 1) << 8)) && F == 0 && !have_u;
+                if ((dual || seed) && !have_u) {
                     float acc[RKP];
 #pragma unroll
                     for (int f = 0; f < RKP; ++f) acc[f] = 0.f;
@@ -463,6 +467,16 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                     for (int c4 = 0; c4 < RKP / 4; ++c4)
                         reinterpret_cast<float4*>(ucol)[c4 * 32] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
                     have_u = true;
+                    if (seed) {
+                        Mask f0 = 0;
+#pragma unroll
+                        for (int f = 0; f < RKP; ++f) f0 |= (acc[f] > 0.f) ? (ONE << f) : (Mask)0;
+                        F = f0 & kmask;
+                        const int p2 = popc_m(F);
+                        dual = (k - p2) < p2;
+                        S = dual ? ((~F) & kmask) : F;
+                        s = dual ? (k - p2) : p2;
+                    }
                 }
             }
             // systems with more than 16 unknowns (possible only for k > 32) do not fit the register templates: the
