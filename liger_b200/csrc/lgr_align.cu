@@ -147,13 +147,12 @@ __global__ void __launch_bounds__(128) k_ann_search(const AnnNode* __restrict__ 
                                                     int dim, const double* __restrict__ blo, const double* __restrict__ bhi, int kk,
                                                     double max_err, const int* __restrict__ qorder, int* __restrict__ nn_idx,
                                                     int* __restrict__ overflow) {
-    extern __shared__ double qs[];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = slot < n;
-    const int q = live ? qorder[slot] : 0;
-    double* qp = qs + threadIdx.x;
-    for (int d = 0; d < dim; ++d) qp[d * blockDim.x] = live ? pts[(size_t)q * dim + d] : 0.0;
     if (!live) return;
+    const int q = qorder[slot];
+    double qv[ANN_MAX_DIM];
+    for (int d = 0; d < dim; ++d) qv[d] = pts[(size_t)q * dim + d];
     double keys[ANN_MAX_K + 1];
     int ids[ANN_MAX_K + 1];
     int cnt = 0;
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(128) k_ann_search(const AnnNode* __restrict__ 
     int sp = 0;
     double bdist = 0.0;
     for (int d = 0; d < dim; ++d) {
-        const double v = qp[d * blockDim.x];
+        const double v = qv[d];
         if (v < blo[d]) {
             const double t = __dsub_rn(blo[d], v);
             bdist = __dadd_rn(bdist, __dmul_rn(t, t));
@@ -193,7 +192,7 @@ __global__ void __launch_bounds__(128) k_ann_search(const AnnNode* __restrict__ 
                     double dist = 0.0;
                     int d = 0;
                     for (; d < dim; ++d) {
-                        const double t = __dsub_rn(qp[d * blockDim.x], pp[d]);
+                        const double t = __dsub_rn(qv[d], pp[d]);
                         dist = __dadd_rn(dist, __dmul_rn(t, t));
                         if (dist > md) break;
                     }
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(128) k_ann_search(const AnnNode* __restrict__ 
                 }
                 break;
             }
-            const double qc = qp[nd.cd * blockDim.x];
+            const double qc = qv[nd.cd];
             const double cut_diff = __dsub_rn(qc, nd.cv);
             int near_child, far_child;
             double box_diff;
@@ -617,8 +616,7 @@ void quantile_norm_core(int d, int k, const int* n, double* const* Hdev, const l
             LGR_CUDA(cudaMemcpyAsync(dlo.p, b.blo.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
             LGR_CUDA(cudaMemcpyAsync(dhi.p, b.bhi.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
             const double max_err = (1.0 + p.eps) * (1.0 + p.eps);
-            const size_t qsmem = (size_t)128 * k * sizeof(double);
-            if (qsmem > 48 * 1024) LGR_CUDA(cudaFuncSetAttribute(k_ann_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));
+            const size_t qsmem = 0;
             LGR_CUDA(cudaEventRecord(s0, st));
             k_ann_search<<<(n[i] + 127) / 128, 128, qsmem, st>>>(
                 nodes.p, (int)b.nodes.size() - 1, dpts.p, n[i], k, dlo.p, dhi.p, kk, max_err, qorder.p, nn.p, overflow.p);
