@@ -127,8 +127,9 @@ struct lgr_ctx {
     long long tilesT = 0;
     bool dense = false;        // the two sweeps run as dense-tile tcgen05 contractions (lgr_dense.cu)
     int dense_mask = 3;        // developer knob LGR_DENSE_MASK: bit 0 = B sweep dense, bit 1 = R sweep dense
-    std::vector<DenseDs> dds_host;
+    std::vector<DenseDs> dds_host;   // one descriptor per (dataset, half of the factors): d for KP = 32, 2 d for KP = 64
     DBuf<DenseDs> dds_dev;
+    int dds_n = 0, dense_max_n = 0;
     int k1_tiles = 0, gh_blocks = 0;
     long long k2_flat = 0;
     bool dshard = false;       // LGR_FLAG_DATASET_SHARD: this rank holds whole datasets; only the W solve's equations are all-reduced
@@ -447,14 +448,18 @@ bool run_stats(lgr_ctx* c, bool fork_ginv_v = false) {
     if (c->dense && (c->dense_mask & 2)) {
         {
             Timed t(c, "k_gram_tc");
-            launch_gram_h(c->dds_dev.p, c->d, c->gh_blocks, c->k, c->num_sms, c->st);
+            launch_gram_h(c->dds_dev.p, c->dds_n, c->gh_blocks, c->num_sms, c->st);
+            if (c->kp == 64) {   // the block of G between the two factor halves (the tensor-core kernel covers the diagonal blocks)
+                launch_gram_cross(c->dds_dev.p, c->dds_n, c->dense_max_n, c->st);
+                c->tm.kernel_launches += 1;
+            }
         }
         if (fork_ginv_v && (c->world == 1 || c->dshard) && side_ok(c)) {
             fork_gram_inv(c, c->specV.p, c->d, c->ev_join_v);
             forked = true;
         }
         Timed t(c, "k_dense_xh");
-        launch_dense_xh(c->dds_dev.p, c->d, c->k2_flat, c->num_sms, c->st);
+        launch_dense_xh(c->dds_dev.p, c->dds_n, c->k2_flat, c->num_sms, c->st);
     } else {
         Timed t(c, "k_spmm_xh");
         launch_spmm_xh(c->ds_dev.p, c->d, c->xh_tiles, c->k, c->kp, c->tc, c->st);
@@ -501,7 +506,7 @@ void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
     }
     if (c->dense && (c->dense_mask & 1)) {
         Timed t(c, "k_dense_ltx");
-        launch_dense_ltx(c->dds_dev.p, c->d, c->k1_tiles, c->num_sms, c->st);
+        launch_dense_ltx(c->dds_dev.p, c->dds_n, c->k1_tiles, c->num_sms, c->st);
     } else {
         Timed t(c, "k_spmm_ltx");
         launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->fuse_u, c->st);
@@ -766,7 +771,7 @@ void products(lgr_ctx* c, int which, double* const* out) {
     if (which == 0) {
         run_prep(c);
         if (c->dense && (c->dense_mask & 1))
-            launch_dense_ltx(c->dds_dev.p, c->d, c->k1_tiles, c->num_sms, c->st);
+            launch_dense_ltx(c->dds_dev.p, c->dds_n, c->k1_tiles, c->num_sms, c->st);
         else
             launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, false, c->st);
     } else {
@@ -931,8 +936,9 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         check_block(a->E[i], a->m, a->E[i].ncol, "E[i]");
         if (a->P && a->P[i].nrow > 0) check_block(a->P[i], a->P[i].nrow, a->E[i].ncol, "P[i]");
     }
-    {   // dense-tile sweeps: every block (shared and unshared) carries a verified-on-upload count structure, k <= 32
-        bool ok = c->kp == 32 && !(c->flags & (LGR_FLAG_NO_DENSE | LGR_FLAG_TENSOR_U | LGR_FLAG_LEGACY_NNLS)) && !getenv("LGR_NO_DENSE");
+    {   // dense-tile sweeps: every block (shared and unshared) carries a verified-on-upload count structure; k <= 32 in one
+        // pass, 32 < k <= 64 in two passes over the entry streams (one per half of the factors)
+        bool ok = (c->kp == 32 || c->kp == 64) && !(c->flags & (LGR_FLAG_NO_DENSE | LGR_FLAG_TENSOR_U | LGR_FLAG_LEGACY_NNLS)) && !getenv("LGR_NO_DENSE");
         for (int i = 0; i < c->d && ok; ++i) {
             ok = a->E[i].row_scale && a->E[i].col_scale;
             if (ok && a->P && a->P[i].nrow > 0) ok = a->P[i].row_scale && a->P[i].col_scale;
@@ -1039,7 +1045,7 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
                 prep_check_same((size_t)D.n, SE.cs64.p, SP.cs64.p, bad_rows.p, c->st);
             }
             dev_f64_to_f32(SE.cs64.p, D.dl.cs.p, (size_t)D.n, c->st);
-            dense_build(D.n, D.rows, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.dl.rs.p, D.dl.cs.p, D.dl, bad_rows.p, c->st);
+            dense_build(D.n, D.rows, D.colptr.p, D.rowidx.p, D.val.p, D.nnz, D.dl.rs.p, D.dl.cs.p, kp / 32, D.dl, bad_rows.p, c->st);
             int hbad = 0;
             LGR_CUDA(cudaMemcpyAsync(&hbad, bad_rows.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
             LGR_CUDA(cudaStreamSynchronize(c->st));
@@ -1165,7 +1171,8 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
         h.sqnorm = sq[i];
         h.Asplit = c->dense ? D.dl.Asplit.p : nullptr;
         h.rs = c->dense ? D.dl.rs.p : nullptr;
-        if (c->dense) {
+        h.asplit_half = c->dense ? D.dl.nstage1 * 8192 : 0;
+        for (int half = 0; c->dense && half < kp / 32; ++half) {
             DenseDs q;
             memset(&q, 0, sizeof(q));
             q.n = D.n;
@@ -1179,16 +1186,19 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
             q.k2_flat_off = c->k2_flat;
             q.seg1 = D.dl.seg1.p;
             q.ent1 = D.dl.ent1.p;
-            q.Asplit = D.dl.Asplit.p;
+            q.ldf = kp;
+            c->dense_max_n = std::max(c->dense_max_n, D.n);
+            q.kloc = std::max(0, std::min(32, c->k - 32 * half));
+            q.Asplit = D.dl.Asplit.p + (size_t)half * h.asplit_half;
             q.seg2 = D.dl.seg2.p;
             q.ent2 = D.dl.ent2.p;
             q.rs = D.dl.rs.p;
             q.cs = D.dl.cs.p;
-            q.B = h.B;
-            q.H = h.H;
-            q.R = h.R;
-            q.G = h.G;
-            q.Hs = D.dl.Hs.p;
+            q.B = h.B + 32 * half;
+            q.H = h.H + 32 * half;
+            q.R = h.R + 32 * half;
+            q.G = h.G + (size_t)(32 * half) * kp + 32 * half;
+            q.Hs = D.dl.Hs.p + (size_t)half * ((size_t)D.dl.ncstage + 2) * 3072;
             c->k1_tiles += D.dl.ntile1;
             c->gh_blocks += (D.n + dense_gram_tile() - 1) / dense_gram_tile();
             c->k2_flat += (long long)D.dl.ngb * D.dl.ncstage;
@@ -1215,8 +1225,9 @@ void create(const lgr_inmf_args* a, lgr_ctx** out) {
     c->colsH = bH;
     c->colsV = bV;
     if (c->dense) {
-        c->dds_dev.alloc((size_t)c->d);
-        LGR_CUDA(cudaMemcpyAsync(c->dds_dev.p, c->dds_host.data(), sizeof(DenseDs) * c->d, cudaMemcpyHostToDevice, c->st));
+        c->dds_n = (int)c->dds_host.size();
+        c->dds_dev.alloc((size_t)c->dds_n);
+        LGR_CUDA(cudaMemcpyAsync(c->dds_dev.p, c->dds_host.data(), sizeof(DenseDs) * c->dds_n, cudaMemcpyHostToDevice, c->st));
     }
     c->ds_dev.alloc((size_t)c->d);
     c->grpH.alloc((size_t)c->d);

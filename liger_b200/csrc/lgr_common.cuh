@@ -111,7 +111,7 @@ struct DsDev {
     const unsigned int* ttag;    // per group of 8: gene
     const float* tval;
     int ngt;                     // gene tiles
-    int pad0;
+    int asplit_half;             // dense path, KP = 64: 16-bit words between the slab images of factors 0..31 and 32..63
     float* L;
     float* H;
     float* B;
@@ -142,6 +142,8 @@ struct DenseDs {
     int ngb;          // 512-gene blocks (k_dense_xh)
     int ncstage;      // 32-cell stages
     int gh_blk_off;   // first flat block in k_gram_h
+    int ldf;          // row stride (floats) of B, H and R, (doubles) of G: KP.  For KP = 64 every dataset has two descriptors,
+    int kloc;         // one per half of the factors (32 operand rows x 3 terms each); kloc = factors of this half
     long long k2_flat_off;   // first flat (gene block, cell stage) index of this dataset
     const int* seg1;
     const unsigned int* ent1;
@@ -249,10 +251,11 @@ struct DenseLayout {
     DBuf<float> rs, cs;
 };
 void dense_build(int n, int rows, const int* colptr, const int* rowidx, const float* val, size_t nnz, const float* rs, const float* cs,
-                 DenseLayout& out, int* bad, cudaStream_t st);
+                 int halves, DenseLayout& out, int* bad, cudaStream_t st);
+void launch_gram_cross(const DenseDs* ds, int nds, int max_n, cudaStream_t st);
 void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st);
 void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st);
-void launch_gram_h(const DenseDs* ds, int nds, int total_items, int k, int num_sms, cudaStream_t st);
+void launch_gram_h(const DenseDs* ds, int nds, int total_items, int num_sms, cudaStream_t st);
 int dense_gram_tile();
 void dense_init();
 

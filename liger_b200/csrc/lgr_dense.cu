@@ -313,7 +313,7 @@ __device__ __forceinline__ unsigned char* align1k(unsigned char* p) {
     return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 
-constexpr int MAX_SDS = 24;   // datasets whose descriptors are cached in shared memory (more: read from global memory)
+constexpr int MAX_SDS = 32;   // datasets whose descriptors are cached in shared memory (more: read from global memory)
 constexpr int K1_NSA = 5;   // A-slab ring of k_dense_ltx (decoupled from the X ring: the slabs are fetched further ahead)
 constexpr size_t K1_SMEM = (size_t)NST * XSTAGE_BYTES + (size_t)K1_NSA * K1_ASTAGE_BYTES + 40 * 8 + 1024;
 constexpr int K2_NSA = 8;   // A-slab ring of k_dense_xh: the converters run up to 8 stages ahead of the MMAs
@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
             const int c0 = (tile - D.k1_tile_off) * TILE_N;
             const int ncell = min(TILE_N, D.n - c0);
             const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-            float* __restrict__ Bout = D.B + (size_t)c0 * 32 + q * 8 + fq;
+            const int ldf = D.ldf;
+            float* __restrict__ Bout = D.B + (size_t)c0 * ldf + q * 8 + fq;
             const float* __restrict__ cs = D.cs + c0;
             mbar_wait(accfull + acc, accph);
             tc_fence_after();
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
                 for (int g = 0; g < 8; ++g) {    // lane (fq, t) stores factor 8 q + fq of cell 4 g + t: 32-byte runs per cell
                     const uint32_t sel = t == 0 ? v[4 * g] : (t == 1 ? v[4 * g + 1] : (t == 2 ? v[4 * g + 2] : v[4 * g + 3]));
                     const int c = j * 32 + 4 * g + t;
-                    if (c < ncell) Bout[(size_t)c * 32] = __uint_as_float(sel) * csv[g];
+                    if (c < ncell) Bout[(size_t)c * ldf] = __uint_as_float(sel) * csv[g];
                 }
             }
             tc_fence_before();
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
                     const int g = g0 + j * 32 + c;
                     if (j * 32 + c < ngene) {
                         const float sum = buf[lane * 33 + c] + buf[(32 + lane) * 33 + c] + buf[(64 + lane) * 33 + c];
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(D.R + (size_t)g * 32 + lane), "f"(sum * __ldg(D.rs + g)) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(D.R + (size_t)g * D.ldf + lane), "f"(sum * __ldg(D.rs + g)) : "memory");
                     }
                 }
             }
@@ -776,7 +777,7 @@ constexpr int GT_WARPS = 5 + GT_CONV_WARPS;   // MMA, 4 epilogue, converters
 constexpr size_t GT_SMEM = (size_t)NST * GT_STAGE_BYTES + 32 * 8 + 1024;
 constexpr uint32_t IDESC_GRAM = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-__global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __restrict__ ds_g, int nds, int total_items, int k) {
+__global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __restrict__ ds_g, int nds, int total_items) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ DenseDs sds[MAX_SDS];
     __shared__ double Gacc[32 * 32];
@@ -865,9 +866,10 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (cur_ds >= 0) {
                 double* G = ds[cur_ds].G;
+                const int k = ds[cur_ds].kloc, ldf = ds[cur_ds].ldf;
                 for (int e = (warp - 1) * 32 + lane; e < 32 * 32; e += 128) {
                     const int fa = e >> 5, fb = e & 31;
-                    if (fa < k && fb < k) atomicAdd(&G[fa * 32 + fb], Gacc[e]);
+                    if (fa < k && fb < k) atomicAdd(&G[fa * ldf + fb], Gacc[e]);
                     Gacc[e] = 0.0;
                 }
             }
@@ -927,13 +929,14 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
             }
             valid = true;
             it_out = it;
-            const float* __restrict__ H = ds[i].H + (size_t)c0 * 32;
+            const int ldf = ds[i].ldf;
+            const float* __restrict__ H = ds[i].H + (size_t)c0 * ldf;
             const int cc = s * (GT_KS * KSTEP) + ks * KSTEP;
             csn = (lane < KSTEP && cc + lane < ncell) ? __ldg(ds[i].cs + c0 + cc + lane) : 0.f;
             // image of k_dense_xh's A slabs: [32-cell stage][k-step][chunk of 8 cells][row t * 32 + f][cell % 8], 6 KB per stage
             img = reinterpret_cast<uint4*>(ds[i].Hs) + ((size_t)((c0 + cc) >> 5) * 6144 + (size_t)(((c0 + cc) >> 4) & 1) * 3072) / 16;
 #pragma unroll
-            for (int j = 0; j < KSTEP; ++j) hn[j] = (cc + j < ncell) ? __ldg(H + (size_t)(cc + j) * 32 + lane) : 0.f;
+            for (int j = 0; j < KSTEP; ++j) hn[j] = (cc + j < ncell) ? __ldg(H + (size_t)(cc + j) * ldf + lane) : 0.f;
         };
         fetch(cur_it, cur_valid);
         while (cur_valid) {
@@ -983,6 +986,91 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
 }
 
 // =====================================================================================================================
+// k_gram_cross (KP = 64 only):  the off-diagonal block of G = H^T H between the two factor halves, G[f, 32 + f'] and its
+// mirror image.  k_gram_tc covers the diagonal blocks (one descriptor per half); the cross block is 2 n 32^2 flops per
+// dataset and runs on the CUDA cores: a CTA stages 64 cells x 64 factors at a time, every thread owns a 2 x 2 patch of the
+// 32 x 32 block (fp32 over the CTA's cells in chunks of 64, fp64 across chunks), one fp64 atomic per entry and CTA.
+// Descriptors 2 i and 2 i + 1 are the halves of dataset i; blockIdx.y = i.  The grid gives a CTA ~32 chunks: with fewer the
+// kernel is nothing but its final atomics.
+// =====================================================================================================================
+constexpr int GX_CHUNKS_PER_CTA = 32;
+__global__ void __launch_bounds__(256) k_gram_cross(const DenseDs* __restrict__ ds) {
+    const DenseDs& D0 = ds[2 * blockIdx.y];
+    const DenseDs& D1 = ds[2 * blockIdx.y + 1];
+    const int n = D0.n, k0 = D0.kloc, k1 = D1.kloc;
+    if (k1 <= 0) return;
+    __shared__ __align__(16) float Hs[64][68];
+    const float* __restrict__ H = D0.H;   // row stride 64; factors 0..31 | 32..63
+    // 64 threads cover the 32 x 32 block with 4 x 4 patches; the four groups of 64 threads take 16 of the 64 staged cells each
+    const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, a0 = (t >> 3) * 4, b0 = (t & 7) * 4;
+    double g[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) g[a][b] = 0.0;
+    for (int c0 = blockIdx.x * 64; c0 < n; c0 += gridDim.x * 64) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+            const int r = e >> 4, q = e & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + r < n) v = __ldg(reinterpret_cast<const float4*>(H + (size_t)(c0 + r) * 64) + q);
+            *reinterpret_cast<float4*>(&Hs[r][4 * q]) = v;
+        }
+        __syncthreads();
+        float s[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) s[a][b] = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = grp * 16 + rr;
+            const float4 x = *reinterpret_cast<const float4*>(&Hs[r][a0]);
+            const float4 y = *reinterpret_cast<const float4*>(&Hs[r][32 + b0]);
+            const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) s[a][b] = fmaf(xs[a], ys[b], s[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) g[a][b] += (double)s[a][b];
+    }
+    // the four row groups are summed in shared memory (it is free now), then one atomic pair per entry
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(&Hs[0][0]);   // 64 threads x 16 doubles = 8 KB, one row group at a time
+    static_assert(sizeof(Hs) >= 64 * 16 * sizeof(double), "reduction buffer");
+    for (int gsrc = 1; gsrc < 4; ++gsrc) {
+        if (grp == gsrc) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) red[(a * 4 + b) * 64 + t] = g[a][b];
+        }
+        __syncthreads();
+        if (grp == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) g[a][b] += red[(a * 4 + b) * 64 + t];
+        }
+        __syncthreads();
+    }
+    if (grp != 0) return;
+    double* G = D0.G;   // 64 x 64
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (a0 + a < k0 && b0 + b < k1) {
+                atomicAdd(&G[(a0 + a) * 64 + 32 + b0 + b], g[a][b]);
+                atomicAdd(&G[(32 + b0 + b) * 64 + a0 + a], g[a][b]);
+            }
+}
+
+// =====================================================================================================================
 // launches
 // =====================================================================================================================
 void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st) {
@@ -1015,10 +1103,17 @@ void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_s
                 h[10], h[12]);
     }
 }
-void launch_gram_h(const DenseDs* ds, int nds, int total_items, int k, int num_sms, cudaStream_t st) {
+void launch_gram_h(const DenseDs* ds, int nds, int total_items, int num_sms, cudaStream_t st) {
     if (total_items <= 0) return;
     const int grid = std::min(total_items, num_sms);
-    k_gram_tc<<<grid, GT_WARPS * 32, GT_SMEM, st>>>(ds, nds, total_items, k);
+    k_gram_tc<<<grid, GT_WARPS * 32, GT_SMEM, st>>>(ds, nds, total_items);
+    LGR_CUDA(cudaGetLastError());
+}
+void launch_gram_cross(const DenseDs* ds, int nds, int max_n, cudaStream_t st) {
+    if (nds <= 0 || max_n <= 0) return;
+    const int chunks = (max_n + 63) / 64;
+    const int ctas = std::max(1, std::min(296, (chunks + GX_CHUNKS_PER_CTA - 1) / GX_CHUNKS_PER_CTA));
+    k_gram_cross<<<dim3(ctas, nds / 2), 256, 0, st>>>(ds);
     LGR_CUDA(cudaGetLastError());
 }
 int dense_gram_tile() { return GT_CELLS; }
@@ -1118,7 +1213,7 @@ static void dense_build_t(int n, int rows, const int* colptr, const int* rowidx,
 }
 
 void dense_build(int n, int rows, const int* colptr, const int* rowidx, const float* val, size_t nnz, const float* rs, const float* cs,
-                 DenseLayout& out, int* bad, cudaStream_t st) {
+                 int halves, DenseLayout& out, int* bad, cudaStream_t st) {
     out.nstage1 = (rows + K1_KS * KSTEP - 1) / (K1_KS * KSTEP);
     out.ntile1 = (n + TILE_N - 1) / TILE_N;
     out.ngb = (rows + 511) / 512;
@@ -1136,11 +1231,12 @@ void dense_build(int n, int rows, const int* colptr, const int* rowidx, const fl
     else
         dense_build_t<unsigned long long>(n, rows, colptr, rowidx, val, nnz, rs, cs, out, bad, nseg1, nseg2, bits1, bits2, st);
     // pre-split factor image of k_dense_ltx: nstage1 x 16 KB, zero (rows of term 3 and rows >= `rows` stay zero)
-    out.Asplit.alloc((size_t)out.nstage1 * K1_ASTAGE_BYTES / 2);
+    // (KP = 64: one image per half of the factors, back to back)
+    out.Asplit.alloc((size_t)halves * out.nstage1 * K1_ASTAGE_BYTES / 2);
     out.Asplit.zero(st);
     // split image of cs * H for k_dense_xh (written by k_gram_tc every iteration): 6 KB per 32-cell stage; k_gram_tc covers
     // whole 64-cell stages, so the last stage pair is allocated in full
-    out.Hs.alloc(((size_t)out.ncstage + 2) * 3072);
+    out.Hs.alloc((size_t)halves * ((size_t)out.ncstage + 2) * 3072);
     out.Hs.zero(st);
 }
 

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(512) k_prep(const DsDev* __restrict__ ds, int 
                 v = D.V[(size_t)gr * KP + f];
                 l = gr < D.m ? W[(size_t)gr * KP + f] : 0.0;
             }
-            if (KP == 32 && D.Asplit) rs = D.rs[gr];
+            if (D.Asplit) rs = D.rs[gr];
         }
         lv[q] = l;
         vv[q] = v;
@@ -55,18 +55,21 @@ __global__ void __launch_bounds__(512) k_prep(const DsDev* __restrict__ ds, int 
         if (r < nr) {
             const int gr = r0 + r;
             D.L[(size_t)gr * KP + f] = (float)l;
-            if (KP == 32 && D.Asplit) {
+            if (D.Asplit) {
                 // operand-slab image of k_dense_ltx: [64-gene stage][k-step of 16][chunk of 8 genes][row 4 f + t][gene % 8],
-                // t = hi / mid / lo bf16 term of rs[g] * L~[g, f] (the three terms sum to the fp32 value exactly)
+                // t = hi / mid / lo bf16 term of rs[g] * L~[g, f] (the three terms sum to the fp32 value exactly).  KP = 64: one
+                // image per half of the factors (f / 32), asplit_half words apart -- the sweeps run once per half
                 const float x = (float)l * rsv[q];
                 const unsigned xb = __float_as_uint(x), hb = xb & 0xFFFF0000u;
                 const float r1 = x - __uint_as_float(hb);
                 const unsigned mb = __float_as_uint(r1) & 0xFFFF0000u;
                 const float r2 = r1 - __uint_as_float(mb);
-                unsigned short* img = D.Asplit + ((size_t)(gr >> 6) * 16384 + ((gr >> 4) & 3) * 4096 + ((gr >> 3) & 1) * 2048 + (gr & 7) * 2) / 2;
-                img[(4 * f + 0) * 8] = (unsigned short)(hb >> 16);
-                img[(4 * f + 1) * 8] = (unsigned short)(mb >> 16);
-                img[(4 * f + 2) * 8] = (unsigned short)(__float_as_uint(r2) >> 16);
+                unsigned short* img = D.Asplit + (size_t)(f >> 5) * D.asplit_half +
+                                      ((size_t)(gr >> 6) * 16384 + ((gr >> 4) & 3) * 4096 + ((gr >> 3) & 1) * 2048 + (gr & 7) * 2) / 2;
+                const int fl = f & 31;
+                img[(4 * fl + 0) * 8] = (unsigned short)(hb >> 16);
+                img[(4 * fl + 1) * 8] = (unsigned short)(mb >> 16);
+                img[(4 * fl + 2) * 8] = (unsigned short)(__float_as_uint(r2) >> 16);
             }
         }
         Ls[r][f] = l;

@@ -187,13 +187,14 @@ def test_uinmf_c5_shape_in_miniature():
     assert np.all(np.diff(out["traj"]) < 0)
 
 
-def test_uinmf_dense_tensor_core_sweeps():
+@pytest.mark.parametrize("k", [24, 44])     # 44: the sweeps run once per half of the factors
+def test_uinmf_dense_tensor_core_sweeps(k):
     """UINMF with count-structured shared AND unshared blocks: the stacked [E_i; P_i] sweeps run as dense-tile tcgen05
     contractions (rows = 1400 + 700: six gene blocks, 33 gene stages), checked against the FP64 oracle from identical
     inits; a different col_scale on an unshared block is refused."""
     import liger_b200
     from liger_b200 import synthetic as syn
-    d, n, m, u, k = 2, 2300, 1400, 700, 24
+    d, n, m, u = 2, 2300, 1400, 700
     Es, Ps, sc, psc = syn.make_numpy(d, n, m, 10, u=u, block=1150, seed=91, return_unshared_scales=True)
     lam = [5.0, 3.0]
     W0, V0, U0, _ = orc.seeded_init(1, m, k, [n] * d, [u] * d)
@@ -272,6 +273,9 @@ def _count_scaled(d, n, m, r, seed, block=1000):
     ("ragged", 3, 1111, 333, 20, 5),         # n not a multiple of 256 / 32, m not a multiple of 64
     ("tiny", 2, 40, 70, 8, 4),               # less than one tile in every dimension
     ("wide", 1, 20000, 1100, 32, 3),         # more tiles than SMs x 1, k = 32 (full factor width), 3 gene blocks
+    ("C4-mini", 2, 2500, 3000, 50, 5),       # k > 32: two passes over the entry streams (factor halves), cross-half Gram block
+    ("k33", 3, 700, 300, 33, 4),             # one factor in the second half
+    ("k62", 1, 1500, 260, 62, 3),            # the widest H solve the register kernels take
 ])
 def test_dense_tensor_core_sweeps_match_oracle_and_gather(name, d, n, m, k, niter):
     """The tcgen05 sweeps (bf16 count tiles x 3-term bf16 split of the scaled factor, fp32 TMEM accumulators) against the
