@@ -517,20 +517,27 @@ void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
     }
     if (fork) LGR_CUDA(cudaStreamWaitEvent(c->st, c->ev_join_h, 0));
     {
-        Timed t(c, "k_nnls_H");
         // fp32, k <= 32: register-resident solver; groups with a singular Gram fall through to k_nnls (flag 16)
         static const bool no_reg = getenv("LGR_NNLS_NO_REG") != nullptr;
         if (!no_reg && !(c->flags & LGR_FLAG_LEGACY_NNLS) && (cold & ~1) == 0 && nnls_reg_supported(c->k, c->kp)) {
-            launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->kp, c->num_sms, c->counters.p, cold, c->st);
             static const bool no_wbig = getenv("LGR_NNLS_NO_WBIG") != nullptr;
-            c->tm.kernel_launches += 1;   // register kernel + mop-up kernel (the timed scope counts one)
-            if (c->kp > 32 && !no_wbig) {   // systems above 16 unknowns: warp-per-column continuation
-                launch_nnls_wbig(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
-                c->tm.kernel_launches += 1;
+            {
+                Timed t(c, "k_nnls_H");
+                launch_nnls_reg(c->grpH.p, c->d, c->colsH, c->k, c->kp, c->num_sms, c->counters.p, cold, c->st);
             }
+            if (c->kp > 32 && !no_wbig) {   // systems above 16 unknowns: continued from the passive set they had reached
+                Timed t(c, "k_nnls_H_big");
+                static const bool warp_cols = getenv("LGR_NNLS_WBIG") != nullptr;   // developer knob: the warp-per-column kernel
+                if (warp_cols)
+                    launch_nnls_wbig(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+                else
+                    launch_nnls_scol(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+            }
+            Timed t(c, "k_nnls_H_mop");   // groups with a singular Gram (normally none: the kernel returns at once)
             launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p,
                         cold | 16 | ((c->kp > 32 && no_wbig) ? 64 : 0), c->st);
         } else {
+            Timed t(c, "k_nnls_H");
             launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p, cold, c->st);
         }
     }
