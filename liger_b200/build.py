@@ -16,7 +16,7 @@ CSRC = os.path.join(ROOT, "csrc")
 LIBDIR = os.path.join(ROOT, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libliger_b200.so")
-SOURCES = ["lgr_kernels.cu", "lgr_nnls.cu", "lgr_nnls_reg.cu", "lgr_nnls_warp.cu", "lgr_nnls_wbig.cu", "lgr_nnls_scol.cu", "lgr_spmm.cu", "lgr_dense.cu", "lgr_tc.cu", "lgr_layout.cu", "lgr_prep.cu", "lgr_stage.cu", "lgr_align.cu", "lgr_centroid.cu", "lgr_online.cu", "lgr_api.cu", "lgr_rng.cpp", "lgr_nccl.cpp"]
+SOURCES = ["lgr_kernels.cu", "lgr_nnls.cu", "lgr_nnls_reg.cu", "lgr_nnls_warp.cu", "lgr_nnls_wbig.cu", "lgr_nnls_scol.cu", "lgr_nnls_pair.cu", "lgr_spmm.cu", "lgr_dense.cu", "lgr_tc.cu", "lgr_layout.cu", "lgr_prep.cu", "lgr_stage.cu", "lgr_align.cu", "lgr_centroid.cu", "lgr_online.cu", "lgr_api.cu", "lgr_rng.cpp", "lgr_nccl.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

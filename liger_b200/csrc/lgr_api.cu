@@ -530,8 +530,12 @@ void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
                 static const bool warp_cols = getenv("LGR_NNLS_WBIG") != nullptr;   // developer knob: the warp-per-column kernel
                 if (warp_cols)
                     launch_nnls_wbig(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
-                else
-                    launch_nnls_scol(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+                else {
+                    static const bool no_pair = getenv("LGR_NNLS_NO_PAIR") != nullptr;
+                    if (!no_pair) launch_nnls_pair(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+                    // systems above 26 unknowns (k > 52 only), or everything flagged without the pair kernel
+                    if (no_pair || c->k > 52) launch_nnls_scol(c->grpH.p, c->d, c->colsH, c->k, c->num_sms, c->counters.p, c->st);
+                }
             }
             Timed t(c, "k_nnls_H_mop");   // groups with a singular Gram (normally none: the kernel returns at once)
             launch_nnls(false, c->grpH.p, c->d, c->colsH, c->k, c->kp, c->cfgF, c->counters.p,

@@ -228,6 +228,9 @@ void nnls_wbig_init();
 // the same hand-over, thread per column with the principal block in shared memory (lgr_nnls_scol.cu): the default
 void launch_nnls_scol(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, cudaStream_t st);
 void nnls_scol_init();
+// systems of 17..26 unknowns: two lanes per column, the principal block in their registers (lgr_nnls_pair.cu)
+void launch_nnls_pair(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, cudaStream_t st);
+void nnls_pair_init();
 bool nnls_wbig64_supported(int k, int kp, long long total_cols, int num_sms);
 void launch_nnls_wbig64(const NnlsGroup* groups, int ngroups, long long total_cols, int k, int num_sms, Counters* cnt, int flags,
                         cudaStream_t st);

@@ -270,6 +270,7 @@ void kernels_init() {
     nnls_reg_init();
     nnls_wbig_init();
     nnls_scol_init();
+    nnls_pair_init();
     spmm_init();
     tc_init();
     dense_init();
