@@ -24,7 +24,7 @@ t = time.time()
 ref = c_oracle.inmf(mats, k, 5.0, niter, W0, V0, trajectory=True)
 tc = time.time() - t
 rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
-res = {"config": name, "niter": niter, "sweeps": path if k <= 32 else "gather (k > 32)", "gpu_seconds": tg, "cpu_oracle_seconds": tc, "cpu_threads": c_oracle.num_threads(),
+res = {"config": name, "niter": niter, "sweeps": path if k <= 32 else (path + (" (two passes: factor halves)" if path == "dense" else "")), "gpu_seconds": tg, "cpu_oracle_seconds": tc, "cpu_threads": c_oracle.num_threads(),
        "rel_W": rel(out["W"], ref["W"]), "rel_V_max": max(rel(a, b) for a, b in zip(out["V"], ref["V"])),
        "rel_H_max": max(rel(a, b) for a, b in zip(out["H"], ref["H"])),
        "obj_traj_max_rel": float(np.max(np.abs(out["traj"] - ref["traj"]) / ref["traj"])),
