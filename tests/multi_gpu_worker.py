@@ -28,9 +28,9 @@ def main():
     dist.broadcast(idt, 0)
     nccl_id = bytes(idt.cpu().numpy().tobytes())
     mode = sys.argv[1]
-    if mode == "dense":      # count-structured synthetic data: the dense-tile tensor-core sweeps on cell shards
+    if mode.startswith("dense"):   # count-structured synthetic data: the dense-tile tensor-core sweeps on cell shards
         from liger_b200 import synthetic as syn
-        d, n, m, k = 3, 2100, 700, 24
+        d, n, m, k = 3, 2100, 700, int(mode[5:] or 24)   # "dense44": k > 32, the sweeps run once per half of the factors
         Es, _, sc = syn.make_numpy(d, n, m, 8, block=700, seed=21, return_scales=True)
         W0, V0, _, _ = orc.seeded_init(1, m, k, [n] * d)
         Cs = [liger_b200.CountScaled(E, rs, cs) for E, (rs, cs) in zip(Es, sc)]

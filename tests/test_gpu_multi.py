@@ -44,19 +44,21 @@ def test_two_gpu_cell_sharding(tmp_path, pbmc, mode):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-def test_two_gpu_dense_sweeps(tmp_path):
-    """The dense-tile tensor-core sweeps on cell shards (slice mode, one all-reduce per iteration) against the C oracle."""
+@pytest.mark.parametrize("k", [24, 44])
+def test_two_gpu_dense_sweeps(tmp_path, k):
+    """The dense-tile tensor-core sweeps on cell shards (slice mode, one all-reduce per iteration) against the C oracle;
+    k = 44: two passes per sweep (factor halves) and the k > 32 H-solve kernels."""
     from liger_b200 import synthetic as syn
     from oracle import c_oracle
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29534", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), "dense", str(tmp_path)]
+           "--master-port", "29534", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), f"dense{k}", str(tmp_path)]
     subprocess.run(cmd, check=True, timeout=600, cwd=ROOT)
-    d, n, m, k = 3, 2100, 700, 24
+    d, n, m = 3, 2100, 700
     Es, _ = syn.make_numpy(d, n, m, 8, block=700, seed=21)
     W0, V0, _, _ = orc.seeded_init(1, m, k, [n] * d)
     ref = c_oracle.inmf(Es, k, 5.0, 6, W0, V0, trajectory=True)
-    r0 = np.load(tmp_path / "dense_rank0.npz")
-    r1 = np.load(tmp_path / "dense_rank1.npz")
+    r0 = np.load(tmp_path / f"dense{k}_rank0.npz")
+    r1 = np.load(tmp_path / f"dense{k}_rank1.npz")
     assert np.array_equal(r0["W"], r1["W"]) and np.array_equal(r0["V0"], r1["V0"])
     assert rel(r0["W"], ref["W"]) < 1e-3 and rel(r0["V0"], ref["V"][0]) < 1e-3
     assert rel(r0["H0"] + r1["H0"], ref["H"][0]) < 1e-3       # slice mode: each rank wrote its own rows
