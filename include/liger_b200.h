@@ -202,9 +202,16 @@ LGR_API int lgr_prep_scaled_view(lgr_prep* p, int32_t i, lgr_csc* view);   /* m 
 LGR_API int lgr_prep_scaled_download(lgr_prep* p, int32_t i, int32_t* colptr, int32_t* rowidx, double* values);
 LGR_API void lgr_prep_destroy(lgr_prep* p);
 
-/* ---- online iNMF, scenario 1 (front end R/integration.R:722-933; the arithmetic is RcppPlanc::onlineINMF, R/integration.R:
-   902-910, which is not part of the reference tree: restated from the published algorithm -- Gao et al. 2021, Algorithm 1 --
-   with the bookkeeping documented in DESIGN.md section 8; PARITY UNPINNED).  k <= 32, d <= 16. ---- */
+/* ---- online iNMF (front end R/integration.R:722-933; the arithmetic is RcppPlanc::onlineINMF, R/integration.R:902-910,
+   which is not part of the reference tree: restated from the published algorithm -- Gao et al. 2021, Algorithm 1 -- with
+   the bookkeeping documented in DESIGN.md section 8; PARITY UNPINNED).  k <= 32, d <= 16.
+   Scenario 1 (n_prev = 0, flags = 0): all d datasets from scratch.
+   Scenario 2 (newDatasets, R/integration.R:755-812; n_prev > 0): datasets [0, n_prev) are the already factorised ones --
+   their matrices are not read; Winit, Vinit[i], Ainit[i], Binit[i] carry their state, which enters the W updates and is
+   returned unchanged -- and the minibatches run over datasets [n_prev, d) only.
+   Scenario 3 (projection = TRUE; LGR_ONLINE_PROJECT): no update at all; H_i of the d given datasets against Winit alone
+   (V = 0).  Only out->H (and objErr = sum ||X_i - W H_i||^2) is written. ---- */
+#define LGR_ONLINE_PROJECT 1u
 typedef struct lgr_online_args {
     int32_t d;               /* datasets */
     int32_t k;
@@ -216,9 +223,14 @@ typedef struct lgr_online_args {
     int32_t hals_iter;       /* [1] HALS sweeps per minibatch */
     uint32_t seed;           /* [1] set.seed(): W draw, the cells V_i starts from, the per-epoch permutations */
     const double* Winit;     /* m x k or NULL */
-    const double* const* Vinit; /* d x (m x k) or NULL (both or neither) */
+    const double* const* Vinit; /* d x (m x k) or NULL (scenario 1: both or neither; scenario 2: entries [0, n_prev) required,
+                                   the others may be NULL = drawn) */
     int32_t device;
-    uint32_t flags;          /* reserved, 0 */
+    uint32_t flags;          /* 0 or LGR_ONLINE_PROJECT */
+    int32_t n_prev;          /* scenario 2: leading datasets that are already factorised (their E entries are ignored) */
+    int32_t pad1;
+    const double* const* Ainit; /* d x (k x k); entries [0, n_prev) are read (scenario 2), else NULL */
+    const double* const* Binit; /* d x (m x k); entries [0, n_prev) are read (scenario 2), else NULL */
 } lgr_online_args;
 typedef struct lgr_online_out {
     double* W;               /* m x k */

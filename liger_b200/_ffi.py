@@ -59,7 +59,8 @@ class lgr_qn_params(C.Structure):
 class lgr_online_args(C.Structure):
     _fields_ = [("d", C.c_int32), ("k", C.c_int32), ("m", C.c_int64), ("E", C.c_void_p), ("lambda_", C.c_double),
                 ("max_epochs", C.c_int32), ("minibatch_size", C.c_int32), ("hals_iter", C.c_int32), ("seed", C.c_uint32),
-                ("Winit", c_double_p), ("Vinit", C.POINTER(c_double_p)), ("device", C.c_int32), ("flags", C.c_uint32)]
+                ("Winit", c_double_p), ("Vinit", C.POINTER(c_double_p)), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("n_prev", C.c_int32), ("pad1", C.c_int32), ("Ainit", C.POINTER(c_double_p)), ("Binit", C.POINTER(c_double_p))]
 
 
 class lgr_online_out(C.Structure):

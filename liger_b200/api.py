@@ -310,34 +310,59 @@ def uinmf(objectList, unsharedList, k=20, lambda_=5.0, niter=30, nCores=2, verbo
 
 
 def online_inmf(objectList, k=20, lambda_=5.0, maxEpochs=5, minibatchSize=5000, HALSiter=1, Winit=None, Vinit=None, seed=1,
-                nCores=2, verbose=False, device=-1):
-    """Scenario 1 of RcppPlanc::onlineINMF (reference call site R/integration.R:902-910): online iNMF over `objectList`
-    from scratch.  PARITY UNPINNED against RcppPlanc (its source is not in the reference tree): the algorithm is the published
-    one, specified line by line in DESIGN.md section 8.  Returns dict(H=[n_i x k], V=[m x k], W, A=[k x k], B=[m x k],
-    objErr) like the R function (H is cell x factor; the caller transposes, R/integration.R:924)."""
-    if (Winit is None) != (Vinit is None):
-        raise ValueError("Winit and Vinit must both be given, or both be None")
-    cs = [_Csc(m) for m in objectList]
-    d = len(cs)
+                nCores=2, verbose=False, device=-1, newDatasets=None, projection=False, Hinit=None, Ainit=None, Binit=None):
+    """RcppPlanc::onlineINMF (reference call site R/integration.R:902-910).  PARITY UNPINNED against RcppPlanc (its source is
+    not in the reference tree): the algorithm is the published one, specified line by line in DESIGN.md section 8.
+    Scenario 1 (newDatasets = None): online iNMF over `objectList` from scratch.
+    Scenario 2 (newDatasets given): `objectList` are the already factorised datasets -- only their number matters, their
+    state comes in as Winit / Vinit / Ainit / Binit (one entry per dataset of objectList) -- and the minibatches run over
+    `newDatasets`; W and the new V_i, A_i, B_i, H_i are learnt, the old ones returned as given (H: Hinit, if passed).
+    Scenario 3 (projection = True): H of `newDatasets` against Winit alone; returns only dict(H=[...]).
+    Returns dict(H=[n_i x k], V=[m x k], W, A=[k x k], B=[m x k], objErr) like the R function (H is cell x factor; the
+    caller transposes, R/integration.R:924)."""
+    if projection:
+        if newDatasets is None or Winit is None:
+            raise ValueError("projection needs newDatasets and Winit")
+        prev, data = [], list(newDatasets)
+    elif newDatasets is not None:
+        prev, data = list(objectList), list(newDatasets)
+        if Winit is None or any(x is None for x in (Vinit, Ainit, Binit)) or \
+                any(len(x) < len(prev) or any(y is None for y in x[:len(prev)]) for x in (Vinit, Ainit, Binit)):
+            raise ValueError("Cannot find complete online iNMF result for current datasets. "
+                             "Please run online_inmf without newDatasets first")
+    else:
+        prev, data = [], list(objectList)
+        if (Winit is None) != (Vinit is None):
+            raise ValueError("Winit and Vinit must both be given, or both be None")
+    cs = [_Csc(m) for m in data]
+    npv, d = len(prev), len(prev) + len(data)
     m = cs[0].shape[0]
-    ns = [c.shape[1] for c in cs]
-    if min(ns) < k:
-        raise ValueError(f"Number of factors (k={k}) should be less than the number of cells in the smallest dataset ({min(ns)}).")
+    ns = [0] * npv + [c.shape[1] for c in cs]
+    if min(ns[npv:]) < k:
+        raise ValueError(f"Number of factors (k={k}) should be less than the number of cells in the smallest dataset ({min(ns[npv:])}).")
     if m < k:
         raise ValueError(f"Number of factors (k={k}) should be less than the number of shared features ({m}).")
-    Earr = (lgr_csc * d)(*[c.struct for c in cs])
+    Earr = (lgr_csc * d)(*([lgr_csc() for _ in range(npv)] + [c.struct for c in cs]))
     a = _ffi.lgr_online_args()
     a.d, a.k, a.m, a.E, a.lambda_ = d, int(k), m, C.cast(Earr, C.c_void_p), float(lambda_)
     a.max_epochs, a.minibatch_size, a.hals_iter, a.seed, a.device = int(maxEpochs), int(minibatchSize), int(HALSiter), int(seed), device
+    a.n_prev, a.flags = npv, (1 if projection else 0)
     keep = []
+
+    def ptr_array(lst):   # d pointers; None entries stay NULL
+        vals = [None if x is None else _f64(x) for x in list(lst) + [None] * (d - len(lst))]
+        arr = (c_double_p * d)(*[C.cast(None, c_double_p) if v is None else _dp(v) for v in vals])
+        keep.extend([vals, arr])
+        return arr
     if Winit is not None:
         W0 = _f64(Winit)
-        V0 = [_f64(v) for v in Vinit]
-        keep = [W0, V0]
+        keep.append(W0)
         a.Winit = _dp(W0)
-        Varr0 = (c_double_p * d)(*[_dp(v) for v in V0])
-        keep.append(Varr0)
-        a.Vinit = Varr0
+    if Vinit is not None and not projection:
+        a.Vinit = ptr_array(Vinit)
+    if npv:
+        a.Ainit = ptr_array(Ainit)
+        a.Binit = ptr_array(Binit)
     W = np.zeros((m, k), order="F")
     V = [np.zeros((m, k), order="F") for _ in range(d)]
     H = [np.zeros((n, k), order="F") for n in ns]
@@ -347,6 +372,10 @@ def online_inmf(objectList, k=20, lambda_=5.0, maxEpochs=5, minibatchSize=5000, 
     arrs = [(c_double_p * d)(*[_dp(x) for x in lst]) for lst in (V, H, A, B)]
     o.W, o.V, o.H, o.A, o.B = _dp(W), arrs[0], arrs[1], arrs[2], arrs[3]
     _ffi.check(_ffi.lib().lgr_online_inmf(C.byref(a), C.byref(o)))
+    if projection:
+        return {"H": H, "objErr": float(o.objErr), "loop_ms": float(o.loop_ms)}
+    for i in range(npv):   # the already factorised datasets keep the H they came with
+        H[i] = None if Hinit is None or Hinit[i] is None else np.asarray(Hinit[i])
     return {"H": H, "V": V, "W": W, "A": A, "B": B, "objErr": float(o.objErr), "iterations": int(o.iterations),
             "loop_ms": float(o.loop_ms)}
 

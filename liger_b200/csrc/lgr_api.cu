@@ -1464,17 +1464,30 @@ int lgr_ctx_objerr_i(lgr_ctx* c, int32_t i, double* obj) {
     });
 }
 // ---------------------------------------------------------------------------------------------------------------------
-// online iNMF, scenario 1 (kernels: lgr_online.cu; specification: DESIGN.md section 8)
+// online iNMF, scenarios 1-3 (kernels: lgr_online.cu; specification: DESIGN.md section 8)
 // ---------------------------------------------------------------------------------------------------------------------
 int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
     return guarded([&] {
         check_device();
-        LGR_REQUIRE(a && o && a->E && o->W && o->V && o->H, "lgr_online_inmf: null argument");
+        LGR_REQUIRE(a && o && a->E && o->H, "lgr_online_inmf: null argument");
+        const bool project = (a->flags & LGR_ONLINE_PROJECT) != 0;   // scenario 3: H of the given datasets against Winit, nothing else
+        const int nprev = a->n_prev;                                  // scenario 2: datasets [0, nprev) are already factorised
+        LGR_REQUIRE(project || (o->W && o->V), "lgr_online_inmf: null argument");
+        LGR_REQUIRE(nprev >= 0 && nprev < a->d, "online iNMF: n_prev must leave at least one dataset to learn from");
+        LGR_REQUIRE(!project || (nprev == 0 && a->Winit), "online iNMF, projection: pass only the new datasets, and Winit");
+        if (nprev > 0) {
+            LGR_REQUIRE(a->Winit && a->Vinit && a->Ainit && a->Binit,
+                        "Cannot find complete online iNMF result for current datasets (Winit, Vinit, Ainit, Binit)");
+            for (int i = 0; i < nprev; ++i)
+                LGR_REQUIRE(a->Vinit[i] && a->Ainit[i] && a->Binit[i],
+                            "Cannot find complete online iNMF result for current datasets (Vinit[i], Ainit[i], Binit[i])");
+        }
         LGR_REQUIRE(a->d >= 1 && a->d <= 16, "online iNMF: 1..16 datasets");
         LGR_REQUIRE(a->k >= 1 && a->k <= 32, "online iNMF: k must be in 1..32");
         LGR_REQUIRE(a->m >= 1 && a->m < (1 << 30), "m out of range");
         LGR_REQUIRE(a->max_epochs >= 1 && a->minibatch_size >= 1 && a->hals_iter >= 1, "online iNMF: bad iteration parameters");
-        LGR_REQUIRE((a->Winit == nullptr) == (a->Vinit == nullptr), "Winit and Vinit must both be given, or both be NULL");
+        LGR_REQUIRE(project || nprev > 0 || (a->Winit == nullptr) == (a->Vinit == nullptr),
+                    "Winit and Vinit must both be given, or both be NULL");
         const int d = a->d, k = a->k, kp = 32, m = (int)a->m;
         int ndev = 0;
         LGR_CUDA(cudaGetDeviceCount(&ndev));
@@ -1490,12 +1503,12 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         kernels_init();
 
         // ---- upload X_i (fp32 CSC), validate ----
-        std::vector<int> n(d);
+        std::vector<int> n(d, 0);
         long long N = 0;
         std::vector<StagedCsc> S(d);
         DBuf<int> bad(1);
         bad.zero(st);
-        for (int i = 0; i < d; ++i) {
+        for (int i = nprev; i < d; ++i) {
             check_block(a->E[i], m, a->E[i].ncol, "E[i]");
             LGR_REQUIRE(a->E[i].location == 0, "online iNMF takes host matrices");
             n[i] = (int)a->E[i].ncol;
@@ -1516,9 +1529,10 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         std::vector<int> scratch;
         std::vector<double> W0((size_t)m * k);
         std::vector<std::vector<double>> V0(d, std::vector<double>((size_t)m * k, 0.0));
-        lgr_r_runif(rng.get(), (int64_t)m * k, 0.0, 2.0, W0.data());
+        // (scenario 1 draws W; scenarios 2 / 3 start from the given W, and only the new datasets draw their V_i)
+        if (nprev == 0 && !project) lgr_r_runif(rng.get(), (int64_t)m * k, 0.0, 2.0, W0.data());
         std::vector<int> picks(k);
-        for (int i = 0; i < d; ++i) {
+        for (int i = nprev; i < d && !project; ++i) {
             rs.sample(n[i], k, scratch, picks.data());
             const lgr_csc& M = a->E[i];
             for (int j = 0; j < k; ++j) {
@@ -1538,29 +1552,29 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
                 for (int g = 0; g < m; ++g) X[(size_t)j * m + g] /= nrm;
             }
         };
-        unit_columns(W0);
-        for (int i = 0; i < d; ++i) unit_columns(V0[i]);
+        if (nprev == 0 && !project) unit_columns(W0);
+        for (int i = nprev; i < d && !project; ++i) unit_columns(V0[i]);
         // minibatch sizes and the walk of every dataset through its per-epoch permutations
         std::vector<int> mb(d), pos(d, 0);
         long long mb_total = 0;
-        for (int i = 0; i < d; ++i) {
+        for (int i = nprev; i < d; ++i) {
             mb[i] = std::max(1, (int)std::nearbyint((double)n[i] / (double)N * (double)a->minibatch_size));
             mb[i] = std::min(mb[i], n[i]);
             mb_total += mb[i];
         }
-        const long long iters = (N * (long long)a->max_epochs) / a->minibatch_size;
-        LGR_REQUIRE(iters >= 1, "online iNMF: minibatchSize is larger than maxEpochs x the number of cells");
+        const long long iters = project ? 0 : (N * (long long)a->max_epochs) / a->minibatch_size;
+        LGR_REQUIRE(project || iters >= 1, "online iNMF: minibatchSize is larger than maxEpochs x the number of cells");
         LGR_REQUIRE((double)iters * (double)mb_total < 2.0e9, "online iNMF: schedule too long");
         std::vector<std::vector<int>> perm(d);
-        for (int i = 0; i < d; ++i) {
+        for (int i = nprev; i < d && !project; ++i) {
             perm[i].resize(n[i]);
             rs.sample(n[i], n[i], scratch, perm[i].data());
         }
         std::vector<int> sched((size_t)iters * mb_total);
         std::vector<long long> ds_off(d + 1, 0);
-        for (int i = 0; i < d; ++i) ds_off[i + 1] = ds_off[i] + mb[i];
+        for (int i = 0; i < d; ++i) ds_off[i + 1] = ds_off[i] + (i >= nprev ? mb[i] : 0);
         for (long long t = 0; t < iters; ++t) {
-            for (int i = 0; i < d; ++i) {
+            for (int i = nprev; i < d; ++i) {
                 int* dst = sched.data() + (size_t)t * mb_total + ds_off[i];
                 int take = mb[i];
                 while (take > 0) {
@@ -1576,7 +1590,7 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
                 }
             }
         }
-        DBuf<int> d_sched(sched.size());
+        DBuf<int> d_sched(std::max<size_t>(sched.size(), 1));
         LGR_CUDA(cudaMemcpyAsync(d_sched.p, sched.data(), sizeof(int) * sched.size(), cudaMemcpyHostToDevice, st));
 
         // ---- device state ----
@@ -1585,7 +1599,7 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         std::vector<DBuf<float>> Lt(d);
         DBuf<double> grams((size_t)d * 4 * kp * kp);   // per dataset: LtL, VtV, CtC, CtC^-1
         DBuf<int> ok(d);
-        DBuf<float> Bmb((size_t)mb_total * kp), Hmb((size_t)mb_total * kp);
+        DBuf<float> Bmb((size_t)std::max<long long>(mb_total, 1) * kp), Hmb((size_t)std::max<long long>(mb_total, 1) * kp);
         DBuf<unsigned long long> masks((size_t)std::max<long long>(mb_total, 1));
         DBuf<Counters> counters(1);
         counters.zero(st);
@@ -1604,7 +1618,11 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
             Lt[i].alloc((size_t)m * kp);
             A[i].zero(st);
             Bs[i].zero(st);
-            upload_factor(a->Vinit ? a->Vinit[i] : V0[i].data(), V[i].p, m, k, kp, st);
+            if (i < nprev) {   // the state of an already factorised dataset (A_i is symmetric: either storage order)
+                upload_factor(a->Ainit[i], A[i].p, k, k, kp, st);
+                upload_factor(a->Binit[i], Bs[i].p, m, k, kp, st);
+            }
+            upload_factor((!project && a->Vinit && a->Vinit[i]) ? a->Vinit[i] : V0[i].data(), V[i].p, m, k, kp, st);
             hV[i] = V[i].p;
             hLt[i] = Lt[i].p;
             double* g4 = grams.p + (size_t)i * 4 * kp * kp;
@@ -1631,14 +1649,15 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         LGR_CUDA(cudaMemcpyAsync(dgrp.p, grp.data(), sizeof(NnlsGroup) * d, cudaMemcpyHostToDevice, st));
         LGR_CUDA(cudaMemcpyAsync(dods.p, ods.data(), sizeof(OnlineDs) * d, cudaMemcpyHostToDevice, st));
         LGR_CUDA(cudaMemcpyAsync(dhds.p, hds.data(), sizeof(HalsDs) * d, cudaMemcpyHostToDevice, st));
+        const int nnew = d - nprev;
         const NnlsConfig cfgF = nnls_config(k, kp, false, prop.multiProcessorCount);
         auto solve_h = [&](const NnlsGroup* g, int ng, long long cols) {   // every solve starts from the empty passive set
             launch_nnls_reg(g, ng, cols, k, kp, prop.multiProcessorCount, counters.p, 1, st);
             launch_nnls(false, g, ng, cols, k, kp, cfgF, counters.p, 1 | 16, st);
         };
         auto grams_now = [&]() {
-            launch_online_gram(W.p, dV.p, d, m, k, dLt.p, dLtL.p, dVtV.p, st);
-            launch_gram_inv(dspecs.p, d, k, kp, st);
+            launch_online_gram(W.p, dV.p + nprev, nnew, m, k, dLt.p + nprev, dLtL.p + nprev, dVtV.p + nprev, st);
+            launch_gram_inv(dspecs.p + nprev, nnew, k, kp, st);
         };
         cudaEvent_t e0, e1;
         LGR_CUDA(cudaEventCreate(&e0));
@@ -1648,7 +1667,7 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         // ---- the minibatch loop: one iteration = ten launches driven by a device-side iteration counter, captured into a
         //      CUDA graph once and replayed (LGR_NO_GRAPH: launched one by one) ----
         std::vector<OnlineX> oxs(d);
-        for (int i = 0; i < d; ++i)
+        for (int i = nprev; i < d; ++i)
             oxs[i] = OnlineX{S[i].colptr.p, S[i].rowidx.p, S[i].val.p, Lt[i].p, Bs[i].p, 1.0 / (double)mb[i], (int)ds_off[i], 0};
         DBuf<OnlineX> doxs(d);
         DBuf<int> t_dev(1);
@@ -1658,13 +1677,16 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         LGR_CUDA(cudaStreamSynchronize(st));
         auto one_iteration = [&]() {
             grams_now();
-            launch_online_ltx_all(doxs.p, d, d_sched.p, (int)mb_total, t_dev.p, Bmb.p, st);
-            solve_h(dgrp.p, d, mb_total);
-            launch_online_stats_all(dods.p, doxs.p, d, m, k, d_sched.p, (int)mb_total, t_dev.p, Hmb.p, st);
-            launch_online_hals(W.p, dhds.p, d, m, k, a->lambda, a->hals_iter, st);
+            launch_online_ltx_all(doxs.p + nprev, nnew, d_sched.p, (int)mb_total, t_dev.p, Bmb.p, st);
+            solve_h(dgrp.p + nprev, nnew, mb_total);
+            launch_online_stats_all(dods.p + nprev, doxs.p + nprev, nnew, m, k, d_sched.p, (int)mb_total, t_dev.p, Hmb.p, st);
+            // W from the statistics of ALL datasets, V_i of the new ones only
+            launch_online_hals(W.p, dhds.p, d, m, k, a->lambda, a->hals_iter, nprev, st);
             launch_online_next(t_dev.p, st);
         };
-        if (getenv("LGR_NO_GRAPH") || iters < 3) {
+        if (project) {
+            // scenario 3: nothing is learnt
+        } else if (getenv("LGR_NO_GRAPH") || iters < 3) {
             for (long long t = 1; t <= iters; ++t) one_iteration();
         } else {
             one_iteration();   // un-captured first pass: lazy per-kernel initialisation (function attributes) happens here
@@ -1696,7 +1718,7 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         std::vector<DBuf<unsigned long long>> mall(d);
         std::vector<NnlsGroup> gall(d);
         long long off = 0;
-        for (int i = 0; i < d; ++i) {
+        for (int i = nprev; i < d; ++i) {
             Hall[i].alloc((size_t)n[i] * kp);
             Ball[i].alloc((size_t)n[i] * kp);
             mall[i].alloc((size_t)n[i]);
@@ -1707,28 +1729,28 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         }
         DBuf<NnlsGroup> dgall(d);
         LGR_CUDA(cudaMemcpyAsync(dgall.p, gall.data(), sizeof(NnlsGroup) * d, cudaMemcpyHostToDevice, st));
-        solve_h(dgall.p, d, off);
+        solve_h(dgall.p + nprev, nnew, off);
         // objErr = sum_i ||X_i||^2 - 2 <H_i, B_i> + tr(H_i^T H_i (L~^T L~ + lambda V^T V))
         DBuf<double> acc((size_t)2 * d), G((size_t)d * kp * kp);
         acc.zero(st);
         G.zero(st);
         std::vector<OnlineDs> gds(d);
-        for (int i = 0; i < d; ++i) {
+        for (int i = nprev; i < d; ++i) {
             launch_online_sumsq(S[i].val.p, S[i].nnz, acc.p + 2 * i, st);
             launch_online_cross(Hall[i].p, Ball[i].p, (size_t)n[i] * kp, acc.p + 2 * i + 1, st);
             gds[i] = OnlineDs{Hall[i].p, n[i], G.p + (size_t)i * kp * kp};
         }
         DBuf<OnlineDs> dgds(d);
         LGR_CUDA(cudaMemcpyAsync(dgds.p, gds.data(), sizeof(OnlineDs) * d, cudaMemcpyHostToDevice, st));
-        launch_online_stats_a(dgds.p, d, k, 0.0, st);   // H^T H / n_i
+        launch_online_stats_a(dgds.p + nprev, nnew, k, 0.0, st);   // H^T H / n_i
         LGR_CUDA(cudaEventRecord(e1, st));
         std::vector<double> hacc((size_t)2 * d), hG((size_t)d * kp * kp), hgr((size_t)d * 4 * kp * kp);
         LGR_CUDA(cudaMemcpyAsync(hacc.data(), acc.p, sizeof(double) * hacc.size(), cudaMemcpyDeviceToHost, st));
         LGR_CUDA(cudaMemcpyAsync(hG.data(), G.p, sizeof(double) * hG.size(), cudaMemcpyDeviceToHost, st));
         LGR_CUDA(cudaMemcpyAsync(hgr.data(), grams.p, sizeof(double) * hgr.size(), cudaMemcpyDeviceToHost, st));
         LGR_CUDA(cudaStreamSynchronize(st));
-        double obj = 0.0;
-        for (int i = 0; i < d; ++i) {
+        double obj = 0.0;   // over the datasets that were read (scenario 2: the new ones)
+        for (int i = nprev; i < d; ++i) {
             double tr = 0.0;
             const double* ctc = hgr.data() + (size_t)i * 4 * kp * kp + 2 * kp * kp;   // L~^T L~ + lambda V^T V
             for (int x = 0; x < k; ++x)
@@ -1755,12 +1777,14 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
             copy_out(host, tmp.p, (size_t)rows * k * sizeof(double), st, false);
             LGR_CUDA(cudaStreamSynchronize(st));
         };
-        factor_out(W.p, m, o->W);
+        if (!project) factor_out(W.p, m, o->W);
         for (int i = 0; i < d; ++i) {
-            factor_out(V[i].p, m, o->V[i]);
-            if (o->B && o->B[i]) factor_out(Bs[i].p, m, o->B[i]);
-            if (o->A && o->A[i]) factor_out(A[i].p, k, o->A[i]);
-            if (o->H[i]) {
+            if (!project) {
+                if (o->V[i]) factor_out(V[i].p, m, o->V[i]);
+                if (o->B && o->B[i]) factor_out(Bs[i].p, m, o->B[i]);
+                if (o->A && o->A[i]) factor_out(A[i].p, k, o->A[i]);
+            }
+            if (i >= nprev && o->H[i]) {
                 DBuf<double> tmp((size_t)n[i] * k);
                 dev_hpad_to_colmajor(Hall[i].p, tmp.p, n[i], k, kp, st);
                 copy_out(o->H[i], tmp.p, (size_t)n[i] * k * sizeof(double), st, false);

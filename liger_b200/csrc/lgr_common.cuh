@@ -333,7 +333,7 @@ void launch_online_gram(const double* W, const double* const* V, int d, int m, i
 void launch_online_ltx(const int* colptr, const int* rowidx, const float* val, const int* cells, int nb, const float* Lt, float* B,
                        cudaStream_t st);
 void launch_online_stats_a(const OnlineDs* ds, int d, int k, double s, cudaStream_t st);
-void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double lambda, int sweeps, cudaStream_t st);
+void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double lambda, int sweeps, int first_v, cudaStream_t st);
 void launch_online_cross(const float* H, const float* B, size_t n, double* out, cudaStream_t st);
 void launch_online_sumsq(const float* x, size_t n, double* out, cudaStream_t st);
 // lgr_centroid.cu: centroidAlign on device-resident FP64 H (column-major n_i x k, read only) -> out (n_i x kd)

@@ -85,7 +85,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 constexpr int HALS_MAX_D = 16;   // datasets whose V row lives in registers (more: several passes would be needed)
 __global__ void __launch_bounds__(256) k_online_hals(double* __restrict__ W, const HalsDs* __restrict__ ds, int d, int m, int k,
-                                                     double lambda, int sweeps) {
+                                                     double lambda, int sweeps, int first_v) {
     extern __shared__ double As[];   // d x 32 x 33
     for (int e = threadIdx.x; e < d * OKP * OKP; e += blockDim.x) {
         const int i = e / (OKP * OKP), r = (e / OKP) % OKP, c = e % OKP;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_online_hals(double* __restrict__ W, con
         for (int j = 0; j < k; ++j) {          // V_i[, j]
 #pragma unroll
             for (int i = 0; i < HALS_MAX_D; ++i) {
-                if (i < d) {
+                if (i >= first_v && i < d) {   // (scenario 2: the V_i of the already factorised datasets stay as they are)
                     const double* Ai = As + (size_t)i * OKP * 33;
                     double p = live ? (w + (1.0 + lambda) * v[i]) * Ai[lane * 33 + j] : 0.0;
                     p = warp_sum(p);
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_online_hals(double* __restrict__ W, con
         W[(size_t)g * OKP + lane] = w;
 #pragma unroll
         for (int i = 0; i < HALS_MAX_D; ++i)
-            if (i < d) ds[i].V[(size_t)g * OKP + lane] = v[i];
+            if (i >= first_v && i < d) ds[i].V[(size_t)g * OKP + lane] = v[i];
     }
 }
 
@@ -229,7 +229,7 @@ void launch_online_stats_a(const OnlineDs* ds, int d, int k, double s, cudaStrea
     k_online_stats_a<<<d, 1024, 0, st>>>(ds, k, s);
     LGR_CUDA(cudaGetLastError());
 }
-void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double lambda, int sweeps, cudaStream_t st) {
+void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double lambda, int sweeps, int first_v, cudaStream_t st) {
     LGR_REQUIRE(d <= HALS_MAX_D, "online iNMF: at most 16 datasets");
     const size_t smem = (size_t)d * OKP * 33 * sizeof(double);
     static bool attr = false;
@@ -237,7 +237,7 @@ void launch_online_hals(double* W, const HalsDs* ds, int d, int m, int k, double
         LGR_CUDA(cudaFuncSetAttribute(k_online_hals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)HALS_MAX_D * OKP * 33 * sizeof(double))));
         attr = true;
     }
-    k_online_hals<<<(unsigned)(((size_t)m * 32 + 255) / 256), 256, smem, st>>>(W, ds, d, m, k, lambda, sweeps);
+    k_online_hals<<<(unsigned)(((size_t)m * 32 + 255) / 256), 256, smem, st>>>(W, ds, d, m, k, lambda, sweeps, first_v);
     LGR_CUDA(cudaGetLastError());
 }
 void launch_online_ltx_all(const OnlineX* xs, int d, const int* sched, int mb_total, const int* t_dev, float* B, cudaStream_t st) {

@@ -127,21 +127,39 @@ def runUINMF(scaleData, scaleUnsharedData, k=20, lambda_=5.0, nIteration=30, nRa
 def runOnlineINMF(scaleData, k=20, lambda_=5.0, newDatasets=None, projection=False, maxEpochs=5, HALSiter=1,
                   minibatchSize=5000, HInit=None, WInit=None, VInit=None, AInit=None, BInit=None, seed=1, nCores=2,
                   verbose=False):
-    """runOnlineINMF.liger, scenario 1 (R/integration.R:722-933): online iNMF of {dataset: scaleData} from scratch.
-    Returns dict(W, H={name: k x n_i}, V, A, B, objErr, uns).  Scenarios 2 and 3 (`newDatasets`) are not built."""
-    if newDatasets is not None or projection:
-        raise NotImplementedError("liger_b200: scenarios 2 and 3 of runOnlineINMF (newDatasets / projection) are not built")
-    if any(x is not None for x in (HInit, AInit, BInit)):
-        raise NotImplementedError("liger_b200: HInit / AInit / BInit belong to scenarios 2 and 3, which are not built")
-    if any(v is None for v in scaleData.values()):
-        raise ValueError("Scaled data not available. Run `scaleNotCenter()` first.")
+    """runOnlineINMF.liger (R/integration.R:722-933) over {dataset: scaleData}.  Scenario 1: online iNMF from scratch.
+    Scenario 2 (`newDatasets` = {name: scaleData of the new datasets}, already normalised and scaled -- the R front end does
+    that at :806-807): `scaleData` names the already factorised datasets, whose W / V / A / B (and H) come in as WInit, VInit,
+    AInit, BInit (HInit) dicts; everything is returned for old and new datasets.  Scenario 3 (`projection` = True): only H
+    of the new datasets, against WInit.  Returns dict(W, H={name: k x n_i}, V, A, B, objErr, uns)."""
     names = list(scaleData.keys())
-    res = api.online_inmf([scaleData[n] for n in names], k=k, lambda_=lambda_, maxEpochs=maxEpochs,
-                          minibatchSize=minibatchSize, HALSiter=HALSiter, Winit=WInit,
-                          Vinit=None if VInit is None else [VInit[n] if isinstance(VInit, dict) else v for n, v in zip(names, VInit)],
-                          seed=seed)
+    pick = lambda init, ns: None if init is None else [init[n] if isinstance(init, dict) else v for n, v in zip(ns, init)]
+    if newDatasets is None:
+        if projection:
+            raise ValueError("projection needs newDatasets")
+        if any(v is None for v in scaleData.values()):
+            raise ValueError("Scaled data not available. Run `scaleNotCenter()` first.")
+        res = api.online_inmf([scaleData[n] for n in names], k=k, lambda_=lambda_, maxEpochs=maxEpochs,
+                              minibatchSize=minibatchSize, HALSiter=HALSiter, Winit=WInit, Vinit=pick(VInit, names), seed=seed)
+        out_names = names
+    else:
+        new_names = list(newDatasets.keys())
+        if any(n in scaleData for n in new_names):
+            raise ValueError("Names of `newDatasets` overlap with existing datasets.")
+        if WInit is None or (not projection and any(x is None for x in (VInit, AInit, BInit))):
+            raise ValueError("Cannot find complete online iNMF result for current datasets. "
+                             "Please run `runOnlineINMF()` without `newDataset` first")
+        res = api.online_inmf([scaleData[n] for n in names], k=k, lambda_=lambda_, maxEpochs=maxEpochs,
+                              minibatchSize=minibatchSize, HALSiter=HALSiter, Winit=WInit, Vinit=pick(VInit, names),
+                              Ainit=pick(AInit, names), Binit=pick(BInit, names),
+                              Hinit=None if HInit is None else [np.asarray(h).T for h in pick(HInit, names)], seed=seed,
+                              newDatasets=[newDatasets[n] for n in new_names], projection=projection)
+        if projection:   # scenario 3: only H of the new datasets (R/integration.R:839-849)
+            return {"H": {n: h.T for n, h in zip(new_names, res["H"])}, "uns": {"factorization": {"k": k, "lambda": lambda_}}}
+        out_names = names + new_names
+    names = out_names
     out = {"W": res["W"], "objErr": res["objErr"], "uns": {"factorization": {"k": k, "lambda": lambda_}}}
-    out["H"] = {n: h.T for n, h in zip(names, res["H"])}            # k x n_i, as the R wrapper stores them (:924)
+    out["H"] = {n: (None if h is None else h.T) for n, h in zip(names, res["H"])}   # k x n_i, as the R wrapper stores them (:924)
     for key in ("V", "A", "B"):
         out[key] = dict(zip(names, res[key]))
     return out

@@ -850,7 +850,7 @@ def test_centroid_align_errors_and_resident(pbmc):
 
 
 # ----------------------------------------------------------------------------------------------
-# online iNMF, scenario 1 (f4; R/integration.R:722-933 -> RcppPlanc::onlineINMF) -- parity unpinned in the reference
+# online iNMF, scenarios 1-3 (f4; R/integration.R:722-933 -> RcppPlanc::onlineINMF) -- parity unpinned in the reference
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("k,mbs,epochs,hals", [(10, 100, 3, 1), (20, 250, 2, 2)])
 def test_online_inmf_matches_oracle(pbmc, k, mbs, epochs, hals):
@@ -884,8 +884,38 @@ def test_online_inmf_front_end_and_inits(pbmc):
     assert rel(fit["W"], ref["W"]) < TOL_FACTOR and rel(fit["H"]["stim"].T, ref["H"][1]) < TOL_FACTOR
     with pytest.raises(ValueError, match="should be less than the number of cells"):
         liger_b200.online_inmf([Es[0][:, :5], Es[1]], k=8)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="Cannot find complete online iNMF result"):
         integration.runOnlineINMF(data, k=8, newDatasets={"x": Es[0]})
+    with pytest.raises(ValueError, match="overlap with existing datasets"):
+        integration.runOnlineINMF(data, k=8, newDatasets={"ctrl": Es[0]}, WInit=W0, VInit=V0)
+
+
+@pytest.mark.parametrize("k,mbs,epochs,hals", [(10, 60, 3, 1), (16, 100, 2, 2)])
+def test_online_inmf_new_datasets_and_projection(pbmc, k, mbs, epochs, hals):
+    """Scenarios 2 and 3 of runOnlineINMF (R/integration.R:755-812, 839-849): `stim` arrives after `ctrl` has been factorised.
+    Scenario 2 learns W and the new dataset's V / A / B / H from the new cells only, with the old dataset's statistics in the
+    W updates and its V / A / B untouched; scenario 3 only solves H against the given W.  Against the numpy restatement
+    from the same state and seed."""
+    import liger_b200
+    from liger_b200 import integration
+    from oracle import online_oracle as oo
+    ctrl, stim = pbmc["Es"]
+    first = oo.online_inmf([ctrl], k, 5.0, max_epochs=2, minibatch_size=75, seed=1)
+    ref = oo.online_inmf_new_datasets(first["W"], first["V"], first["A"], first["B"], [stim], k, 5.0, max_epochs=epochs,
+                                      minibatch_size=mbs, hals_iter=hals, seed=2)
+    fit = integration.runOnlineINMF({"ctrl": ctrl}, k=k, newDatasets={"stim": stim}, maxEpochs=epochs, minibatchSize=mbs,
+                                    HALSiter=hals, seed=2, WInit=first["W"], VInit={"ctrl": first["V"][0]},
+                                    AInit={"ctrl": first["A"][0]}, BInit={"ctrl": first["B"][0]}, HInit={"ctrl": first["H"][0].T})
+    assert rel(fit["W"], ref["W"]) < TOL_FACTOR
+    assert np.array_equal(fit["V"]["ctrl"], first["V"][0]) and np.array_equal(fit["A"]["ctrl"], first["A"][0])
+    assert np.array_equal(fit["B"]["ctrl"], first["B"][0]) and np.array_equal(fit["H"]["ctrl"], first["H"][0].T)
+    assert rel(fit["V"]["stim"], ref["V"][1]) < TOL_FACTOR and rel(fit["H"]["stim"].T, ref["H"][0]) < TOL_FACTOR
+    assert rel(fit["A"]["stim"], ref["A"][1]) < TOL_FACTOR and rel(fit["B"]["stim"], ref["B"][1]) < TOL_FACTOR
+    assert abs(fit["objErr"] - ref["objErr"]) < TOL_OBJ * ref["objErr"]
+    assert not np.allclose(fit["W"], first["W"])                      # W did move
+    proj = integration.runOnlineINMF({"ctrl": ctrl}, k=k, newDatasets={"stim": stim}, projection=True, WInit=first["W"])
+    assert set(proj.keys()) == {"H", "uns"} and proj["H"]["stim"].shape == (k, 300)
+    assert rel(proj["H"]["stim"].T, oo.project(first["W"], [stim])[0]) < TOL_FACTOR
 
 
 def test_alignment_and_online_fuzz():
