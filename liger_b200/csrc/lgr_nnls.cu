@@ -554,7 +554,10 @@ void launch_nnls(bool is_double, const NnlsGroup* groups, int ngroups, long long
     const int threads = nw * 32;
     const size_t smem = nnls_layout(kp, nw, cfg.pool_elems, is_double ? 8 : 4).total;
     long long want = (total_cols + threads - 1) / threads;   // at least one column per lane
-    const int grid = (int)(want < cfg.grid_cap ? want : cfg.grid_cap);
+    int grid = (int)(want < cfg.grid_cap ? want : cfg.grid_cap);
+    // mop-up launches (flag 16: only what the fast kernels left behind, normally nothing) pay for their empty pass: one CTA
+    // per SM at most, so that the pass is a single wave of CTAs that exit at once
+    if ((flags & 16) && grid > num_sms) grid = num_sms;
     if (is_double) {
         if (kp == 32)
             k_nnls<double, 32><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cfg.pool_elems, cnt, flags);

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
     float* stage = wbase + lane * 4;
     float* zcol = wbase + 4 * RBUF + lane;
     __shared__ int next_col;
-    __shared__ int hist[18];
+    __shared__ int hist[36];   // bins (side, system size): 17 primal, 17 dual; [34] = systems above 8 unknowns
     __shared__ unsigned short order[RSUBK];
     Mask* fmask = reinterpret_cast<Mask*>(smem_raw + L.fmask);   // warm-start passive sets of the pass
 
@@ -329,43 +329,44 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         unsigned long long* __restrict__ masks_g = grp.mask + c0;
         const float* __restrict__ upre_g = grp.u ? reinterpret_cast<const float*>(grp.u) + (size_t)c0 * RKP : nullptr;
       for (int sub0 = 0; sub0 < ccols; sub0 += RSUBK) {
-        // ---- order this sub-chunk's columns by the size of the system their warm start implies (largest first):
-        //      the lanes of a warp then solve systems of similar size and the small templates are actually used ----
+        // ---- order this sub-chunk's columns by the side and the size of the system their warm start implies (primal
+        //      systems first, largest first): the lanes of a warp then solve systems of similar size (the small templates
+        //      are actually used) from the same matrix (G or P: the 128-bit row reads of the dense products are then
+        //      one broadcast per warp instead of two) ----
         const int nsub = min(RSUBK, ccols - sub0);
         const float* __restrict__ rhs = rhs_g + (size_t)sub0 * RKP;
         float* __restrict__ xout = xout_g + (size_t)sub0 * RKP;
         unsigned long long* __restrict__ masks = masks_g + sub0;
         const float* __restrict__ upre = upre_g ? upre_g + (size_t)sub0 * RKP : nullptr;
         __syncthreads();   // previous sub-chunk fully drained (order[] / counters are reused)
-        if (tid < 18) hist[tid] = 0;
+        for (int e = tid; e < 36; e += blockDim.x) hist[e] = 0;   // (a small batch runs with a single warp)
         __syncthreads();
+        const bool by_side = (flags & 64) == 0;   // (developer knob LGR_NNLS_REG_NOSIDE: order by size only)
+        auto bin_of = [&](int p) { return ((by_side && (k - p) < p) ? 17 : 0) + 16 - min(min(p, k - p), 16); };
         for (int c = tid; c < nsub; c += blockDim.x) {
             const Mask f0 = cold_start ? (Mask)0 : ((Mask)masks[c] & kmask);
             fmask[c] = f0;
-            const int p = popc_m(f0);
-            atomicAdd(&hist[16 - min(min(p, k - p), 16)], 1);
+            atomicAdd(&hist[bin_of(popc_m(f0))], 1);
         }
         __syncthreads();
         if (tid == 0) {
-            int run = 0;
-            for (int b = 0; b < 17; ++b) {
+            int run = 0, big = 0;
+            for (int b = 0; b < 34; ++b) {
                 const int h = hist[b];
+                if (b % 17 < 8) big += h;   // systems of more than 8 unknowns
                 hist[b] = run;
                 run += h;
-                if (b == 7) hist[17] = run;   // columns whose system has more than 8 unknowns
             }
+            hist[34] = big;
             next_col = 0;
         }
         __syncthreads();
-        for (int c = tid; c < nsub; c += blockDim.x) {
-            const int p = popc_m(fmask[c]);
-            order[atomicAdd(&hist[16 - min(min(p, k - p), 16)], 1)] = (unsigned short)c;
-        }
+        for (int c = tid; c < nsub; c += blockDim.x) order[atomicAdd(&hist[bin_of(popc_m(fmask[c]))], 1)] = (unsigned short)c;
         __syncthreads();
 
         // round barrier only while the big unrolled templates dominate (they do not fit the instruction cache: the
         // warps then walk the code together); a pass of mostly small systems runs barrier-free
-        const bool sync_pass = sync_rounds && hist[17] * 4 > nsub;
+        const bool sync_pass = sync_rounds && hist[34] * 4 > nsub;
         bool active = false, exhausted = false, have_u = false;
         int col = 0, state = 0, nxt = -1;
         Mask F = 0;
@@ -523,7 +524,8 @@ void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols,
     long long want = (total_cols + threads - 1) / threads;
     const int grid = (int)(want < num_sms ? want : num_sms);
     static const bool sync_rounds = getenv("LGR_NNLS_REG_NOSYNC") == nullptr;
-    const int fl = flags | (sync_rounds ? 32 : 0);
+    static const bool no_side = getenv("LGR_NNLS_REG_NOSIDE") != nullptr;
+    const int fl = flags | (sync_rounds ? 32 : 0) | (no_side ? 64 : 0);
     if (kp == 32)
         k_nnls_reg<32><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, fl);
     else
