@@ -351,7 +351,8 @@ def roofline_of(job, res, args, hbm_peak, peak_src, with_traffic):
             tf_peak = 1400.0
         cfg = job.cfg
         gp = ((cfg["m"] + 63) // 64) * 64
-        flops = 2.0 * 128 * gp * job.n_local      # per sweep: every (cell, gene) pair meets the 128-row operand slab once
+        halves = 2 if cfg["k"] > 32 else 1        # k > 32: one pass per half of the factors
+        flops = 2.0 * 128 * gp * job.n_local * halves   # per sweep: every (cell, gene) pair meets the 128-row operand slab once per pass
         tensor = {"peak_tflops": tf_peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM, seconds-long loop)",
                   "note": "flops of the issued tcgen05.mma tiles (128 x 256 x 16 bf16, 96 of the 128 rows carry data)"}
         for kn in ("k_dense_ltx", "k_dense_xh"):
