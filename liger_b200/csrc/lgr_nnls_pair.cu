@@ -12,8 +12,13 @@
 //     exchange it by shuffles (one per entry) and update their own rows -- every update is an independent FMA on registers;
 //   * forward substitution runs on the owner of each row, backward substitution sums the two lanes' partial columns; the
 //     solution is replicated in both lanes by shuffles;
-//   * the k-vector products (u = P b, x = u - P_:A y_A, y = G_:F x_F - b) are split by coordinate: lane p owns factors
-//     32 p .. 32 p + 31 (128-bit reads of the matrix rows, shared by all lanes of the same parity);
+//   * the k-vector products x = u - P_:A y_A, y = G_:F x_F - b are split by coordinate: lane p owns the 16-byte chunks
+//     2 c + p of a factor row (factors 8 c + 4 p .. + 3, c = 0 .. 7), so the two parities read neighbouring chunks of a
+//     matrix row -- with a contiguous split (factors 32 p ..) they were 128 bytes apart, the same banks: ncu counted 8
+//     shared-memory wavefronts per 128-bit read instead of 4, and these reads are 86 % of the kernel's wavefronts;
+//   * u = P b (once per column, when it first takes the dual side) is computed by the WHOLE warp for one column at a time
+//     (lane f: u_f and u_f+32, columns of the symmetric P read conflict free): a round in which one pair needs u no longer
+//     makes all sixteen pairs run the 400 row reads of a product;
 //   * b, u and the expanded solution of the pair's column sit in per-warp shared-memory tiles [factor][column of the warp].
 //
 // Measured on one GPU's shard of C4 (500 k columns, k = 50, first iterations): the warp-per-column Gauss-Jordan kernel
@@ -38,6 +43,8 @@ constexpr unsigned long long PDEFER = 1ull << 63;
 constexpr unsigned FULL = 0xffffffffu;
 
 __host__ __device__ constexpr int poff(int m) { return m * (m + 1); }   // first register of local row m (capacity 2 m + 2)
+// factor owned by lane parity p at local position q = 4 c + e: chunk 2 c + p of the row, element e
+__device__ __forceinline__ int fown(int q, int p) { return ((q >> 2) << 3) + 4 * p + (q & 3); }
 
 __device__ __forceinline__ void pffma2(float& d0, float& d1, float a0, float a1, float b) {
     unsigned long long d, a, bb;
@@ -139,7 +146,7 @@ template <int SMAX>
 __device__ __forceinline__ bool round_pair(const int k, const unsigned long long kmask, const bool dual, const unsigned long long S,
                                            const float* __restrict__ Mat, const float* bt, const float* ut, float* zc,
                                            unsigned long long& F, int& state, const float tol, const int MAXIT, Counters* cnt,
-                                           unsigned long long& pivots, float* __restrict__ xhalf, const bool live, const int p,
+                                           unsigned long long& pivots, float* __restrict__ xrow, const bool live, const int p,
                                            const int lane) {
     constexpr int M = SMAX / 2;
     constexpr int NR = poff(M);
@@ -209,20 +216,19 @@ __device__ __forceinline__ bool round_pair(const int k, const unsigned long long
         }
     }
     __syncwarp();
-    // ---- the k-vector of the other side, this lane's 32 coordinates:  dual  x = u + P (sgn z),  primal  y = -b + G (sgn z) ----
+    // ---- the k-vector of the other side, this lane's 32 coordinates (fown):  dual  x = u + P (sgn z),  primal  y = -b + G (sgn z) ----
     float acc[32];
     {
-        const float* rh = rhs + (32 * p) * PCW;
         const float sg0 = dual ? 1.f : -1.f;
 #pragma unroll
-        for (int f = 0; f < 32; ++f) acc[f] = sg0 * rh[f * PCW];
+        for (int f = 0; f < 32; ++f) acc[f] = sg0 * rhs[fown(f, p) * PCW];
     }
     for (int g = 0; g < k; ++g) {
         const float zg = zc[g * PCW];
-        const float4* row = reinterpret_cast<const float4*>(Mat + g * PMST + 32 * p);
+        const float4* row = reinterpret_cast<const float4*>(Mat + g * PMST) + p;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const float4 m4 = row[c];
+            const float4 m4 = row[2 * c];
             pffma2(acc[4 * c + 0], acc[4 * c + 1], m4.x, m4.y, zg);
             pffma2(acc[4 * c + 2], acc[4 * c + 3], m4.z, m4.w, zg);
         }
@@ -242,10 +248,13 @@ __device__ __forceinline__ bool round_pair(const int k, const unsigned long long
         uint32_t neg = 0;
 #pragma unroll
         for (int f = 0; f < 32; ++f) neg |= (acc[f] < -thr) ? (1u << f) : 0u;
-        const unsigned long long other = dual ? F : ((~F) & kmask);
-        neg &= (uint32_t)(other >> (32 * p));
-        const uint32_t lo = __shfl_sync(FULL, neg, lane & ~1), hi = __shfl_sync(FULL, neg, lane | 1);
-        infeas |= (unsigned long long)lo | ((unsigned long long)hi << 32);
+        // local bit 4 c + e is factor 8 c + 4 p + e: spread the nibbles, mask with the other side's set, merge the two lanes
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mine |= (unsigned long long)((neg >> (4 * c)) & 0xFu) << (8 * c + 4 * p);
+        mine &= dual ? F : ((~F) & kmask);
+        const uint32_t plo = __shfl_xor_sync(FULL, (uint32_t)mine, 1), phi = __shfl_xor_sync(FULL, (uint32_t)(mine >> 32), 1);
+        infeas |= mine | (unsigned long long)plo | ((unsigned long long)phi << 32);
     }
     int alpha = state & 0xff, beta = (state >> 8) & 0xff, iter = state >> 16;
     if (!live) return false;
@@ -268,18 +277,18 @@ __device__ __forceinline__ bool round_pair(const int k, const unsigned long long
         return true;
     }
     if (infeas != 0ull && !p) atomicAdd(&cnt->nnls_unconverged, 1ull);
-    // ---- solved: this lane's half of the x row ----
+    // ---- solved: this lane's chunks of the x row ----
     if (dual) {
 #pragma unroll
         for (int f = 0; f < 32; ++f)
-            if (!((F >> (32 * p + f)) & 1ull) || !(acc[f] > 0.f)) acc[f] = 0.f;
+            if (!((F >> fown(f, p)) & 1ull) || !(acc[f] > 0.f)) acc[f] = 0.f;
     } else {
 #pragma unroll
-        for (int f = 0; f < 32; ++f) acc[f] = fmaxf(zc[(32 * p + f) * PCW], 0.f);
+        for (int f = 0; f < 32; ++f) acc[f] = fmaxf(zc[fown(f, p) * PCW], 0.f);
     }
-    float4* x4 = reinterpret_cast<float4*>(xhalf);
+    float4* x4 = reinterpret_cast<float4*>(xrow) + p;   // chunks 2 c + p of the 64-float row
 #pragma unroll
-    for (int c = 0; c < 8; ++c) x4[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+    for (int c = 0; c < 8; ++c) x4[2 * c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
     return false;
 }
 
@@ -394,11 +403,11 @@ __global__ void __launch_bounds__(PWARPS * 32, 1) k_nnls_pair(const NnlsGroup* _
                         if (wants) {
                             if (ci < nflag) {
                                 col = order[ci];
-                                const float4* b4 = reinterpret_cast<const float4*>(rhs + (size_t)col * PKP + 32 * p);
+                                const float4* b4 = reinterpret_cast<const float4*>(rhs + (size_t)col * PKP) + p;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float4 v = __ldg(b4 + i);
-                                    float* dst = bt + (32 * p + 4 * i) * PCW;
+                                    const float4 v = __ldg(b4 + 2 * i);
+                                    float* dst = bt + (8 * i + 4 * p) * PCW;
                                     dst[0] = v.x;
                                     dst[PCW] = v.y;
                                     dst[2 * PCW] = v.z;
@@ -437,39 +446,40 @@ __global__ void __launch_bounds__(PWARPS * 32, 1) k_nnls_pair(const NnlsGroup* _
                         dual = false;
                     }
                 }
-                // ---- u = P b, once per column, when it first takes the dual side: this lane's 32 coordinates ----
-                if (__any_sync(FULL, active && dual && !have_u)) {
-                    const bool need = active && dual && !have_u;
-                    float acc[32];
-#pragma unroll
-                    for (int f = 0; f < 32; ++f) acc[f] = 0.f;
-                    for (int t = 0; t < k; ++t) {
-                        const float bv = bt[t * PCW];
-                        const float4* row = reinterpret_cast<const float4*>(Ps + t * PMST + 32 * p);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float4 m4 = row[c];
-                            pffma2(acc[4 * c + 0], acc[4 * c + 1], m4.x, m4.y, bv);
-                            pffma2(acc[4 * c + 2], acc[4 * c + 3], m4.z, m4.w, bv);
-                        }
-                    }
+                // ---- u = P b, once per column, when it first takes the dual side.  The whole warp works on one column at a time:
+                //      lane f forms u_f and u_f+32 from columns f, f + 32 of the symmetric P (consecutive words: conflict free)
+                //      and b broadcast from the tile ----
+                {
+                    unsigned need = __ballot_sync(FULL, active && dual && !have_u && !p);
                     if (need) {
-#pragma unroll
-                        for (int f = 0; f < 32; ++f) ut[(32 * p + f) * PCW] = acc[f];
-                        have_u = true;
+                        while (need) {
+                            const int cwn = (__ffs((int)need) - 1) >> 1;
+                            need &= need - 1;
+                            const float* bcol = wbase + cwn;
+                            float a0 = 0.f, a1 = 0.f;
+                            for (int t = 0; t < k; ++t) {
+                                const float bv = bcol[t * PCW];
+                                a0 = fmaf(Ps[t * PMST + lane], bv, a0);
+                                a1 = fmaf(Ps[t * PMST + 32 + lane], bv, a1);
+                            }
+                            float* ucol = wbase + PTILE + cwn;
+                            ucol[lane * PCW] = a0;
+                            ucol[(32 + lane) * PCW] = a1;
+                        }
+                        if (active && dual) have_u = true;
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
                 const bool big = __syncthreads_or(s > 22) != 0;
                 const float* Mat = dual ? Ps : Gs;
-                float* xhalf = xout + (size_t)col * PKP + 32 * p;
+                float* xrow = xout + (size_t)col * PKP;
                 // every lane runs the round (an idle pair solves an identity system into its own tile column and registers):
                 // the shuffles and warp barriers inside are unconditional
                 bool still;
                 if (!big)
-                    still = round_pair<22>(k, kmask, dual, S, Mat, bt, ut, zc, F, state, tol, MAXIT, cnt, pivots_local, xhalf, active, p, lane);
+                    still = round_pair<22>(k, kmask, dual, S, Mat, bt, ut, zc, F, state, tol, MAXIT, cnt, pivots_local, xrow, active, p, lane);
                 else
-                    still = round_pair<26>(k, kmask, dual, S, Mat, bt, ut, zc, F, state, tol, MAXIT, cnt, pivots_local, xhalf, active, p, lane);
+                    still = round_pair<26>(k, kmask, dual, S, Mat, bt, ut, zc, F, state, tol, MAXIT, cnt, pivots_local, xrow, active, p, lane);
                 if (active) {
                     if (!still) {
                         if (!p) masks[col] = F;   // clears the flag
