@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(PWARPS * 32, 1) k_nnls_pair(const NnlsGroup* _
     float* ut = wbase + PTILE + cw;       // u = P b
     float* zc = wbase + 2 * PTILE + cw;   // expanded solution
     __shared__ int next_col;
-    __shared__ int hist[34];
+    __shared__ int hist[68];   // bins (side, system size): 33 primal, 33 dual; [66] = flagged columns of the pass
     const unsigned long long kmask = (1ull << k) - 1ull;   // k <= 62
     const int MAXIT = 4 * k + 16;
     if (!p) {   // rhs of the padding unknowns
@@ -350,38 +350,35 @@ __global__ void __launch_bounds__(PWARPS * 32, 1) k_nnls_pair(const NnlsGroup* _
             const float* __restrict__ rhs = rhs_g + (size_t)sub0 * PKP;
             float* __restrict__ xout = xout_g + (size_t)sub0 * PKP;
             unsigned long long* __restrict__ masks = masks_g + sub0;
-            // ---- the flagged columns of this pass, ordered by the size of their system (largest first) ----
+            // ---- the flagged columns of this pass, ordered by the side and the size of their system (primal first, largest
+            //      first): the pairs of a warp then read the rows of ONE matrix in the products (two distinct 16-byte
+            //      addresses per 128-bit read -- the two parities -- instead of four) ----
             __syncthreads();
-            if (tid < 34) hist[tid] = 0;
+            if (tid < 68) hist[tid] = 0;
             __syncthreads();
+            auto bin_of = [&](int pc) { return ((k - pc) < pc ? 33 : 0) + 32 - min(min(pc, k - pc), 32); };
             for (int c = tid; c < nsub; c += blockDim.x) {
                 const unsigned long long mk = masks[c];
-                if (mk & PDEFER) {
-                    const int pc = __popcll(mk & kmask);
-                    atomicAdd(&hist[32 - min(min(pc, k - pc), 32)], 1);
-                }
+                if (mk & PDEFER) atomicAdd(&hist[bin_of(__popcll(mk & kmask))], 1);
             }
             __syncthreads();
             if (tid == 0) {
                 int run = 0;
-                for (int b = 0; b < 33; ++b) {
+                for (int b = 0; b < 66; ++b) {
                     const int h = hist[b];
                     hist[b] = run;
                     run += h;
                 }
-                hist[33] = run;   // flagged columns of the pass
+                hist[66] = run;   // flagged columns of the pass
                 next_col = 0;
             }
             __syncthreads();
             for (int c = tid; c < nsub; c += blockDim.x) {
                 const unsigned long long mk = masks[c];
-                if (mk & PDEFER) {
-                    const int pc = __popcll(mk & kmask);
-                    order[atomicAdd(&hist[32 - min(min(pc, k - pc), 32)], 1)] = (unsigned short)c;
-                }
+                if (mk & PDEFER) order[atomicAdd(&hist[bin_of(__popcll(mk & kmask))], 1)] = (unsigned short)c;
             }
             __syncthreads();
-            const int nflag = hist[33];
+            const int nflag = hist[66];
             if (nflag == 0) continue;   // CTA-uniform
 
             bool active = false, exhausted = false, have_u = false;
