@@ -450,7 +450,10 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 // every fresh column takes it first and starts from F = {u > 0}, the support of the clipped unconstrained
                 // solution, instead of from the empty set (which reaches the same point two rounds later)
                 const bool seed = state == (3 | ((k + 1) << 8)) && F == 0 && !have_u;
-                if ((dual || seed) && !have_u) {
+                // (a column that is about to be handed over -- more than 16 unknowns, k > 32 -- does not need u here: the
+                //  continuation kernel forms its own)
+                const bool hand_over = KP > 32 && s > 16 && !seed;
+                if ((dual || seed) && !have_u && !hand_over) {
                     float acc[RKP];
 #pragma unroll
                     for (int f = 0; f < RKP; ++f) acc[f] = 0.f;
