@@ -601,10 +601,15 @@ def main():
             gc.collect()
             torch.cuda.empty_cache()
             c4 = dict(CONFIGS["C4"])
-            j4 = Job(c4, c4["n_per"] // world, rank, world, local_rank, nccl_id, pin=False)
+            # same placement rule as the headline run: 16 datasets over 8 ranks = two whole datasets per GPU, unless cell
+            # sharding was asked for
+            p4 = "datasets" if args.placement != "cells" else "cells"
+            j4 = Job(c4, c4["n_per"] if p4 == "datasets" else c4["n_per"] // world, rank, world, local_rank, nccl_id, pin=False,
+                     placement=p4)
             r4 = timed_runs(j4, args, barrier, allmax)
             rf4 = roofline_of(j4, r4, args, hbm_peak, peak_src, False)
-            extra["C4"] = {"workload": "C4: 16 datasets x 250000 cells x 3000 genes (4 M cells) split over 8 GPUs, 5% density, k=50",
+            extra["C4"] = {"workload": "C4: 16 datasets x 250000 cells x 3000 genes (4 M cells) over 8 GPUs (" +
+                                       ("two whole datasets per GPU" if p4 == "datasets" else "cell shards") + "), 5% density, k=50",
                            "total_cells": j4.n_total, "value": j4.n_total * args.steps / (r4["loop_ms"] * 1e-3),
                            "ms_per_step": r4["loop_ms"] / args.steps, "warm_ms_per_step": r4["warm_ms"] / args.steps,
                            "comm_ms_per_step": r4["comm_ms"] / args.steps, "objErr": r4["obj"],
