@@ -192,3 +192,34 @@ def test_quantile_norm_oracle_pieces():
     # max_factor: first maximum of the scaled columns, -1 for an all-zero row
     H = np.array([[1.0, 2.0], [3.0, 0.5], [0.0, 0.0], [2.0, 2.0]])
     assert qn.max_factor(H).tolist() == [2, 1, -1, 2]
+
+
+def test_online_oracle_scenarios(pbmc):
+    """The online iNMF restatement (unpinned against RcppPlanc, see its header): scenario 1 lowers the objective with more
+    epochs; scenario 2 leaves the already factorised dataset's V / A / B alone, moves W, and fits the new dataset better
+    than a projection onto the old W does; scenario 3 is the plain non-negative projection onto W."""
+    from oracle import online_oracle as oo
+    ctrl, stim = pbmc["Es"]
+    k = 8
+    a = oo.online_inmf([ctrl, stim], k, 5.0, max_epochs=1, minibatch_size=100, seed=1)
+    b = oo.online_inmf([ctrl, stim], k, 5.0, max_epochs=4, minibatch_size=100, seed=1)
+    assert b["objErr"] < a["objErr"] and b["iterations"] == 4 * a["iterations"] == 24
+    first = oo.online_inmf([ctrl], k, 5.0, max_epochs=2, minibatch_size=75, seed=1)
+    keep = [x.copy() for x in (first["V"][0], first["A"][0], first["B"][0])]
+    s2 = oo.online_inmf_new_datasets(first["W"], first["V"], first["A"], first["B"], [stim], k, 5.0, max_epochs=3,
+                                     minibatch_size=60, seed=2)
+    assert s2["iterations"] == 300 * 3 // 60 and len(s2["V"]) == 2 and len(s2["H"]) == 1
+    assert all(np.array_equal(x, y) for x, y in zip(keep, (s2["V"][0], s2["A"][0], s2["B"][0])))
+    assert not np.allclose(s2["W"], first["W"]) and s2["W"].min() > 0 and s2["V"][1].min() > 0
+    Hp = oo.project(first["W"], [stim])[0]
+    assert Hp.shape == (300, k) and Hp.min() >= 0
+    resid = lambda W, V, H: float(np.linalg.norm(stim.toarray() - (W + V) @ H.T))
+    assert resid(s2["W"], s2["V"][1], s2["H"][0]) < resid(first["W"], np.zeros_like(first["W"]), Hp)
+    # the projection is the NNLS solution: no feasible perturbation of a cell's loadings lowers its residual
+    j = 17
+    x = stim[:, j].toarray().ravel()
+    base = np.linalg.norm(x - first["W"] @ Hp[j])
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        h = np.maximum(Hp[j] + 1e-3 * rng.standard_normal(k), 0.0)
+        assert np.linalg.norm(x - first["W"] @ h) >= base - 1e-12
