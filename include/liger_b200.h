@@ -245,6 +245,26 @@ typedef struct lgr_online_out {
 } lgr_online_out;
 LGR_API int lgr_online_inmf(const lgr_online_args* args, lgr_online_out* out);
 
+/* ---- online iNMF over matrices that are not in host memory as a whole.  The reference streams them from disk: scaleData kept
+   in an HDF5 group is wrapped as RcppPlanc's H5SpMat (R/integration.R:745-750, .H5GroupToH5SpMat R/h5Utility.R:356-363) and
+   read chunk by chunk.  Here the caller supplies a reader of column chunks; the library pulls every dataset through it once
+   (chunk_cols columns at a time) into its resident fp32 copy in HBM -- 180 GB hold ~2e10 non-zeros, so the device is the
+   cache the on-disk path lacks -- and then runs exactly lgr_online_inmf's loop.  args->E[i] carries only nrow / ncol for the
+   datasets that are read (pointers ignored).  The reader fills, for columns [col0, col0 + ncol) of `dataset`: colptr
+   (ncol + 1 entries, starting at 0), rowidx and values (at most `capacity` entries) and returns the chunk's number of
+   non-zeros; if the chunk does not fit it returns -(needed capacity) and is called again; any other negative value aborts
+   (LGR_ERR_INVALID).  It is also asked for single columns (the k cells a new V_i starts from). ---- */
+typedef int64_t (*lgr_read_cols_fn)(void* user, int32_t dataset, int64_t col0, int64_t ncol, int32_t* colptr, int32_t* rowidx,
+                                    double* values, int64_t capacity);
+typedef struct lgr_chunk_source {
+    lgr_read_cols_fn read_cols;
+    void* user;
+    const int64_t* nnz;      /* d entries: non-zeros of every dataset (HDF5: the length of its data array) */
+    int64_t chunk_cols;      /* [1000] columns per call */
+    int64_t max_chunk_nnz;   /* first guess of the capacity (the reader can ask for more) */
+} lgr_chunk_source;
+LGR_API int lgr_online_inmf_chunked(const lgr_online_args* args, const lgr_chunk_source* src, lgr_online_out* out);
+
 /* ---- factor alignment: quantileNorm (R/integration.R:1621-1711 .quantileNorm.HList; src/quantile_norm.cpp:8-67
    max_factor_rcpp / cluster_vote_rcpp; RANN::nn2 = ANN 1.1.2 kd-tree search; stats::quantile type 7; stats::approxfun
    rule = 2; base::sample) -- the consumer of the H_i, run where they live.  Defaults of the reference in brackets. ---- */

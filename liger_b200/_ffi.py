@@ -63,6 +63,15 @@ class lgr_online_args(C.Structure):
                 ("n_prev", C.c_int32), ("pad1", C.c_int32), ("Ainit", C.POINTER(c_double_p)), ("Binit", C.POINTER(c_double_p))]
 
 
+READ_COLS_FN = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                           C.POINTER(C.c_double), C.c_int64)
+
+
+class lgr_chunk_source(C.Structure):
+    _fields_ = [("read_cols", READ_COLS_FN), ("user", C.c_void_p), ("nnz", C.POINTER(C.c_int64)), ("chunk_cols", C.c_int64),
+                ("max_chunk_nnz", C.c_int64)]
+
+
 class lgr_online_out(C.Structure):
     _fields_ = [("W", c_double_p), ("V", C.POINTER(c_double_p)), ("H", C.POINTER(c_double_p)), ("A", C.POINTER(c_double_p)),
                 ("B", C.POINTER(c_double_p)), ("objErr", C.c_double), ("iterations", C.c_int32), ("pad0", C.c_int32),
@@ -93,7 +102,7 @@ _lib = None
 EXPORTS = [
     "lgr_inmf", "lgr_uinmf", "lgr_bppnnls_prod", "lgr_objerr_i", "lgr_ctx_create", "lgr_ctx_reset",
     "lgr_ctx_iterate", "lgr_ctx_run", "lgr_ctx_objective", "lgr_ctx_solve", "lgr_ctx_set_factors", "lgr_ctx_products",
-    "lgr_ctx_objerr_i", "lgr_quantile_norm", "lgr_ctx_quantile_norm", "lgr_centroid_align", "lgr_ctx_centroid_align", "lgr_online_inmf", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
+    "lgr_ctx_objerr_i", "lgr_quantile_norm", "lgr_ctx_quantile_norm", "lgr_centroid_align", "lgr_ctx_centroid_align", "lgr_online_inmf", "lgr_online_inmf_chunked", "lgr_ctx_download", "lgr_ctx_timings", "lgr_ctx_stream",
     "lgr_ctx_kernel_times", "lgr_ctx_set_kernel_timing", "lgr_ctx_destroy", "lgr_r_set_seed", "lgr_r_runif",
     "lgr_r_free", "lgr_last_error", "lgr_device_count", "lgr_version", "lgr_nccl_unique_id", "lgr_host_alloc",
     "lgr_host_free", "lgr_normalize_csc", "lgr_row_vars_sparse", "lgr_scale_not_center_by_row",
@@ -133,6 +142,7 @@ def lib():
                                      C.POINTER(c_double_p), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)),
                                      C.POINTER(C.POINTER(C.c_int32)), C.c_int32]
     L.lgr_online_inmf.argtypes = [C.POINTER(lgr_online_args), C.POINTER(lgr_online_out)]
+    L.lgr_online_inmf_chunked.argtypes = [C.POINTER(lgr_online_args), C.POINTER(lgr_chunk_source), C.POINTER(lgr_online_out)]
     L.lgr_ctx_centroid_align.argtypes = [C.c_void_p, C.POINTER(lgr_ca_params), C.POINTER(c_double_p)]
     L.lgr_ctx_quantile_norm.argtypes = [C.c_void_p, C.POINTER(lgr_qn_params), C.POINTER(c_double_p),
                                         C.POINTER(C.POINTER(C.c_int32)), C.POINTER(lgr_qn_info)]

@@ -310,7 +310,8 @@ def uinmf(objectList, unsharedList, k=20, lambda_=5.0, niter=30, nCores=2, verbo
 
 
 def online_inmf(objectList, k=20, lambda_=5.0, maxEpochs=5, minibatchSize=5000, HALSiter=1, Winit=None, Vinit=None, seed=1,
-                nCores=2, verbose=False, device=-1, newDatasets=None, projection=False, Hinit=None, Ainit=None, Binit=None):
+                nCores=2, verbose=False, device=-1, newDatasets=None, projection=False, Hinit=None, Ainit=None, Binit=None,
+                chunk_source=None):
     """RcppPlanc::onlineINMF (reference call site R/integration.R:902-910).  PARITY UNPINNED against RcppPlanc (its source is
     not in the reference tree): the algorithm is the published one, specified line by line in DESIGN.md section 8.
     Scenario 1 (newDatasets = None): online iNMF over `objectList` from scratch.
@@ -318,6 +319,10 @@ def online_inmf(objectList, k=20, lambda_=5.0, maxEpochs=5, minibatchSize=5000, 
     state comes in as Winit / Vinit / Ainit / Binit (one entry per dataset of objectList) -- and the minibatches run over
     `newDatasets`; W and the new V_i, A_i, B_i, H_i are learnt, the old ones returned as given (H: Hinit, if passed).
     Scenario 3 (projection = True): H of `newDatasets` against Winit alone; returns only dict(H=[...]).
+    `chunk_source` (the reference's on-disk path: scaleData as an H5SpMat read chunk by chunk, R/integration.R:745-750): a dict
+    `{"read": f(dataset, col0, ncol) -> (colptr, rowidx, values), "shapes": [(m, n_i)], "nnz": [...], "chunk_cols": 1000}`
+    describing the matrices that are learnt from (scenario 1: objectList, else newDatasets -- pass None entries there); the
+    library pulls every dataset through `read` once into its HBM-resident copy (lgr_online_inmf_chunked).
     Returns dict(H=[n_i x k], V=[m x k], W, A=[k x k], B=[m x k], objErr) like the R function (H is cell x factor; the
     caller transposes, R/integration.R:924)."""
     if projection:
@@ -334,15 +339,27 @@ def online_inmf(objectList, k=20, lambda_=5.0, maxEpochs=5, minibatchSize=5000, 
         prev, data = [], list(objectList)
         if (Winit is None) != (Vinit is None):
             raise ValueError("Winit and Vinit must both be given, or both be None")
-    cs = [_Csc(m) for m in data]
     npv, d = len(prev), len(prev) + len(data)
-    m = cs[0].shape[0]
-    ns = [0] * npv + [c.shape[1] for c in cs]
+    if chunk_source is None:
+        cs = [_Csc(m) for m in data]
+        structs = [c.struct for c in cs]
+        shapes = [c.shape for c in cs]
+    else:
+        shapes = [tuple(int(x) for x in sh) for sh in chunk_source["shapes"]]
+        if len(shapes) != len(data):
+            raise ValueError("chunk_source['shapes'] needs one (m, n_i) per dataset that is read")
+        structs = []
+        for sh in shapes:
+            st = lgr_csc()
+            st.nrow, st.ncol = sh
+            structs.append(st)
+    m = shapes[0][0]
+    ns = [0] * npv + [sh[1] for sh in shapes]
     if min(ns[npv:]) < k:
         raise ValueError(f"Number of factors (k={k}) should be less than the number of cells in the smallest dataset ({min(ns[npv:])}).")
     if m < k:
         raise ValueError(f"Number of factors (k={k}) should be less than the number of shared features ({m}).")
-    Earr = (lgr_csc * d)(*([lgr_csc() for _ in range(npv)] + [c.struct for c in cs]))
+    Earr = (lgr_csc * d)(*([lgr_csc() for _ in range(npv)] + structs))
     a = _ffi.lgr_online_args()
     a.d, a.k, a.m, a.E, a.lambda_ = d, int(k), m, C.cast(Earr, C.c_void_p), float(lambda_)
     a.max_epochs, a.minibatch_size, a.hals_iter, a.seed, a.device = int(maxEpochs), int(minibatchSize), int(HALSiter), int(seed), device
@@ -371,7 +388,37 @@ def online_inmf(objectList, k=20, lambda_=5.0, maxEpochs=5, minibatchSize=5000, 
     o = _ffi.lgr_online_out()
     arrs = [(c_double_p * d)(*[_dp(x) for x in lst]) for lst in (V, H, A, B)]
     o.W, o.V, o.H, o.A, o.B = _dp(W), arrs[0], arrs[1], arrs[2], arrs[3]
-    _ffi.check(_ffi.lib().lgr_online_inmf(C.byref(a), C.byref(o)))
+    if chunk_source is None:
+        _ffi.check(_ffi.lib().lgr_online_inmf(C.byref(a), C.byref(o)))
+    else:
+        read = chunk_source["read"]
+        failure = []
+
+        def _cb(user, ds, c0, nc, colptr, rowidx, values, cap):   # called on this thread, inside lgr_online_inmf_chunked
+            try:
+                cp, ri, vv = read(int(ds) - npv, int(c0), int(nc))
+                cp = np.asarray(cp, dtype=np.int64)
+                got = int(cp[-1] - cp[0])
+                if got > cap:
+                    return -got
+                np.ctypeslib.as_array(colptr, (int(nc) + 1,))[:] = cp - cp[0]
+                if got:
+                    np.ctypeslib.as_array(rowidx, (got,))[:] = np.asarray(ri, dtype=np.int32)[:got]
+                    np.ctypeslib.as_array(values, (got,))[:] = np.asarray(vv, dtype=np.float64)[:got]
+                return got
+            except Exception as e:      # an exception must not cross the C frames
+                failure.append(e)
+                return -1
+        src = _ffi.lgr_chunk_source()
+        cb = _ffi.READ_COLS_FN(_cb)
+        nnz_arr = (C.c_int64 * d)(*([0] * npv + [int(x) for x in chunk_source["nnz"]]))
+        src.read_cols, src.user, src.nnz = cb, None, nnz_arr
+        src.chunk_cols = int(chunk_source.get("chunk_cols", 1000))
+        src.max_chunk_nnz = int(chunk_source.get("max_chunk_nnz", 0))
+        code = _ffi.lib().lgr_online_inmf_chunked(C.byref(a), C.byref(src), C.byref(o))
+        if failure:
+            raise failure[0]
+        _ffi.check(code)
     if projection:
         return {"H": H, "objErr": float(o.objErr), "loop_ms": float(o.loop_ms)}
     for i in range(npv):   # the already factorised datasets keep the H they came with

@@ -1466,9 +1466,10 @@ int lgr_ctx_objerr_i(lgr_ctx* c, int32_t i, double* obj) {
 // ---------------------------------------------------------------------------------------------------------------------
 // online iNMF, scenarios 1-3 (kernels: lgr_online.cu; specification: DESIGN.md section 8)
 // ---------------------------------------------------------------------------------------------------------------------
-int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
+static int online_impl(const lgr_online_args* a, lgr_online_out* o, const lgr_chunk_source* src) {
     return guarded([&] {
         check_device();
+        LGR_REQUIRE(!src || (src->read_cols && src->nnz), "lgr_online_inmf_chunked: the source needs read_cols and nnz");
         LGR_REQUIRE(a && o && a->E && o->H, "lgr_online_inmf: null argument");
         const bool project = (a->flags & LGR_ONLINE_PROJECT) != 0;   // scenario 3: H of the given datasets against Winit, nothing else
         const int nprev = a->n_prev;                                  // scenario 2: datasets [0, nprev) are already factorised
@@ -1508,14 +1509,75 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
         std::vector<StagedCsc> S(d);
         DBuf<int> bad(1);
         bad.zero(st);
+        // chunked source: every dataset is pulled through the caller's reader once, chunk by chunk, into the resident fp32 CSC
+        // (the host never holds a whole matrix; HBM is the cache the reference's on-disk H5SpMat path does not have)
+        const int64_t chunk_cols = src ? (src->chunk_cols > 0 ? src->chunk_cols : 1000) : 0;
+        std::vector<int32_t> hcol, hrow;
+        std::vector<double> hval;
+        DBuf<double> v64;
+        auto pull_chunk = [&](int i, int64_t c0, int64_t nc, size_t& cap) -> int64_t {   // fills hcol / hrow / hval, returns nnz
+            for (;;) {
+                hcol.assign((size_t)nc + 1, 0);
+                if (hrow.size() < cap) {
+                    hrow.resize(cap);
+                    hval.resize(cap);
+                }
+                const int64_t got = src->read_cols(src->user, i, c0, nc, hcol.data(), hrow.data(), hval.data(), (int64_t)cap);
+                if (got < 0 && (size_t)(-got) > cap) {   // the reader asks for more room
+                    cap = (size_t)(-got);
+                    continue;
+                }
+                LGR_REQUIRE(got >= 0 && (size_t)got <= cap, "chunk reader failed");
+                LGR_REQUIRE(hcol[0] == 0 && hcol[(size_t)nc] == got, "chunk reader: column pointers must run from 0 to the chunk's nnz");
+                for (int64_t j = 1; j <= nc; ++j) LGR_REQUIRE(hcol[(size_t)j] >= hcol[(size_t)j - 1], "chunk reader: column pointers must be non-decreasing");
+                return got;
+            }
+        };
+        size_t cap = src ? (size_t)std::max<int64_t>(src->max_chunk_nnz, 1024) : 0;
         for (int i = nprev; i < d; ++i) {
-            check_block(a->E[i], m, a->E[i].ncol, "E[i]");
-            LGR_REQUIRE(a->E[i].location == 0, "online iNMF takes host matrices");
+            if (!src) {
+                check_block(a->E[i], m, a->E[i].ncol, "E[i]");
+                LGR_REQUIRE(a->E[i].location == 0, "online iNMF takes host matrices");
+            } else {
+                LGR_REQUIRE(a->E[i].nrow == m && a->E[i].ncol >= 1 && a->E[i].ncol < (int64_t)0x7fffffff, "E[i]: bad shape");
+                LGR_REQUIRE(src->nnz[i] >= 0 && src->nnz[i] < (int64_t)0x7fffffff, "E[i]: nnz out of range");
+            }
             n[i] = (int)a->E[i].ncol;
             LGR_REQUIRE(n[i] >= k, "Number of factors (k) should be less than the number of cells in the smallest dataset.");
             N += n[i];
-            stage_csc(a->E[i], 0, n[i], S[i], st, false, false);
-            finish_csc(S[i], m, bad.p, st);
+            if (!src) {
+                stage_csc(a->E[i], 0, n[i], S[i], st, false, false);
+                finish_csc(S[i], m, bad.p, st);
+                continue;
+            }
+            StagedCsc& T = S[i];
+            T.base = 0;
+            T.nnz = (size_t)src->nnz[i];
+            T.colptr.alloc((size_t)n[i] + 1);
+            T.rowidx.alloc(std::max<size_t>(T.nnz, 1));
+            T.val.alloc(std::max<size_t>(T.nnz, 1));
+            int64_t running = 0;
+            for (int64_t c0 = 0; c0 < n[i]; c0 += chunk_cols) {
+                const int64_t nc = std::min<int64_t>(chunk_cols, n[i] - c0);
+                const int64_t got = pull_chunk(i, c0, nc, cap);
+                LGR_REQUIRE(running + got <= (int64_t)T.nnz, "chunk reader: more non-zeros than announced");
+                for (int64_t j = 0; j <= nc; ++j) hcol[(size_t)j] += (int32_t)running;
+                const bool last = c0 + nc == n[i];
+                copy_in(T.colptr.p + c0, hcol.data(), (size_t)(nc + (last ? 1 : 0)) * sizeof(int), st, false);
+                if (got) {
+                    if (v64.n < (size_t)got) {
+                        LGR_CUDA(cudaStreamSynchronize(st));
+                        v64.release();
+                        v64.alloc(std::max(cap, (size_t)got));
+                    }
+                    copy_in(T.rowidx.p + running, hrow.data(), (size_t)got * sizeof(int), st, false);
+                    copy_in(v64.p, hval.data(), (size_t)got * sizeof(double), st, false);
+                    dev_f64_to_f32(v64.p, T.val.p + running, (size_t)got, st);
+                }
+                running += got;
+            }
+            LGR_REQUIRE(running == (int64_t)T.nnz, "chunk reader: fewer non-zeros than announced");
+            if (T.nnz) prep_check_rows(T.nnz, T.rowidx.p, m, bad.p, st);
         }
         LGR_REQUIRE(m >= k, "Number of factors (k) should be less than the number of shared features.");
         int hbad = 0;
@@ -1537,6 +1599,14 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
             const lgr_csc& M = a->E[i];
             for (int j = 0; j < k; ++j) {
                 const int c = picks[j];
+                if (src) {   // the sampled cell, through the reader (in double precision, like the in-memory path)
+                    const int64_t got = pull_chunk(i, c, 1, cap);
+                    for (int64_t p = 0; p < got; ++p) {
+                        LGR_REQUIRE(hrow[(size_t)p] >= 0 && hrow[(size_t)p] < m, "chunk reader: row index out of range");
+                        V0[i][(size_t)j * m + hrow[(size_t)p]] += hval[(size_t)p];
+                    }
+                    continue;
+                }
                 for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p) {
                     const double v = M.value_dtype == LGR_F32 ? (double)static_cast<const float*>(M.values)[p]
                                                                : static_cast<const double*>(M.values)[p];
@@ -1792,6 +1862,13 @@ int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) {
             }
         }
     });
+}
+
+int lgr_online_inmf(const lgr_online_args* a, lgr_online_out* o) { return online_impl(a, o, nullptr); }
+// the same over matrices that only exist as column chunks behind a reader (on-disk H5SpMat in the reference)
+int lgr_online_inmf_chunked(const lgr_online_args* a, const lgr_chunk_source* src, lgr_online_out* o) {
+    if (!src) return guarded([&] { LGR_REQUIRE(false, "lgr_online_inmf_chunked: null source"); });
+    return online_impl(a, o, src);
 }
 
 // centroidAlign of host matrices
