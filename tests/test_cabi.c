@@ -1,7 +1,8 @@
 /* Plain-C caller of the liger_b200 ABI (include/liger_b200.h), compiled with gcc by tests/test_abi.py.
  *
  *   test_cabi nogpu   argument errors, the R RNG known answer, and -- without a device -- LGR_ERR_NO_DEVICE
- *   test_cabi gpu     a small iNMF (explicit inits, then in-library inits), lgr_bppnnls_prod and lgr_objerr_i
+ *   test_cabi gpu     a small iNMF (explicit inits, then in-library inits), lgr_bppnnls_prod and lgr_objerr_i, online iNMF from
+ *                     arrays and through a column-chunk reader
  *
  * The numbers checked here need no oracle: closed forms (diagonal Gram), invariants (non-negativity, identical
  * results of two identical calls up to fp32 reduction order, objective decreasing) and R's documented
@@ -41,6 +42,25 @@ static void toy_csc(int m, int n, unsigned seed, int32_t** p, int32_t** i, doubl
         }
     }
     (*p)[n] = nnz;
+}
+
+/* a column-chunk reader over in-memory CSC arrays (stands in for an HDF5 reader): see lgr_chunk_source */
+typedef struct toy_source {
+    int32_t* const* p;
+    int32_t* const* ri;
+    double* const* x;
+    int calls;
+} toy_source;
+static int64_t toy_read_cols(void* user, int32_t ds, int64_t col0, int64_t ncol, int32_t* colptr, int32_t* rowidx, double* values,
+                             int64_t capacity) {
+    toy_source* S = (toy_source*)user;
+    const int32_t b = S->p[ds][col0], e = S->p[ds][col0 + ncol];
+    S->calls += 1;
+    if (e - b > capacity) return -(int64_t)(e - b);
+    for (int64_t j = 0; j <= ncol; ++j) colptr[j] = S->p[ds][col0 + j] - b;
+    memcpy(rowidx, S->ri[ds] + b, (size_t)(e - b) * sizeof(int32_t));
+    memcpy(values, S->x[ds] + b, (size_t)(e - b) * sizeof(double));
+    return e - b;
 }
 
 static int run_nogpu(void) {
@@ -173,6 +193,56 @@ static int run_gpu(void) {
         CHECK(lgr_inmf(&a, &o) == LGR_ERR_INVALID);
         ri[0][3] = saved;
         CHECK(lgr_inmf(&a, &o) == LGR_OK);
+    }
+    /* online iNMF from the arrays and through a reader of column chunks (lgr_online_inmf_chunked): same factors */
+    {
+        lgr_online_args oa;
+        memset(&oa, 0, sizeof(oa));
+        oa.d = D;
+        oa.k = K;
+        oa.m = M;
+        oa.E = E;
+        oa.lambda = 5.0;
+        oa.max_epochs = 3;
+        oa.minibatch_size = 30;
+        oa.hals_iter = 1;
+        oa.seed = 4;
+        oa.device = -1;
+        double Wa[M * K], Wb[M * K], Vx[D][M * K];
+        double* Vp[D] = {Vx[0], Vx[1]};
+        double* Hp[D] = {Ha, Hb};
+        lgr_online_out oo;
+        memset(&oo, 0, sizeof(oo));
+        oo.W = Wa;
+        oo.V = Vp;
+        oo.H = Hp;
+        CHECK(lgr_online_inmf(&oa, &oo) == LGR_OK);
+        CHECK(oo.iterations == (n[0] + n[1]) * 3 / 30 && oo.objErr > 0);
+        const double obj_a = oo.objErr;
+        lgr_csc shapes[D];
+        memset(shapes, 0, sizeof(shapes));
+        int64_t nnz[D];
+        for (int i = 0; i < D; ++i) {
+            shapes[i].nrow = M;
+            shapes[i].ncol = n[i];
+            nnz[i] = p[i][n[i]];
+        }
+        toy_source ts = {p, ri, x, 0};
+        lgr_chunk_source src = {toy_read_cols, &ts, nnz, 16, 8};   /* 16 columns per chunk; capacity 8: the reader asks for more */
+        oa.E = shapes;
+        oo.W = Wb;
+        CHECK(lgr_online_inmf_chunked(&oa, &src, &oo) == LGR_OK);
+        CHECK(ts.calls >= (n[0] + 15) / 16 + (n[1] + 15) / 16 + 2 * K);
+        double num = 0, den = 0;
+        for (int j = 0; j < M * K; ++j) {
+            num += (Wb[j] - Wa[j]) * (Wb[j] - Wa[j]);
+            den += Wa[j] * Wa[j];
+        }
+        CHECK(sqrt(num / den) < 1e-6);
+        CHECK(fabs(oo.objErr - obj_a) < 1e-6 * obj_a);
+        nnz[1] += 3;   /* announced more than the reader delivers */
+        CHECK(lgr_online_inmf_chunked(&oa, &src, &oo) == LGR_ERR_INVALID);
+        CHECK(lgr_online_inmf_chunked(&oa, NULL, &oo) == LGR_ERR_INVALID);
     }
     printf("cabi gpu ok objErr=%.6f\n", o.objErr);
     return 0;
