@@ -448,7 +448,7 @@ bool run_stats(lgr_ctx* c, bool fork_ginv_v = false) {
     if (c->dense && (c->dense_mask & 2)) {
         {
             Timed t(c, "k_gram_tc");
-            launch_gram_h(c->dds_dev.p, c->dds_n, c->gh_blocks, c->num_sms, c->st);
+            launch_gram_h(c->dds_dev.p, c->dds_n, c->gh_blocks, c->kp, c->num_sms, c->st);
             if (c->kp == 64) {   // the block of G between the two factor halves (the tensor-core kernel covers the diagonal blocks)
                 launch_gram_cross(c->dds_dev.p, c->dds_n, c->dense_max_n, c->st);
                 c->tm.kernel_launches += 1;
@@ -459,7 +459,7 @@ bool run_stats(lgr_ctx* c, bool fork_ginv_v = false) {
             forked = true;
         }
         Timed t(c, "k_dense_xh");
-        launch_dense_xh(c->dds_dev.p, c->dds_n, c->k2_flat, c->num_sms, c->st);
+        launch_dense_xh(c->dds_dev.p, c->dds_n, c->k2_flat, c->kp, c->num_sms, c->st);
     } else {
         Timed t(c, "k_spmm_xh");
         launch_spmm_xh(c->ds_dev.p, c->d, c->xh_tiles, c->k, c->kp, c->tc, c->st);
@@ -506,7 +506,7 @@ void enqueue_solve_h(lgr_ctx* c, int cold, double* obj_slot) {
     }
     if (c->dense && (c->dense_mask & 1)) {
         Timed t(c, "k_dense_ltx");
-        launch_dense_ltx(c->dds_dev.p, c->dds_n, c->k1_tiles, c->num_sms, c->st);
+        launch_dense_ltx(c->dds_dev.p, c->dds_n, c->k1_tiles, c->kp, c->num_sms, c->st);
     } else {
         Timed t(c, "k_spmm_ltx");
         launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, c->fuse_u, c->st);
@@ -782,7 +782,7 @@ void products(lgr_ctx* c, int which, double* const* out) {
     if (which == 0) {
         run_prep(c);
         if (c->dense && (c->dense_mask & 1))
-            launch_dense_ltx(c->dds_dev.p, c->dds_n, c->k1_tiles, c->num_sms, c->st);
+            launch_dense_ltx(c->dds_dev.p, c->dds_n, c->k1_tiles, c->kp, c->num_sms, c->st);
         else
             launch_spmm_ltx_tiled(c->ds_dev.p, c->d, c->ltx_blocks, c->kp, c->cb, c->gt, false, c->st);
     } else {

@@ -259,9 +259,9 @@ struct DenseLayout {
 void dense_build(int n, int rows, const int* colptr, const int* rowidx, const float* val, size_t nnz, const float* rs, const float* cs,
                  int halves, DenseLayout& out, int* bad, cudaStream_t st);
 void launch_gram_cross(const DenseDs* ds, int nds, int max_n, cudaStream_t st);
-void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st);
-void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st);
-void launch_gram_h(const DenseDs* ds, int nds, int total_items, int num_sms, cudaStream_t st);
+void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int ldf, int num_sms, cudaStream_t st);
+void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int ldf, int num_sms, cudaStream_t st);
+void launch_gram_h(const DenseDs* ds, int nds, int total_items, int ldf, int num_sms, cudaStream_t st);
 int dense_gram_tile();
 void dense_init();
 

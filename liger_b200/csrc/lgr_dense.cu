@@ -364,6 +364,9 @@ __device__ __forceinline__ const DenseDs* cache_ds(const DenseDs* __restrict__ d
 // `fullA` = the copy's transaction bytes, `emptyA` = tcgen05.commit); it runs further ahead than the X ring.  The slabs are
 // contiguous images written by k_prep, so the copies are 1-D bulk copies (cp.async.bulk, UBLKCP), not tensor-map loads.
 // =====================================================================================================================
+// LDF: row stride of B (= KP: 32, or 64 when the sweep runs once per half of the factors) as a compile-time constant -- the
+// epilogue's address arithmetic shares its issue slots with the scatter warps
+template <int LDF>
 __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* __restrict__ ds_g, int nds, int total_tiles, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ DenseDs sds[MAX_SDS];
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k_dense_ltx(const DenseDs* _
             const int c0 = (tile - D.k1_tile_off) * TILE_N;
             const int ncell = min(TILE_N, D.n - c0);
             const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-            const int ldf = D.ldf;
+            constexpr int ldf = LDF;
             float* __restrict__ Bout = D.B + (size_t)c0 * ldf + q * 8 + fq;
             const float* __restrict__ cs = D.cs + c0;
             mbar_wait(accfull + acc, accph);
@@ -584,6 +587,7 @@ __device__ __forceinline__ K2Pos k2_item(const DenseDs* __restrict__ ds, int nds
 constexpr int K2_WARPS_TOTAL = 6 + SCAT_WARPS;   // A producer, MMA, 4 epilogue, scatter
 constexpr int K2_IMG_STAGE_BYTES = K2_KS * 2 * 96 * 16;   // 6 KB: the 96 used rows of the four [128 x 8] chunks of a stage
 
+template <int LDF>
 __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const DenseDs* __restrict__ ds_g, int nds, long long total_flat, int dbg) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ DenseDs sds[MAX_SDS];
@@ -740,7 +744,7 @@ __global__ void __launch_bounds__(K2_WARPS_TOTAL * 32, 1) k_dense_xh(const Dense
                     const int g = g0 + j * 32 + c;
                     if (j * 32 + c < ngene) {
                         const float sum = buf[lane * 33 + c] + buf[(32 + lane) * 33 + c] + buf[(64 + lane) * 33 + c];
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(D.R + (size_t)g * D.ldf + lane), "f"(sum * __ldg(D.rs + g)) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(D.R + (size_t)g * LDF + lane), "f"(sum * __ldg(D.rs + g)) : "memory");
                     }
                 }
             }
@@ -777,6 +781,7 @@ constexpr int GT_WARPS = 5 + GT_CONV_WARPS;   // MMA, 4 epilogue, converters
 constexpr size_t GT_SMEM = (size_t)NST * GT_STAGE_BYTES + 32 * 8 + 1024;
 constexpr uint32_t IDESC_GRAM = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
+template <int LDF>
 __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __restrict__ ds_g, int nds, int total_items) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ DenseDs sds[MAX_SDS];
@@ -866,7 +871,8 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (cur_ds >= 0) {
                 double* G = ds[cur_ds].G;
-                const int k = ds[cur_ds].kloc, ldf = ds[cur_ds].ldf;
+                const int k = ds[cur_ds].kloc;
+                constexpr int ldf = LDF;
                 for (int e = (warp - 1) * 32 + lane; e < 32 * 32; e += 128) {
                     const int fa = e >> 5, fb = e & 31;
                     if (fa < k && fb < k) atomicAdd(&G[fa * ldf + fb], Gacc[e]);
@@ -929,7 +935,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32, 1) k_gram_tc(const DenseDs* __r
             }
             valid = true;
             it_out = it;
-            const int ldf = ds[i].ldf;
+            constexpr int ldf = LDF;
             const float* __restrict__ H = ds[i].H + (size_t)c0 * ldf;
             const int cc = s * (GT_KS * KSTEP) + ks * KSTEP;
             csn = (lane < KSTEP && cc + lane < ncell) ? __ldg(ds[i].cs + c0 + cc + lane) : 0.f;
@@ -1073,12 +1079,15 @@ __global__ void __launch_bounds__(256) k_gram_cross(const DenseDs* __restrict__ 
 // =====================================================================================================================
 // launches
 // =====================================================================================================================
-void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, cudaStream_t st) {
+void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int ldf, int num_sms, cudaStream_t st) {
     if (total_tiles <= 0) return;
     const int grid = std::min(total_tiles, num_sms);
     static const int dbg = (getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0) |
                            ((getenv("LGR_PF_AHEAD") ? atoi(getenv("LGR_PF_AHEAD")) / 256 : PF_AHEAD / 256) << 8);   // developer knob: 1 no scatter, 2 no MMA, 4 no H loads
-    k_dense_ltx<<<grid, K1_WARPS * 32, K1_SMEM, st>>>(ds, nds, total_tiles, dbg);
+    if (ldf == 32)
+        k_dense_ltx<32><<<grid, K1_WARPS * 32, K1_SMEM, st>>>(ds, nds, total_tiles, dbg);
+    else
+        k_dense_ltx<64><<<grid, K1_WARPS * 32, K1_SMEM, st>>>(ds, nds, total_tiles, dbg);
     LGR_CUDA(cudaGetLastError());
     if (dbg & 16) {
         unsigned long long h[16];
@@ -1088,12 +1097,15 @@ void launch_dense_ltx(const DenseDs* ds, int nds, int total_tiles, int num_sms, 
                 h[2], h[4]);
     }
 }
-void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_sms, cudaStream_t st) {
+void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int ldf, int num_sms, cudaStream_t st) {
     if (total_flat <= 0) return;
     const int grid = (int)std::min<long long>(total_flat, num_sms);
     static const int dbg = (getenv("LGR_DENSE_DBG") ? atoi(getenv("LGR_DENSE_DBG")) : 0) |
                            ((getenv("LGR_PF_AHEAD") ? atoi(getenv("LGR_PF_AHEAD")) / 256 : PF_AHEAD / 256) << 8);
-    k_dense_xh<<<grid, K2_WARPS_TOTAL * 32, K2_SMEM, st>>>(ds, nds, total_flat, dbg);
+    if (ldf == 32)
+        k_dense_xh<32><<<grid, K2_WARPS_TOTAL * 32, K2_SMEM, st>>>(ds, nds, total_flat, dbg);
+    else
+        k_dense_xh<64><<<grid, K2_WARPS_TOTAL * 32, K2_SMEM, st>>>(ds, nds, total_flat, dbg);
     LGR_CUDA(cudaGetLastError());
     if (dbg & 16) {
         unsigned long long h[16];
@@ -1103,10 +1115,13 @@ void launch_dense_xh(const DenseDs* ds, int nds, long long total_flat, int num_s
                 h[10], h[12]);
     }
 }
-void launch_gram_h(const DenseDs* ds, int nds, int total_items, int num_sms, cudaStream_t st) {
+void launch_gram_h(const DenseDs* ds, int nds, int total_items, int ldf, int num_sms, cudaStream_t st) {
     if (total_items <= 0) return;
     const int grid = std::min(total_items, num_sms);
-    k_gram_tc<<<grid, GT_WARPS * 32, GT_SMEM, st>>>(ds, nds, total_items);
+    if (ldf == 32)
+        k_gram_tc<32><<<grid, GT_WARPS * 32, GT_SMEM, st>>>(ds, nds, total_items);
+    else
+        k_gram_tc<64><<<grid, GT_WARPS * 32, GT_SMEM, st>>>(ds, nds, total_items);
     LGR_CUDA(cudaGetLastError());
 }
 void launch_gram_cross(const DenseDs* ds, int nds, int max_n, cudaStream_t st) {
@@ -1118,9 +1133,12 @@ void launch_gram_cross(const DenseDs* ds, int nds, int max_n, cudaStream_t st) {
 }
 int dense_gram_tile() { return GT_CELLS; }
 void dense_init() {
-    LGR_CUDA(cudaFuncSetAttribute(k_dense_ltx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
-    LGR_CUDA(cudaFuncSetAttribute(k_dense_xh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
-    LGR_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_dense_ltx<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_dense_ltx<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_dense_xh<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_dense_xh<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_gram_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
+    LGR_CUDA(cudaFuncSetAttribute(k_gram_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
 }
 
 // =====================================================================================================================

@@ -37,7 +37,7 @@ for fn, c in counts.items():
     print(f"{dem[:60]:60s} " + " ".join(f"{c.get(w, 0):7d}" for w in want))
 # excerpt: the issue loop of the dense B sweep
 print("\n# excerpt: MMA issue section of k_dense_ltx (tcgen05.mma -> UTCHMMA with uniform-register descriptors, tcgen05.commit -> UTCBAR)")
-one = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3lgr11k_dense_ltxEPKNS_7DenseDsEiii", lib], capture_output=True, text=True).stdout.splitlines()
+one = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3lgr11k_dense_ltxILi32EEEvPKNS_7DenseDsEiii", lib], capture_output=True, text=True).stdout.splitlines()
 idx = [i for i, l in enumerate(one) if "UTCHMMA" in l]
 if idx:
     for l in one[max(idx[0] - 12, 0):idx[-1] + 8]:
