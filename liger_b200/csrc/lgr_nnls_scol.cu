@@ -4,11 +4,17 @@
 // warm-start mask (bit 63); this kernel continues them from the passive set they had reached.  Same problem, same exchange
 // rule and the same tolerances as lgr_nnls_reg.cu (reference: RcppPlanc::bppnnls_prod, call site R/cINMF.R:481).
 //
-// Why not a warp per column (lgr_nnls_wbig.cu, which this replaces on the H solves): a Gauss-Jordan sweep that moves its
+// Role: systems of up to 26 unknowns go to k_nnls_pair (lgr_nnls_pair.cu: two lanes per column, block in registers, ~2 x
+// faster than this kernel); what is left for this one are the systems of 27..31 unknowns (k > 52) and, with
+// LGR_NNLS_NO_PAIR, everything k_nnls_reg<64> flags.
+//
+// Why not a warp per column (lgr_nnls_wbig.cu, the round-1 continuation kernel): a Gauss-Jordan sweep that moves its
 // pivot row by shuffles spends ~2500 warp instructions per column and round at s = 25; a thread that owns its column
 // spends s^3 / 6 FMAs, ~300 warp instructions per column.  The price is storage: the lower triangle of an s x s block does
 // not fit the register file above s = 16, so it lives in shared memory, [word][thread] (conflict free), and the
 // factorisation is row by row (Cholesky-Banachiewicz, two columns at a time: three shared-memory reads per two FMAs).
+// 183 KB of triangles leave one warp per scheduler, so every FMA waits for its shared-memory operands: measured 4.1-4.8 ms
+// on a C4 shard against 4.8-6.0 ms for the warp-per-column kernel (and 1.8-2.2 ms for k_nnls_pair).
 // b and u = P b stay in registers (the matrix no longer needs them).  All loops run to the warp's largest system, columns
 // are ordered by system size, smaller systems are padded with identity rows (index 64 of the staged matrix), so a warp
 // never diverges inside a round.
