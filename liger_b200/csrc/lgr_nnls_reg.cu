@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
     Mask* fmask = reinterpret_cast<Mask*>(smem_raw + L.fmask);   // warm-start passive sets of the pass
 
     const bool cold_start = (flags & 1) != 0;
+    const bool defer_all = KP > 32 && (flags & 128) != 0;   // developer knob LGR_NNLS_PAIR_ALL: every column goes to the continuation kernel
     const bool sync_rounds = (flags & 32) != 0;   // CTA-wide round barrier: the warps walk the unrolled code together (I-cache)
     const Mask kmask = (k >= (int)(8 * sizeof(Mask))) ? ~(Mask)0 : ((ONE << k) - ONE);
     const int MAXIT = 4 * k + 16;
@@ -346,7 +347,9 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         for (int c = tid; c < nsub; c += blockDim.x) {
             const Mask f0 = cold_start ? (Mask)0 : ((Mask)masks[c] & kmask);
             fmask[c] = f0;
-            atomicAdd(&hist[bin_of(popc_m(f0))], 1);
+            const int p0 = popc_m(f0);
+            atomicAdd(&hist[bin_of(p0)], 1);
+            if (KP > 32 && min(p0, k - p0) > 16) atomicAdd(&hist[35], 1);   // systems this kernel hands over anyway
         }
         __syncthreads();
         if (tid == 0) {
@@ -367,6 +370,10 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
         // round barrier only while the big unrolled templates dominate (they do not fit the instruction cache: the
         // warps then walk the code together); a pass of mostly small systems runs barrier-free
         const bool sync_pass = sync_rounds && hist[34] * 4 > nsub;
+        // k > 32: when most columns of the pass go to the continuation kernel anyway, all of them do -- it runs eight warps
+        // per SM against this kernel's four (measured on a C4 shard: -0.2 to -0.3 ms per iteration while the systems are big,
+        // +0.3 to +0.6 ms if applied when they are small)
+        const bool defer_pass = defer_all || (KP > 32 && (flags & 256) == 0 && hist[35] * 2 > nsub);
         bool active = false, exhausted = false, have_u = false;
         int col = 0, state = 0, nxt = -1;
         Mask F = 0;
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
                 const bool seed = state == (3 | ((k + 1) << 8)) && F == 0 && !have_u;
                 // (a column that is about to be handed over -- more than 16 unknowns, k > 32 -- does not need u here: the
                 //  continuation kernel forms its own)
-                const bool hand_over = KP > 32 && s > 16 && !seed;
+                const bool hand_over = KP > 32 && (s > 16 || defer_pass) && !seed;
                 if ((dual || seed) && !have_u && !hand_over) {
                     float acc[RKP];
 #pragma unroll
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(256, 1) k_nnls_reg(const NnlsGroup* __restrict
             }
             // systems with more than 16 unknowns (possible only for k > 32) do not fit the register templates: the
             // column is handed to k_nnls with its current passive set (flag bit in the warm-start mask)
-            if (KP > 32 && active && s > 16) {
+            if (KP > 32 && active && (s > 16 || defer_pass)) {
                 masks[col] = (unsigned long long)F | DEFER_BIT;
                 active = false;
                 s = 0;
@@ -528,7 +535,8 @@ void launch_nnls_reg(const NnlsGroup* groups, int ngroups, long long total_cols,
     const int grid = (int)(want < num_sms ? want : num_sms);
     static const bool sync_rounds = getenv("LGR_NNLS_REG_NOSYNC") == nullptr;
     static const bool no_side = getenv("LGR_NNLS_REG_NOSIDE") != nullptr;
-    const int fl = flags | (sync_rounds ? 32 : 0) | (no_side ? 64 : 0);
+    static const bool pair_all = getenv("LGR_NNLS_PAIR_ALL") != nullptr, pair_min = getenv("LGR_NNLS_PAIR_MIN") != nullptr;
+    const int fl = flags | (sync_rounds ? 32 : 0) | (no_side ? 64 : 0) | (pair_all ? 128 : 0) | (pair_min ? 256 : 0);
     if (kp == 32)
         k_nnls_reg<32><<<grid, threads, smem, st>>>(groups, ngroups, total_cols, k, cnt, fl);
     else
