@@ -389,8 +389,9 @@ def test_restarts_and_explicit_inits(pbmc):
     import liger_b200
     a = liger_b200.run_inmf_list(pbmc["Es"], k=12, nIteration=3, nRandomStarts=1, seed=4)
     b = liger_b200.run_inmf_list(pbmc["Es"], k=12, nIteration=3, nRandomStarts=3, seed=4)
-    # the GPU run is not bitwise reproducible (fp32 atomics), so equal-init restarts tie to ~1e-9 and any may win
-    assert rel(a["W"], b["W"]) < 1e-5 and b["bestSeed"] in (4, 5, 6)
+    # the GPU run is not bitwise reproducible (fp32 atomics): equal-init restarts tie to ~1e-9, and a tie keeps the first
+    # restart, as the reference's strict `<` does
+    assert rel(a["W"], b["W"]) < 1e-5 and b["bestSeed"] == 4
     assert abs(a["objErr"] - b["objErr"]) < 1e-6 * a["objErr"]
     W0, V0, _, _ = orc.seeded_init(9, 173, 12, [300, 300])
     c = liger_b200.run_inmf_list(pbmc["Es"], k=12, nIteration=3, WInit=W0, VInit=V0)
